@@ -1,0 +1,151 @@
+/* ppde_b200 — C-ABI of the B200-native PPDE hot path (libppde_b200.so).
+ *
+ * The reference (pemami4911/ppde) has NO native boundary: its hot path is a duck-typed
+ * Python protocol.  This header is the boundary a maintainer binds under
+ * that protocol (ctypes stub in INTEGRATION.md).  Every entry point is a stateless launcher:
+ * plain device pointers + sizes + a cudaStream_t (passed as void*), returns 0 or a
+ * cudaError_t value, never aborts, allocates nothing.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference root):
+ *   ppde_potts_symmetrize        PottsModel.__init__ parameter load          ppde/nets.py:245-262
+ *   ppde_potts_full              PottsModel.hamiltonian/forward + autograd   ppde/nets.py:282-299, ppde/energy.py:106-108
+ *   ppde_potts_incremental       same quantity at y, reusing the field at x  
+ *   ppde_cnn_forward             OnehotCNN.forward x3, EnsembleProtein mean  ppde/nets.py:363-376,434-442
+ *   ppde_cnn_backward_combine    autograd through the CNN + PoE sum          ppde/energy.py:104-108
+ *   ppde_pas_propose             PPDE_PAS.run forward path loop              ppde/protein_samplers/ppde.py:67-116
+ *                                 + mut_distance / mutation_mask / safe_logits_to_probs  ppde/utils.py:5-28,106-111
+ *   ppde_pas_reverse_accept      reverse proposal, MH accept, reset, history ppde/protein_samplers/ppde.py:122-153,172-183
+ *   ppde_onehot_to_aa / ppde_aa_to_onehot   seqs_to_onehot / onehot2seq      ppde/third_party/hsu/data_utils.py:150-175
+ *   ppde_population_metrics      mut_distance mean, #accepted (logging)      ppde/protein_samplers/ppde.py:162-168
+ *   ppde_sequence_hash           diversity_score (unique sequences)          scripts/make_figures.py:38-49
+ *
+ * Data layout (all row-major, device memory):
+ *   residues     uint8  [n, aa_stride]   aa_stride >= L, multiple of 16; alphabet ACDEFGHIKLMNPQRSTVWY = 0..19
+ *   gradient     float  [rows, 20*L]     entry (i,a) at i*20+a — same flattening as the reference's reshape(n,-1)
+ *   Potts field  float  [rows, D]        D = 20*Lp, window positions only
+ *   Jsym         float  [D, D]           Jsym[(i,a),(j,l)] = (J[i,j,a,l] + J[j,i,l,a]) / 2
+ *   G / Gp pools: rows [0,n) and [n,2n) are the two private rows of chain b (b and n+b);
+ *                 rows >= 2n are shared "fixed" rows (wild type, paper-mode anchors).
+ */
+#ifndef PPDE_B200_H
+#define PPDE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPDE_MAX_NETS 4
+#define PPDE_MAX_SUBSTEPS 32
+
+typedef struct ppde_potts {
+    int32_t L;          /* full sequence length */
+    int32_t Lp;         /* Potts window length (contiguous) */
+    int32_t win_lo;     /* first window position, 0-based inclusive (index_list[0] - offset) */
+    int32_t D;          /* 20 * Lp */
+    const float* Jsym;  /* [D, D] */
+    const float* h;     /* [D] */
+    const uint8_t* wt;  /* [L] */
+    float wt_H;         /* H(wt), subtracted from every energy (forward(delta=True)) */
+    int32_t _pad;
+} ppde_potts_t;
+
+typedef struct ppde_cnn_net {
+    const float* T0;    /* [5][20][C]   T0[t][a][c] = encoder.weight[c][a][t] */
+    const float* b0;    /* [C]          encoder.bias */
+    const float* W1;    /* [2C][C]      embedding.0.weight */
+    const float* W1T;   /* [C][2C]      its transpose (forward K-major operand) */
+    const float* b1;    /* [2C]         embedding.0.bias */
+    const float* d;     /* [2C]         decoder.weight[0] */
+    const float* W0r;   /* [C][5][20]   W0r[c][t][a] = encoder.weight[c][a][t] (backward) */
+    float c;            /* decoder.bias */
+    int32_t _pad;
+} ppde_cnn_net_t;
+
+typedef struct ppde_cnn {
+    int32_t n_nets;     /* 3 in the reference (EnsembleProtein) */
+    int32_t C;          /* channels = L */
+    int32_t L;
+    int32_t P;          /* L - 4 conv output positions */
+    ppde_cnn_net_t net[PPDE_MAX_NETS];
+} ppde_cnn_t;
+
+typedef struct ppde_chains {
+    int32_t n;            /* local chains */
+    int32_t chain_offset; /* global id of local chain 0 (random streams are indexed by global id) */
+    int32_t L;
+    int32_t aa_stride;
+    uint8_t* aa;          /* [n, aa_stride] current state */
+    uint8_t* aa_y;        /* [n, aa_stride] proposal y */
+    int32_t* row_cur;     /* [n] pool row holding G / Gp of the current state */
+    float* G;             /* pool [2n + n_fixed, 20L] */
+    float* Gp;            /* pool [2n + n_fixed, D] */
+    float* E;             /* [n] energy of current state */
+    float* fit;           /* [n] CNN-ensemble fitness of current state */
+    float* E_y;           /* [n] */
+    float* fit_y;         /* [n] */
+    float* Epotts_y;      /* [n] */
+    /* fixed rows */
+    int32_t n_fixed;
+    int32_t row_wt;            /* pool row of the wild type (>= 2n) */
+    const float* E_fixed;      /* [n_fixed] */
+    const float* fit_fixed;    /* [n_fixed] */
+    const uint8_t* aa_fixed;   /* [n_fixed, aa_stride] */
+    const int32_t* anchor_fixed; /* [n] fixed-row index (0..n_fixed-1) of each chain's paper-mode anchor, or NULL */
+    /* per-iteration trace (always written; tiny) */
+    int32_t* U;           /* [n] path length */
+    int32_t* idx;         /* [S, n] flat proposal index i*20+a */
+    uint8_t* old_aa;      /* [S, n] residue at the proposed position before the move */
+    float* lqf;           /* [S, n] forward log-prob */
+    float* lqr;           /* [S, n] reverse log-prob */
+    float* log_acc;       /* [n] */
+    uint8_t* accept;      /* [n] */
+    /* run-level outputs */
+    float* E_hist;        /* [T+1, n] or NULL */
+    float* fit_hist;      /* [T+1, n] or NULL */
+    float* best_E;        /* [n] */
+    float* best_fit;      /* [n] */
+    uint8_t* best_aa;     /* [n, aa_stride] */
+    uint8_t* traj_aa;     /* [T+1, aa_stride] states of chain `traj_chain`, or NULL */
+    int32_t traj_chain;   /* local index, -1 if not on this rank */
+    int32_t _pad;
+} ppde_chains_t;
+
+typedef struct ppde_pas_params {
+    int32_t S;            /* sub-steps per iteration = 2*pas-1 (fixed; masked by U) */
+    int32_t nmut_threshold; /* INT32_MAX when --nmut_threshold 0 */
+    int32_t paper_results;
+    int32_t t;            /* iteration index (stream counter) */
+    uint64_t seed;
+    const float* uniforms; /* optional materialised proposal uniforms [S, n, 20L]; NULL = Philox in-kernel */
+    const int32_t* t_dev;  /* optional device-resident iteration counter (CUDA-graph replay); NULL = use t */
+} ppde_pas_params_t;
+
+const char* ppde_version(void);
+int ppde_last_launch_count(void);   /* kernels launched by this library since load (bench's gpu_launches) */
+
+int ppde_potts_symmetrize(const float* J, int32_t Lp, float* Jsym, void* stream);
+int ppde_potts_full(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
+                    float* Gp, int64_t Gp_stride, float* Epotts, void* stream);
+int ppde_potts_incremental(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
+int ppde_cnn_forward(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
+                     unsigned long long* mkey /* [n, n_nets, 2C] */, void* stream);
+int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
+                              int32_t n, const unsigned long long* mkey, float lamda,
+                              const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
+                              const float* Epotts, float* G, int64_t G_stride, const int32_t* g_rows,
+                              float* E, float* fit, void* stream);
+int ppde_step_rows(const ppde_chains_t* c, int32_t* rows_y, void* stream);
+int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
+int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
+
+int ppde_onehot_to_aa(const float* x, int32_t n, int32_t L, uint8_t* aa, int32_t aa_stride, void* stream);
+int ppde_aa_to_onehot(const uint8_t* aa, int32_t aa_stride, int32_t n, int32_t L, float* x, void* stream);
+int ppde_population_metrics(const uint8_t* aa, int32_t aa_stride, int32_t n, int32_t L, const uint8_t* wt,
+                            int32_t* dist /* [n] */, unsigned long long* hash /* [n] */, void* stream);
+int ppde_counter_add(int32_t* t_dev, int32_t inc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,107 @@
+// Shared device helpers for the PPDE hot-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define PPDE_Q 20                      // residue alphabet size (ppde/third_party/hsu/data_utils.py:48-72)
+#define PPDE_EPS 1.1920928955078125e-07f   // torch.finfo(float32).eps used by clamp_probs
+#define PPDE_MAX_S 32                  // max sub-steps per iteration (2*pas-1)
+
+namespace ppde {
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Bit-identical to ppde_b200/philox.py (Random123 known answers are tested on both sides).
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ a;
+            uint32_t n2 = hi0 ^ c3 ^ b;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+enum { KIND_PROPOSAL = 0, KIND_PATHLEN = 1, KIND_ACCEPT = 2 };
+
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {      // strictly inside (0,1), exact
+    return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
+}
+
+// ---------------------------------------------------------------- block reductions
+// All threads must call. `red` is a __shared__ scratch of >= 33 floats (or 2x for the pair version).
+template <int NT>
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    constexpr int NW = NT / 32;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) r = fmaxf(r, red[w]);
+    return r;
+}
+
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    constexpr int NW = NT / 32;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) r += red[w];     // fixed order: deterministic
+    return r;
+}
+
+template <int NT>
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    constexpr int NW = NT / 32;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = red[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) r += red[w];
+    return r;
+}
+
+// argmax with lowest-index tie break (torch.argmax / torch.max on CPU return the first maximum).
+template <int NT>
+__device__ __forceinline__ void block_argmax(float& v, int& idx, float* redv, int* redi) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    constexpr int NW = NT / 32;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { redv[threadIdx.x >> 5] = v; redi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    v = redv[0]; idx = redi[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+        float ov = redv[w]; int oi = redi[w];
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+
+__device__ __forceinline__ float clamp_prob(float p) {          // torch.distributions.utils.clamp_probs
+    return fminf(fmaxf(p, PPDE_EPS), 1.0f - PPDE_EPS);
+}
+
+}  // namespace ppde

@@ -1,0 +1,286 @@
+// Path-auxiliary proposal, reverse proposal and Metropolis-Hastings commit.
+//
+// Reference: PPDE_PAS.run inner loop             ppde/protein_samplers/ppde.py:65-153
+//            mut_distance / mutation_mask          ppde/utils.py:5-28
+//            safe_logits_to_probs                  ppde/utils.py:106-111
+//            torch.distributions.Categorical       (__init__ renormalise, sample = multinomial =
+//                                                   argmax p/Exp(1), log_prob = log(clamp(p)))
+// Index-form semantics: SURVEY.md Appendix A.  One CTA per chain; the chain's gradient row
+// [20L] lives in shared memory for all S sub-steps (it is frozen along the path, ppde.py:98).
+#include "common.cuh"
+#include "../../include/ppde_b200.h"
+#include "launch.cuh"
+
+namespace ppde {
+
+__device__ __forceinline__ int y_row(int row_cur, int b, int n) { return row_cur == b ? n + b : b; }
+
+// softmax -> clamp -> renormalise statistics of one logit vector held in shared memory.
+// On return sP[j] = clamp(exp(l_j - m1) / s2) and the function returns s3 = sum_j sP[j].
+// (utils.py:106-111: logits - logsumexp, softmax, clamp_probs; Categorical.__init__: p / p.sum())
+template <int NT>
+__device__ __forceinline__ float softmax_clamp_inplace(float* sP, int n4, float* red) {
+    float4* p4 = reinterpret_cast<float4*>(sP);
+    float mx = -INFINITY;
+    for (int q = threadIdx.x; q < n4; q += NT) {
+        float4 v = p4[q];
+        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    const float m1 = block_max<NT>(mx, red);
+    const float off = (m1 == -INFINITY) ? 0.f : m1;
+    float sum = 0.f;
+    for (int q = threadIdx.x; q < n4; q += NT) {
+        float4 v = p4[q];
+        v.x = expf(v.x - off); v.y = expf(v.y - off); v.z = expf(v.z - off); v.w = expf(v.w - off);
+        p4[q] = v;
+        sum += (v.x + v.y) + (v.z + v.w);
+    }
+    const float s2 = block_sum<NT>(sum, red);
+    float sum3 = 0.f;
+    for (int q = threadIdx.x; q < n4; q += NT) {
+        float4 v = p4[q];
+        v.x = clamp_prob(v.x / s2); v.y = clamp_prob(v.y / s2);
+        v.z = clamp_prob(v.z / s2); v.w = clamp_prob(v.w / s2);
+        p4[q] = v;
+        sum3 += (v.x + v.y) + (v.z + v.w);
+    }
+    return block_sum<NT>(sum3, red);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = c.L, NE = L * PPDE_Q, n4 = NE / 4;
+    float* sG = reinterpret_cast<float*>(smem_raw);          // [20L] gradient row (frozen)
+    float* sP = sG + NE;                                     // [20L] logits -> probabilities
+    float* sCur = sP + NE;                                   // [L]  G[i, aa_i]
+    uint8_t* sAA = reinterpret_cast<uint8_t*>(sCur + L);     // [L]  evolving state
+    uint8_t* sWT = sAA + ((L + 15) & ~15);                   // [L]
+    __shared__ float red[33];
+    __shared__ int redi[33];
+    __shared__ int s_idx;
+
+    const int b = blockIdx.x;
+    const uint32_t gid = (uint32_t)(c.chain_offset + b);
+    const int t = p.t_dev ? *p.t_dev : p.t;
+    const Philox rng(p.seed);
+    const int lo = m.win_lo, hi = m.win_lo + m.Lp - 1;
+
+    {   // stage the row and the state
+        const float4* g4 = reinterpret_cast<const float4*>(c.G + (int64_t)c.row_cur[b] * NE);
+        float4* s4 = reinterpret_cast<float4*>(sG);
+        for (int q = threadIdx.x; q < n4; q += NT) s4[q] = g4[q];
+        const uint8_t* ax = c.aa + (int64_t)b * c.aa_stride;
+        for (int i = threadIdx.x; i < L; i += NT) { sAA[i] = ax[i]; sWT[i] = m.wt[i]; }
+    }
+    const int span = p.S;                                      // 2*pas-1 values: U in {1..S}  (ppde.py:67)
+    const int U = 1 + (int)(rng(0u, gid, (uint32_t)t, (uint32_t)(KIND_PATHLEN << 16)).x % (uint32_t)span);
+    if (threadIdx.x == 0) c.U[b] = U;
+    __syncthreads();
+
+    for (int s = 0; s < p.S; ++s) {
+        // edit distance to WT and the threshold flag (utils.py:5-14, ppde.py:86-91)
+        int dpart = 0;
+        for (int i = threadIdx.x; i < L; i += NT) {
+            dpart += (sAA[i] != sWT[i]);
+            sCur[i] = sG[i * PPDE_Q + sAA[i]];
+        }
+        const int dist = block_sum_int<NT>(dpart, redi);       // (barrier inside also publishes sCur)
+        const bool at_thr = dist >= p.nmut_threshold;
+        // Taylor logits with the revert-only mask and the window mask (ppde.py:95-104, utils.py:17-28)
+        float4* p4 = reinterpret_cast<float4*>(sP);
+        const float4* g4 = reinterpret_cast<const float4*>(sG);
+        for (int q = threadIdx.x; q < n4; q += NT) {
+            const int i = q / 5, a0 = (q - i * 5) * 4;
+            float4 g = g4[q];
+            const float gc = sCur[i];
+            float4 l;
+            l.x = (g.x - gc) * 0.5f; l.y = (g.y - gc) * 0.5f; l.z = (g.z - gc) * 0.5f; l.w = (g.w - gc) * 0.5f;
+            if (i < lo || i > hi) {
+                l.x = l.y = l.z = l.w = -INFINITY;
+            } else if (at_thr) {
+                const int w = (sAA[i] != sWT[i]) ? (int)sWT[i] : -1;   // the only legal target: revert to WT
+                if (a0 + 0 != w) l.x = -INFINITY;
+                if (a0 + 1 != w) l.y = -INFINITY;
+                if (a0 + 2 != w) l.z = -INFINITY;
+                if (a0 + 3 != w) l.w = -INFINITY;
+            }
+            p4[q] = l;
+        }
+        __syncthreads();
+        const float s3 = softmax_clamp_inplace<NT>(sP, n4, red);
+        // exponential race: argmax_j p_j / E_j, E_j = -log(u_j)  (= torch.multinomial(p, 1, True))
+        float best = -1.f; int bidx = 0x7fffffff;
+        const float* um = p.uniforms ? p.uniforms + ((int64_t)s * c.n + b) * NE : nullptr;
+        for (int q = threadIdx.x; q < n4; q += NT) {
+            float4 u;
+            if (um) {
+                u = reinterpret_cast<const float4*>(um)[q];
+            } else {
+                uint4 w = rng((uint32_t)q, gid, (uint32_t)t, (uint32_t)(s | (KIND_PROPOSAL << 16)));
+                u = make_float4(u32_to_unit(w.x), u32_to_unit(w.y), u32_to_unit(w.z), u32_to_unit(w.w));
+            }
+            float4 pr = p4[q];
+            float r0 = (pr.x / s3) / (-logf(u.x));
+            float r1 = (pr.y / s3) / (-logf(u.y));
+            float r2 = (pr.z / s3) / (-logf(u.z));
+            float r3 = (pr.w / s3) / (-logf(u.w));
+            if (r0 > best) { best = r0; bidx = q * 4; }
+            if (r1 > best) { best = r1; bidx = q * 4 + 1; }
+            if (r2 > best) { best = r2; bidx = q * 4 + 2; }
+            if (r3 > best) { best = r3; bidx = q * 4 + 3; }
+        }
+        block_argmax<NT>(best, bidx, red, redi);
+        if (threadIdx.x == 0) {
+            const int pos = bidx / PPDE_Q, a = bidx - pos * PPDE_Q;
+            const int64_t o = (int64_t)s * c.n + b;
+            c.idx[o] = bidx;
+            c.old_aa[o] = sAA[pos];
+            c.lqf[o] = logf(clamp_prob(sP[bidx] / s3));            // Categorical.log_prob
+            if (s < U) sAA[pos] = (uint8_t)a;                      // ppde.py:111-115 (masked by u_mask)
+            s_idx = bidx;
+        }
+        __syncthreads();
+    }
+    uint8_t* ay = c.aa_y + (int64_t)b * c.aa_stride;
+    for (int i = threadIdx.x; i < L; i += NT) ay[i] = sAA[i];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pas_reverse_accept_kernel(ppde_potts_t m, ppde_chains_t c,
+                                                                ppde_pas_params_t p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = c.L, NE = L * PPDE_Q, n4 = NE / 4;
+    float* sG = reinterpret_cast<float*>(smem_raw);          // [20L] gradient row at y
+    float* sP = sG + NE;                                     // [20L]
+    float* sCur = sP + NE;                                   // [L]
+    uint8_t* sZ = reinterpret_cast<uint8_t*>(sCur + L);      // [L] trajectory state
+    __shared__ float red[33];
+    __shared__ int redi[33];
+    __shared__ int s_flag;
+
+    const int b = blockIdx.x, n = c.n;
+    const uint32_t gid = (uint32_t)(c.chain_offset + b);
+    const int t = p.t_dev ? *p.t_dev : p.t;
+    const int rx = c.row_cur[b];
+    const int ry = y_row(rx, b, n);
+    uint8_t* ax = c.aa + (int64_t)b * c.aa_stride;
+    const uint8_t* ay = c.aa_y + (int64_t)b * c.aa_stride;
+    {
+        const float4* g4 = reinterpret_cast<const float4*>(c.G + (int64_t)ry * NE);
+        float4* s4 = reinterpret_cast<float4*>(sG);
+        for (int q = threadIdx.x; q < n4; q += NT) s4[q] = g4[q];
+        for (int i = threadIdx.x; i < L; i += NT) sZ[i] = ax[i];
+    }
+    const int U = c.U[b];
+    __syncthreads();
+
+    float log_ratio = 0.f;
+    for (int s = 0; s < p.S; ++s) {
+        const int64_t o = (int64_t)s * n + b;
+        const int cidx = c.idx[o];
+        if (threadIdx.x == 0 && s < U) sZ[cidx / PPDE_Q] = (uint8_t)(cidx % PPDE_Q);   // state AFTER move s
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += NT) sCur[i] = sG[i * PPDE_Q + sZ[i]];
+        __syncthreads();
+        float4* p4 = reinterpret_cast<float4*>(sP);
+        const float4* g4 = reinterpret_cast<const float4*>(sG);
+        for (int q = threadIdx.x; q < n4; q += NT) {              // NO masks on the reverse path (ppde.py:126-127)
+            const float gc = sCur[q / 5];
+            float4 g = g4[q];
+            p4[q] = make_float4((g.x - gc) * 0.5f, (g.y - gc) * 0.5f, (g.z - gc) * 0.5f, (g.w - gc) * 0.5f);
+        }
+        __syncthreads();
+        const float s3 = softmax_clamp_inplace<NT>(sP, n4, red);
+        if (threadIdx.x == 0) {
+            const float lqr = logf(clamp_prob(sP[cidx] / s3));
+            c.lqr[o] = lqr;
+            if (s < U) log_ratio += lqr - c.lqf[o];               // u_mask * (rev - fwd), ppde.py:132
+        }
+        __syncthreads();
+    }
+
+    if (threadIdx.x == 0) {
+        const float e_x = c.E[b], f_x = c.fit[b];
+        const float e_y = c.E_y[b], f_y = c.fit_y[b];
+        const float log_acc = (e_y - e_x) + log_ratio;             // ppde.py:135-136
+        const float u = u32_to_unit(Philox(p.seed)(0u, gid, (uint32_t)t, (uint32_t)(KIND_ACCEPT << 16)).x);
+        const bool acc = expf(log_acc) >= u;                       // '>=' (ppde.py:138); NaN rejects
+        c.log_acc[b] = log_acc;
+        c.accept[b] = acc ? 1 : 0;
+        const float e_rec = acc ? e_y : e_x, f_rec = acc ? f_y : f_x;   // ppde.py:141-143
+        if (c.E_hist) c.E_hist[(int64_t)(t + 1) * n + b] = e_rec;
+        if (c.fit_hist) c.fit_hist[(int64_t)(t + 1) * n + b] = f_rec;
+        // 0: keep current state; 1: take y; 2: fall back to the paper-mode anchor
+        s_flag = acc ? 1 : (p.paper_results ? 2 : 0);
+        if (acc) { c.E[b] = e_y; c.fit[b] = f_y; c.row_cur[b] = ry; }
+        else if (p.paper_results) {                                // x is never refreshed: reject = back to x0 (ppde.py:76-77,139)
+            const int f = c.anchor_fixed ? c.anchor_fixed[b] : (c.row_wt - 2 * n);
+            c.E[b] = c.E_fixed[f]; c.fit[b] = c.fit_fixed[f]; c.row_cur[b] = 2 * n + f;
+        }
+        const bool better = e_rec > c.best_E[b];                   // strict: first occurrence of the max (ppde.py:173)
+        if (better) { c.best_E[b] = e_rec; c.best_fit[b] = f_rec; }
+        s_flag |= better ? 4 : 0;
+    }
+    __syncthreads();
+    const int flag = s_flag & 3;
+    const bool better = (s_flag & 4) != 0;
+    const uint8_t* src = ax;
+    if (flag == 1) src = ay;
+    else if (flag == 2) {
+        const int f = c.anchor_fixed ? c.anchor_fixed[b] : (c.row_wt - 2 * n);
+        src = c.aa_fixed + (int64_t)f * c.aa_stride;
+    }
+    // recorded state (post-accept, pre-reset): best-of-history and the random trajectory (ppde.py:142,146,172-183)
+    int dpart = 0;
+    for (int i = threadIdx.x; i < L; i += NT) {
+        const uint8_t v = src[i];
+        sZ[i] = v;
+        dpart += (v != m.wt[i]);
+        if (better) c.best_aa[(int64_t)b * c.aa_stride + i] = v;
+        if (c.traj_aa && b == c.traj_chain) c.traj_aa[(int64_t)(t + 1) * c.aa_stride + i] = v;
+    }
+    const int dist = block_sum_int<NT>(dpart, redi);
+    const bool reset = !p.paper_results && dist >= p.nmut_threshold;   // hard reset to WT (ppde.py:148-153)
+    for (int i = threadIdx.x; i < L; i += NT) ax[i] = reset ? m.wt[i] : sZ[i];
+    if (reset && threadIdx.x == 0) {
+        const int f = c.row_wt - 2 * n;
+        c.E[b] = c.E_fixed[f]; c.fit[b] = c.fit_fixed[f]; c.row_cur[b] = c.row_wt;
+    }
+}
+
+}  // namespace ppde
+
+using namespace ppde;
+
+static size_t pas_smem(int L) { return (size_t)(2 * L * PPDE_Q + L) * sizeof(float) + 2 * ((L + 15) & ~15); }
+
+extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p,
+                                void* stream) {
+    if (c->n <= 0) return 0;
+    if (p->S < 1 || p->S > PPDE_MAX_S) return (int)cudaErrorInvalidValue;
+    size_t smem = pas_smem(c->L);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(pas_propose_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    pas_propose_kernel<128><<<c->n, 128, smem, (cudaStream_t)stream>>>(*m, *c, *p);
+    return launch_done();
+}
+
+extern "C" int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p,
+                                       void* stream) {
+    if (c->n <= 0) return 0;
+    if (p->S < 1 || p->S > PPDE_MAX_S) return (int)cudaErrorInvalidValue;
+    size_t smem = pas_smem(c->L);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(pas_reverse_accept_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    pas_reverse_accept_kernel<128><<<c->n, 128, smem, (cudaStream_t)stream>>>(*m, *c, *p);
+    return launch_done();
+}

@@ -1,0 +1,335 @@
+"""Device-resident model + chain state and the per-iteration launch sequence.
+
+Host mirror of the reference's hot loop (ppde/protein_samplers/ppde.py:65-153) and energy
+(ppde/energy.py:97-108) on top of the C-ABI kernels.  PyTorch is used for device memory
+and streams only; every arithmetic step is a kernel of libppde_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ChainsT, CnnT, PasParamsT, PottsT
+
+Q = 20
+INT32_MAX = int(np.iinfo(np.int32).max)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("ppde_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device(device if device is not None else "cuda")
+
+
+def aa_stride_for(L):
+    return (L + 15) // 16 * 16
+
+
+class PoEModel:
+    """Product-of-experts weights resident in HBM (replicated on every GPU).
+
+    J [Lp,Lp,20,20], h [Lp,20]  : potts.pkl 'J_ij', 'h_i' (ppde/nets.py:247-251)
+    win_lo                      : index_list[0] - offset (ppde/nets.py:257-261)
+    cnn                         : list of dicts W0[C,20,5] b0 W1[2C,C] b1 d[2C] c (OnehotCNN state, nets.py:350-361)
+    lamda                       : --energy_lamda (ppde/energy.py:74)
+    """
+
+    def __init__(self, wt_aa, J, h, win_lo, cnn, lamda, device=None):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        dev = self.device
+        wt_aa = np.asarray(wt_aa, dtype=np.uint8)
+        self.L = int(wt_aa.shape[0])
+        self.Lp = int(J.shape[0])
+        self.win_lo = int(win_lo)
+        self.D = Q * self.Lp
+        self.NE = Q * self.L
+        self.lamda = float(lamda)
+        if self.win_lo < 0 or self.win_lo + self.Lp > self.L:
+            raise ValueError("Potts window outside the sequence")
+        self.aa_stride = aa_stride_for(self.L)
+        with torch.cuda.device(dev):
+            Jd = torch.as_tensor(np.ascontiguousarray(J, dtype=np.float32)).to(dev)
+            self.Jsym = torch.empty(self.D, self.D, dtype=torch.float32, device=dev)
+            _lib.check(self.lib.ppde_potts_symmetrize(_ptr(Jd), self.Lp, _ptr(self.Jsym), _stream()), "potts_symmetrize")
+            torch.cuda.current_stream().synchronize()
+            del Jd
+            self.h = torch.as_tensor(np.ascontiguousarray(h, dtype=np.float32).reshape(-1)).to(dev)
+            wt_pad = np.zeros(self.aa_stride, dtype=np.uint8)
+            wt_pad[:self.L] = wt_aa
+            self.wt = torch.from_numpy(wt_pad).to(dev)
+            self.wt_host = wt_aa.copy()
+            self.potts = PottsT(L=self.L, Lp=self.Lp, win_lo=self.win_lo, D=self.D, Jsym=self.Jsym.data_ptr(),
+                                h=self.h.data_ptr(), wt=self.wt.data_ptr(), wt_H=0.0)
+            # H(wt): same kernel, same arithmetic as every later evaluation (ppde/nets.py:262)
+            gp = torch.empty(1, self.D, dtype=torch.float32, device=dev)
+            ep = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.check(self.lib.ppde_potts_full(C.byref(self.potts), _ptr(self.wt), self.aa_stride, 1, _ptr(gp), self.D,
+                                                _ptr(ep), _stream()), "potts_full(wt)")
+            self.wt_H = float(ep.item())
+            self.potts.wt_H = self.wt_H
+            # CNN ensemble
+            self.n_nets = len(cnn)
+            if self.n_nets > _lib.MAX_NETS:
+                raise ValueError("too many ensemble members")
+            self.C = self.L
+            self.P = self.L - 4
+            self._cnn_keep = []
+            self.cnn = CnnT(n_nets=self.n_nets, C=self.C, L=self.L, P=self.P)
+            for k, net in enumerate(cnn):
+                W0 = torch.as_tensor(np.asarray(net["W0"], dtype=np.float32))
+                if tuple(W0.shape) != (self.C, Q, 5):
+                    raise ValueError(f"encoder.weight must be [{self.C},20,5], got {tuple(W0.shape)}")
+                W1 = torch.as_tensor(np.asarray(net["W1"], dtype=np.float32))
+                t = {
+                    "T0": W0.permute(2, 1, 0).contiguous(),            # [5][20][C]
+                    "b0": torch.as_tensor(np.asarray(net["b0"], dtype=np.float32)),
+                    "W1": W1.contiguous(),
+                    "W1T": W1.t().contiguous(),
+                    "b1": torch.as_tensor(np.asarray(net["b1"], dtype=np.float32)),
+                    "d": torch.as_tensor(np.asarray(net["d"], dtype=np.float32).reshape(-1)),
+                    "W0r": W0.permute(0, 2, 1).contiguous(),           # [C][5][20]
+                }
+                t = {kk: v.to(dev) for kk, v in t.items()}
+                self._cnn_keep.append(t)
+                cn = self.cnn.net[k]
+                for kk, v in t.items():
+                    setattr(cn, kk, v.data_ptr())
+                cn.c = float(np.asarray(net["c"]).reshape(-1)[0])
+        self._mkey = None
+
+    # -- scratch ------------------------------------------------------------------------------
+    def mkey(self, n):
+        need = n * self.n_nets * 2 * self.C
+        if self._mkey is None or self._mkey.numel() < need:
+            self._mkey = torch.empty(need, dtype=torch.int64, device=self.device)
+        return self._mkey
+
+    # -- full evaluation ------------------------------------------------------------------------
+    def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True):
+        """Energy (+ gradient field) of n states `aa` [n, aa_stride] written into pool rows
+        g_row0.. / gp_row0.. (contiguous). E, fit, Epotts: float tensors [n]."""
+        lib = self.lib
+        st = _stream()
+        gp_ptr = C.c_void_p(Gp.data_ptr() + gp_row0 * self.D * 4)
+        _lib.check(lib.ppde_potts_full(C.byref(self.potts), _ptr(aa), self.aa_stride, n, gp_ptr, self.D,
+                                       _ptr(Epotts), st), "potts_full")
+        mk = self.mkey(n)
+        _lib.check(lib.ppde_cnn_forward(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st), "cnn_forward")
+        g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
+        _lib.check(lib.ppde_cnn_backward_combine(
+            C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+            gp_ptr, self.D, C.c_void_p(0), _ptr(Epotts), g_ptr, self.NE, C.c_void_p(0), _ptr(E), _ptr(fit), st),
+            "cnn_backward_combine")
+
+    def onehot_to_aa(self, x):
+        n, L, q = x.shape
+        if L != self.L or q != Q:
+            raise ValueError(f"expected one-hot [n,{self.L},20], got {tuple(x.shape)}")
+        x = x.detach().to(self.device, torch.float32).contiguous()
+        aa = torch.zeros(n, self.aa_stride, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.ppde_onehot_to_aa(_ptr(x), n, L, _ptr(aa), self.aa_stride, _stream()), "onehot_to_aa")
+        return aa
+
+    def aa_to_onehot(self, aa, n=None):
+        n = aa.shape[0] if n is None else n
+        x = torch.empty(n, self.L, Q, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.ppde_aa_to_onehot(_ptr(aa), self.aa_stride, n, self.L, _ptr(x), _stream()), "aa_to_onehot")
+        return x
+
+    def energy(self, aa, want_grad=True):
+        """(E [n], fit [n], G [n,L,20] or None, Epotts [n]) for residue states aa [n, aa_stride] on device."""
+        n = aa.shape[0]
+        dev = self.device
+        E = torch.empty(n, dtype=torch.float32, device=dev)
+        fit = torch.empty(n, dtype=torch.float32, device=dev)
+        Ep = torch.empty(n, dtype=torch.float32, device=dev)
+        Gp = torch.empty(n, self.D, dtype=torch.float32, device=dev)
+        G = torch.empty(n, self.NE, dtype=torch.float32, device=dev) if want_grad else None
+        self.evaluate_into(aa, n, G, 0, Gp, 0, E, fit, Ep, want_grad)
+        return E, fit, (G.view(n, self.L, Q) if want_grad else None), Ep
+
+
+class ChainEngine:
+    """n local chains of the PPDE sampler (one engine per GPU / rank)."""
+
+    def __init__(self, model: PoEModel, n, pas_length=2, nmut_threshold=0, paper_results=False, seed=0,
+                 chain_offset=0, num_steps=None, traj_chain=-1):
+        self.m = model
+        self.lib = model.lib
+        self.n = int(n)
+        self.S = 2 * int(pas_length) - 1
+        if not (1 <= self.S <= _lib.MAX_SUBSTEPS):
+            raise ValueError(f"ppde_pas_length must give 1 <= 2*pas-1 <= {_lib.MAX_SUBSTEPS}")
+        self.thr = int(nmut_threshold) if nmut_threshold else INT32_MAX      # ppde.py:15-17
+        self.paper = bool(paper_results)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.chain_offset = int(chain_offset)
+        self.T = num_steps
+        self.t = 0
+        self.traj_chain = int(traj_chain)
+        self._allocated = False
+        self._graph = None
+
+    # -- allocation ------------------------------------------------------------------------------
+    def _alloc(self, n_fixed):
+        m, n, dev = self.m, self.n, self.m.device
+        f32, i32, u8 = torch.float32, torch.int32, torch.uint8
+        S = self.S
+        self.n_fixed = n_fixed
+        rows = 2 * n + n_fixed
+        self.G = torch.empty(rows, m.NE, dtype=f32, device=dev)
+        self.Gp = torch.empty(rows, m.D, dtype=f32, device=dev)
+        self.aa = torch.zeros(n, m.aa_stride, dtype=u8, device=dev)
+        self.aa_y = torch.zeros(n, m.aa_stride, dtype=u8, device=dev)
+        self.row_cur = torch.zeros(n, dtype=i32, device=dev)
+        self.rows_y = torch.zeros(n, dtype=i32, device=dev)
+        self.E = torch.zeros(n, dtype=f32, device=dev)
+        self.fit = torch.zeros(n, dtype=f32, device=dev)
+        self.E_y = torch.zeros(n, dtype=f32, device=dev)
+        self.fit_y = torch.zeros(n, dtype=f32, device=dev)
+        self.Epotts_y = torch.zeros(n, dtype=f32, device=dev)
+        self.E_fixed = torch.zeros(n_fixed, dtype=f32, device=dev)
+        self.fit_fixed = torch.zeros(n_fixed, dtype=f32, device=dev)
+        self.aa_fixed = torch.zeros(n_fixed, m.aa_stride, dtype=u8, device=dev)
+        self.anchor_fixed = None
+        self.U = torch.zeros(n, dtype=i32, device=dev)
+        self.idx = torch.zeros(S, n, dtype=i32, device=dev)
+        self.old_aa = torch.zeros(S, n, dtype=u8, device=dev)
+        self.lqf = torch.zeros(S, n, dtype=f32, device=dev)
+        self.lqr = torch.zeros(S, n, dtype=f32, device=dev)
+        self.log_acc = torch.zeros(n, dtype=f32, device=dev)
+        self.accept = torch.zeros(n, dtype=u8, device=dev)
+        T = self.T
+        self.E_hist = torch.zeros(T + 1, n, dtype=f32, device=dev) if T is not None else None
+        self.fit_hist = torch.zeros(T + 1, n, dtype=f32, device=dev) if T is not None else None
+        self.best_E = torch.zeros(n, dtype=f32, device=dev)
+        self.best_fit = torch.zeros(n, dtype=f32, device=dev)
+        self.best_aa = torch.zeros(n, m.aa_stride, dtype=u8, device=dev)
+        local_traj = (T is not None and 0 <= self.traj_chain < n)
+        self.traj_aa = torch.zeros(T + 1, m.aa_stride, dtype=u8, device=dev) if local_traj else None
+        self.t_dev = torch.zeros(1, dtype=i32, device=dev)
+        self._allocated = True
+
+    def _struct(self):
+        m, n = self.m, self.n
+        c = ChainsT(n=n, chain_offset=self.chain_offset, L=m.L, aa_stride=m.aa_stride)
+        for name in ("aa", "aa_y", "row_cur", "G", "Gp", "E", "fit", "E_y", "fit_y", "Epotts_y", "E_fixed",
+                     "fit_fixed", "aa_fixed", "U", "idx", "old_aa", "lqf", "lqr", "log_acc", "accept",
+                     "best_E", "best_fit", "best_aa"):
+            setattr(c, name, getattr(self, name).data_ptr())
+        c.anchor_fixed = self.anchor_fixed.data_ptr() if self.anchor_fixed is not None else None
+        c.E_hist = self.E_hist.data_ptr() if self.E_hist is not None else None
+        c.fit_hist = self.fit_hist.data_ptr() if self.fit_hist is not None else None
+        c.traj_aa = self.traj_aa.data_ptr() if self.traj_aa is not None else None
+        c.traj_chain = self.traj_chain if self.traj_aa is not None else -1
+        c.n_fixed = self.n_fixed
+        c.row_wt = 2 * n
+        return c
+
+    # -- t = 0 --------------------------------------------------------------------------------------
+    def init_population(self, aa0, anchor=None):
+        """aa0: uint8 device tensor [n, aa_stride] (initial population; ppde.py:32-47).
+        anchor: paper-mode `x` (ppde.py:35,76-77) — defaults to aa0, as in the reference."""
+        m, n = self.m, self.n
+        with torch.cuda.device(m.device):
+            wt_row = m.wt[None, :m.L]
+            all_wt = bool((aa0[:, :m.L] == wt_row).all().item())
+            anchor = aa0 if anchor is None else anchor
+            per_chain_anchor = self.paper and not bool((anchor[:, :m.L] == wt_row).all().item())
+            self._alloc(1 + (n if per_chain_anchor else 0))
+            self.aa.copy_(aa0)
+            self.aa_fixed[0].copy_(m.wt)
+            if per_chain_anchor:
+                self.aa_fixed[1:].copy_(anchor)
+                self.anchor_fixed = torch.arange(1, n + 1, dtype=torch.int32, device=m.device)
+            ep = torch.empty(self.n_fixed, dtype=torch.float32, device=m.device)
+            m.evaluate_into(self.aa_fixed, self.n_fixed, self.G, 2 * n, self.Gp, 2 * n, self.E_fixed, self.fit_fixed, ep)
+            if all_wt:
+                self.row_cur.fill_(2 * n)
+                self.E.copy_(self.E_fixed[0].expand(n)); self.fit.copy_(self.fit_fixed[0].expand(n))
+            else:
+                epn = torch.empty(n, dtype=torch.float32, device=m.device)
+                m.evaluate_into(self.aa, n, self.G, 0, self.Gp, 0, self.E, self.fit, epn)
+                self.row_cur.copy_(torch.arange(n, dtype=torch.int32, device=m.device))
+            self.best_E.copy_(self.E); self.best_fit.copy_(self.fit); self.best_aa.copy_(self.aa)
+            if self.E_hist is not None:
+                self.E_hist[0].copy_(self.E); self.fit_hist[0].copy_(self.fit)
+            if self.traj_aa is not None:
+                self.traj_aa[0].copy_(self.aa[self.traj_chain])
+            self.t = 0
+            self.t_dev.zero_()
+            self.chains = self._struct()
+            self._graph = None
+
+    # -- one iteration ------------------------------------------------------------------------------
+    def _params(self, t, uniforms=None, use_t_dev=False):
+        return PasParamsT(S=self.S, nmut_threshold=self.thr, paper_results=int(self.paper), t=int(t), seed=self.seed,
+                          uniforms=uniforms.data_ptr() if uniforms is not None else None,
+                          t_dev=self.t_dev.data_ptr() if use_t_dev else None)
+
+    def _launch_step(self, p):
+        m, lib, c, n = self.m, self.lib, self.chains, self.n
+        st = _stream()
+        _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_propose")
+        _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(c), C.byref(p), st), "potts_incremental")
+        _lib.check(lib.ppde_step_rows(C.byref(c), _ptr(self.rows_y), st), "step_rows")
+        mk = m.mkey(n)
+        _lib.check(lib.ppde_cnn_forward(C.byref(m.cnn), _ptr(self.aa_y), m.aa_stride, n, _ptr(mk), st), "cnn_forward")
+        _lib.check(lib.ppde_cnn_backward_combine(
+            C.byref(m.cnn), C.byref(m.potts), _ptr(self.aa_y), m.aa_stride, n, _ptr(mk), m.lamda,
+            _ptr(self.Gp), m.D, _ptr(self.rows_y), _ptr(self.Epotts_y), _ptr(self.G), m.NE, _ptr(self.rows_y),
+            _ptr(self.E_y), _ptr(self.fit_y), st), "cnn_backward_combine")
+        _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_reverse_accept")
+
+    def step(self, uniforms=None):
+        """One MCMC iteration (eager launches). `uniforms`: optional float32 device tensor
+        [S, n, 20L] replacing the in-kernel Philox proposal stream (parity mode)."""
+        with torch.cuda.device(self.m.device):
+            self._launch_step(self._params(self.t, uniforms))
+        self.t += 1
+
+    def run_steps(self, k, use_graph=True):
+        """k iterations; the fixed-S launch sequence is captured once in a CUDA graph and replayed,
+        with the iteration counter living on the device."""
+        if not use_graph:
+            for _ in range(k):
+                self.step()
+            return
+        with torch.cuda.device(self.m.device):
+            if self._graph is None:
+                self.m.mkey(self.n)
+                self.t_dev.fill_(self.t)
+                p = self._params(0, None, use_t_dev=True)
+                self._graph_params = p
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self._launch_step(p)
+                    _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
+                self._graph = g
+            else:
+                self.t_dev.fill_(self.t)
+            for _ in range(k):
+                self._graph.replay()
+        self.t += k
+
+    # -- results ------------------------------------------------------------------------------------
+    def population_metrics(self):
+        """(edit distance int32 [n], sequence hash int64 [n]) of the current states (device tensors)."""
+        m = self.m
+        dist = torch.empty(self.n, dtype=torch.int32, device=m.device)
+        h = torch.empty(self.n, dtype=torch.int64, device=m.device)
+        _lib.check(self.lib.ppde_population_metrics(_ptr(self.aa), m.aa_stride, self.n, m.L, _ptr(m.wt), _ptr(dist),
+                                                    _ptr(h), _stream()), "population_metrics")
+        return dist, h
