@@ -116,6 +116,8 @@ typedef struct ppde_pas_params {
     int32_t nmut_threshold; /* INT32_MAX when --nmut_threshold 0 */
     int32_t paper_results;
     int32_t t;            /* iteration index (stream counter) */
+    int32_t min_pos;      /* proposals outside [min_pos, max_pos] are masked (run() arguments, ppde.py:59-63) */
+    int32_t max_pos;      /* inclusive */
     uint64_t seed;
     const float* uniforms; /* optional materialised proposal uniforms [S, n, 20L]; NULL = Philox in-kernel */
     const int32_t* t_dev;  /* optional device-resident iteration counter (CUDA-graph replay); NULL = use t */

@@ -336,44 +336,13 @@ class PortSampler:
                 e_hist.numpy(), f_hist.numpy(), traj)
 
 
-def synthetic_potts(Lp, seed=0, sigma_j=0.05, sigma_h=0.5, symmetric=True, zero_diag=True):
-    """J [Lp,Lp,20,20] f32 and h [Lp,20] f32 (SURVEY.md §8d synthetic inputs).
-    Key layout of potts.pkl as read at ppde/nets.py:247-251."""
-    rng = np.random.default_rng(seed)
-    J = (rng.standard_normal((Lp, Lp, 20, 20)) * sigma_j).astype(np.float32)
-    if symmetric:
-        J = (0.5 * (J + J.transpose(1, 0, 3, 2))).astype(np.float32)
-    if zero_diag:
-        J[np.arange(Lp), np.arange(Lp)] = 0.0
-    h = (rng.standard_normal((Lp, 20)) * sigma_h).astype(np.float32)
-    return J, h
+from ppde_b200.synthetic import synthetic_potts, synthetic_cnn, synthetic_problem  # noqa: E402,F401
 
 
-def synthetic_cnn(L, seeds=(0, 1, 2)):
-    """OnehotCNN(20,5,L) with torch's default init bounds (ppde/nets.py:350-361)."""
-    cnn = []
-    for k in seeds:
-        g = torch.Generator().manual_seed(k)
-        C = L
-        b0 = 1 / math.sqrt(20 * 5); b1 = 1 / math.sqrt(C); b2 = 1 / math.sqrt(2 * C)
-
-        def uni(shape, bound):
-            return ((torch.rand(shape, generator=g) * 2 - 1) * bound).numpy().astype(np.float32)
-        cnn.append({"W0": uni((C, 20, 5), b0), "b0": uni((C,), b0),
-                    "W1": uni((2 * C, C), b1), "b1": uni((2 * C,), b1),
-                    "d": uni((2 * C,), b2), "c": uni((1,), b2)})
-    return cnn
-
-
-def synthetic_weights(L, seed=0, lamda=1.0, window=None, sigma_j=0.05, sigma_h=0.5, wt=None):
-    """SURVEY.md §8d synthetic inputs: symmetric zero-diagonal Potts, default-init
-    OnehotCNN(20,5,L) x3 (torch seeds 0,1,2), uniform random WT."""
-    lo, hi = window if window is not None else (0, L - 1)
-    J, h = synthetic_potts(hi - lo + 1, seed, sigma_j, sigma_h)
-    if wt is None:
-        wt = np.random.default_rng(seed + 1000).integers(0, 20, size=L).astype(np.uint8)
-    return Weights(wt=np.asarray(wt, dtype=np.uint8), J=J, h=h, win_lo=lo,
-                   cnn=synthetic_cnn(L), lamda=lamda)
+def synthetic_weights(L, seed=0, lamda=1.0, window=None, sigma_j=0.05, sigma_h=0.5):
+    """Weights for the SURVEY.md §8d synthetic problem (same arrays the CUDA path is given)."""
+    pr = synthetic_problem(L, seed, window, sigma_j, sigma_h)
+    return Weights(wt=pr["wt"], J=pr["J"], h=pr["h"], win_lo=pr["win_lo"], cnn=pr["cnn"], lamda=lamda)
 
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
     const uint32_t gid = (uint32_t)(c.chain_offset + b);
     const int t = p.t_dev ? *p.t_dev : p.t;
     const Philox rng(p.seed);
-    const int lo = m.win_lo, hi = m.win_lo + m.Lp - 1;
+    const int lo = p.min_pos, hi = p.max_pos;
 
     {   // stage the row and the state
         const float4* g4 = reinterpret_cast<const float4*>(c.G + (int64_t)c.row_cur[b] * NE);

@@ -49,8 +49,9 @@ class PoEModel:
         dev = self.device
         wt_aa = np.asarray(wt_aa, dtype=np.uint8)
         self.L = int(wt_aa.shape[0])
-        self.Lp = int(J.shape[0])
-        self.win_lo = int(win_lo)
+        self.has_potts = J is not None          # False: ProteinSupervised (CNN-only, ppde/energy.py:143-164)
+        self.Lp = int(J.shape[0]) if self.has_potts else 0
+        self.win_lo = int(win_lo) if self.has_potts else 0
         self.D = Q * self.Lp
         self.NE = Q * self.L
         self.lamda = float(lamda)
@@ -58,12 +59,16 @@ class PoEModel:
             raise ValueError("Potts window outside the sequence")
         self.aa_stride = aa_stride_for(self.L)
         with torch.cuda.device(dev):
-            Jd = torch.as_tensor(np.ascontiguousarray(J, dtype=np.float32)).to(dev)
             self.Jsym = torch.empty(self.D, self.D, dtype=torch.float32, device=dev)
-            _lib.check(self.lib.ppde_potts_symmetrize(_ptr(Jd), self.Lp, _ptr(self.Jsym), _stream()), "potts_symmetrize")
-            torch.cuda.current_stream().synchronize()
-            del Jd
-            self.h = torch.as_tensor(np.ascontiguousarray(h, dtype=np.float32).reshape(-1)).to(dev)
+            self.h = torch.zeros(max(self.D, 1), dtype=torch.float32, device=dev)
+            if self.has_potts:
+                if tuple(J.shape) != (self.Lp, self.Lp, Q, Q) or tuple(np.shape(h)) != (self.Lp, Q):
+                    raise ValueError(f"J must be [Lp,Lp,20,20] and h [Lp,20]; got {tuple(J.shape)}, {tuple(np.shape(h))}")
+                Jd = torch.as_tensor(np.ascontiguousarray(J, dtype=np.float32)).to(dev)
+                _lib.check(self.lib.ppde_potts_symmetrize(_ptr(Jd), self.Lp, _ptr(self.Jsym), _stream()), "potts_symmetrize")
+                torch.cuda.current_stream().synchronize()
+                del Jd
+                self.h = torch.as_tensor(np.ascontiguousarray(h, dtype=np.float32).reshape(-1)).to(dev)
             wt_pad = np.zeros(self.aa_stride, dtype=np.uint8)
             wt_pad[:self.L] = wt_aa
             self.wt = torch.from_numpy(wt_pad).to(dev)
@@ -71,12 +76,14 @@ class PoEModel:
             self.potts = PottsT(L=self.L, Lp=self.Lp, win_lo=self.win_lo, D=self.D, Jsym=self.Jsym.data_ptr(),
                                 h=self.h.data_ptr(), wt=self.wt.data_ptr(), wt_H=0.0)
             # H(wt): same kernel, same arithmetic as every later evaluation (ppde/nets.py:262)
-            gp = torch.empty(1, self.D, dtype=torch.float32, device=dev)
-            ep = torch.empty(1, dtype=torch.float32, device=dev)
-            _lib.check(self.lib.ppde_potts_full(C.byref(self.potts), _ptr(self.wt), self.aa_stride, 1, _ptr(gp), self.D,
-                                                _ptr(ep), _stream()), "potts_full(wt)")
-            self.wt_H = float(ep.item())
-            self.potts.wt_H = self.wt_H
+            self.wt_H = 0.0
+            if self.has_potts:
+                gp = torch.empty(1, self.D, dtype=torch.float32, device=dev)
+                ep = torch.empty(1, dtype=torch.float32, device=dev)
+                _lib.check(self.lib.ppde_potts_full(C.byref(self.potts), _ptr(self.wt), self.aa_stride, 1, _ptr(gp),
+                                                    self.D, _ptr(ep), _stream()), "potts_full(wt)")
+                self.wt_H = float(ep.item())
+                self.potts.wt_H = self.wt_H
             # CNN ensemble
             self.n_nets = len(cnn)
             if self.n_nets > _lib.MAX_NETS:
@@ -120,15 +127,17 @@ class PoEModel:
         g_row0.. / gp_row0.. (contiguous). E, fit, Epotts: float tensors [n]."""
         lib = self.lib
         st = _stream()
-        gp_ptr = C.c_void_p(Gp.data_ptr() + gp_row0 * self.D * 4)
-        _lib.check(lib.ppde_potts_full(C.byref(self.potts), _ptr(aa), self.aa_stride, n, gp_ptr, self.D,
-                                       _ptr(Epotts), st), "potts_full")
+        gp_ptr, ep_ptr = C.c_void_p(0), C.c_void_p(0)
+        if self.has_potts:
+            gp_ptr, ep_ptr = C.c_void_p(Gp.data_ptr() + gp_row0 * self.D * 4), _ptr(Epotts)
+            _lib.check(lib.ppde_potts_full(C.byref(self.potts), _ptr(aa), self.aa_stride, n, gp_ptr, self.D,
+                                           ep_ptr, st), "potts_full")
         mk = self.mkey(n)
         _lib.check(lib.ppde_cnn_forward(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st), "cnn_forward")
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
         _lib.check(lib.ppde_cnn_backward_combine(
             C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
-            gp_ptr, self.D, C.c_void_p(0), _ptr(Epotts), g_ptr, self.NE, C.c_void_p(0), _ptr(E), _ptr(fit), st),
+            gp_ptr, self.D, C.c_void_p(0), ep_ptr, g_ptr, self.NE, C.c_void_p(0), _ptr(E), _ptr(fit), st),
             "cnn_backward_combine")
 
     def onehot_to_aa(self, x):
@@ -152,7 +161,7 @@ class PoEModel:
         dev = self.device
         E = torch.empty(n, dtype=torch.float32, device=dev)
         fit = torch.empty(n, dtype=torch.float32, device=dev)
-        Ep = torch.empty(n, dtype=torch.float32, device=dev)
+        Ep = torch.zeros(n, dtype=torch.float32, device=dev)
         Gp = torch.empty(n, self.D, dtype=torch.float32, device=dev)
         G = torch.empty(n, self.NE, dtype=torch.float32, device=dev) if want_grad else None
         self.evaluate_into(aa, n, G, 0, Gp, 0, E, fit, Ep, want_grad)
@@ -163,7 +172,7 @@ class ChainEngine:
     """n local chains of the PPDE sampler (one engine per GPU / rank)."""
 
     def __init__(self, model: PoEModel, n, pas_length=2, nmut_threshold=0, paper_results=False, seed=0,
-                 chain_offset=0, num_steps=None, traj_chain=-1):
+                 chain_offset=0, num_steps=None, traj_chain=-1, min_pos=None, max_pos=None):
         self.m = model
         self.lib = model.lib
         self.n = int(n)
@@ -177,6 +186,10 @@ class ChainEngine:
         self.T = num_steps
         self.t = 0
         self.traj_chain = int(traj_chain)
+        # proposal window = run()'s (min_pos, max_pos), inclusive (ppde.py:59-63); default: the Potts window
+        self.min_pos = int(min_pos) if min_pos is not None else (model.win_lo if model.has_potts else 0)
+        self.max_pos = int(max_pos) if max_pos is not None else (
+            model.win_lo + model.Lp - 1 if model.has_potts else model.L - 1)
         self._allocated = False
         self._graph = None
 
@@ -273,7 +286,8 @@ class ChainEngine:
 
     # -- one iteration ------------------------------------------------------------------------------
     def _params(self, t, uniforms=None, use_t_dev=False):
-        return PasParamsT(S=self.S, nmut_threshold=self.thr, paper_results=int(self.paper), t=int(t), seed=self.seed,
+        return PasParamsT(S=self.S, nmut_threshold=self.thr, paper_results=int(self.paper), t=int(t),
+                          min_pos=self.min_pos, max_pos=self.max_pos, seed=self.seed,
                           uniforms=uniforms.data_ptr() if uniforms is not None else None,
                           t_dev=self.t_dev.data_ptr() if use_t_dev else None)
 
@@ -281,13 +295,15 @@ class ChainEngine:
         m, lib, c, n = self.m, self.lib, self.chains, self.n
         st = _stream()
         _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_propose")
-        _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(c), C.byref(p), st), "potts_incremental")
+        if m.has_potts:
+            _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(c), C.byref(p), st), "potts_incremental")
         _lib.check(lib.ppde_step_rows(C.byref(c), _ptr(self.rows_y), st), "step_rows")
         mk = m.mkey(n)
         _lib.check(lib.ppde_cnn_forward(C.byref(m.cnn), _ptr(self.aa_y), m.aa_stride, n, _ptr(mk), st), "cnn_forward")
         _lib.check(lib.ppde_cnn_backward_combine(
             C.byref(m.cnn), C.byref(m.potts), _ptr(self.aa_y), m.aa_stride, n, _ptr(mk), m.lamda,
-            _ptr(self.Gp), m.D, _ptr(self.rows_y), _ptr(self.Epotts_y), _ptr(self.G), m.NE, _ptr(self.rows_y),
+            _ptr(self.Gp) if m.has_potts else C.c_void_p(0), m.D, _ptr(self.rows_y),
+            _ptr(self.Epotts_y) if m.has_potts else C.c_void_p(0), _ptr(self.G), m.NE, _ptr(self.rows_y),
             _ptr(self.E_y), _ptr(self.fit_y), st), "cnn_backward_combine")
         _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_reverse_accept")
 

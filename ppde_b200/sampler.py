@@ -1,0 +1,133 @@
+"""PPDE path-auxiliary sampler with the reference's interface (ppde/protein_samplers/ppde.py:8-192).
+
+    sampler = PPDE_PAS(args)          # args.ppde_pas_length, args.nmut_threshold, args.paper_results [, args.seed]
+    best_x, best_energy, best_fitness, energy_history, fitness_history, random_traj = \
+        sampler.run(initial_population, num_steps, energy_function, min_pos, max_pos, oracle, log_every)
+
+Differences from the reference that are deliberate and documented in DESIGN.md:
+  * randomness comes from indexed Philox streams keyed by (seed, t, sub-step, global chain, entry)
+    instead of the global torch/numpy generators (ppde_b200/philox.py);
+  * the energy/gradient at the current state is cached from the previous iteration (Potts field
+    updated incrementally) instead of being recomputed;
+  * the population is not copied to the host every iteration (ppde.py:142,146): best-of-history and
+    the random trajectory are tracked on the device with the same first-maximum rule (ppde.py:173);
+  * under torch.distributed each rank runs its contiguous block of chains; the returned 6-tuple is
+    the whole population on every rank.
+"""
+import numpy as np
+import torch
+
+from . import dist as D
+from .energy import as_b200_energy
+from .engine import ChainEngine
+
+
+class PPDE_PAS:
+    def __init__(self, args):
+        self.ppde_temp = 2                                   # ppde.py:11 (g(t) = sqrt(t)); baked into the kernels
+        self.ppde_pas_length = args.ppde_pas_length
+        self.nmut_threshold = args.nmut_threshold
+        self.paper_results = args.paper_results
+        if self.nmut_threshold == 0:
+            self.nmut_threshold = np.iinfo(np.int32).max      # ppde.py:15-17
+        self.seed = int(getattr(args, "seed", 0))
+        self.use_graph = bool(getattr(args, "ppde_cuda_graph", True))
+        self.verbose = bool(getattr(args, "ppde_verbose", True))
+        # True: `initial_population` is this rank's shard (equal sizes on every rank) and the returned
+        # 6-tuple covers the local chains only; False (reference behaviour): global population in and out.
+        self.local_population = bool(getattr(args, "ppde_local_population", False))
+        self.engine = None
+
+    def approximate_energy_change(self, score_change):       # ppde.py:20-21
+        return score_change / self.ppde_temp
+
+    def _print(self, *a, **k):
+        if self.verbose and D.world()[0] == 0:
+            print(*a, **k)
+
+    def run(self, initial_population, num_steps, energy_function, min_pos, max_pos, oracle, log_every=50):
+        """initial_population: float one-hot [n_chains, L, 20] (the GLOBAL population on every rank)."""
+        self._print(min_pos, max_pos)
+        energy = as_b200_energy(energy_function)
+        m = energy.model
+        rank, ws = D.world()
+        if self.local_population:
+            n = int(initial_population.size(0)) * ws
+            lo, hi = D.shard_range(n, rank, ws)
+            pop_local = initial_population
+        else:
+            n = int(initial_population.size(0))
+            lo, hi = D.shard_range(n, rank, ws)
+            pop_local = initial_population[lo:hi]
+        random_idx = np.random.randint(0, n)                  # ppde.py:37 (numpy global generator)
+        own_rank, own_local = D.owner_of(random_idx, n, ws)
+        thr = 0 if self.nmut_threshold == np.iinfo(np.int32).max else self.nmut_threshold
+
+        with torch.cuda.device(m.device):
+            aa0 = m.onehot_to_aa(pop_local)
+            eng = ChainEngine(m, hi - lo, self.ppde_pas_length, thr, self.paper_results, seed=self.seed,
+                              chain_offset=lo, num_steps=num_steps,
+                              traj_chain=own_local if own_rank == rank else -1,
+                              min_pos=int(min_pos), max_pos=int(max_pos))
+            eng.init_population(aa0)
+            self.engine = eng
+
+            def gather_host(t):
+                return D.all_gather_cat(t, n).cpu().numpy()
+
+            # iteration-0 report (ppde.py:48-57)
+            if oracle is not None:
+                gt = gather_host(oracle(m.aa_to_onehot(eng.aa)).detach().float().reshape(-1))
+            e0, f0 = gather_host(eng.E_hist[0]), gather_host(eng.fit_hist[0])
+            eq, fq = np.quantile(e0, [0.5, 0.9]), np.quantile(f0, [0.5, 0.9])
+            self._print(f'[Iteration 0] energy: 50% {eq[0]:.3f}, 90% {eq[1]:.3f}')
+            self._print(f'[Iteration 0] pred fit 50% {fq[0]:.3f}, 90% {fq[1]:.3f}')
+            if oracle is not None:
+                gq = np.quantile(gt, [0.5, 0.9])
+                self._print(f'[Iteration 0] oracle fit 50% {gq[0]:.3f}, 90% {gq[1]:.3f}')
+            self._print('')
+
+            t = 0
+            while t < num_steps:
+                # next iteration i >= t that logs: i > 0 and (i + 1) % log_every == 0  (ppde.py:155)
+                i = max(t, 1)
+                i += (-(i + 1)) % log_every
+                stop = min(i + 1, num_steps)
+                eng.run_steps(stop - t, use_graph=self.use_graph)
+                t = stop
+                if t == i + 1:
+                    self._log(eng, m, oracle, i, n, gather_host)
+
+            # final 6-tuple (ppde.py:172-192)
+            if self.local_population:
+                gat = lambda t, dim=0: t
+            else:
+                gat = lambda t, dim=0: D.all_gather_cat(t, n, dim=dim)
+            best_x = m.aa_to_onehot(gat(eng.best_aa)).to(initial_population.device)
+            best_e, best_f = gat(eng.best_E).cpu().numpy(), gat(eng.best_fit).cpu().numpy()
+            e_hist = gat(eng.E_hist, 1).cpu().numpy()
+            f_hist = gat(eng.fit_hist, 1).cpu().numpy()
+            traj = eng.traj_aa if eng.traj_aa is not None else torch.zeros(
+                num_steps + 1, m.aa_stride, dtype=torch.uint8, device=m.device)
+            traj = D.broadcast_from(traj, own_rank)
+            random_traj = list(m.aa_to_onehot(traj).cpu().numpy())
+        return best_x, best_e, best_f, e_hist, f_hist, random_traj
+
+    def _log(self, eng, m, oracle, i, n, gather_host):
+        e = gather_host(eng.E_hist[i + 1]); f = gather_host(eng.fit_hist[i + 1])
+        dist_d, hashes = eng.population_metrics()
+        rep_dist = gather_host(dist_d.float())
+        acc = gather_host(eng.accept.float())
+        gt = None
+        if oracle is not None:
+            gt = gather_host(oracle(m.aa_to_onehot(eng.aa)).detach().float().reshape(-1))
+        rep = D.population_report(e, f, gt, acc, rep_dist, gather_host(hashes))
+        self.last_report = rep
+        self._print(f'[Iteration {i}] energy: 50% {rep["energy_q"][0]:.3f}, 90% {rep["energy_q"][1]:.3f}', flush=True)
+        self._print(f'[Iteration {i}] pred 50% {rep["fitness_q"][0]:.3f}, 90% {rep["fitness_q"][1]:.3f}', flush=True)
+        if gt is not None:
+            self._print(f'[Iteration {i}] oracle 50% {rep["oracle_q"][0]:.3f}, 90% {rep["oracle_q"][1]:.3f}', flush=True)
+        self._print(f'   # accepted = {rep["accepted"]}')
+        self._print(f'   # dist = {rep["mean_dist"]}')
+        self._print(f'   # diversity = {rep["diversity_pct"]:.1f}%')
+        self._print('', flush=True)
