@@ -59,6 +59,8 @@ typedef struct ppde_cnn_net {
     const float* d;     /* [2C]         decoder.weight[0] */
     const float* W0r;   /* [C][5][20]   W0r[c][t][a] = encoder.weight[c][a][t] (backward) */
     float c;            /* decoder.bias */
+    float w1_scale;     /* power of two: max|W1| * w1_scale in [2^13, 2^14)  (fp16 operand split, tensor-core path) */
+    float r1_scale;     /* power of two: (upper bound of r1) * r1_scale in [2^13, 2^14) */
     int32_t _pad;
 } ppde_cnn_net_t;
 
@@ -132,6 +134,9 @@ int ppde_potts_full(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride,
 int ppde_potts_incremental(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
 int ppde_cnn_forward(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                      unsigned long long* mkey /* [n, n_nets, 2C] */, void* stream);
+/* same contract as ppde_cnn_forward, on the tcgen05 tensor cores (needs C <= 256); writes every key, no memset */
+int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
+                        unsigned long long* mkey /* [n, n_nets, 2C] */, void* stream);
 int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                               int32_t n, const unsigned long long* mkey, float lamda,
                               const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,

@@ -22,7 +22,7 @@ class PottsT(C.Structure):
 
 class CnnNetT(C.Structure):
     _fields_ = [("T0", vp), ("b0", vp), ("W1", vp), ("W1T", vp), ("b1", vp), ("d", vp), ("W0r", vp),
-                ("c", C.c_float), ("_pad", C.c_int32)]
+                ("c", C.c_float), ("w1_scale", C.c_float), ("r1_scale", C.c_float), ("_pad", C.c_int32)]
 
 
 class CnnT(C.Structure):
@@ -54,6 +54,7 @@ SIGNATURES = {
     "ppde_potts_full": (C.c_int, [C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp]),
     "ppde_potts_incremental": (C.c_int, [C.POINTER(PottsT), C.POINTER(ChainsT), C.POINTER(PasParamsT), vp]),
     "ppde_cnn_forward": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp]),
+    "ppde_cnn_forward_tc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp]),
     "ppde_cnn_backward_combine": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp,
                                             C.c_float, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp]),
     "ppde_step_rows": (C.c_int, [C.POINTER(ChainsT), vp, vp]),

@@ -1,0 +1,398 @@
+// CNN-ensemble forward on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Computes, for every chain b, net k and hidden channel j (reference: OnehotCNN.forward,
+// ppde/nets.py:363-376):   m[j] = max_p relu(b1[j] + sum_c W1[j,c] * r1[p,c]),  p*_j = lowest arg-max
+// with r1[p,c] = relu(b0[c] + sum_{t<5} W0[c, aa[p+t], t])  (one-hot conv = 5 table gathers).
+//
+// GEMM view (per net):  D[j, (b,p)] = W1[j, :] . r1[(b,p), :]     M = 2C channels, N = positions, K = C.
+//   * A = W1 tile (128 channels x K) lives in TENSOR MEMORY for the whole kernel (fp16 hi + lo halves,
+//     written once with tcgen05.st) -> the MMA reads no shared memory for A.
+//   * B = r1 tile (N_tile positions x 64-wide K chunk) is PRODUCED on the fly by 8 producer warps from a
+//     shared-memory copy of the conv table (b0 folded in), split into fp16 hi/lo, and stored K-major with the
+//     128-byte swizzle the UMMA descriptor expects; a 3-slot ring of chunks pipelines producers and MMA.
+//   * fp32 parity: x*y ~ xh*yh + xh*yl + xl*yh with fp32 accumulation in TMEM (3 fp16 MMAs per K step).
+//     fp16 carries 11 significand bits, so hi+lo holds 22 bits and the dropped xl*yl term is ~2^-22 relative;
+//     both operands are pre-scaled by per-net powers of two (w1_scale, r1_scale; undone exactly in the epilogue)
+//     so that the lo halves stay in fp16's normal range.
+//   * D (128 channels x N_tile positions, fp32) is double-buffered in TMEM; 4 epilogue warps read it with
+//     tcgen05.ld (thread = channel), add bias, relu, and keep a running (max, first arg-max) in registers
+//     across the tiles of a chain, then write the 64-bit winner key.  No atomics, no memset.
+// Warp roles: warps 0-3 epilogue (TMEM lane quarters), warp 4 MMA issuer (one elected lane), warps 5-12 producers.
+// Persistent grid: CTA -> (net, channel tile) x contiguous block of chains.
+#include "common.cuh"
+#include "../../include/ppde_b200.h"
+#include "launch.cuh"
+#include <cuda_fp16.h>
+
+namespace ppde {
+namespace tc {
+
+constexpr int NT_EPI = 128;
+constexpr int NT_PROD = 256;
+constexpr int NTHREADS = NT_EPI + 32 + NT_PROD;   // 416
+constexpr int WARP_MMA = 4;
+constexpr int NSLOT = 3;
+constexpr int KCH = 64;                            // K elements per chunk = one 128-byte swizzle row of fp16
+constexpr int MAT_BYTES = 128 * KCH * 2;           // one [128 x 64] fp16 operand matrix (16 KB)
+constexpr int SLOT_BYTES = 2 * MAT_BYTES;          // hi + lo
+constexpr int TMEM_COLS = 512;
+constexpr int D_COL0 = 256;                        // accumulators: columns [256,384) and [384,512)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE;\n"
+        " bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]   (A from tensor memory, K-major; f16 x f16 -> fp32)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// K-major, 128-byte-swizzled operand matrix: rows of 64 halves (128 B), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    // c=f32 (bit4), a=f16 (bits 7..9 = 0), b=f16 (bits 10..12 = 0), both K-major, N>>3 at 17, M>>4 at 24
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo_k, float hi_k) {       // low 16 bits = even k
+    __half2 v = __floats2half2_rn(lo_k, hi_k);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float h_round(float x) { return __half2float(__float2half_rn(x)); }
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+struct Params {
+    ppde_cnn_t m;
+    const uint8_t* aa;
+    int aa_stride;
+    int n;
+    unsigned long long* mkey;
+    int n_tile;           // positions per tile (multiple of 16, <= 128)
+    int tiles_per_chain;
+    int ctas_per_combo;
+    int MT;               // channel tiles of 128
+    int nch;              // K chunks of 64
+    int kpad;             // K rounded up to 16
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int C = prm.m.C, P = prm.m.P, J2 = 2 * C;
+    const int KS = prm.nch * KCH;                                     // padded table row length
+    // NSLOT x (hi 16 KB | lo 16 KB); the 128-byte swizzle is a function of address bits, so align to 1024 B
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* sT0 = reinterpret_cast<float*>(ring + NSLOT * SLOT_BYTES);   // [100][KS], b0 folded into tap 0
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sT0 + 100 * KS);
+    uint64_t* full = bars;              // [NSLOT] producers -> MMA
+    uint64_t* empty = bars + NSLOT;     // [NSLOT] MMA -> producers
+    uint64_t* dfull = empty + NSLOT;    // [2]     MMA -> epilogue
+    uint64_t* dempty = dfull + 2;       // [2]     epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+
+    const int combo = blockIdx.x / prm.ctas_per_combo;
+    const int within = blockIdx.x - combo * prm.ctas_per_combo;
+    if (combo >= prm.m.n_nets * prm.MT) return;
+    const int k = combo / prm.MT, mt = combo - k * prm.MT;
+    const ppde_cnn_net_t net = prm.m.net[k];
+    const int b_lo = (int)((int64_t)prm.n * within / prm.ctas_per_combo);
+    const int b_hi = (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_combo);
+    const int ntiles = (b_hi - b_lo) * prm.tiles_per_chain;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- one-time setup ---------------------------------------------------------------------
+    for (int e = threadIdx.x; e < 100 * KS; e += NTHREADS) {
+        const int row = e / KS, c = e - row * KS;
+        float v = 0.f;
+        if (c < C) {
+            v = net.T0[(size_t)row * C + c];
+            if (row < PPDE_Q) v += net.b0[c];                         // tap 0 rows carry the bias
+        }
+        sT0[e] = v;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], NT_PROD / 32); mbar_init(&empty[s], 1); }
+        for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI); }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // A = W1 rows [mt*128, +128) -> TMEM: lane = channel, 32-bit column = two consecutive k (fp16 hi at
+        // columns [0, kpad/2), residual lo at [kpad/2, kpad)).
+        const int j = mt * 128 + warp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int ks = 0; ks < prm.kpad / 16; ++ks) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c0 = ks * 16 + 2 * q;
+                const float w0 = (j < J2 && c0 < C) ? net.W1[(size_t)j * C + c0] * net.w1_scale : 0.f;
+                const float w1 = (j < J2 && c0 + 1 < C) ? net.W1[(size_t)j * C + c0 + 1] * net.w1_scale : 0.f;
+                const float h0 = h_round(w0), h1 = h_round(w1);
+                hi[q] = pack_h2(h0, h1);
+                lo[q] = pack_h2(w0 - h0, w1 - h1);
+            }
+            tmem_st8(lane_addr + ks * 8, hi);
+            tmem_st8(lane_addr + prm.kpad / 2 + ks * 8, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- role dispatch --------------------------------------------------------------------------
+    if (warp < 4) {
+        // ===== EPILOGUE: thread = channel j =====
+        const int j = mt * 128 + warp * 32 + lane;
+        const float bias = (j < J2) ? net.b1[j] : 0.f;
+        const float unscale = 1.f / (net.w1_scale * net.r1_scale);     // exact: both scales are powers of two
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+        float best = -1.f;
+        int bp = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int buf = it & 1;
+            const int b = b_lo + it / prm.tiles_per_chain;
+            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+            const int p0 = tn * prm.n_tile;
+            const int valid = min(prm.n_tile, P - p0);
+            if (tn == 0) { best = -1.f; bp = 0; }
+            mbar_wait(&dfull[buf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            for (int cg = 0; cg * 32 < valid; ++cg) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + buf * 128 + cg * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = fmaf(__uint_as_float(r[i]), unscale, bias);
+                    v = v > 0.f ? v : 0.f;
+                    if (cg * 32 + i < valid && v > best) { best = v; bp = p0 + cg * 32 + i; }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&dempty[buf]);
+            if (tn == prm.tiles_per_chain - 1 && j < J2) {
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)bp);
+                prm.mkey[((size_t)b * prm.m.n_nets + k) * J2 + j] = key;
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // ===== MMA ISSUER (one lane) =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, prm.n_tile);
+            const uint32_t ring_addr = smem_u32(ring);
+            int slot = 0;
+            uint32_t sphase = 0;
+            const int last_ksteps = (prm.kpad - (prm.nch - 1) * KCH) / 16;
+            for (int it = 0; it < ntiles; ++it) {
+                const int buf = it & 1;
+                if (it >= 2) mbar_wait(&dempty[buf], (uint32_t)(((it >> 1) + 1) & 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
+                for (int kc = 0; kc < prm.nch; ++kc) {
+                    mbar_wait(&full[slot], sphase);
+                    tc_fence_after();
+                    const uint64_t dhi = make_b_desc(ring_addr + slot * SLOT_BYTES);
+                    const uint64_t dlo = make_b_desc(ring_addr + slot * SLOT_BYTES + MAT_BYTES);
+                    const int ksteps = (kc == prm.nch - 1) ? last_ksteps : KCH / 16;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
+                        const uint32_t a_lo = a_hi + prm.kpad / 2;
+                        const uint64_t koff = (uint64_t)(ks * 2);                 // +32 bytes per K step (>>4)
+                        mma_ts(d_tmem, a_hi, dhi + koff, idesc, (kc | ks) ? 1u : 0u);
+                        mma_ts(d_tmem, a_hi, dlo + koff, idesc, 1u);
+                        mma_ts(d_tmem, a_lo, dhi + koff, idesc, 1u);
+                    }
+                    tc_commit(&empty[slot]);                                      // frees the ring slot when the MMAs retire
+                    if (++slot == NSLOT) { slot = 0; sphase ^= 1; }
+                }
+                tc_commit(&dfull[buf]);                                           // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== PRODUCERS: r1 chunk -> fp16 hi/lo, K-major SW128 =====
+        const float r1_scale = net.r1_scale;
+        const int pw = warp - 5;                         // 0..7
+        const int g = lane & 7, q = lane >> 3;           // g: channel group, q: row within the warp's 4 rows
+        const int rsub = 16 * (pw >> 2) + (pw & 3) + 4 * q;   // row inside a 32-row pass
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int b = b_lo + it / prm.tiles_per_chain;
+            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+            const int p0 = tn * prm.n_tile;
+            const int valid = min(prm.n_tile, P - p0);
+            const uint8_t* a = prm.aa + (size_t)b * prm.aa_stride + p0;
+            int trow[4][5];                                // table row (t*20 + aa[p+t]) * KS for my 4 rows
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 32 * i + rsub;
+#pragma unroll
+                for (int t = 0; t < 5; ++t) trow[i][t] = (r < valid) ? (t * PPDE_Q + a[r + t]) * KS : 0;
+            }
+            for (int kc = 0; kc < prm.nch; ++kc) {
+                mbar_wait(&empty[slot], phase ^ 1);
+                unsigned char* mat_hi = ring + slot * SLOT_BYTES;
+                unsigned char* mat_lo = mat_hi + MAT_BYTES;
+                const int cb = kc * KCH;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 32 * i + rsub;
+                    if (r < valid) {
+                        // channels cb + 4g..4g+3 and cb + 32 + 4g..+3  (conflict-free 128-byte phases)
+                        float4 z0 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 4 * g);
+                        float4 z1 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 32 + 4 * g);
+#pragma unroll
+                        for (int t = 1; t < 5; ++t) {
+                            const float4 u0 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 4 * g);
+                            const float4 u1 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 32 + 4 * g);
+                            z0.x += u0.x; z0.y += u0.y; z0.z += u0.z; z0.w += u0.w;
+                            z1.x += u1.x; z1.y += u1.y; z1.z += u1.z; z1.w += u1.w;
+                        }
+                        float v[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = fmaxf(v[2 * e], 0.f) * r1_scale, x1 = fmaxf(v[2 * e + 1], 0.f) * r1_scale;
+                            const float h0 = h_round(x0), h1 = h_round(x1);
+                            hi[e] = pack_h2(h0, h1);
+                            lo[e] = pack_h2(x0 - h0, x1 - h1);
+                        }
+                        // element (row r, k) at (r/8)*1024 + (r%8)*128 + ((k/8) ^ (r%8))*16 + (k%8)*2
+                        const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
+                        const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);          // k = 4g
+                        const int o1 = rbase + ((((g >> 1) + 4) ^ (r & 7)) << 4) + ((g & 1) << 3);    // k = 32 + 4g
+                        *reinterpret_cast<uint2*>(mat_hi + o0) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2*>(mat_hi + o1) = make_uint2(hi[2], hi[3]);
+                        *reinterpret_cast<uint2*>(mat_lo + o0) = make_uint2(lo[0], lo[1]);
+                        *reinterpret_cast<uint2*>(mat_lo + o1) = make_uint2(lo[2], lo[3]);
+                    }
+                }
+                fence_proxy_async();                      // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[slot]);
+                if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+            }
+        }
+    }
+
+    // ---- teardown -----------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+}  // namespace tc
+}  // namespace ppde
+
+using namespace ppde;
+
+// Best positions-per-tile: multiple of 16 in [64,128] minimising padded work.
+static int choose_n_tile(int P, int* tiles) {
+    int best_n = 128, best_cost = 1 << 30;
+    for (int nt = 128; nt >= 64; nt -= 16) {
+        const int t = (P + nt - 1) / nt;
+        const int cost = t * nt + 8 * t;          // padded positions + a small per-tile overhead
+        if (cost < best_cost) { best_cost = cost; best_n = nt; *tiles = t; }
+    }
+    return best_n;
+}
+
+extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
+                                   unsigned long long* mkey, void* stream) {
+    if (n <= 0) return 0;
+    if (m->C > 256 || m->P < 1) return (int)cudaErrorInvalidValue;       // A must fit 256 TMEM columns
+    tc::Params prm;
+    prm.m = *m;
+    prm.aa = aa;
+    prm.aa_stride = aa_stride;
+    prm.n = n;
+    prm.mkey = mkey;
+    prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
+    prm.MT = (2 * m->C + 127) / 128;
+    prm.kpad = (m->C + 15) / 16 * 16;
+    prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int combos = m->n_nets * prm.MT;
+    prm.ctas_per_combo = sms / combos;
+    if (prm.ctas_per_combo < 1) prm.ctas_per_combo = 1;
+    if (prm.ctas_per_combo > n) prm.ctas_per_combo = n;
+    const size_t smem = (size_t)tc::NSLOT * tc::SLOT_BYTES + (size_t)100 * prm.nch * tc::KCH * sizeof(float) +
+                        16 * sizeof(uint64_t) + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::cnn_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    tc::cnn_forward_tc_kernel<<<combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
+    return launch_done();
+}

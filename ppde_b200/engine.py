@@ -112,7 +112,22 @@ class PoEModel:
                 for kk, v in t.items():
                     setattr(cn, kk, v.data_ptr())
                 cn.c = float(np.asarray(net["c"]).reshape(-1)[0])
+                # power-of-two operand scales for the fp16 hi/lo split of the tensor-core path
+                w1max = float(W1.abs().max())
+                r1max = float((torch.as_tensor(np.asarray(net["b0"], dtype=np.float32))
+                               + W0.amax(dim=1).clamp_min(0).sum(dim=1)).clamp_min(0).max())   # bound on relu(conv)
+                cn.w1_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(w1max, 1e-30)))))
+                cn.r1_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(r1max, 1e-30)))))
         self._mkey = None
+        # CNN forward implementation: tcgen05 tensor-core kernel (needs the W1 tile in 256 TMEM columns,
+        # i.e. C <= 256) or the fp32 SIMT kernel.  PPDE_CNN_FORWARD=simt forces the latter (A/B tests).
+        import os
+        want = os.environ.get("PPDE_CNN_FORWARD", "tc")
+        self.cnn_forward_impl = "tc" if (want == "tc" and self.C <= 256) else "simt"
+
+    def cnn_forward(self, aa, n, mk, st):
+        fn = self.lib.ppde_cnn_forward_tc if self.cnn_forward_impl == "tc" else self.lib.ppde_cnn_forward
+        _lib.check(fn(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st), "cnn_forward_" + self.cnn_forward_impl)
 
     # -- scratch ------------------------------------------------------------------------------
     def mkey(self, n):
@@ -133,7 +148,7 @@ class PoEModel:
             _lib.check(lib.ppde_potts_full(C.byref(self.potts), _ptr(aa), self.aa_stride, n, gp_ptr, self.D,
                                            ep_ptr, st), "potts_full")
         mk = self.mkey(n)
-        _lib.check(lib.ppde_cnn_forward(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st), "cnn_forward")
+        self.cnn_forward(aa, n, mk, st)
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
         _lib.check(lib.ppde_cnn_backward_combine(
             C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
@@ -299,7 +314,7 @@ class ChainEngine:
             _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(c), C.byref(p), st), "potts_incremental")
         _lib.check(lib.ppde_step_rows(C.byref(c), _ptr(self.rows_y), st), "step_rows")
         mk = m.mkey(n)
-        _lib.check(lib.ppde_cnn_forward(C.byref(m.cnn), _ptr(self.aa_y), m.aa_stride, n, _ptr(mk), st), "cnn_forward")
+        m.cnn_forward(self.aa_y, n, mk, st)
         _lib.check(lib.ppde_cnn_backward_combine(
             C.byref(m.cnn), C.byref(m.potts), _ptr(self.aa_y), m.aa_stride, n, _ptr(mk), m.lamda,
             _ptr(self.Gp) if m.has_potts else C.c_void_p(0), m.D, _ptr(self.rows_y),
