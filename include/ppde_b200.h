@@ -58,9 +58,12 @@ typedef struct ppde_cnn_net {
     const float* b1;    /* [2C]         embedding.0.bias */
     const float* d;     /* [2C]         decoder.weight[0] */
     const float* W0r;   /* [C][5][20]   W0r[c][t][a] = encoder.weight[c][a][t] (backward) */
+    const float* W1p;   /* [2C][kpad]   embedding.0.weight with rows zero-padded to kpad = roundup(C,16) floats */
     float c;            /* decoder.bias */
     float w1_scale;     /* power of two: max|W1| * w1_scale in [2^13, 2^14)  (fp16 operand split, tensor-core path) */
     float r1_scale;     /* power of two: (upper bound of r1) * r1_scale in [2^13, 2^14) */
+    float w0_scale;     /* power of two for encoder.weight (tensor-core backward) */
+    float adj_scale;    /* power of two for the adjoint rows sum_j d_j W1[j,c] (tensor-core backward) */
     int32_t _pad;
 } ppde_cnn_net_t;
 
@@ -142,6 +145,13 @@ int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t* pm, const
                               const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                               const float* Epotts, float* G, int64_t G_stride, const int32_t* g_rows,
                               float* E, float* fit, void* stream);
+/* gradient part of ppde_cnn_backward_combine on the tensor cores: G rows = Gp(window) + lamda/n_nets * sum_k dfit_k/dx.
+ * Energies / fitness come from ppde_cnn_backward_combine(..., G = NULL, ...). Needs C <= 256. */
+int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
+                         int32_t n, const unsigned long long* mkey, float lamda,
+                         const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
+                         float* G, int64_t G_stride, const int32_t* g_rows,
+                         float* scratch /* [n_nets, n, 20L] */, void* stream);
 int ppde_step_rows(const ppde_chains_t* c, int32_t* rows_y, void* stream);
 int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
 int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);

@@ -21,8 +21,9 @@ class PottsT(C.Structure):
 
 
 class CnnNetT(C.Structure):
-    _fields_ = [("T0", vp), ("b0", vp), ("W1", vp), ("W1T", vp), ("b1", vp), ("d", vp), ("W0r", vp),
-                ("c", C.c_float), ("w1_scale", C.c_float), ("r1_scale", C.c_float), ("_pad", C.c_int32)]
+    _fields_ = [("T0", vp), ("b0", vp), ("W1", vp), ("W1T", vp), ("b1", vp), ("d", vp), ("W0r", vp), ("W1p", vp),
+                ("c", C.c_float), ("w1_scale", C.c_float), ("r1_scale", C.c_float), ("w0_scale", C.c_float),
+                ("adj_scale", C.c_float), ("_pad", C.c_int32)]
 
 
 class CnnT(C.Structure):
@@ -57,6 +58,8 @@ SIGNATURES = {
     "ppde_cnn_forward_tc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp]),
     "ppde_cnn_backward_combine": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp,
                                             C.c_float, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp]),
+    "ppde_cnn_backward_tc": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
+                                       vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]),
     "ppde_step_rows": (C.c_int, [C.POINTER(ChainsT), vp, vp]),
     "ppde_pas_propose": (C.c_int, [C.POINTER(PottsT), C.POINTER(ChainsT), C.POINTER(PasParamsT), vp]),
     "ppde_pas_reverse_accept": (C.c_int, [C.POINTER(PottsT), C.POINTER(ChainsT), C.POINTER(PasParamsT), vp]),

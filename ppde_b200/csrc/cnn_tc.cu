@@ -348,6 +348,373 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
     }
 }
 
+
+// =====================================================================================================
+// Backward of the CNN ensemble on the tensor cores (same skeleton as the forward kernel).
+//
+//   dfit_k/dx[i,a] = sum_t sum_c A[i-t,c] W0[c,a,t],   A[p,c] = 1[r1[p,c]>0] * sum_{j: p*_j=p, m_j>0} d_j W1[j,c]
+//
+// GEMM view (per net):  Y[(t,a), p] = sum_c W0[c,a,t] * A[p,c]      M = 100 (t,a) rows (padded to 128), N = positions, K = C.
+//   * A-operand  = W0^T tile (100 x K), fp16 hi/lo, resident in TENSOR MEMORY per net.
+//   * B-operand  = adjoint rows, PRODUCED on the fly: the producers bucket the <= 2C arg-max winners of the chain
+//     by position (counting sort in shared memory), recompute the relu mask of r1 from the conv table, gather-sum
+//     the winners' W1 rows from L2 (coalesced 256-byte row segments) and write fp16 hi/lo K-major SW128 chunks.
+//   * Epilogue   = tcgen05.ld (thread = (t,a)), deterministic col2im through a small smem tile into the chain's
+//     [20L] gradient accumulator, flushed into the pool row:  G = Gp(window) + lamda/n_nets * sum_k dfit_k/dx.
+// CTA -> (net, contiguous block of chains); per-net partial gradients go to a scratch buffer and a streaming
+// kernel forms  G = Gp(window) + lamda/n_nets * (Gc_0 + Gc_1 + Gc_2)  in a fixed order (deterministic).
+constexpr int BW_NSLOT = 2;
+constexpr int YS = 33;                 // sY row stride (floats)
+
+struct BwdParams {
+    ppde_cnn_t m;
+    ppde_potts_t pm;
+    const uint8_t* aa;
+    int aa_stride;
+    int n;
+    const unsigned long long* mkey;
+    float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
+    int ctas_per_net;
+    int n_tile, tiles_per_chain, nch, kpad;
+};
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __grid_constant__ BwdParams prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
+    const int KS = prm.kpad;                                           // table row length (+ tail pad below)
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* sT0 = reinterpret_cast<float*>(ring + BW_NSLOT * SLOT_BYTES);    // [100][KS] + 64 floats tail pad
+    float* sGc = sT0 + 100 * KS + 64;                                  // [NE] chain accumulator
+    float* sY = sGc + NE;                                              // [100][YS]
+    float* sDj = sY + 100 * YS;                                        // [J2] d_j of active winners
+    int* sPst = reinterpret_cast<int*>(sDj + J2);                      // [J2] p*_j or -1
+    int* sStart = sPst + J2;                                           // [P+1]
+    int* sFill = sStart + (P + 1);                                     // [P]
+    int* sList = sFill + P;                                            // [J2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sList + J2) + 7) & ~(uintptr_t)7);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + BW_NSLOT;
+    uint64_t* dfull = empty + BW_NSLOT;
+    uint64_t* dempty = dfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+
+    const int k = blockIdx.x / prm.ctas_per_net;                       // this CTA's net
+    const int within = blockIdx.x - k * prm.ctas_per_net;
+    if (k >= prm.m.n_nets) return;
+    const int b_lo = (int)((int64_t)prm.n * within / prm.ctas_per_net);
+    const int b_hi = (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_net);
+    const int ntiles = (b_hi - b_lo) * prm.tiles_per_chain;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BW_NSLOT; ++s) { mbar_init(&full[s], NT_PROD / 32); mbar_init(&empty[s], 1); }
+        for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI); }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int e = threadIdx.x; e < NE; e += NTHREADS) sGc[e] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // pipeline state persists across the nets
+    int p_slot = 0; uint32_t p_phase = 0;      // producers
+    int m_slot = 0; uint32_t m_phase = 0;      // MMA issuer
+    const int git = 0;
+
+    {
+        const ppde_cnn_net_t net = prm.m.net[k];
+        // ---- per-net setup: conv table (bias folded) -> smem, W0^T (scaled, fp16 hi/lo) -> TMEM ----
+        for (int e = threadIdx.x; e < 100 * KS + 64; e += NTHREADS) {
+            const int row = e / KS, c = e - row * KS;
+            float v = 0.f;
+            if (row < 100 && c < C) {
+                v = net.T0[(size_t)row * C + c];
+                if (row < PPDE_Q) v += net.b0[c];
+            }
+            sT0[e] = v;
+        }
+        if (warp < 4) {
+            const int nrow = warp * 32 + lane;                           // (t,a) = (nrow / 20, nrow % 20)
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int ks = 0; ks < prm.kpad / 16; ++ks) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c0 = ks * 16 + 2 * q;
+                    const float w0 = (nrow < 100 && c0 < C) ? net.W0r[(size_t)c0 * 100 + nrow] * net.w0_scale : 0.f;
+                    const float w1 = (nrow < 100 && c0 + 1 < C) ? net.W0r[(size_t)(c0 + 1) * 100 + nrow] * net.w0_scale : 0.f;
+                    const float h0 = h_round(w0), h1 = h_round(w1);
+                    hi[q] = pack_h2(h0, h1);
+                    lo[q] = pack_h2(w0 - h0, w1 - h1);
+                }
+                tmem_st8(lane_addr + ks * 8, hi);
+                tmem_st8(lane_addr + prm.kpad / 2 + ks * 8, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+
+        if (warp < 4) {
+            // ===== EPILOGUE: thread = output row (t,a) =====
+            const int nrow = warp * 32 + lane;
+            const int tid = threadIdx.x;                                  // 0..127
+            const float unscale = 1.f / (net.w0_scale * net.adj_scale);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+            for (int it = 0; it < ntiles; ++it) {
+                const int gt = git + it;
+                const int buf = gt & 1;
+                const int b = b_lo + it / prm.tiles_per_chain;
+                const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+                const int p0 = tn * prm.n_tile;
+                const int valid = min(prm.n_tile, P - p0);
+                mbar_wait(&dfull[buf], (uint32_t)((gt >> 1) & 1));
+                tc_fence_after();
+                for (int cg = 0; cg * 32 < valid; ++cg) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_addr + buf * 128 + cg * 32, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if ((cg + 1) * 32 >= valid) {                         // last read of this accumulator
+                        tc_fence_before();
+                        mbar_arrive(&dempty[buf]);
+                    }
+                    if (nrow < 100) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sY[nrow * YS + i] = __uint_as_float(r[i]) * unscale;
+                    }
+                    named_bar(2, NT_EPI);
+                    // col2im, fixed summation order: output (i,a) = sum_t Y[(t,a), i - t]
+                    const int nv = min(32, valid - cg * 32);
+                    for (int o = tid; o < 36 * PPDE_Q; o += NT_EPI) {
+                        const int di = o / PPDE_Q, a = o - di * PPDE_Q;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) {
+                            const int pp = di - t;
+                            if (pp >= 0 && pp < nv) acc += sY[(t * PPDE_Q + a) * YS + pp];
+                        }
+                        const int i = p0 + cg * 32 + di;
+                        if (i < L) sGc[i * PPDE_Q + a] += acc;
+                    }
+                    named_bar(2, NT_EPI);
+                }
+                if (tn == prm.tiles_per_chain - 1) {
+                    // flush the chain's partial gradient (streaming float4 stores) and clear the accumulator
+                    float4* dst = reinterpret_cast<float4*>(prm.Gc + ((size_t)k * prm.n + b) * NE);
+                    float4* src = reinterpret_cast<float4*>(sGc);
+                    for (int e = tid; e < NE / 4; e += NT_EPI) {
+                        __stcs(dst + e, src[e]);
+                        src[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    named_bar(2, NT_EPI);
+                }
+            }
+        } else if (warp == WARP_MMA) {
+            if (lane == 0) {
+                const uint32_t idesc = make_idesc(128, prm.n_tile);
+                const uint32_t ring_addr = smem_u32(ring);
+                const int last_ksteps = (prm.kpad - (prm.nch - 1) * KCH) / 16;
+                for (int it = 0; it < ntiles; ++it) {
+                    const int gt = git + it;
+                    const int buf = gt & 1;
+                    if (gt >= 2) mbar_wait(&dempty[buf], (uint32_t)(((gt >> 1) + 1) & 1));
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
+                    for (int kc = 0; kc < prm.nch; ++kc) {
+                        mbar_wait(&full[m_slot], m_phase);
+                        tc_fence_after();
+                        const uint64_t dhi = make_b_desc(ring_addr + m_slot * SLOT_BYTES);
+                        const uint64_t dlo = make_b_desc(ring_addr + m_slot * SLOT_BYTES + MAT_BYTES);
+                        const int ksteps = (kc == prm.nch - 1) ? last_ksteps : KCH / 16;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
+                            const uint32_t a_lo = a_hi + prm.kpad / 2;
+                            const uint64_t koff = (uint64_t)(ks * 2);
+                            mma_ts(d_tmem, a_hi, dhi + koff, idesc, (kc | ks) ? 1u : 0u);
+                            mma_ts(d_tmem, a_hi, dlo + koff, idesc, 1u);
+                            mma_ts(d_tmem, a_lo, dhi + koff, idesc, 1u);
+                        }
+                        tc_commit(&empty[m_slot]);
+                        if (++m_slot == BW_NSLOT) { m_slot = 0; m_phase ^= 1; }
+                    }
+                    tc_commit(&dfull[buf]);
+                }
+            }
+        } else {
+            // ===== PRODUCERS: adjoint rows =====
+            const int ptid = threadIdx.x - (WARP_MMA + 1) * 32;           // 0..255
+            const int pw = warp - 5;
+            const int g = lane & 7, q = lane >> 3;
+            const int rsub = 16 * (pw >> 2) + (pw & 3) + 4 * q;
+            const float adj_scale = net.adj_scale;
+            for (int it = 0; it < ntiles; ++it) {
+                const int b = b_lo + it / prm.tiles_per_chain;
+                const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+                const int p0 = tn * prm.n_tile;
+                const int valid = min(prm.n_tile, P - p0);
+                if (tn == 0) {
+                    // bucket this chain's winners by position (counting sort; order inside a bucket fixed at use)
+                    named_bar(1, NT_PROD);
+                    for (int i = ptid; i <= P; i += NT_PROD) { sStart[i] = 0; if (i < P) sFill[i] = 0; }
+                    named_bar(1, NT_PROD);
+                    const unsigned long long* keys = prm.mkey + ((size_t)b * prm.m.n_nets + k) * J2;
+                    for (int j = ptid; j < J2; j += NT_PROD) {
+                        const unsigned long long key = keys[j];
+                        const float mj = __uint_as_float((unsigned)(key >> 32));
+                        const int pst = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
+                        const bool active = (mj > 0.f) && pst >= 0 && pst < P;     // relu'(0) = 0
+                        sPst[j] = active ? pst : -1;
+                        sDj[j] = net.d[j];
+                        if (active) atomicAdd(&sStart[pst + 1], 1);
+                    }
+                    named_bar(1, NT_PROD);
+                    if (pw == 0) {                                        // exclusive scan of P+1 counters by one warp
+                        const int per = (P + 1 + 31) / 32;
+                        int run = 0;
+                        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) run += sStart[i];
+                        int incl = run;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        int base = incl - run;
+                        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) { base += sStart[i]; sStart[i] = base; }
+                    }
+                    named_bar(1, NT_PROD);
+                    for (int j = ptid; j < J2; j += NT_PROD) {
+                        const int pst = sPst[j];
+                        if (pst >= 0) sList[sStart[pst] + atomicAdd(&sFill[pst], 1)] = j;
+                    }
+                    named_bar(1, NT_PROD);
+                    for (int pp = ptid; pp < P; pp += NT_PROD) {          // ascending channel order inside each bucket
+                        const int s0 = sStart[pp], s1 = sStart[pp + 1];
+                        for (int u = s0 + 1; u < s1; ++u) {
+                            const int v = sList[u];
+                            int w = u - 1;
+                            while (w >= s0 && sList[w] > v) { sList[w + 1] = sList[w]; --w; }
+                            sList[w + 1] = v;
+                        }
+                    }
+                    named_bar(1, NT_PROD);
+                }
+                const uint8_t* a = prm.aa + (size_t)b * prm.aa_stride + p0;
+                int trow[4][5];
+                int ls0[4], ls1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 32 * i + rsub;
+                    const bool ok = r < valid;
+                    ls0[i] = ok ? sStart[p0 + r] : 0;
+                    ls1[i] = ok ? sStart[p0 + r + 1] : 0;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) trow[i][t] = ok ? (t * PPDE_Q + a[r + t]) * KS : 0;
+                }
+                for (int kc = 0; kc < prm.nch; ++kc) {
+                    mbar_wait(&empty[p_slot], p_phase ^ 1);
+                    unsigned char* mat_hi = ring + p_slot * SLOT_BYTES;
+                    unsigned char* mat_lo = mat_hi + MAT_BYTES;
+                    const int cb = kc * KCH;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 32 * i + rsub;
+                        if (r >= prm.n_tile) continue;
+                        uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+                        if (ls1[i] > ls0[i]) {
+                            float4 z0 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 4 * g);
+                            float4 z1 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 32 + 4 * g);
+#pragma unroll
+                            for (int t = 1; t < 5; ++t) {
+                                const float4 u0 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 4 * g);
+                                const float4 u1 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 32 + 4 * g);
+                                z0.x += u0.x; z0.y += u0.y; z0.z += u0.z; z0.w += u0.w;
+                                z1.x += u1.x; z1.y += u1.y; z1.z += u1.z; z1.w += u1.w;
+                            }
+                            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll 4
+                            for (int u = ls0[i]; u < ls1[i]; ++u) {               // ascending channel order: deterministic sum
+                                const int jn = sList[u];
+                                const float dj = sDj[jn];
+                                const float* wrow = net.W1p + (size_t)jn * prm.kpad + cb;
+                                if (cb + 4 * g < prm.kpad) {
+                                    const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + 4 * g));
+                                    s0.x = fmaf(dj, w.x, s0.x); s0.y = fmaf(dj, w.y, s0.y); s0.z = fmaf(dj, w.z, s0.z); s0.w = fmaf(dj, w.w, s0.w);
+                                }
+                                if (cb + 32 + 4 * g < prm.kpad) {
+                                    const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + 32 + 4 * g));
+                                    s1.x = fmaf(dj, w.x, s1.x); s1.y = fmaf(dj, w.y, s1.y); s1.z = fmaf(dj, w.z, s1.z); s1.w = fmaf(dj, w.w, s1.w);
+                                }
+                            }
+                            const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float x0 = (zz[2 * e] > 0.f ? ss[2 * e] : 0.f) * adj_scale;
+                                const float x1 = (zz[2 * e + 1] > 0.f ? ss[2 * e + 1] : 0.f) * adj_scale;
+                                const float h0 = h_round(x0), h1 = h_round(x1);
+                                hi[e] = pack_h2(h0, h1);
+                                lo[e] = pack_h2(x0 - h0, x1 - h1);
+                            }
+                        }
+                        const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
+                        const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);
+                        const int o1 = rbase + ((((g >> 1) + 4) ^ (r & 7)) << 4) + ((g & 1) << 3);
+                        *reinterpret_cast<uint2*>(mat_hi + o0) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2*>(mat_hi + o1) = make_uint2(hi[2], hi[3]);
+                        *reinterpret_cast<uint2*>(mat_lo + o0) = make_uint2(lo[0], lo[1]);
+                        *reinterpret_cast<uint2*>(mat_lo + o1) = make_uint2(lo[2], lo[3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[p_slot]);
+                    if (++p_slot == BW_NSLOT) { p_slot = 0; p_phase ^= 1; }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+
+__global__ void cnn_grad_combine_kernel(int n, int NE, int n_nets, float scale, ppde_potts_t pm,
+                                        const float* __restrict__ Gc, const float* __restrict__ Gp, int64_t Gp_stride,
+                                        const int32_t* __restrict__ gp_rows, float* __restrict__ G, int64_t G_stride,
+                                        const int32_t* __restrict__ g_rows) {
+    const int b = blockIdx.x;
+    const int wlo = pm.win_lo * PPDE_Q, whi = (pm.win_lo + pm.Lp) * PPDE_Q;     // multiples of 4
+    float4* g = reinterpret_cast<float4*>(G + (int64_t)(g_rows ? g_rows[b] : b) * G_stride);
+    const float* gp = Gp ? Gp + (int64_t)(gp_rows ? gp_rows[b] : b) * Gp_stride : nullptr;
+    for (int q = threadIdx.x; q < NE / 4; q += blockDim.x) {
+        float4 acc = __ldcs(reinterpret_cast<const float4*>(Gc + (size_t)b * NE) + q);
+        for (int k = 1; k < n_nets; ++k) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(Gc + ((size_t)k * n + b) * NE) + q);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int e = q * 4;
+        if (gp && e >= wlo && e < whi) base = *reinterpret_cast<const float4*>(gp + (e - wlo));
+        g[q] = make_float4(fmaf(scale, acc.x, base.x), fmaf(scale, acc.y, base.y), fmaf(scale, acc.z, base.z),
+                           fmaf(scale, acc.w, base.w));
+    }
+}
+
 }  // namespace tc
 }  // namespace ppde
 
@@ -394,5 +761,42 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
         configured = smem;
     }
     tc::cnn_forward_tc_kernel<<<combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
+    return launch_done();
+}
+
+extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
+                                    int32_t n, const unsigned long long* mkey, float lamda,
+                                    const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
+                                    float* G, int64_t G_stride, const int32_t* g_rows, float* scratch, void* stream) {
+    if (n <= 0) return 0;
+    if (m->C > 256 || m->P < 1 || !scratch) return (int)cudaErrorInvalidValue;
+    tc::BwdParams prm;
+    prm.m = *m; prm.pm = *pm; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey;
+    prm.Gc = scratch;
+    prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
+    prm.kpad = (m->C + 15) / 16 * 16;
+    prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    prm.ctas_per_net = sms / m->n_nets;
+    if (prm.ctas_per_net < 1) prm.ctas_per_net = 1;
+    if (prm.ctas_per_net > n) prm.ctas_per_net = n;
+    const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
+    const size_t smem = 1024 + (size_t)tc::BW_NSLOT * tc::SLOT_BYTES +
+                        ((size_t)100 * prm.kpad + 64 + (size_t)L * PPDE_Q + 100 * tc::YS + J2) * sizeof(float) +
+                        ((size_t)J2 + (P + 1) + P + J2) * sizeof(int) + 8 + 16 * sizeof(uint64_t);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::cnn_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::cnn_backward_tc_kernel<<<m->n_nets * prm.ctas_per_net, tc::NTHREADS, smem, st>>>(prm);
+    int r = launch_done();
+    if (r) return r;
+    tc::cnn_grad_combine_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
+                                                   Gp, Gp_stride, gp_rows, G, G_stride, g_rows);
     return launch_done();
 }

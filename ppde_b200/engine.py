@@ -106,6 +106,10 @@ class PoEModel:
                     "d": torch.as_tensor(np.asarray(net["d"], dtype=np.float32).reshape(-1)),
                     "W0r": W0.permute(0, 2, 1).contiguous(),           # [C][5][20]
                 }
+                kpad = (self.C + 15) // 16 * 16
+                W1p = torch.zeros(2 * self.C, kpad, dtype=torch.float32)
+                W1p[:, :self.C] = W1
+                t["W1p"] = W1p
                 t = {kk: v.to(dev) for kk, v in t.items()}
                 self._cnn_keep.append(t)
                 cn = self.cnn.net[k]
@@ -118,18 +122,46 @@ class PoEModel:
                                + W0.amax(dim=1).clamp_min(0).sum(dim=1)).clamp_min(0).max())   # bound on relu(conv)
                 cn.w1_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(w1max, 1e-30)))))
                 cn.r1_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(r1max, 1e-30)))))
+                dvec = torch.as_tensor(np.asarray(net["d"], dtype=np.float32).reshape(-1))
+                adjmax = float((dvec.abs()[:, None] * W1.abs()).sum(0).max())      # bound on |sum_j d_j W1[j,c]|
+                cn.w0_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(float(W0.abs().max()), 1e-30)))))
+                cn.adj_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(adjmax, 1e-30)))))
         self._mkey = None
         # CNN forward implementation: tcgen05 tensor-core kernel (needs the W1 tile in 256 TMEM columns,
         # i.e. C <= 256) or the fp32 SIMT kernel.  PPDE_CNN_FORWARD=simt forces the latter (A/B tests).
         import os
         want = os.environ.get("PPDE_CNN_FORWARD", "tc")
         self.cnn_forward_impl = "tc" if (want == "tc" and self.C <= 256) else "simt"
+        wantb = os.environ.get("PPDE_CNN_BACKWARD", "tc")
+        self.cnn_backward_impl = "tc" if (wantb == "tc" and self.C <= 256) else "simt"
 
     def cnn_forward(self, aa, n, mk, st):
         fn = self.lib.ppde_cnn_forward_tc if self.cnn_forward_impl == "tc" else self.lib.ppde_cnn_forward
         _lib.check(fn(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st), "cnn_forward_" + self.cnn_forward_impl)
 
+    def cnn_backward_combine(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, st):
+        """fit / E from the winners, then (if g_ptr) the gradient rows G = Gp(window) + lamda/n_nets * sum_k dfit_k/dx."""
+        lib = self.lib
+        null = C.c_void_p(0)
+        if self.cnn_backward_impl == "tc" and g_ptr:
+            _lib.check(lib.ppde_cnn_backward_combine(
+                C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+                null, self.D, null, ep_ptr, null, self.NE, null, _ptr(E), _ptr(fit), st), "cnn_fit")
+            _lib.check(lib.ppde_cnn_backward_tc(
+                C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(self.grad_scratch(n)), st), "cnn_backward_tc")
+        else:
+            _lib.check(lib.ppde_cnn_backward_combine(
+                C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+                gp_ptr, self.D, gp_rows, ep_ptr, g_ptr, self.NE, g_rows, _ptr(E), _ptr(fit), st), "cnn_backward_combine")
+
     # -- scratch ------------------------------------------------------------------------------
+    def grad_scratch(self, n):
+        need = self.n_nets * n * self.NE
+        if getattr(self, "_gscratch", None) is None or self._gscratch.numel() < need:
+            self._gscratch = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self._gscratch
+
     def mkey(self, n):
         need = n * self.n_nets * 2 * self.C
         if self._mkey is None or self._mkey.numel() < need:
@@ -150,10 +182,8 @@ class PoEModel:
         mk = self.mkey(n)
         self.cnn_forward(aa, n, mk, st)
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
-        _lib.check(lib.ppde_cnn_backward_combine(
-            C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
-            gp_ptr, self.D, C.c_void_p(0), ep_ptr, g_ptr, self.NE, C.c_void_p(0), _ptr(E), _ptr(fit), st),
-            "cnn_backward_combine")
+        self.cnn_backward_combine(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr if want_grad else None,
+                                  C.c_void_p(0), E, fit, st)
 
     def onehot_to_aa(self, x):
         n, L, q = x.shape
@@ -315,11 +345,9 @@ class ChainEngine:
         _lib.check(lib.ppde_step_rows(C.byref(c), _ptr(self.rows_y), st), "step_rows")
         mk = m.mkey(n)
         m.cnn_forward(self.aa_y, n, mk, st)
-        _lib.check(lib.ppde_cnn_backward_combine(
-            C.byref(m.cnn), C.byref(m.potts), _ptr(self.aa_y), m.aa_stride, n, _ptr(mk), m.lamda,
-            _ptr(self.Gp) if m.has_potts else C.c_void_p(0), m.D, _ptr(self.rows_y),
-            _ptr(self.Epotts_y) if m.has_potts else C.c_void_p(0), _ptr(self.G), m.NE, _ptr(self.rows_y),
-            _ptr(self.E_y), _ptr(self.fit_y), st), "cnn_backward_combine")
+        m.cnn_backward_combine(self.aa_y, n, mk, _ptr(self.Gp) if m.has_potts else C.c_void_p(0), _ptr(self.rows_y),
+                               _ptr(self.Epotts_y) if m.has_potts else C.c_void_p(0), _ptr(self.G), _ptr(self.rows_y),
+                               self.E_y, self.fit_y, st)
         _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_reverse_accept")
 
     def step(self, uniforms=None):
@@ -339,6 +367,7 @@ class ChainEngine:
         with torch.cuda.device(self.m.device):
             if self._graph is None:
                 self.m.mkey(self.n)
+                self.m.grad_scratch(self.n)
                 self.t_dev.fill_(self.t)
                 p = self._params(0, None, use_t_dev=True)
                 self._graph_params = p

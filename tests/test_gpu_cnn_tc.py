@@ -63,3 +63,39 @@ def test_tc_forward_matches_simt_and_oracle(L, n):
         torch.cuda.synchronize()
         e = np.max(np.abs(fit.cpu().numpy() - fit_ref) / np.maximum(np.abs(fit_ref), 1e-2))
         assert e < 1e-4, f"{impl}: fitness rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("L,n", [(40, 9), (104, 40), (238, 150)])
+def test_tc_backward_matches_simt_and_oracle(L, n):
+    from ppde_b200.engine import PoEModel
+    w = port.synthetic_weights(L, seed=L + 1, lamda=3.0, window=(1, L - 2))
+    m = PoEModel(w.wt, w.J, w.h, w.win_lo, w.cnn, w.lamda, device="cuda:0")
+    rng = np.random.default_rng(L)
+    aa = np.tile(w.wt, (n, 1))
+    for b in range(1, n):
+        pos = rng.integers(0, L, size=min(b, L))
+        aa[b, pos] = rng.integers(0, 20, size=pos.shape[0])
+    aa[n - 1, 5:11] = aa[n - 1, 20:26]             # repeated 5-mers: exact max-pool ties
+    pad = np.zeros((n, m.aa_stride), dtype=np.uint8); pad[:, :L] = aa
+    aad = torch.from_numpy(pad).to(m.device)
+    out = {}
+    for impl in ("simt", "tc"):
+        m.cnn_forward_impl = impl
+        m.cnn_backward_impl = impl
+        E, fit, G, Ep = m.energy(aad)
+        torch.cuda.synchronize()
+        out[impl] = (E.cpu().numpy(), fit.cpu().numpy(), G.cpu().numpy())
+    gs, gt = out["simt"][2], out["tc"][2]
+    scale = np.abs(gs).max(axis=(1, 2), keepdims=True)
+    err = np.max(np.abs(gs - gt) / scale)
+    assert err < 2e-5, f"tc vs simt gradient, relative to each chain's max |g|: {err:.3e}"
+    en = port.PortEnergy(w)
+    k = min(n, 12)
+    e_ref, f_ref, g_ref = en.get_energy_and_grads(port.aa_to_onehot(aa[-k:]))
+    g_ref = g_ref.numpy()
+    gscale = np.maximum(np.abs(g_ref), np.abs(g_ref).max(axis=(1, 2), keepdims=True) * 1e-2)
+    err = np.max(np.abs(gt[-k:] - g_ref) / gscale)
+    assert err < 1e-4, f"tc gradient vs oracle autograd: {err:.3e}"
+    e_ref = e_ref.numpy()
+    err = np.max(np.abs(out["tc"][0][-k:] - e_ref) / np.maximum(np.abs(e_ref), abs(m.wt_H)))
+    assert err < 1e-4, f"tc energy vs oracle: {err:.3e}"
