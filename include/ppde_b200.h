@@ -137,9 +137,11 @@ int ppde_potts_full(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride,
 int ppde_potts_incremental(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
 int ppde_cnn_forward(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                      unsigned long long* mkey /* [n, n_nets, 2C] */, void* stream);
-/* same contract as ppde_cnn_forward, on the tcgen05 tensor cores (needs C <= 256); writes every key, no memset */
+/* same contract as ppde_cnn_forward, on the tcgen05 tensor cores (needs C <= 256); writes every key, no memset.
+ * r1mask (optional, [n, n_nets, P, 32] bytes): bit c of a position's 32 bytes = relu mask of the conv layer, consumed
+ * by ppde_cnn_backward_tc. */
 int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
-                        unsigned long long* mkey /* [n, n_nets, 2C] */, void* stream);
+                        unsigned long long* mkey /* [n, n_nets, 2C] */, uint8_t* r1mask, void* stream);
 int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                               int32_t n, const unsigned long long* mkey, float lamda,
                               const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
@@ -151,6 +153,7 @@ int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint
                          int32_t n, const unsigned long long* mkey, float lamda,
                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                          float* G, int64_t G_stride, const int32_t* g_rows,
+                         const uint8_t* r1mask /* from ppde_cnn_forward_tc */,
                          float* scratch /* [n_nets, n, 20L] */, void* stream);
 int ppde_step_rows(const ppde_chains_t* c, int32_t* rows_y, void* stream);
 int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);

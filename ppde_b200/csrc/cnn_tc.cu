@@ -17,7 +17,7 @@
 //   * D (128 channels x N_tile positions, fp32) is double-buffered in TMEM; 4 epilogue warps read it with
 //     tcgen05.ld (thread = channel), add bias, relu, and keep a running (max, first arg-max) in registers
 //     across the tiles of a chain, then write the 64-bit winner key.  No atomics, no memset.
-// Warp roles: warps 0-3 epilogue (TMEM lane quarters), warp 4 MMA issuer (one elected lane), warps 5-12 producers.
+// Warp roles: warps 0-3 epilogue (TMEM lane quarters), warp 4 MMA issuer (one elected lane), warps 5-20 producers.
 // Persistent grid: CTA -> (net, channel tile) x contiguous block of chains.
 #include "common.cuh"
 #include "../../include/ppde_b200.h"
@@ -28,8 +28,8 @@ namespace ppde {
 namespace tc {
 
 constexpr int NT_EPI = 128;
-constexpr int NT_PROD = 256;
-constexpr int NTHREADS = NT_EPI + 32 + NT_PROD;   // 416
+constexpr int NT_PROD = 512;                       // 16 producer warps (4 per scheduler): the producers are issue/latency bound
+constexpr int NTHREADS = NT_EPI + 32 + NT_PROD;   // 672
 constexpr int WARP_MMA = 4;
 constexpr int NSLOT = 3;
 constexpr int KCH = 64;                            // K elements per chunk = one 128-byte swizzle row of fp16
@@ -96,6 +96,16 @@ __device__ __forceinline__ uint32_t pack_h2(float lo_k, float hi_k) {       // l
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float h_round(float x) { return __half2float(__float2half_rn(x)); }
+// packed fp32 add (FADD2 on sm_100): halves the issue slots of the 5-tap table sums
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+}
+// x (>= 0, pre-scaled) -> fp16 hi (top 11 significand bits, by truncation: exact in fp16) and the exact fp32 residual
+__device__ __forceinline__ float h_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
@@ -120,6 +130,7 @@ struct Params {
     int aa_stride;
     int n;
     unsigned long long* mkey;
+    uint8_t* r1mask;      // optional [n, n_nets, P, 32]: bit c of a position's 32 bytes = (r1[p,c] > 0), for the backward
     int n_tile;           // positions per tile (multiple of 16, <= 128)
     int tiles_per_chain;
     int ctas_per_combo;
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
             v = net.T0[(size_t)row * C + c];
             if (row < PPDE_Q) v += net.b0[c];                         // tap 0 rows carry the bias
         }
-        sT0[e] = v;
+        sT0[e] = v * net.r1_scale;                                    // power of two: exact; r1 comes out pre-scaled
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], NT_PROD / 32); mbar_init(&empty[s], 1); }
@@ -274,10 +285,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
         }
     } else {
         // ===== PRODUCERS: r1 chunk -> fp16 hi/lo, K-major SW128 =====
-        const float r1_scale = net.r1_scale;
-        const int pw = warp - 5;                         // 0..7
-        const int g = lane & 7, q = lane >> 3;           // g: channel group, q: row within the warp's 4 rows
-        const int rsub = 16 * (pw >> 2) + (pw & 3) + 4 * q;   // row inside a 32-row pass
+        // lane = g + 8q: g = channel group (channels cb+4g..+3 and cb+32+4g..+3: conflict-free 128-byte LDS phases),
+        // q = one of the warp's 4 rows; rows {x, x+4, x+8, x+12} per warp keep the 8-byte swizzled stores conflict-free.
+        const int pw = warp - 5;                         // 0..15
+        const int g = lane & 7, q = lane >> 3;
+        const int rsub = 16 * (pw >> 2) + (pw & 3) + 4 * q;   // row inside a 64-row pass
         int slot = 0;
         uint32_t phase = 0;
         for (int it = 0; it < ntiles; ++it) {
@@ -286,41 +298,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
             const int p0 = tn * prm.n_tile;
             const int valid = min(prm.n_tile, P - p0);
             const uint8_t* a = prm.aa + (size_t)b * prm.aa_stride + p0;
-            int trow[4][5];                                // table row (t*20 + aa[p+t]) * KS for my 4 rows
+            const float* trow[2][5];                       // table rows (t*20 + aa[p+t]) of my 2 rows, at my channel group
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = 32 * i + rsub;
+            for (int i = 0; i < 2; ++i) {
+                const int r = 64 * i + rsub;
 #pragma unroll
-                for (int t = 0; t < 5; ++t) trow[i][t] = (r < valid) ? (t * PPDE_Q + a[r + t]) * KS : 0;
+                for (int t = 0; t < 5; ++t)
+                    trow[i][t] = sT0 + ((r < valid) ? (t * PPDE_Q + a[r + t]) * KS : 0) + 4 * g;
             }
+            // the MT CTAs that share a chain block produce identical r1 tiles: they take turns writing the relu mask
+            const bool emit_mask = (prm.r1mask != nullptr) && (it % prm.MT == mt);
+            uint32_t mbits[2] = {0u, 0u};                  // nibble 2*kc + h = (r1 > 0) of channels kc*64 + 32h + 4g ..
             for (int kc = 0; kc < prm.nch; ++kc) {
                 mbar_wait(&empty[slot], phase ^ 1);
                 unsigned char* mat_hi = ring + slot * SLOT_BYTES;
                 unsigned char* mat_lo = mat_hi + MAT_BYTES;
                 const int cb = kc * KCH;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = 32 * i + rsub;
+                for (int i = 0; i < 2; ++i) {
+                    const int r = 64 * i + rsub;
                     if (r < valid) {
-                        // channels cb + 4g..4g+3 and cb + 32 + 4g..+3  (conflict-free 128-byte phases)
-                        float4 z0 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 4 * g);
-                        float4 z1 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 32 + 4 * g);
+                        float4 z0 = *reinterpret_cast<const float4*>(trow[i][0] + cb);
+                        float4 z1 = *reinterpret_cast<const float4*>(trow[i][0] + cb + 32);
+                        float2 a0 = make_float2(z0.x, z0.y), a1 = make_float2(z0.z, z0.w);
+                        float2 a2 = make_float2(z1.x, z1.y), a3 = make_float2(z1.z, z1.w);
 #pragma unroll
                         for (int t = 1; t < 5; ++t) {
-                            const float4 u0 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 4 * g);
-                            const float4 u1 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 32 + 4 * g);
-                            z0.x += u0.x; z0.y += u0.y; z0.z += u0.z; z0.w += u0.w;
-                            z1.x += u1.x; z1.y += u1.y; z1.z += u1.z; z1.w += u1.w;
+                            const float4 u0 = *reinterpret_cast<const float4*>(trow[i][t] + cb);
+                            const float4 u1 = *reinterpret_cast<const float4*>(trow[i][t] + cb + 32);
+                            a0 = add2(a0, make_float2(u0.x, u0.y)); a1 = add2(a1, make_float2(u0.z, u0.w));
+                            a2 = add2(a2, make_float2(u1.x, u1.y)); a3 = add2(a3, make_float2(u1.z, u1.w));
                         }
-                        float v[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                        const float v[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+                        uint32_t nib = 0u;
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float x0 = fmaxf(v[2 * e], 0.f) * r1_scale, x1 = fmaxf(v[2 * e + 1], 0.f) * r1_scale;
-                            const float h0 = h_round(x0), h1 = h_round(x1);
+                            nib |= (__float_as_int(v[2 * e]) > 0 ? 1u : 0u) << (2 * e);
+                            nib |= (__float_as_int(v[2 * e + 1]) > 0 ? 1u : 0u) << (2 * e + 1);
+                            const float x0 = fmaxf(v[2 * e], 0.f), x1 = fmaxf(v[2 * e + 1], 0.f);
+                            const float h0 = h_trunc(x0), h1 = h_trunc(x1);
                             hi[e] = pack_h2(h0, h1);
                             lo[e] = pack_h2(x0 - h0, x1 - h1);
                         }
+                        mbits[i] |= nib << (8 * kc);
                         // element (row r, k) at (r/8)*1024 + (r%8)*128 + ((k/8) ^ (r%8))*16 + (k%8)*2
                         const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
                         const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);          // k = 4g
@@ -335,6 +356,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[slot]);
                 if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+            }
+            if (emit_mask) {
+                // word w of a row's 256 mask bits = channels 32w..32w+31 = nibble w of the row's 8 lanes:
+                // 8x8 nibble transpose across those lanes (3 butterfly stages), then one coalesced 32-byte store per row
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = 64 * i + rsub;
+                    uint32_t word = mbits[i];
+                    uint32_t o = __shfl_xor_sync(0xffffffffu, word, 4);
+                    word = (g & 4) ? ((word & 0xFFFF0000u) | ((o >> 16) & 0x0000FFFFu)) : ((word & 0x0000FFFFu) | ((o << 16) & 0xFFFF0000u));
+                    o = __shfl_xor_sync(0xffffffffu, word, 2);
+                    word = (g & 2) ? ((word & 0xFF00FF00u) | ((o >> 8) & 0x00FF00FFu)) : ((word & 0x00FF00FFu) | ((o << 8) & 0xFF00FF00u));
+                    o = __shfl_xor_sync(0xffffffffu, word, 1);
+                    word = (g & 1) ? ((word & 0xF0F0F0F0u) | ((o >> 4) & 0x0F0F0F0Fu)) : ((word & 0x0F0F0F0Fu) | ((o << 4) & 0xF0F0F0F0u));
+                    if (r < valid)
+                        reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)b * prm.m.n_nets + k) * P + p0 + r) * 32)[g] = word;
+                }
             }
         }
     }
@@ -363,7 +401,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
 //     [20L] gradient accumulator, flushed into the pool row:  G = Gp(window) + lamda/n_nets * sum_k dfit_k/dx.
 // CTA -> (net, contiguous block of chains); per-net partial gradients go to a scratch buffer and a streaming
 // kernel forms  G = Gp(window) + lamda/n_nets * (Gc_0 + Gc_1 + Gc_2)  in a fixed order (deterministic).
-constexpr int BW_NSLOT = 2;
+constexpr int BW_NSLOT = 3;
+constexpr int BW_NT_PROD = 512;        // 16 producer warps: the W1 gathers are L2-latency bound, more warps = more loads in flight
+constexpr int BW_NTHREADS = NT_EPI + 32 + BW_NT_PROD;   // 672
 constexpr int YS = 33;                 // sY row stride (floats)
 
 struct BwdParams {
@@ -373,6 +413,7 @@ struct BwdParams {
     int aa_stride;
     int n;
     const unsigned long long* mkey;
+    const uint8_t* r1mask;              // [n, n_nets, P, 32] relu mask bits written by the forward kernel
     float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
     int ctas_per_net;
     int n_tile, tiles_per_chain, nch, kpad;
@@ -382,13 +423,11 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __grid_constant__ BwdParams prm) {
+__global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
-    const int KS = prm.kpad;                                           // table row length (+ tail pad below)
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* sT0 = reinterpret_cast<float*>(ring + BW_NSLOT * SLOT_BYTES);    // [100][KS] + 64 floats tail pad
-    float* sGc = sT0 + 100 * KS + 64;                                  // [NE] chain accumulator
+    float* sGc = reinterpret_cast<float*>(ring + BW_NSLOT * SLOT_BYTES);    // [NE] chain accumulator
     float* sY = sGc + NE;                                              // [100][YS]
     float* sDj = sY + 100 * YS;                                        // [J2] d_j of active winners
     int* sPst = reinterpret_cast<int*>(sDj + J2);                      // [J2] p*_j or -1
@@ -411,7 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BW_NSLOT; ++s) { mbar_init(&full[s], NT_PROD / 32); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < BW_NSLOT; ++s) { mbar_init(&full[s], BW_NT_PROD / 32); mbar_init(&empty[s], 1); }
         for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI); }
         fence_barrier_init();
     }
@@ -420,7 +459,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
                      "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int e = threadIdx.x; e < NE; e += NTHREADS) sGc[e] = 0.f;
+    for (int e = threadIdx.x; e < NE; e += BW_NTHREADS) sGc[e] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -433,16 +472,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
 
     {
         const ppde_cnn_net_t net = prm.m.net[k];
-        // ---- per-net setup: conv table (bias folded) -> smem, W0^T (scaled, fp16 hi/lo) -> TMEM ----
-        for (int e = threadIdx.x; e < 100 * KS + 64; e += NTHREADS) {
-            const int row = e / KS, c = e - row * KS;
-            float v = 0.f;
-            if (row < 100 && c < C) {
-                v = net.T0[(size_t)row * C + c];
-                if (row < PPDE_Q) v += net.b0[c];
-            }
-            sT0[e] = v;
-        }
+        // ---- per-net setup: W0^T (scaled, fp16 hi/lo) -> TMEM ----
         if (warp < 4) {
             const int nrow = warp * 32 + lane;                           // (t,a) = (nrow / 20, nrow % 20)
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -553,10 +583,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
             }
         } else {
             // ===== PRODUCERS: adjoint rows =====
-            const int ptid = threadIdx.x - (WARP_MMA + 1) * 32;           // 0..255
-            const int pw = warp - 5;
+            const int ptid = threadIdx.x - (WARP_MMA + 1) * 32;           // 0..511
+            const int pw = warp - 5;                                      // 0..15
             const int g = lane & 7, q = lane >> 3;
-            const int rsub = 16 * (pw >> 2) + (pw & 3) + 4 * q;
+            const int rsub = 16 * (pw >> 2) + (pw & 3) + 4 * q;           // row inside a 64-row pass
             const float adj_scale = net.adj_scale;
             for (int it = 0; it < ntiles; ++it) {
                 const int b = b_lo + it / prm.tiles_per_chain;
@@ -564,12 +594,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
                 const int p0 = tn * prm.n_tile;
                 const int valid = min(prm.n_tile, P - p0);
                 if (tn == 0) {
-                    // bucket this chain's winners by position (counting sort; order inside a bucket fixed at use)
-                    named_bar(1, NT_PROD);
-                    for (int i = ptid; i <= P; i += NT_PROD) { sStart[i] = 0; if (i < P) sFill[i] = 0; }
-                    named_bar(1, NT_PROD);
+                    // bucket this chain's winners by position (counting sort, then ascending channel order per bucket)
+                    named_bar(1, BW_NT_PROD);
+                    for (int i = ptid; i <= P; i += BW_NT_PROD) { sStart[i] = 0; if (i < P) sFill[i] = 0; }
+                    named_bar(1, BW_NT_PROD);
                     const unsigned long long* keys = prm.mkey + ((size_t)b * prm.m.n_nets + k) * J2;
-                    for (int j = ptid; j < J2; j += NT_PROD) {
+                    for (int j = ptid; j < J2; j += BW_NT_PROD) {
                         const unsigned long long key = keys[j];
                         const float mj = __uint_as_float((unsigned)(key >> 32));
                         const int pst = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
@@ -578,8 +608,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
                         sDj[j] = net.d[j];
                         if (active) atomicAdd(&sStart[pst + 1], 1);
                     }
-                    named_bar(1, NT_PROD);
-                    if (pw == 0) {                                        // exclusive scan of P+1 counters by one warp
+                    named_bar(1, BW_NT_PROD);
+                    if (pw == 0) {                                        // scan of P+1 counters by one warp
                         const int per = (P + 1 + 31) / 32;
                         int run = 0;
                         for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) run += sStart[i];
@@ -592,13 +622,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
                         int base = incl - run;
                         for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) { base += sStart[i]; sStart[i] = base; }
                     }
-                    named_bar(1, NT_PROD);
-                    for (int j = ptid; j < J2; j += NT_PROD) {
+                    named_bar(1, BW_NT_PROD);
+                    for (int j = ptid; j < J2; j += BW_NT_PROD) {
                         const int pst = sPst[j];
                         if (pst >= 0) sList[sStart[pst] + atomicAdd(&sFill[pst], 1)] = j;
                     }
-                    named_bar(1, NT_PROD);
-                    for (int pp = ptid; pp < P; pp += NT_PROD) {          // ascending channel order inside each bucket
+                    named_bar(1, BW_NT_PROD);
+                    for (int pp = ptid; pp < P; pp += BW_NT_PROD) {
                         const int s0 = sStart[pp], s1 = sStart[pp + 1];
                         for (int u = s0 + 1; u < s1; ++u) {
                             const int v = sList[u];
@@ -607,65 +637,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_backward_tc_kernel(const __gr
                             sList[w + 1] = v;
                         }
                     }
-                    named_bar(1, NT_PROD);
+                    named_bar(1, BW_NT_PROD);
                 }
-                const uint8_t* a = prm.aa + (size_t)b * prm.aa_stride + p0;
-                int trow[4][5];
-                int ls0[4], ls1[4];
+                int ls0[2], ls1[2];
+                const uint8_t* mrow[2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = 32 * i + rsub;
+                for (int i = 0; i < 2; ++i) {
+                    const int r = 64 * i + rsub;
                     const bool ok = r < valid;
                     ls0[i] = ok ? sStart[p0 + r] : 0;
                     ls1[i] = ok ? sStart[p0 + r + 1] : 0;
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) trow[i][t] = ok ? (t * PPDE_Q + a[r + t]) * KS : 0;
+                    mrow[i] = prm.r1mask + (((size_t)b * prm.m.n_nets + k) * P + p0 + (ok ? r : 0)) * 32;
                 }
                 for (int kc = 0; kc < prm.nch; ++kc) {
                     mbar_wait(&empty[p_slot], p_phase ^ 1);
                     unsigned char* mat_hi = ring + p_slot * SLOT_BYTES;
                     unsigned char* mat_lo = mat_hi + MAT_BYTES;
                     const int cb = kc * KCH;
+                    const bool in0 = cb + 4 * g < prm.kpad, in1 = cb + 32 + 4 * g < prm.kpad;
+                    // relu-mask bytes of my rows for this chunk (8 bytes = 64 channels), issued with the gathers
+                    uint2 mb[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = 32 * i + rsub;
+                    for (int i = 0; i < 2; ++i) {
+                        mb[i] = make_uint2(0u, 0u);
+                        if (ls1[i] > ls0[i]) mb[i] = __ldg(reinterpret_cast<const uint2*>(mrow[i] + (cb >> 3)));
+                    }
+                    // gather-sum the winners' W1 row segments (ascending channel order per row: deterministic),
+                    // two winners of both rows per iteration -> up to 8 independent 16-byte L2 loads in flight per thread
+                    float4 s0[2], s1[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) { s0[i] = make_float4(0.f, 0.f, 0.f, 0.f); s1[i] = s0[i]; }
+                    const int maxlen = max(ls1[0] - ls0[0], ls1[1] - ls0[1]);
+                    for (int u = 0; u < maxlen; u += 2) {
+                        float dj[2][2];
+                        float4 w0[2][2], w1[2][2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                dj[i][v] = 0.f;
+                                w0[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                w1[i][v] = w0[i][v];
+                                if (ls0[i] + u + v < ls1[i]) {
+                                    const int jn = sList[ls0[i] + u + v];
+                                    dj[i][v] = sDj[jn];
+                                    const float* wrow = net.W1p + (size_t)jn * prm.kpad + cb;
+                                    if (in0) w0[i][v] = __ldg(reinterpret_cast<const float4*>(wrow + 4 * g));
+                                    if (in1) w1[i][v] = __ldg(reinterpret_cast<const float4*>(wrow + 32 + 4 * g));
+                                }
+                            }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                s0[i].x = fmaf(dj[i][v], w0[i][v].x, s0[i].x); s0[i].y = fmaf(dj[i][v], w0[i][v].y, s0[i].y);
+                                s0[i].z = fmaf(dj[i][v], w0[i][v].z, s0[i].z); s0[i].w = fmaf(dj[i][v], w0[i][v].w, s0[i].w);
+                                s1[i].x = fmaf(dj[i][v], w1[i][v].x, s1[i].x); s1[i].y = fmaf(dj[i][v], w1[i][v].y, s1[i].y);
+                                s1[i].z = fmaf(dj[i][v], w1[i][v].z, s1[i].z); s1[i].w = fmaf(dj[i][v], w1[i][v].w, s1[i].w);
+                            }
+                    }
+                    // mask, scale, fp16 hi/lo split, swizzled store (zeros for rows without winners)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = 64 * i + rsub;
                         if (r >= prm.n_tile) continue;
-                        uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
-                        if (ls1[i] > ls0[i]) {
-                            float4 z0 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 4 * g);
-                            float4 z1 = *reinterpret_cast<const float4*>(sT0 + trow[i][0] + cb + 32 + 4 * g);
+                        const uint32_t w_lo = (g >> 1) < 4 ? mb[i].x : 0u;      // bytes 0..3 hold channels cb .. cb+31
+                        const uint32_t nib0 = (w_lo >> (8 * (g >> 1) + 4 * (g & 1))) & 15u;          // channels cb + 4g ..
+                        const uint32_t nib1 = (mb[i].y >> (8 * (g >> 1) + 4 * (g & 1))) & 15u;       // channels cb + 32 + 4g ..
+                        const uint32_t msk = nib0 | (nib1 << 4);
+                        const float ss[8] = {s0[i].x, s0[i].y, s0[i].z, s0[i].w, s1[i].x, s1[i].y, s1[i].z, s1[i].w};
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int t = 1; t < 5; ++t) {
-                                const float4 u0 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 4 * g);
-                                const float4 u1 = *reinterpret_cast<const float4*>(sT0 + trow[i][t] + cb + 32 + 4 * g);
-                                z0.x += u0.x; z0.y += u0.y; z0.z += u0.z; z0.w += u0.w;
-                                z1.x += u1.x; z1.y += u1.y; z1.z += u1.z; z1.w += u1.w;
-                            }
-                            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-#pragma unroll 4
-                            for (int u = ls0[i]; u < ls1[i]; ++u) {               // ascending channel order: deterministic sum
-                                const int jn = sList[u];
-                                const float dj = sDj[jn];
-                                const float* wrow = net.W1p + (size_t)jn * prm.kpad + cb;
-                                if (cb + 4 * g < prm.kpad) {
-                                    const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + 4 * g));
-                                    s0.x = fmaf(dj, w.x, s0.x); s0.y = fmaf(dj, w.y, s0.y); s0.z = fmaf(dj, w.z, s0.z); s0.w = fmaf(dj, w.w, s0.w);
-                                }
-                                if (cb + 32 + 4 * g < prm.kpad) {
-                                    const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + 32 + 4 * g));
-                                    s1.x = fmaf(dj, w.x, s1.x); s1.y = fmaf(dj, w.y, s1.y); s1.z = fmaf(dj, w.z, s1.z); s1.w = fmaf(dj, w.w, s1.w);
-                                }
-                            }
-                            const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-                            const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float x0 = (zz[2 * e] > 0.f ? ss[2 * e] : 0.f) * adj_scale;
-                                const float x1 = (zz[2 * e + 1] > 0.f ? ss[2 * e + 1] : 0.f) * adj_scale;
-                                const float h0 = h_round(x0), h1 = h_round(x1);
-                                hi[e] = pack_h2(h0, h1);
-                                lo[e] = pack_h2(x0 - h0, x1 - h1);
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = ((msk >> (2 * e)) & 1u) ? ss[2 * e] * adj_scale : 0.f;
+                            const float x1 = ((msk >> (2 * e + 1)) & 1u) ? ss[2 * e + 1] * adj_scale : 0.f;
+                            const float h0 = h_round(x0), h1 = h_round(x1);
+                            hi[e] = pack_h2(h0, h1);
+                            lo[e] = pack_h2(x0 - h0, x1 - h1);
                         }
                         const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
                         const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);
@@ -732,7 +780,7 @@ static int choose_n_tile(int P, int* tiles) {
 }
 
 extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
-                                   unsigned long long* mkey, void* stream) {
+                                   unsigned long long* mkey, uint8_t* r1mask, void* stream) {
     if (n <= 0) return 0;
     if (m->C > 256 || m->P < 1) return (int)cudaErrorInvalidValue;       // A must fit 256 TMEM columns
     tc::Params prm;
@@ -741,6 +789,7 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     prm.aa_stride = aa_stride;
     prm.n = n;
     prm.mkey = mkey;
+    prm.r1mask = r1mask;
     prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
     prm.MT = (2 * m->C + 127) / 128;
     prm.kpad = (m->C + 15) / 16 * 16;
@@ -767,12 +816,14 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
 extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                                     int32_t n, const unsigned long long* mkey, float lamda,
                                     const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
-                                    float* G, int64_t G_stride, const int32_t* g_rows, float* scratch, void* stream) {
+                                    float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
+                                    float* scratch, void* stream) {
     if (n <= 0) return 0;
-    if (m->C > 256 || m->P < 1 || !scratch) return (int)cudaErrorInvalidValue;
+    if (m->C > 256 || m->P < 1 || !scratch || !r1mask) return (int)cudaErrorInvalidValue;
     tc::BwdParams prm;
     prm.m = *m; prm.pm = *pm; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey;
     prm.Gc = scratch;
+    prm.r1mask = r1mask;
     prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
     prm.kpad = (m->C + 15) / 16 * 16;
     prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
@@ -783,8 +834,9 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
     if (prm.ctas_per_net < 1) prm.ctas_per_net = 1;
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
+    (void)C;
     const size_t smem = 1024 + (size_t)tc::BW_NSLOT * tc::SLOT_BYTES +
-                        ((size_t)100 * prm.kpad + 64 + (size_t)L * PPDE_Q + 100 * tc::YS + J2) * sizeof(float) +
+                        ((size_t)L * PPDE_Q + 100 * tc::YS + J2) * sizeof(float) +
                         ((size_t)J2 + (P + 1) + P + J2) * sizeof(int) + 8 + 16 * sizeof(uint64_t);
     static size_t configured = 0;
     if (smem > configured) {
@@ -793,7 +845,7 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
         configured = smem;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    tc::cnn_backward_tc_kernel<<<m->n_nets * prm.ctas_per_net, tc::NTHREADS, smem, st>>>(prm);
+    tc::cnn_backward_tc_kernel<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
     int r = launch_done();
     if (r) return r;
     tc::cnn_grad_combine_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,

@@ -136,20 +136,26 @@ class PoEModel:
         self.cnn_backward_impl = "tc" if (wantb == "tc" and self.C <= 256) else "simt"
 
     def cnn_forward(self, aa, n, mk, st):
-        fn = self.lib.ppde_cnn_forward_tc if self.cnn_forward_impl == "tc" else self.lib.ppde_cnn_forward
-        _lib.check(fn(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st), "cnn_forward_" + self.cnn_forward_impl)
+        if self.cnn_forward_impl == "tc":
+            rm = _ptr(self.r1mask(n)) if self.cnn_backward_impl == "tc" else C.c_void_p(0)
+            _lib.check(self.lib.ppde_cnn_forward_tc(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), rm, st),
+                       "cnn_forward_tc")
+        else:
+            _lib.check(self.lib.ppde_cnn_forward(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st),
+                       "cnn_forward")
 
     def cnn_backward_combine(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, st):
         """fit / E from the winners, then (if g_ptr) the gradient rows G = Gp(window) + lamda/n_nets * sum_k dfit_k/dx."""
         lib = self.lib
         null = C.c_void_p(0)
-        if self.cnn_backward_impl == "tc" and g_ptr:
+        if self.cnn_backward_impl == "tc" and self.cnn_forward_impl == "tc" and g_ptr:
             _lib.check(lib.ppde_cnn_backward_combine(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
                 null, self.D, null, ep_ptr, null, self.NE, null, _ptr(E), _ptr(fit), st), "cnn_fit")
             _lib.check(lib.ppde_cnn_backward_tc(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
-                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(self.grad_scratch(n)), st), "cnn_backward_tc")
+                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(self.r1mask(n)), _ptr(self.grad_scratch(n)), st),
+                "cnn_backward_tc")
         else:
             _lib.check(lib.ppde_cnn_backward_combine(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
@@ -161,6 +167,12 @@ class PoEModel:
         if getattr(self, "_gscratch", None) is None or self._gscratch.numel() < need:
             self._gscratch = torch.empty(need, dtype=torch.float32, device=self.device)
         return self._gscratch
+
+    def r1mask(self, n):
+        need = n * self.n_nets * self.P * 32
+        if getattr(self, "_r1mask", None) is None or self._r1mask.numel() < need:
+            self._r1mask = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._r1mask
 
     def mkey(self, n):
         need = n * self.n_nets * 2 * self.C
@@ -368,6 +380,7 @@ class ChainEngine:
             if self._graph is None:
                 self.m.mkey(self.n)
                 self.m.grad_scratch(self.n)
+                self.m.r1mask(self.n)
                 self.t_dev.fill_(self.t)
                 p = self._params(0, None, use_t_dev=True)
                 self._graph_params = p
