@@ -329,19 +329,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
                             a0 = add2(a0, make_float2(u0.x, u0.y)); a1 = add2(a1, make_float2(u0.z, u0.w));
                             a2 = add2(a2, make_float2(u1.x, u1.y)); a3 = add2(a3, make_float2(u1.z, u1.w));
                         }
-                        const float v[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-                        uint32_t nib = 0u;
+                        if (emit_mask) {                   // warp-uniform: only every MT-th tile writes mask bits
+                            const float v[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+                            uint32_t nib = 0u;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) nib |= (__float_as_int(v[e]) > 0 ? 1u : 0u) << e;
+                            mbits[i] |= nib << (8 * kc);
+                            }
+                        // relu, fp16 hi by truncation, exact residual (packed), pack
+
+                        float2 x[4] = {a0, a1, a2, a3};
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            nib |= (__float_as_int(v[2 * e]) > 0 ? 1u : 0u) << (2 * e);
-                            nib |= (__float_as_int(v[2 * e + 1]) > 0 ? 1u : 0u) << (2 * e + 1);
-                            const float x0 = fmaxf(v[2 * e], 0.f), x1 = fmaxf(v[2 * e + 1], 0.f);
-                            const float h0 = h_trunc(x0), h1 = h_trunc(x1);
-                            hi[e] = pack_h2(h0, h1);
-                            lo[e] = pack_h2(x0 - h0, x1 - h1);
+                            x[e].x = fmaxf(x[e].x, 0.f); x[e].y = fmaxf(x[e].y, 0.f);
+                            const float2 h = make_float2(h_trunc(x[e].x), h_trunc(x[e].y));
+                            const float2 l = add2(x[e], make_float2(-h.x, -h.y));
+                            hi[e] = pack_h2(h.x, h.y);
+                            lo[e] = pack_h2(l.x, l.y);
                         }
-                        mbits[i] |= nib << (8 * kc);
+
                         // element (row r, k) at (r/8)*1024 + (r%8)*128 + ((k/8) ^ (r%8))*16 + (k%8)*2
                         const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
                         const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);          // k = 4g

@@ -1,0 +1,99 @@
+"""Host-side logic that needs no GPU: random streams, sharding, file readers, logging schedule."""
+import os
+
+import numpy as np
+import pytest
+
+from ppde_b200 import dist as D
+from ppde_b200 import philox, weights
+from ppde_b200.synthetic import synthetic_problem
+
+
+def test_philox_random123_known_answers():
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(*ctr, *key)
+        assert tuple(int(x) for x in got) == want
+
+
+def test_streams_are_indexed_by_global_chain():
+    u_all = philox.proposal_uniforms(9, 3, 1, np.arange(8), 50)
+    u_sh = philox.proposal_uniforms(9, 3, 1, np.arange(4, 8), 50)
+    assert np.array_equal(u_all[4:], u_sh)
+    assert u_all.min() > 0 and u_all.max() < 1
+    U = philox.path_lengths(9, 3, np.arange(1000), 2)
+    assert set(np.unique(U)) == {1, 2, 3}
+    U10 = philox.path_lengths(9, 3, np.arange(4000), 10)
+    assert U10.min() == 1 and U10.max() == 19
+
+
+def test_shard_ranges_cover_population():
+    for n in (1, 7, 128, 65536, 65537):
+        for ws in (1, 2, 3, 8):
+            spans = [D.shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == D.shard_sizes(n, ws)
+            if n >= ws:
+                assert D.owner_of(n - 1, n, ws) == (ws - 1, sizes[-1] - 1)
+
+
+def test_population_report_matches_reference_definitions():
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal(200).astype(np.float32)
+    rep = D.population_report(e, e * 2, e * 3, (e > 0), np.arange(200), np.arange(200) % 50)
+    assert np.allclose(rep["energy_q"], np.quantile(e, [0.5, 0.9]))       # ppde.py:158-160
+    assert rep["accepted"] == float((e > 0).sum())                          # ppde.py:167
+    assert rep["mean_dist"] == pytest.approx(99.5)                          # ppde.py:168
+    assert rep["diversity_pct"] == pytest.approx(25.0)                      # make_figures.py:38-49
+
+
+def test_fasta_reader_and_offset_rule(tmp_path):
+    f = tmp_path / "wt.fasta"
+    f.write_text(">PABP_YEAST/115-210 some description\nQRDPS\nLRKKG\n>second\nAC\n")
+    seqs, ids = weights.read_fasta(str(f))
+    assert seqs == ["QRDPSLRKKG", "AC"] and ids == ["PABP_YEAST/115-210", "second"]
+    assert weights.fasta_offset(ids[0]) == 115 and weights.fasta_offset("sarkisyan_wt") == 1   # nets.py:257-261
+    aa = weights.seq_to_aa("ACDEFGHIKLMNPQRSTVWY")
+    assert list(aa) == list(range(20)) and weights.aa_to_seq(aa) == "ACDEFGHIKLMNPQRSTVWY"
+    with pytest.raises(ValueError):
+        weights.seq_to_aa("AXB")
+
+
+def test_potts_pickle_reader(tmp_path):
+    import pickle
+    pr = synthetic_problem(10, window=(2, 7))
+    with open(tmp_path / "potts.pkl", "wb") as fh:
+        pickle.dump({"J_ij": pr["J"], "h_i": pr["h"], "index_list": np.arange(2, 8) + 115, "reg_coef": 2.5}, fh)
+    got = weights.load_potts(str(tmp_path), "PABP_YEAST/115-210")
+    assert got["win_lo"] == 2 and got["win_hi"] == 7 and got["reg_coef"] == 2.5
+    assert got["J"].shape == (6, 6, 20, 20)
+
+
+def test_sampler_log_schedule():
+    """Logging fires after iteration i when i > 0 and (i+1) % log_every == 0 (ppde.py:155)."""
+    def fired(num_steps, log_every):
+        out, t = [], 0
+        while t < num_steps:
+            i = max(t, 1)
+            i += (-(i + 1)) % log_every
+            stop = min(i + 1, num_steps)
+            t = stop
+            if t == i + 1:
+                out.append(i)
+        return out
+    for T, le in ((100, 50), (10, 3), (7, 1), (5, 10)):
+        want = [i for i in range(T) if i > 0 and (i + 1) % le == 0]
+        assert fired(T, le) == want
+
+
+def test_sampler_constructor_flag_semantics():
+    import argparse
+    from ppde_b200.sampler import PPDE_PAS
+    s = PPDE_PAS(argparse.Namespace(ppde_pas_length=3, nmut_threshold=0, paper_results=True))
+    assert s.nmut_threshold == np.iinfo(np.int32).max and s.ppde_temp == 2 and s.paper_results   # ppde.py:9-17
+    assert s.approximate_energy_change(4.0) == 2.0
