@@ -251,7 +251,7 @@ def main():
         flops_fwd = 3 * 2 * P * Cc * 2 * Cc * n                    # 3*2*P*C*2C per chain
         t_fwd = breakdown["cnn_forward"] * 1e-3
         achieved = flops_fwd / t_fwd / 1e12
-        roof = {"kernel": "cnn_forward_tc_kernel" if m.cnn_forward_impl == "tc" else "cnn_forward_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
+        roof = {"kernel": ("cnn_forward_tc2_kernel" if os.environ.get("PPDE_TC_CTAS", "2") != "1" else "cnn_forward_tc_kernel") if m.cnn_forward_impl == "tc" else "cnn_forward_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 # dram__bytes_read+write of this kernel from the committed `ncu --set full` capture
                 # (profiles/r01_cnn_forward_tc_v2_summary.txt: 228.5 MB at 8192 chains), scaled to this launch

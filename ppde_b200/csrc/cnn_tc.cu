@@ -23,6 +23,7 @@
 #include "../../include/ppde_b200.h"
 #include "launch.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace ppde {
 namespace tc {
@@ -393,6 +394,295 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
     }
 }
 
+
+// =====================================================================================================
+// 2-CTA variant of the forward kernel (cta_group::2): a cluster of two CTAs (one TPC) computes M = 256 channels
+// (two channel tiles) per MMA.  Each CTA keeps ITS 128-channel W1 tile in its own tensor memory and PRODUCES only
+// half of the positions of every tile (the B operand of a cta_group::2 MMA is split along N across the pair), so the
+// r1 production cost per MMA flop — the bottleneck of the 1-CTA kernel (4x redundant across channel tiles) — halves,
+// and so does the shared-memory traffic of the B operand per CTA.  The leader CTA (rank 0) issues the MMAs;
+// `full` / `dempty` barriers live in the leader and collect arrivals from both CTAs (mapa + cluster-scope arrive),
+// `empty` / `dfull` are signalled in both CTAs by multicast tcgen05.commit.
+constexpr int NSLOT2 = 6;
+constexpr int MAT2_BYTES = 64 * KCH * 2;          // one [64 x 64] fp16 operand half-matrix (8 KB)
+constexpr int SLOT2_BYTES = 2 * MAT2_BYTES;       // hi + lo
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_LOOP_C:\n"
+        " mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_C;\n"
+        " bra WAIT_LOOP_C;\n"
+        "DONE_C:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {        // both CTAs' barrier at this offset
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int C = prm.m.C, P = prm.m.P, J2 = 2 * C;
+    const int KS = prm.nch * KCH;
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* sT0 = reinterpret_cast<float*>(ring + NSLOT2 * SLOT2_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sT0 + 100 * KS);
+    uint64_t* full = bars;                 // [NSLOT2] (leader's copy is the live one)
+    uint64_t* empty = bars + NSLOT2;       // [NSLOT2] local
+    uint64_t* dfull = empty + NSLOT2;      // [2] local
+    uint64_t* dempty = dfull + 2;          // [2] (leader's copy is the live one)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int MP = prm.MT;                                   // here: number of channel-tile PAIRS
+    const int combo = pair / prm.ctas_per_combo;             // ctas_per_combo = pairs per (net, channel-tile pair)
+    const int within = pair - combo * prm.ctas_per_combo;
+    const bool idle = combo >= prm.m.n_nets * MP;            // whole cluster idle (uniform over the pair)
+    const int k = idle ? 0 : combo / MP, mp = idle ? 0 : combo - k * MP;
+    const int mt = mp * 2 + (int)rank;
+    const ppde_cnn_net_t net = prm.m.net[k];
+    const int b_lo = idle ? 0 : (int)((int64_t)prm.n * within / prm.ctas_per_combo);
+    const int b_hi = idle ? 0 : (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_combo);
+    const int ntiles = (b_hi - b_lo) * prm.tiles_per_chain;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_half = prm.n_tile >> 1;
+
+    for (int e = threadIdx.x; e < 100 * KS; e += NTHREADS) {
+        const int row = e / KS, c = e - row * KS;
+        float v = 0.f;
+        if (c < C) {
+            v = net.T0[(size_t)row * C + c];
+            if (row < PPDE_Q) v += net.b0[c];
+        }
+        sT0[e] = v * net.r1_scale;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT2; ++s) { mbar_init(&full[s], 2 * (NT_PROD / 32)); mbar_init(&empty[s], 1); }
+        for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], 2 * NT_EPI); }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                    // barrier inits and TMEM allocation visible to the peer
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        const int j = mt * 128 + warp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int ks = 0; ks < prm.kpad / 16; ++ks) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c0 = ks * 16 + 2 * q;
+                const float w0 = (j < J2 && c0 < C) ? net.W1[(size_t)j * C + c0] * net.w1_scale : 0.f;
+                const float w1 = (j < J2 && c0 + 1 < C) ? net.W1[(size_t)j * C + c0 + 1] * net.w1_scale : 0.f;
+                const float h0 = h_round(w0), h1 = h_round(w1);
+                hi[q] = pack_h2(h0, h1);
+                lo[q] = pack_h2(w0 - h0, w1 - h1);
+            }
+            tmem_st8(lane_addr + ks * 8, hi);
+            tmem_st8(lane_addr + prm.kpad / 2 + ks * 8, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                    // both CTAs' A tiles are in place before the leader issues any MMA
+    tc_fence_after();
+
+    if (warp < 4) {
+        // ===== EPILOGUE (both CTAs): thread = channel j of this CTA's tile =====
+        const int j = mt * 128 + warp * 32 + lane;
+        const float bias = (j < J2) ? net.b1[j] : 0.f;
+        const float unscale = 1.f / (net.w1_scale * net.r1_scale);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+        float best = -1.f;
+        int bp = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int buf = it & 1;
+            const int b = b_lo + it / prm.tiles_per_chain;
+            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+            const int p0 = tn * prm.n_tile;
+            const int valid = min(prm.n_tile, P - p0);
+            if (tn == 0) { best = -1.f; bp = 0; }
+            mbar_wait(&dfull[buf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            for (int cg = 0; cg * 32 < valid; ++cg) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + buf * 128 + cg * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = fmaf(__uint_as_float(r[i]), unscale, bias);
+                    v = v > 0.f ? v : 0.f;
+                    if (cg * 32 + i < valid && v > best) { best = v; bp = p0 + cg * 32 + i; }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(&dempty[buf], 0);
+            if (tn == prm.tiles_per_chain - 1 && j < J2) {
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)bp);
+                prm.mkey[((size_t)b * prm.m.n_nets + k) * J2 + j] = key;
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // ===== MMA ISSUER: one lane of the LEADER CTA =====
+        if (rank == 0 && lane == 0) {
+            const uint32_t idesc = make_idesc(256, prm.n_tile);
+            const uint32_t ring_addr = smem_u32(ring);
+            int slot = 0;
+            uint32_t sphase = 0;
+            const int last_ksteps = (prm.kpad - (prm.nch - 1) * KCH) / 16;
+            for (int it = 0; it < ntiles; ++it) {
+                const int buf = it & 1;
+                if (it >= 2) mbar_wait_cluster(&dempty[buf], (uint32_t)(((it >> 1) + 1) & 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
+                for (int kc = 0; kc < prm.nch; ++kc) {
+                    mbar_wait_cluster(&full[slot], sphase);
+                    tc_fence_after();
+                    const uint64_t dhi = make_b_desc(ring_addr + slot * SLOT2_BYTES);
+                    const uint64_t dlo = make_b_desc(ring_addr + slot * SLOT2_BYTES + MAT2_BYTES);
+                    const int ksteps = (kc == prm.nch - 1) ? last_ksteps : KCH / 16;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
+                        const uint32_t a_lo = a_hi + prm.kpad / 2;
+                        const uint64_t koff = (uint64_t)(ks * 2);
+                        mma_ts2(d_tmem, a_hi, dhi + koff, idesc, (kc | ks) ? 1u : 0u);
+                        mma_ts2(d_tmem, a_hi, dlo + koff, idesc, 1u);
+                        mma_ts2(d_tmem, a_lo, dhi + koff, idesc, 1u);
+                    }
+                    tc_commit2(&empty[slot]);
+                    if (++slot == NSLOT2) { slot = 0; sphase ^= 1; }
+                }
+                tc_commit2(&dfull[buf]);
+            }
+        }
+    } else {
+        // ===== PRODUCERS (both CTAs): rows [rank*n_half, (rank+1)*n_half) of every tile, one row per thread =====
+        const int pw = warp - 5;
+        const int g = lane & 7, q = lane >> 3;
+        const int r = 16 * (pw >> 2) + (pw & 3) + 4 * q;      // local row 0..63
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int b = b_lo + it / prm.tiles_per_chain;
+            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+            const int p0 = tn * prm.n_tile + (int)rank * n_half;           // first position of MY half
+            const int valid = min(n_half, P - p0);                         // may be <= 0
+            const bool ok = r < valid;
+            const uint8_t* a = prm.aa + (size_t)b * prm.aa_stride + p0;
+            const float* trow[5];
+#pragma unroll
+            for (int t = 0; t < 5; ++t) trow[t] = sT0 + (ok ? (t * PPDE_Q + a[r + t]) * KS : 0) + 4 * g;
+            const bool emit_mask = (prm.r1mask != nullptr) && (it % MP == mp);
+            uint32_t mbits = 0u;
+            for (int kc = 0; kc < prm.nch; ++kc) {
+                mbar_wait(&empty[slot], phase ^ 1);
+                unsigned char* mat_hi = ring + slot * SLOT2_BYTES;
+                unsigned char* mat_lo = mat_hi + MAT2_BYTES;
+                const int cb = kc * KCH;
+                if (ok) {
+                    float4 z0 = *reinterpret_cast<const float4*>(trow[0] + cb);
+                    float4 z1 = *reinterpret_cast<const float4*>(trow[0] + cb + 32);
+                    float2 a0 = make_float2(z0.x, z0.y), a1 = make_float2(z0.z, z0.w);
+                    float2 a2 = make_float2(z1.x, z1.y), a3 = make_float2(z1.z, z1.w);
+#pragma unroll
+                    for (int t = 1; t < 5; ++t) {
+                        const float4 u0 = *reinterpret_cast<const float4*>(trow[t] + cb);
+                        const float4 u1 = *reinterpret_cast<const float4*>(trow[t] + cb + 32);
+                        a0 = add2(a0, make_float2(u0.x, u0.y)); a1 = add2(a1, make_float2(u0.z, u0.w));
+                        a2 = add2(a2, make_float2(u1.x, u1.y)); a3 = add2(a3, make_float2(u1.z, u1.w));
+                    }
+                    if (emit_mask) {
+                        const float v[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+                        uint32_t nib = 0u;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) nib |= (__float_as_int(v[e]) > 0 ? 1u : 0u) << e;
+                        mbits |= nib << (8 * kc);
+                    }
+                    float2 x[4] = {a0, a1, a2, a3};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        x[e].x = fmaxf(x[e].x, 0.f); x[e].y = fmaxf(x[e].y, 0.f);
+                        const float2 h = make_float2(h_trunc(x[e].x), h_trunc(x[e].y));
+                        const float2 l = add2(x[e], make_float2(-h.x, -h.y));
+                        hi[e] = pack_h2(h.x, h.y);
+                        lo[e] = pack_h2(l.x, l.y);
+                    }
+                    const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
+                    const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);
+                    const int o1 = rbase + ((((g >> 1) + 4) ^ (r & 7)) << 4) + ((g & 1) << 3);
+                    *reinterpret_cast<uint2*>(mat_hi + o0) = make_uint2(hi[0], hi[1]);
+                    *reinterpret_cast<uint2*>(mat_hi + o1) = make_uint2(hi[2], hi[3]);
+                    *reinterpret_cast<uint2*>(mat_lo + o0) = make_uint2(lo[0], lo[1]);
+                    *reinterpret_cast<uint2*>(mat_lo + o1) = make_uint2(lo[2], lo[3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&full[slot], 0);
+                if (++slot == NSLOT2) { slot = 0; phase ^= 1; }
+            }
+            if (emit_mask) {
+                uint32_t word = mbits;
+                uint32_t o = __shfl_xor_sync(0xffffffffu, word, 4);
+                word = (g & 4) ? ((word & 0xFFFF0000u) | ((o >> 16) & 0x0000FFFFu)) : ((word & 0x0000FFFFu) | ((o << 16) & 0xFFFF0000u));
+                o = __shfl_xor_sync(0xffffffffu, word, 2);
+                word = (g & 2) ? ((word & 0xFF00FF00u) | ((o >> 8) & 0x00FF00FFu)) : ((word & 0x00FF00FFu) | ((o << 8) & 0xFF00FF00u));
+                o = __shfl_xor_sync(0xffffffffu, word, 1);
+                word = (g & 1) ? ((word & 0xF0F0F0F0u) | ((o >> 4) & 0x0F0F0F0Fu)) : ((word & 0x0F0F0F0Fu) | ((o << 4) & 0xF0F0F0F0u));
+                if (ok) reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)b * prm.m.n_nets + k) * P + p0 + r) * 32)[g] = word;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                    // the peer may still be reading my smem / signalling my barriers
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
 
 // =====================================================================================================
 // Backward of the CNN ensemble on the tensor cores (same skeleton as the forward kernel).
@@ -786,10 +1076,28 @@ static int choose_n_tile(int P, int* tiles) {
     return best_n;
 }
 
+// positions-per-tile for the 2-CTA kernel: multiple of 32 (N of a cta_group::2 MMA), split in two halves
+static int choose_n_tile2(int P, int* tiles) {
+    int best_n = 128, best_cost = 1 << 30;
+    for (int nt = 128; nt >= 64; nt -= 32) {
+        const int t = (P + nt - 1) / nt;
+        const int cost = t * nt + 8 * t;
+        if (cost < best_cost) { best_cost = cost; best_n = nt; *tiles = t; }
+    }
+    return best_n;
+}
+
+static int g_forward_variant = -1;         // -1: read PPDE_TC_CTAS once (default 2); 1 or 2
+extern "C" int ppde_set_forward_variant(int ctas) { g_forward_variant = (ctas == 1) ? 1 : 2; return 0; }
+
 extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                                    unsigned long long* mkey, uint8_t* r1mask, void* stream) {
     if (n <= 0) return 0;
     if (m->C > 256 || m->P < 1) return (int)cudaErrorInvalidValue;       // A must fit 256 TMEM columns
+    if (g_forward_variant < 0) {
+        const char* e = getenv("PPDE_TC_CTAS");
+        g_forward_variant = (e && e[0] == '1') ? 1 : 2;
+    }
     tc::Params prm;
     prm.m = *m;
     prm.aa = aa;
@@ -797,13 +1105,33 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     prm.n = n;
     prm.mkey = mkey;
     prm.r1mask = r1mask;
-    prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
-    prm.MT = (2 * m->C + 127) / 128;
     prm.kpad = (m->C + 15) / 16 * 16;
     prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int MT = (2 * m->C + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_forward_variant == 2) {
+        prm.n_tile = choose_n_tile2(m->P, &prm.tiles_per_chain);
+        prm.MT = (MT + 1) / 2;                                             // channel-tile pairs
+        const int combos = m->n_nets * prm.MT;
+        prm.ctas_per_combo = (sms / 2) / combos;                           // cluster pairs per combo
+        if (prm.ctas_per_combo < 1) prm.ctas_per_combo = 1;
+        if (prm.ctas_per_combo > n) prm.ctas_per_combo = n;
+        const size_t smem = (size_t)tc::NSLOT2 * tc::SLOT2_BYTES + (size_t)100 * prm.nch * tc::KCH * sizeof(float) +
+                            32 * sizeof(uint64_t) + 1024;
+        static size_t configured2 = 0;
+        if (smem > configured2) {
+            cudaError_t e = cudaFuncSetAttribute(tc::cnn_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            configured2 = smem;
+        }
+        tc::cnn_forward_tc2_kernel<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, st>>>(prm);
+        return launch_done();
+    }
+    prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
+    prm.MT = MT;
     const int combos = m->n_nets * prm.MT;
     prm.ctas_per_combo = sms / combos;
     if (prm.ctas_per_combo < 1) prm.ctas_per_combo = 1;
@@ -816,7 +1144,7 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
         if (e != cudaSuccess) return (int)e;
         configured = smem;
     }
-    tc::cnn_forward_tc_kernel<<<combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
+    tc::cnn_forward_tc_kernel<<<combos * prm.ctas_per_combo, tc::NTHREADS, smem, st>>>(prm);
     return launch_done();
 }
 
