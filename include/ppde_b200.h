@@ -156,7 +156,7 @@ int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint
                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                          float* G, int64_t G_stride, const int32_t* g_rows,
                          const uint8_t* r1mask /* from ppde_cnn_forward_tc */,
-                         float* scratch /* [n_nets, n, 20L] */, void* stream);
+                         float* scratch /* n_nets*n*20L floats + n*n_nets*roundup8(P+1+4C) uint16 */, void* stream);
 int ppde_step_rows(const ppde_chains_t* c, int32_t* rows_y, void* stream);
 int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
 int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);

@@ -698,10 +698,71 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
 //     [20L] gradient accumulator, flushed into the pool row:  G = Gp(window) + lamda/n_nets * sum_k dfit_k/dx.
 // CTA -> (net, contiguous block of chains); per-net partial gradients go to a scratch buffer and a streaming
 // kernel forms  G = Gp(window) + lamda/n_nets * (Gc_0 + Gc_1 + Gc_2)  in a fixed order (deterministic).
-constexpr int BW_NSLOT = 3;
-constexpr int BW_NT_PROD = 512;        // 16 producer warps: the W1 gathers are L2-latency bound, more warps = more loads in flight
+// Winner lists for the backward: one block per (chain, net) decodes the 2C arg-max keys, drops channels whose max is
+// 0 (relu'(0) = 0), counting-sorts them by position and orders each bucket by channel (deterministic adjoint sums).
+// Record layout (uint16): start[P+1] | list[J2] (channel) | row[J2] (position), padded to `rec` entries.
+__global__ void __launch_bounds__(128) cnn_winner_sort_kernel(int n_nets, int C, int P, const unsigned long long* __restrict__ mkey,
+                                                              uint16_t* __restrict__ wl, int rec) {
+    extern __shared__ int sw[];
+    const int J2 = 2 * C;
+    int* sStart = sw;                 // [P+1]
+    int* sFill = sStart + (P + 1);    // [P]
+    int* sPst = sFill + P;            // [J2]
+    int* sList = sPst + J2;           // [J2]
+    const size_t bk = blockIdx.x;     // b * n_nets + k
+    const unsigned long long* keys = mkey + bk * J2;
+    for (int i = threadIdx.x; i <= P; i += 128) { sStart[i] = 0; if (i < P) sFill[i] = 0; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < J2; j += 128) {
+        const unsigned long long key = keys[j];
+        const float mj = __uint_as_float((unsigned)(key >> 32));
+        const int pst = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
+        const bool active = (mj > 0.f) && pst >= 0 && pst < P;
+        sPst[j] = active ? pst : -1;
+        if (active) atomicAdd(&sStart[pst + 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = (P + 1 + 31) / 32;
+        int run = 0;
+        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) run += sStart[i];
+        int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int base = incl - run;
+        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) { base += sStart[i]; sStart[i] = base; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < J2; j += 128) {
+        const int pst = sPst[j];
+        if (pst >= 0) sList[sStart[pst] + atomicAdd(&sFill[pst], 1)] = j;
+    }
+    __syncthreads();
+    uint16_t* out = wl + bk * rec;
+    for (int pp = threadIdx.x; pp < P; pp += 128) {
+        const int s0 = sStart[pp], s1 = sStart[pp + 1];
+        for (int u = s0 + 1; u < s1; ++u) {
+            const int v = sList[u];
+            int w = u - 1;
+            while (w >= s0 && sList[w] > v) { sList[w + 1] = sList[w]; --w; }
+            sList[w + 1] = v;
+        }
+        for (int u = s0; u < s1; ++u) { out[(P + 1) + u] = (uint16_t)sList[u]; out[(P + 1) + J2 + u] = (uint16_t)pp; }
+    }
+    for (int i = threadIdx.x; i <= P; i += 128) out[i] = (uint16_t)sStart[i];
+}
+
+constexpr int BW_NT = 64;               // positions per tile (N of the MMA)
+constexpr int BW_NT_PROD = 512;         // 16 producer warps = 8 gather sets of 64 threads
 constexpr int BW_NTHREADS = NT_EPI + 32 + BW_NT_PROD;   // 672
-constexpr int YS = 33;                 // sY row stride (floats)
+constexpr int BW_MAT = BW_NT * KCH * 2; // one [64 x 64] fp16 operand matrix (8 KB)
+constexpr int BW_SLOT = 2 * BW_MAT;     // hi + lo
+constexpr int BW_MAXCH = 4;             // K chunks per tile (kpad <= 256)
+constexpr int YS = 33;                  // sY row stride (floats)
 
 struct BwdParams {
     ppde_cnn_t m;
@@ -711,31 +772,42 @@ struct BwdParams {
     int n;
     const unsigned long long* mkey;
     const uint8_t* r1mask;              // [n, n_nets, P, 32] relu mask bits written by the forward kernel
+    const uint16_t* wl; int rec;        // winner records from cnn_winner_sort_kernel
     float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
     int ctas_per_net;
-    int n_tile, tiles_per_chain, nch, kpad;
+    int tiles_per_chain, nch, kpad;
+    int dbg;                            // profiling experiments only (PPDE_BWD_DEBUG): 1 = skip col2im, 2 = skip gathers
 };
 
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Producers (16 warps = 8 sets of 64 threads), per tile of 64 positions:
+//   set s owns rows [8s, 8s+8) of the tile, whose winners are one contiguous run of the (position, channel)-sorted
+//   list; thread tl of a set owns channels 4tl..4tl+3 of the whole K extent.  It streams its 16-byte piece of each
+//   winner's W1 row from L2 (two register batches of 4 loads, the next batch in flight while one is consumed, all
+//   lanes useful), accumulates d_j * W1[j, :] in registers in ascending channel order (deterministic), and when a row
+//   is complete applies the relu mask (bits from the forward), the power-of-two scale and the fp16 hi/lo split and
+//   stores its 8 bytes straight into the K-major SW128 operand slot of its K chunk.  No fp32 staging, one fence and
+//   one arrive per slot and warp.  The ring holds two tiles (2 x nch slots); winner lists and mask words of the next
+//   chain / tile are prefetched into the other half of double buffers.
 __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
+    const int nslot = 2 * prm.nch;
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* sGc = reinterpret_cast<float*>(ring + BW_NSLOT * SLOT_BYTES);    // [NE] chain accumulator
+    float* sGc = reinterpret_cast<float*>(ring + 2 * BW_MAXCH * BW_SLOT);   // [NE] chain accumulator
     float* sY = sGc + NE;                                              // [100][YS]
-    float* sDj = sY + 100 * YS;                                        // [J2] d_j of active winners
-    int* sPst = reinterpret_cast<int*>(sDj + J2);                      // [J2] p*_j or -1
-    int* sStart = sPst + J2;                                           // [P+1]
-    int* sFill = sStart + (P + 1);                                     // [P]
-    int* sList = sFill + P;                                            // [J2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sList + J2) + 7) & ~(uintptr_t)7);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + BW_NSLOT;
-    uint64_t* dfull = empty + BW_NSLOT;
-    uint64_t* dempty = dfull + 2;
+    float* sDj = sY + 100 * YS;                                        // [J2] decoder weights
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sDj + J2);           // [2][BW_NT][8] relu mask words (double-buffered)
+    int* sLists = reinterpret_cast<int*>(sMask + 2 * BW_NT * 8);       // [2] x { start[P+1] | list[J2] | row[J2] }
+    const int LSZ = (P + 1) + 2 * J2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sLists + 2 * LSZ) + 7) & ~(uintptr_t)7);
+    uint64_t* full = bars;                      // [2*BW_MAXCH]
+    uint64_t* empty = bars + 2 * BW_MAXCH;      // [2*BW_MAXCH]
+    uint64_t* dfull = empty + 2 * BW_MAXCH;     // [2]
+    uint64_t* dempty = dfull + 2;               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
 
     const int k = blockIdx.x / prm.ctas_per_net;                       // this CTA's net
@@ -745,9 +817,10 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
     const int b_hi = (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_net);
     const int ntiles = (b_hi - b_lo) * prm.tiles_per_chain;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ppde_cnn_net_t net = prm.m.net[k];
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BW_NSLOT; ++s) { mbar_init(&full[s], BW_NT_PROD / 32); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], BW_NT_PROD / 32); mbar_init(&empty[s], 1); }
         for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI); }
         fence_barrier_init();
     }
@@ -757,286 +830,266 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     for (int e = threadIdx.x; e < NE; e += BW_NTHREADS) sGc[e] = 0.f;
+    for (int j = threadIdx.x; j < J2; j += BW_NTHREADS) sDj[j] = net.d[j];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // pipeline state persists across the nets
-    int p_slot = 0; uint32_t p_phase = 0;      // producers
-    int m_slot = 0; uint32_t m_phase = 0;      // MMA issuer
-    const int git = 0;
-
-    {
-        const ppde_cnn_net_t net = prm.m.net[k];
-        // ---- per-net setup: W0^T (scaled, fp16 hi/lo) -> TMEM ----
-        if (warp < 4) {
-            const int nrow = warp * 32 + lane;                           // (t,a) = (nrow / 20, nrow % 20)
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int ks = 0; ks < prm.kpad / 16; ++ks) {
-                uint32_t hi[8], lo[8];
+    if (warp < 4) {   // A = W0^T (scaled, fp16 hi/lo) -> TMEM: lane = (t,a) row
+        const int nrow = warp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int ks = 0; ks < prm.kpad / 16; ++ks) {
+            uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int c0 = ks * 16 + 2 * q;
-                    const float w0 = (nrow < 100 && c0 < C) ? net.W0r[(size_t)c0 * 100 + nrow] * net.w0_scale : 0.f;
-                    const float w1 = (nrow < 100 && c0 + 1 < C) ? net.W0r[(size_t)(c0 + 1) * 100 + nrow] * net.w0_scale : 0.f;
-                    const float h0 = h_round(w0), h1 = h_round(w1);
-                    hi[q] = pack_h2(h0, h1);
-                    lo[q] = pack_h2(w0 - h0, w1 - h1);
-                }
-                tmem_st8(lane_addr + ks * 8, hi);
-                tmem_st8(lane_addr + prm.kpad / 2 + ks * 8, lo);
+            for (int q = 0; q < 8; ++q) {
+                const int c0 = ks * 16 + 2 * q;
+                const float w0 = (nrow < 100 && c0 < C) ? net.W0r[(size_t)c0 * 100 + nrow] * net.w0_scale : 0.f;
+                const float w1 = (nrow < 100 && c0 + 1 < C) ? net.W0r[(size_t)(c0 + 1) * 100 + nrow] * net.w0_scale : 0.f;
+                const float h0 = h_round(w0), h1 = h_round(w1);
+                hi[q] = pack_h2(h0, h1);
+                lo[q] = pack_h2(w0 - h0, w1 - h1);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tmem_st8(lane_addr + ks * 8, hi);
+            tmem_st8(lane_addr + prm.kpad / 2 + ks * 8, lo);
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
-        if (warp < 4) {
-            // ===== EPILOGUE: thread = output row (t,a) =====
-            const int nrow = warp * 32 + lane;
-            const int tid = threadIdx.x;                                  // 0..127
-            const float unscale = 1.f / (net.w0_scale * net.adj_scale);
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+    if (warp < 4) {
+        // ===== EPILOGUE: thread = output row (t,a); deterministic col2im into the chain accumulator =====
+        const int nrow = warp * 32 + lane;
+        const int tid = threadIdx.x;
+        const float unscale = 1.f / (net.w0_scale * net.adj_scale);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int buf = it & 1;
+            const int b = b_lo + it / prm.tiles_per_chain;
+            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+            const int p0 = tn * BW_NT;
+            const int valid = min(BW_NT, P - p0);
+            mbar_wait(&dfull[buf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            for (int cg = 0; cg * 32 < valid; ++cg) {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + buf * 128 + cg * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if ((cg + 1) * 32 >= valid) {                         // last read of this accumulator
+                    tc_fence_before();
+                    mbar_arrive(&dempty[buf]);
+                }
+                if (nrow < 100) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sY[nrow * YS + i] = __uint_as_float(r[i]) * unscale;
+                }
+                named_bar(2, NT_EPI);
+                // col2im, fixed summation order: output (i,a) = sum_t Y[(t,a), i - t]
+                const int nv = min(32, valid - cg * 32);
+                for (int o = tid; o < ((prm.dbg & 1) ? 0 : 36 * PPDE_Q); o += NT_EPI) {
+                    const int di = o / PPDE_Q, a = o - di * PPDE_Q;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) {
+                        const int pp = di - t;
+                        if (pp >= 0 && pp < nv) acc += sY[(t * PPDE_Q + a) * YS + pp];
+                    }
+                    const int i = p0 + cg * 32 + di;
+                    if (i < L) sGc[i * PPDE_Q + a] += acc;
+                }
+                named_bar(2, NT_EPI);
+            }
+            if (tn == prm.tiles_per_chain - 1) {
+                // flush the chain's partial gradient (streaming float4 stores) and clear the accumulator
+                float4* dst = reinterpret_cast<float4*>(prm.Gc + ((size_t)k * prm.n + b) * NE);
+                float4* src = reinterpret_cast<float4*>(sGc);
+                for (int e = tid; e < NE / 4; e += NT_EPI) {
+                    __stcs(dst + e, src[e]);
+                    src[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                named_bar(2, NT_EPI);
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, BW_NT);
+            const uint32_t ring_addr = smem_u32(ring);
+            const int last_ksteps = (prm.kpad - (prm.nch - 1) * KCH) / 16;
             for (int it = 0; it < ntiles; ++it) {
-                const int gt = git + it;
-                const int buf = gt & 1;
-                const int b = b_lo + it / prm.tiles_per_chain;
-                const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
-                const int p0 = tn * prm.n_tile;
-                const int valid = min(prm.n_tile, P - p0);
-                mbar_wait(&dfull[buf], (uint32_t)((gt >> 1) & 1));
+                const int buf = it & 1;
+                const uint32_t par = (uint32_t)((it >> 1) & 1);
+                if (it >= 2) mbar_wait(&dempty[buf], par ^ 1);
                 tc_fence_after();
-                for (int cg = 0; cg * 32 < valid; ++cg) {
-                    uint32_t r[32];
-                    tmem_ld32(lane_addr + buf * 128 + cg * 32, r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if ((cg + 1) * 32 >= valid) {                         // last read of this accumulator
-                        tc_fence_before();
-                        mbar_arrive(&dempty[buf]);
-                    }
-                    if (nrow < 100) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) sY[nrow * YS + i] = __uint_as_float(r[i]) * unscale;
-                    }
-                    named_bar(2, NT_EPI);
-                    // col2im, fixed summation order: output (i,a) = sum_t Y[(t,a), i - t]
-                    const int nv = min(32, valid - cg * 32);
-                    for (int o = tid; o < 36 * PPDE_Q; o += NT_EPI) {
-                        const int di = o / PPDE_Q, a = o - di * PPDE_Q;
-                        float acc = 0.f;
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) {
-                            const int pp = di - t;
-                            if (pp >= 0 && pp < nv) acc += sY[(t * PPDE_Q + a) * YS + pp];
-                        }
-                        const int i = p0 + cg * 32 + di;
-                        if (i < L) sGc[i * PPDE_Q + a] += acc;
-                    }
-                    named_bar(2, NT_EPI);
-                }
-                if (tn == prm.tiles_per_chain - 1) {
-                    // flush the chain's partial gradient (streaming float4 stores) and clear the accumulator
-                    float4* dst = reinterpret_cast<float4*>(prm.Gc + ((size_t)k * prm.n + b) * NE);
-                    float4* src = reinterpret_cast<float4*>(sGc);
-                    for (int e = tid; e < NE / 4; e += NT_EPI) {
-                        __stcs(dst + e, src[e]);
-                        src[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    named_bar(2, NT_EPI);
-                }
-            }
-        } else if (warp == WARP_MMA) {
-            if (lane == 0) {
-                const uint32_t idesc = make_idesc(128, prm.n_tile);
-                const uint32_t ring_addr = smem_u32(ring);
-                const int last_ksteps = (prm.kpad - (prm.nch - 1) * KCH) / 16;
-                for (int it = 0; it < ntiles; ++it) {
-                    const int gt = git + it;
-                    const int buf = gt & 1;
-                    if (gt >= 2) mbar_wait(&dempty[buf], (uint32_t)(((gt >> 1) + 1) & 1));
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
-                    for (int kc = 0; kc < prm.nch; ++kc) {
-                        mbar_wait(&full[m_slot], m_phase);
-                        tc_fence_after();
-                        const uint64_t dhi = make_b_desc(ring_addr + m_slot * SLOT_BYTES);
-                        const uint64_t dlo = make_b_desc(ring_addr + m_slot * SLOT_BYTES + MAT_BYTES);
-                        const int ksteps = (kc == prm.nch - 1) ? last_ksteps : KCH / 16;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
-                            const uint32_t a_lo = a_hi + prm.kpad / 2;
-                            const uint64_t koff = (uint64_t)(ks * 2);
-                            mma_ts(d_tmem, a_hi, dhi + koff, idesc, (kc | ks) ? 1u : 0u);
-                            mma_ts(d_tmem, a_hi, dlo + koff, idesc, 1u);
-                            mma_ts(d_tmem, a_lo, dhi + koff, idesc, 1u);
-                        }
-                        tc_commit(&empty[m_slot]);
-                        if (++m_slot == BW_NSLOT) { m_slot = 0; m_phase ^= 1; }
-                    }
-                    tc_commit(&dfull[buf]);
-                }
-            }
-        } else {
-            // ===== PRODUCERS: adjoint rows =====
-            const int ptid = threadIdx.x - (WARP_MMA + 1) * 32;           // 0..511
-            const int pw = warp - 5;                                      // 0..15
-            const int g = lane & 7, q = lane >> 3;
-            const int rsub = 16 * (pw >> 2) + (pw & 3) + 4 * q;           // row inside a 64-row pass
-            const float adj_scale = net.adj_scale;
-            for (int it = 0; it < ntiles; ++it) {
-                const int b = b_lo + it / prm.tiles_per_chain;
-                const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
-                const int p0 = tn * prm.n_tile;
-                const int valid = min(prm.n_tile, P - p0);
-                if (tn == 0) {
-                    // bucket this chain's winners by position (counting sort, then ascending channel order per bucket)
-                    named_bar(1, BW_NT_PROD);
-                    for (int i = ptid; i <= P; i += BW_NT_PROD) { sStart[i] = 0; if (i < P) sFill[i] = 0; }
-                    named_bar(1, BW_NT_PROD);
-                    const unsigned long long* keys = prm.mkey + ((size_t)b * prm.m.n_nets + k) * J2;
-                    for (int j = ptid; j < J2; j += BW_NT_PROD) {
-                        const unsigned long long key = keys[j];
-                        const float mj = __uint_as_float((unsigned)(key >> 32));
-                        const int pst = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
-                        const bool active = (mj > 0.f) && pst >= 0 && pst < P;     // relu'(0) = 0
-                        sPst[j] = active ? pst : -1;
-                        sDj[j] = net.d[j];
-                        if (active) atomicAdd(&sStart[pst + 1], 1);
-                    }
-                    named_bar(1, BW_NT_PROD);
-                    if (pw == 0) {                                        // scan of P+1 counters by one warp
-                        const int per = (P + 1 + 31) / 32;
-                        int run = 0;
-                        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) run += sStart[i];
-                        int incl = run;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                            if (lane >= o) incl += v;
-                        }
-                        int base = incl - run;
-                        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) { base += sStart[i]; sStart[i] = base; }
-                    }
-                    named_bar(1, BW_NT_PROD);
-                    for (int j = ptid; j < J2; j += BW_NT_PROD) {
-                        const int pst = sPst[j];
-                        if (pst >= 0) sList[sStart[pst] + atomicAdd(&sFill[pst], 1)] = j;
-                    }
-                    named_bar(1, BW_NT_PROD);
-                    for (int pp = ptid; pp < P; pp += BW_NT_PROD) {
-                        const int s0 = sStart[pp], s1 = sStart[pp + 1];
-                        for (int u = s0 + 1; u < s1; ++u) {
-                            const int v = sList[u];
-                            int w = u - 1;
-                            while (w >= s0 && sList[w] > v) { sList[w + 1] = sList[w]; --w; }
-                            sList[w + 1] = v;
-                        }
-                    }
-                    named_bar(1, BW_NT_PROD);
-                }
-                int ls0[2], ls1[2];
-                const uint8_t* mrow[2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = 64 * i + rsub;
-                    const bool ok = r < valid;
-                    ls0[i] = ok ? sStart[p0 + r] : 0;
-                    ls1[i] = ok ? sStart[p0 + r + 1] : 0;
-                    mrow[i] = prm.r1mask + (((size_t)b * prm.m.n_nets + k) * P + p0 + (ok ? r : 0)) * 32;
-                }
+                const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
                 for (int kc = 0; kc < prm.nch; ++kc) {
-                    mbar_wait(&empty[p_slot], p_phase ^ 1);
-                    unsigned char* mat_hi = ring + p_slot * SLOT_BYTES;
-                    unsigned char* mat_lo = mat_hi + MAT_BYTES;
-                    const int cb = kc * KCH;
-                    const bool in0 = cb + 4 * g < prm.kpad, in1 = cb + 32 + 4 * g < prm.kpad;
-                    // relu-mask bytes of my rows for this chunk (8 bytes = 64 channels), issued with the gathers
-                    uint2 mb[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        mb[i] = make_uint2(0u, 0u);
-                        if (ls1[i] > ls0[i]) mb[i] = __ldg(reinterpret_cast<const uint2*>(mrow[i] + (cb >> 3)));
+                    const int slot = buf * prm.nch + kc;
+                    mbar_wait(&full[slot], par);
+                    tc_fence_after();
+                    const uint64_t dhi = make_b_desc(ring_addr + slot * BW_SLOT);
+                    const uint64_t dlo = make_b_desc(ring_addr + slot * BW_SLOT + BW_MAT);
+                    const int ksteps = (kc == prm.nch - 1) ? last_ksteps : KCH / 16;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
+                        const uint32_t a_lo = a_hi + prm.kpad / 2;
+                        const uint64_t koff = (uint64_t)(ks * 2);
+                        mma_ts(d_tmem, a_hi, dhi + koff, idesc, (kc | ks) ? 1u : 0u);
+                        mma_ts(d_tmem, a_hi, dlo + koff, idesc, 1u);
+                        mma_ts(d_tmem, a_lo, dhi + koff, idesc, 1u);
                     }
-                    // gather-sum the winners' W1 row segments (ascending channel order per row: deterministic),
-                    // two winners of both rows per iteration -> up to 8 independent 16-byte L2 loads in flight per thread
-                    float4 s0[2], s1[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) { s0[i] = make_float4(0.f, 0.f, 0.f, 0.f); s1[i] = s0[i]; }
-                    const int maxlen = max(ls1[0] - ls0[0], ls1[1] - ls0[1]);
-                    for (int u = 0; u < maxlen; u += 2) {
-                        float dj[2][2];
-                        float4 w0[2][2], w1[2][2];
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int v = 0; v < 2; ++v) {
-                                dj[i][v] = 0.f;
-                                w0[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                w1[i][v] = w0[i][v];
-                                if (ls0[i] + u + v < ls1[i]) {
-                                    const int jn = sList[ls0[i] + u + v];
-                                    dj[i][v] = sDj[jn];
-                                    const float* wrow = net.W1p + (size_t)jn * prm.kpad + cb;
-                                    if (in0) w0[i][v] = __ldg(reinterpret_cast<const float4*>(wrow + 4 * g));
-                                    if (in1) w1[i][v] = __ldg(reinterpret_cast<const float4*>(wrow + 32 + 4 * g));
-                                }
-                            }
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int v = 0; v < 2; ++v) {
-                                s0[i].x = fmaf(dj[i][v], w0[i][v].x, s0[i].x); s0[i].y = fmaf(dj[i][v], w0[i][v].y, s0[i].y);
-                                s0[i].z = fmaf(dj[i][v], w0[i][v].z, s0[i].z); s0[i].w = fmaf(dj[i][v], w0[i][v].w, s0[i].w);
-                                s1[i].x = fmaf(dj[i][v], w1[i][v].x, s1[i].x); s1[i].y = fmaf(dj[i][v], w1[i][v].y, s1[i].y);
-                                s1[i].z = fmaf(dj[i][v], w1[i][v].z, s1[i].z); s1[i].w = fmaf(dj[i][v], w1[i][v].w, s1[i].w);
-                            }
-                    }
-                    // mask, scale, fp16 hi/lo split, swizzled store (zeros for rows without winners)
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int r = 64 * i + rsub;
-                        if (r >= prm.n_tile) continue;
-                        const uint32_t w_lo = (g >> 1) < 4 ? mb[i].x : 0u;      // bytes 0..3 hold channels cb .. cb+31
-                        const uint32_t nib0 = (w_lo >> (8 * (g >> 1) + 4 * (g & 1))) & 15u;          // channels cb + 4g ..
-                        const uint32_t nib1 = (mb[i].y >> (8 * (g >> 1) + 4 * (g & 1))) & 15u;       // channels cb + 32 + 4g ..
-                        const uint32_t msk = nib0 | (nib1 << 4);
-                        const float ss[8] = {s0[i].x, s0[i].y, s0[i].z, s0[i].w, s1[i].x, s1[i].y, s1[i].z, s1[i].w};
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float x0 = ((msk >> (2 * e)) & 1u) ? ss[2 * e] * adj_scale : 0.f;
-                            const float x1 = ((msk >> (2 * e + 1)) & 1u) ? ss[2 * e + 1] * adj_scale : 0.f;
-                            const float h0 = h_round(x0), h1 = h_round(x1);
-                            hi[e] = pack_h2(h0, h1);
-                            lo[e] = pack_h2(x0 - h0, x1 - h1);
-                        }
-                        const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
-                        const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);
-                        const int o1 = rbase + ((((g >> 1) + 4) ^ (r & 7)) << 4) + ((g & 1) << 3);
-                        *reinterpret_cast<uint2*>(mat_hi + o0) = make_uint2(hi[0], hi[1]);
-                        *reinterpret_cast<uint2*>(mat_hi + o1) = make_uint2(hi[2], hi[3]);
-                        *reinterpret_cast<uint2*>(mat_lo + o0) = make_uint2(lo[0], lo[1]);
-                        *reinterpret_cast<uint2*>(mat_lo + o1) = make_uint2(lo[2], lo[3]);
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[p_slot]);
-                    if (++p_slot == BW_NSLOT) { p_slot = 0; p_phase ^= 1; }
+                    tc_commit(&empty[slot]);
                 }
+                tc_commit(&dfull[buf]);
             }
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
+    } else {
+        // ===== PRODUCERS =====
+        const int ptid = threadIdx.x - (WARP_MMA + 1) * 32;           // 0..511
+        const int pw = warp - 5;                                      // 0..15
+        const int ts = pw >> 1;                                       // gather set 0..7: rows [8 ts, 8 ts + 8)
+        const int tl = (pw & 1) * 32 + lane;                          // 0..63: channels 4 tl .. 4 tl + 3
+        const bool gact = 4 * tl < prm.kpad;
+        const float adj_scale = net.adj_scale;
+        const int my_kc = tl >> 4;                                    // K chunk of my channels
+        const int my_sw = (tl & 15) >> 1, my_half = (tl & 1) << 3;    // 16-byte chunk index inside the 128-byte row, 8-byte half
+        const float* wbase = net.W1p + 4 * tl;
+        auto load_lists = [&](int bb, int* dstbuf, bool direct, uint32_t (&pre)[3]) {
+            const uint16_t* recp = prm.wl + ((size_t)bb * prm.m.n_nets + k) * prm.rec;
+            // record = start[P+1] | list[J2] | row[J2]: LSZ uint16 -> <= 3 per thread (LSZ <= 3*512)
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int i = ptid + u * BW_NT_PROD;
+                if (i < LSZ) { const uint32_t v = recp[i]; if (direct) dstbuf[i] = (int)v; else pre[u] = v; }
+            }
+        };
+        uint32_t pre[3] = {0u, 0u, 0u};
+        if (ntiles > 0) load_lists(b_lo, sLists, true, pre);
+        // mask word of (row ptid/8, word ptid%8) for the first tile
+        if (ntiles > 0) {
+            const int mr = ptid >> 3, mw = ptid & 7;
+            const int valid0 = min(BW_NT, P);
+            sMask[ptid] = (mr < valid0)
+                ? __ldg(reinterpret_cast<const uint32_t*>(prm.r1mask + (((size_t)b_lo * prm.m.n_nets + k) * P + mr) * 32) + mw) : 0u;
+        }
+        named_bar(1, BW_NT_PROD);
+        for (int it = 0; it < ntiles; ++it) {
+            const int ci = it / prm.tiles_per_chain;                  // chain index inside this CTA
+            const int b = b_lo + ci;
+            const int tn = it - ci * prm.tiles_per_chain;
+            const int p0 = tn * BW_NT;
+            const int valid = min(BW_NT, P - p0);
+            const int* sStart = sLists + (ci & 1) * LSZ;
+            const int* sList = sStart + (P + 1);
+            const int* sRow = sList + J2;
+            const uint32_t* mcur = sMask + (it & 1) * BW_NT * 8;
+            // prefetch: next tile's mask word and (at the first tile of a chain) the next chain's winner lists
+            uint32_t mnext = 0u;
+            const bool has_next = it + 1 < ntiles;
+            if (has_next) {
+                const int ci2 = (it + 1) / prm.tiles_per_chain;
+                const int tn2 = (it + 1) - ci2 * prm.tiles_per_chain;
+                const int mr = ptid >> 3, mw = ptid & 7;
+                const int v2 = min(BW_NT, P - tn2 * BW_NT);
+                if (mr < v2)
+                    mnext = __ldg(reinterpret_cast<const uint32_t*>(
+                                prm.r1mask + (((size_t)(b_lo + ci2) * prm.m.n_nets + k) * P + tn2 * BW_NT + mr) * 32) + mw);
+            }
+            const bool pf_lists = (tn == 0) && (b + 1 < b_hi);
+            if (pf_lists) load_lists(b + 1, nullptr, false, pre);
+
+            // the tile's ring slots must have been drained by the MMAs of tile it-2
+            const int sbase = (it & 1) * prm.nch;
+            const uint32_t par = (uint32_t)((it >> 1) & 1);
+            for (int kc = 0; kc < prm.nch; ++kc) mbar_wait(&empty[sbase + kc], par ^ 1);
+            unsigned char* mat_hi = ring + (sbase + my_kc) * BW_SLOT;
+            unsigned char* mat_lo = mat_hi + BW_MAT;
+
+            if (gact) {
+                const int r0 = 8 * ts, r1 = min(8 * ts + 8, valid);
+                const int eA = (r0 < valid) ? sStart[p0 + r0] : 0;
+                const int eB = (r0 < valid && !(prm.dbg & 2)) ? sStart[p0 + r1] : eA;
+                int next_r = r0, cur = -1;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                auto store_row = [&](int r, const float4& a4, bool zero) {
+                    uint32_t h01 = 0u, h23 = 0u, l01 = 0u, l23 = 0u;
+                    if (!zero) {
+                        const uint32_t nib = (mcur[r * 8 + (tl >> 3)] >> (4 * (tl & 7))) & 15u;
+                        const float x0 = (nib & 1u) ? a4.x * adj_scale : 0.f, x1 = (nib & 2u) ? a4.y * adj_scale : 0.f;
+                        const float x2 = (nib & 4u) ? a4.z * adj_scale : 0.f, x3 = (nib & 8u) ? a4.w * adj_scale : 0.f;
+                        const float h0 = h_round(x0), h1 = h_round(x1), h2 = h_round(x2), h3 = h_round(x3);
+                        h01 = pack_h2(h0, h1); h23 = pack_h2(h2, h3);
+                        l01 = pack_h2(x0 - h0, x1 - h1); l23 = pack_h2(x2 - h2, x3 - h3);
+                    }
+                    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((my_sw ^ (r & 7)) << 4) + my_half;
+                    *reinterpret_cast<uint2*>(mat_hi + off) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(mat_lo + off) = make_uint2(l01, l23);
+                };
+                float4 wA[4], wB[4];
+                float dA[4], dB[4];
+                int rA_[4], rB_[4];
+                auto issue = [&](float4 (&w)[4], float (&dj)[4], int (&rr)[4], int e0) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        rr[v] = -1; dj[v] = 0.f; w[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e0 + v < eB) {
+                            const int jn = sList[e0 + v];
+                            rr[v] = sRow[e0 + v] - p0;
+                            dj[v] = sDj[jn];
+                            w[v] = __ldg(reinterpret_cast<const float4*>(wbase + (size_t)jn * prm.kpad));
+                        }
+                    }
+                };
+                auto consume = [&](const float4 (&w)[4], const float (&dj)[4], const int (&rr)[4]) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int r = rr[v];
+                        if (r < 0) continue;
+                        if (r != cur) {
+                            if (cur >= 0) { store_row(cur, acc, false); next_r = cur + 1; }
+                            for (; next_r < r; ++next_r) store_row(next_r, acc, true);
+                            cur = r;
+                            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        const float d = dj[v];
+                        acc.x = fmaf(d, w[v].x, acc.x); acc.y = fmaf(d, w[v].y, acc.y);
+                        acc.z = fmaf(d, w[v].z, acc.z); acc.w = fmaf(d, w[v].w, acc.w);
+                    }
+                };
+                if (eA < eB) issue(wA, dA, rA_, eA);
+                for (int eb = eA; eb < eB; eb += 8) {
+                    if (eb + 4 < eB) issue(wB, dB, rB_, eb + 4);
+                    consume(wA, dA, rA_);
+                    if (eb + 4 < eB) {
+                        if (eb + 8 < eB) issue(wA, dA, rA_, eb + 8);
+                        consume(wB, dB, rB_);
+                    }
+                }
+                if (cur >= 0) { store_row(cur, acc, false); next_r = cur + 1; }
+                for (; next_r < r1; ++next_r) store_row(next_r, acc, true);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0)
+                for (int kc = 0; kc < prm.nch; ++kc) mbar_arrive(&full[sbase + kc]);
+            // publish the prefetched data into the other halves of the double buffers
+            if (has_next) sMask[((it + 1) & 1) * BW_NT * 8 + ptid] = mnext;
+            if (pf_lists) {
+                int* dstbuf = sLists + ((ci + 1) & 1) * LSZ;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) { const int i = ptid + u * BW_NT_PROD; if (i < LSZ) dstbuf[i] = (int)pre[u]; }
+            }
+            named_bar(1, BW_NT_PROD);      // next tile's masks / next chain's lists visible; this tile's readers are done
+        }
     }
 
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     if (warp == WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
-
 
 __global__ void cnn_grad_combine_kernel(int n, int NE, int n_nets, float scale, ppde_potts_t pm,
                                         const float* __restrict__ Gc, const float* __restrict__ Gp, int64_t Gp_stride,
@@ -1159,7 +1212,8 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
     prm.m = *m; prm.pm = *pm; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey;
     prm.Gc = scratch;
     prm.r1mask = r1mask;
-    prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
+    { const char* e = getenv("PPDE_BWD_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
+    prm.tiles_per_chain = (m->P + tc::BW_NT - 1) / tc::BW_NT;
     prm.kpad = (m->C + 15) / 16 * 16;
     prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
     int dev = 0, sms = 148;
@@ -1169,10 +1223,10 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
     if (prm.ctas_per_net < 1) prm.ctas_per_net = 1;
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
-    (void)C;
-    const size_t smem = 1024 + (size_t)tc::BW_NSLOT * tc::SLOT_BYTES +
-                        ((size_t)L * PPDE_Q + 100 * tc::YS + J2) * sizeof(float) +
-                        ((size_t)J2 + (P + 1) + P + J2) * sizeof(int) + 8 + 16 * sizeof(uint64_t);
+    if ((P + 1) + 2 * J2 > 3 * tc::BW_NT_PROD) return (int)cudaErrorInvalidValue;
+    const size_t smem = 1024 + (size_t)2 * tc::BW_MAXCH * tc::BW_SLOT +
+                        ((size_t)L * PPDE_Q + 100 * tc::YS + J2 + 2 * tc::BW_NT * 8) * sizeof(float) +
+                        2 * ((size_t)(P + 1) + 2 * J2) * sizeof(int) + 8 + 24 * sizeof(uint64_t);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc::cnn_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1180,6 +1234,14 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
         configured = smem;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // winner records live behind the per-net gradient scratch: [n_nets*n*20L floats][n*n_nets*rec uint16]
+    const int rec = ((P + 1) + 2 * J2 + 7) & ~7;
+    uint16_t* wl = reinterpret_cast<uint16_t*>(scratch + (size_t)m->n_nets * n * L * PPDE_Q);
+    prm.wl = wl;
+    prm.rec = rec;
+    tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
+    int r0 = launch_done();
+    if (r0) return r0;
     tc::cnn_backward_tc_kernel<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
     int r = launch_done();
     if (r) return r;
