@@ -762,7 +762,7 @@ constexpr int BW_NTHREADS = NT_EPI + 32 + BW_NT_PROD;   // 672
 constexpr int BW_MAT = BW_NT * KCH * 2; // one [64 x 64] fp16 operand matrix (8 KB)
 constexpr int BW_SLOT = 2 * BW_MAT;     // hi + lo
 constexpr int BW_MAXCH = 4;             // K chunks per tile (kpad <= 256)
-constexpr int YS = 33;                  // sY row stride (floats)
+constexpr int YS = 65;                  // sY row stride (floats): 64 columns + 1 (conflict-free column writes)
 
 struct BwdParams {
     ppde_cnn_t m;
@@ -801,9 +801,9 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
     float* sY = sGc + NE;                                              // [100][YS]
     float* sDj = sY + 100 * YS;                                        // [J2] decoder weights
     uint32_t* sMask = reinterpret_cast<uint32_t*>(sDj + J2);           // [2][BW_NT][8] relu mask words (double-buffered)
-    int* sLists = reinterpret_cast<int*>(sMask + 2 * BW_NT * 8);       // [2] x { start[P+1] | list[J2] | row[J2] }
-    const int LSZ = (P + 1) + 2 * J2;
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sLists + 2 * LSZ) + 7) & ~(uintptr_t)7);
+    // [2] x winner record { start[P+1] | list[J2] | row[J2] } as uint16, `rec` entries each (16-byte multiple)
+    uint16_t* sLists = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sMask + 2 * BW_NT * 8) + 15) & ~(uintptr_t)15);
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sLists + 2 * prm.rec) + 7) & ~(uintptr_t)7);
     uint64_t* full = bars;                      // [2*BW_MAXCH]
     uint64_t* empty = bars + 2 * BW_MAXCH;      // [2*BW_MAXCH]
     uint64_t* dfull = empty + 2 * BW_MAXCH;     // [2]
@@ -873,30 +873,33 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
             const int valid = min(BW_NT, P - p0);
             mbar_wait(&dfull[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            for (int cg = 0; cg * 32 < valid; ++cg) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + buf * 128 + cg * 32, r);
+            {
+                // the whole 64-column accumulator in one go: two TMEM loads in flight, one wait, one hand-back
+                uint32_t r0[32], r1[32];
+                tmem_ld32(lane_addr + buf * 128, r0);
+                if (valid > 32) tmem_ld32(lane_addr + buf * 128 + 32, r1);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if ((cg + 1) * 32 >= valid) {                         // last read of this accumulator
-                    tc_fence_before();
-                    mbar_arrive(&dempty[buf]);
-                }
+                tc_fence_before();
+                mbar_arrive(&dempty[buf]);
                 if (nrow < 100) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) sY[nrow * YS + i] = __uint_as_float(r[i]) * unscale;
+                    for (int i = 0; i < 32; ++i) sY[nrow * YS + i] = __uint_as_float(r0[i]) * unscale;
+                    if (valid > 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sY[nrow * YS + 32 + i] = __uint_as_float(r1[i]) * unscale;
+                    }
                 }
                 named_bar(2, NT_EPI);
                 // col2im, fixed summation order: output (i,a) = sum_t Y[(t,a), i - t]
-                const int nv = min(32, valid - cg * 32);
-                for (int o = tid; o < ((prm.dbg & 1) ? 0 : 36 * PPDE_Q); o += NT_EPI) {
+                for (int o = tid; o < ((prm.dbg & 1) ? 0 : (valid + 4) * PPDE_Q); o += NT_EPI) {
                     const int di = o / PPDE_Q, a = o - di * PPDE_Q;
                     float acc = 0.f;
 #pragma unroll
                     for (int t = 0; t < 5; ++t) {
                         const int pp = di - t;
-                        if (pp >= 0 && pp < nv) acc += sY[(t * PPDE_Q + a) * YS + pp];
+                        if (pp >= 0 && pp < valid) acc += sY[(t * PPDE_Q + a) * YS + pp];
                     }
-                    const int i = p0 + cg * 32 + di;
+                    const int i = p0 + di;
                     if (i < L) sGc[i * PPDE_Q + a] += acc;
                 }
                 named_bar(2, NT_EPI);
@@ -954,24 +957,28 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         const int my_kc = tl >> 4;                                    // K chunk of my channels
         const int my_sw = (tl & 15) >> 1, my_half = (tl & 1) << 3;    // 16-byte chunk index inside the 128-byte row, 8-byte half
         const float* wbase = net.W1p + 4 * tl;
-        auto load_lists = [&](int bb, int* dstbuf, bool direct, uint32_t (&pre)[3]) {
-            const uint16_t* recp = prm.wl + ((size_t)bb * prm.m.n_nets + k) * prm.rec;
-            // record = start[P+1] | list[J2] | row[J2]: LSZ uint16 -> <= 3 per thread (LSZ <= 3*512)
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int i = ptid + u * BW_NT_PROD;
-                if (i < LSZ) { const uint32_t v = recp[i]; if (direct) dstbuf[i] = (int)v; else pre[u] = v; }
-            }
+        // cp.async prefetches (no register staging): 16-byte pieces of a winner record, 4-byte mask words
+        auto cp16 = [](void* dst, const void* src) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
         };
-        uint32_t pre[3] = {0u, 0u, 0u};
-        if (ntiles > 0) load_lists(b_lo, sLists, true, pre);
-        // mask word of (row ptid/8, word ptid%8) for the first tile
-        if (ntiles > 0) {
+        auto cp4 = [](void* dst, const void* src) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+        };
+        auto fetch_lists = [&](int bb, int bufi) {
+            const uint16_t* recp = prm.wl + ((size_t)bb * prm.m.n_nets + k) * prm.rec;
+            for (int i = ptid; i * 8 < prm.rec; i += BW_NT_PROD) cp16(sLists + (size_t)bufi * prm.rec + i * 8, recp + i * 8);
+        };
+        auto fetch_mask = [&](int it2) {        // my word of tile it2's mask rows: (row ptid/8, word ptid%8)
+            const int ci2 = it2 / prm.tiles_per_chain;
+            const int tn2 = it2 - ci2 * prm.tiles_per_chain;
             const int mr = ptid >> 3, mw = ptid & 7;
-            const int valid0 = min(BW_NT, P);
-            sMask[ptid] = (mr < valid0)
-                ? __ldg(reinterpret_cast<const uint32_t*>(prm.r1mask + (((size_t)b_lo * prm.m.n_nets + k) * P + mr) * 32) + mw) : 0u;
-        }
+            uint32_t* dst = sMask + (it2 & 1) * BW_NT * 8 + ptid;
+            if (mr < min(BW_NT, P - tn2 * BW_NT))
+                cp4(dst, reinterpret_cast<const uint32_t*>(
+                             prm.r1mask + (((size_t)(b_lo + ci2) * prm.m.n_nets + k) * P + tn2 * BW_NT + mr) * 32) + mw);
+        };
+        if (ntiles > 0) { fetch_lists(b_lo, 0); fetch_mask(0); }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
         named_bar(1, BW_NT_PROD);
         for (int it = 0; it < ntiles; ++it) {
             const int ci = it / prm.tiles_per_chain;                  // chain index inside this CTA
@@ -979,24 +986,17 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
             const int tn = it - ci * prm.tiles_per_chain;
             const int p0 = tn * BW_NT;
             const int valid = min(BW_NT, P - p0);
-            const int* sStart = sLists + (ci & 1) * LSZ;
-            const int* sList = sStart + (P + 1);
-            const int* sRow = sList + J2;
+            const uint16_t* sStart = sLists + (size_t)(ci & 1) * prm.rec;
+            const uint16_t* sList = sStart + (P + 1);
+            const uint16_t* sRow = sList + J2;
             const uint32_t* mcur = sMask + (it & 1) * BW_NT * 8;
-            // prefetch: next tile's mask word and (at the first tile of a chain) the next chain's winner lists
-            uint32_t mnext = 0u;
+            // prefetch the next tile's mask words (my set's rows: ptid/8 = 8 ts + ...) and, at the first tile of a chain,
+            // the next chain's winner record, straight into the other halves of the double buffers
             const bool has_next = it + 1 < ntiles;
-            if (has_next) {
-                const int ci2 = (it + 1) / prm.tiles_per_chain;
-                const int tn2 = (it + 1) - ci2 * prm.tiles_per_chain;
-                const int mr = ptid >> 3, mw = ptid & 7;
-                const int v2 = min(BW_NT, P - tn2 * BW_NT);
-                if (mr < v2)
-                    mnext = __ldg(reinterpret_cast<const uint32_t*>(
-                                prm.r1mask + (((size_t)(b_lo + ci2) * prm.m.n_nets + k) * P + tn2 * BW_NT + mr) * 32) + mw);
-            }
+            if (has_next) fetch_mask(it + 1);
             const bool pf_lists = (tn == 0) && (b + 1 < b_hi);
-            if (pf_lists) load_lists(b + 1, nullptr, false, pre);
+            if (pf_lists) fetch_lists(b + 1, (ci + 1) & 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
 
             // the tile's ring slots must have been drained by the MMAs of tile it-2
             const int sbase = (it & 1) * prm.nch;
@@ -1072,14 +1072,12 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
             __syncwarp();
             if (lane == 0)
                 for (int kc = 0; kc < prm.nch; ++kc) mbar_arrive(&full[sbase + kc]);
-            // publish the prefetched data into the other halves of the double buffers
-            if (has_next) sMask[((it + 1) & 1) * BW_NT * 8 + ptid] = mnext;
-            if (pf_lists) {
-                int* dstbuf = sLists + ((ci + 1) & 1) * LSZ;
-#pragma unroll
-                for (int u = 0; u < 3; ++u) { const int i = ptid + u * BW_NT_PROD; if (i < LSZ) dstbuf[i] = (int)pre[u]; }
-            }
-            named_bar(1, BW_NT_PROD);      // next tile's masks / next chain's lists visible; this tile's readers are done
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            // mask words of a tile row are fetched by the 8 threads ptid = 8*row + w, i.e. by the set that owns the row:
+            // a 64-thread barrier per set publishes them; sets are otherwise free to run ahead of each other
+            named_bar(3 + ts, 64);
+            if (tn == prm.tiles_per_chain - 1 && has_next)
+                named_bar(1, BW_NT_PROD);  // chain boundary: the next chain's record is complete and nobody reads the old one
         }
     }
 
@@ -1223,10 +1221,10 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
     if (prm.ctas_per_net < 1) prm.ctas_per_net = 1;
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
-    if ((P + 1) + 2 * J2 > 3 * tc::BW_NT_PROD) return (int)cudaErrorInvalidValue;
+    const int rec_ = ((P + 1) + 2 * J2 + 7) & ~7;
     const size_t smem = 1024 + (size_t)2 * tc::BW_MAXCH * tc::BW_SLOT +
                         ((size_t)L * PPDE_Q + 100 * tc::YS + J2 + 2 * tc::BW_NT * 8) * sizeof(float) +
-                        2 * ((size_t)(P + 1) + 2 * J2) * sizeof(int) + 8 + 24 * sizeof(uint64_t);
+                        2 * (size_t)rec_ * sizeof(uint16_t) + 16 + 8 + 24 * sizeof(uint64_t);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc::cnn_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
