@@ -399,13 +399,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __gri
 // 2-CTA variant of the forward kernel (cta_group::2): a cluster of two CTAs (one TPC) computes M = 256 channels
 // (two channel tiles) per MMA.  Each CTA keeps ITS 128-channel W1 tile in its own tensor memory and PRODUCES only
 // half of the positions of every tile (the B operand of a cta_group::2 MMA is split along N across the pair), so the
-// r1 production cost per MMA flop — the bottleneck of the 1-CTA kernel (4x redundant across channel tiles) — halves,
-// and so does the shared-memory traffic of the B operand per CTA.  The leader CTA (rank 0) issues the MMAs;
-// `full` / `dempty` barriers live in the leader and collect arrivals from both CTAs (mapa + cluster-scope arrive),
-// `empty` / `dfull` are signalled in both CTAs by multicast tcgen05.commit.
+// r1 production cost per MMA flop halves, and so does the shared-memory traffic of the B operand per CTA.
+//
+// Tiles: tile t of a chain covers positions [128 t, 128 t + N_t), N_t = min(128, roundup16(P - 128 t)); CTA `rank`
+// produces rows [rank N_t/2, (rank+1) N_t/2).  Rows past P-1 replicate position P-1: a duplicate column can never beat
+// the original under the strict `>` / lowest-index rule, so the epilogue needs no per-column validity test.
+//
+// Synchronisation (per 64-wide K chunk = ring slot):
+//   producers (16 warps / CTA)  --fullL[slot] (local, 16 warp arrivals)-->  leader's MMA thread (rank 0)
+//                                                                     \-->  rank 1's forwarder thread --fullR[slot]
+//                                                                           (one remote arrive / chunk)--> leader
+//   leader MMA  --tcgen05.commit multicast--> empty[slot] in both CTAs (slot free), dfull[buf] in both CTAs
+//   epilogue warps (4 / CTA) --dempty[buf] in the leader (one arrive per warp)--> leader MMA
+// The only cluster-scope (expensive) arrives are 1 per chunk (forwarder) and 4 per tile (rank 1's epilogue warps).
 constexpr int NSLOT2 = 6;
 constexpr int MAT2_BYTES = 64 * KCH * 2;          // one [64 x 64] fp16 operand half-matrix (8 KB)
 constexpr int SLOT2_BYTES = 2 * MAT2_BYTES;       // hi + lo
+constexpr int NT2 = 128;                          // positions per full tile
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -448,19 +458,87 @@ __device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64
         "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// explicit shared-space accesses with 32-bit addresses and immediate offsets (generic LD/ST cost 64-bit address math
+// and the slower generic path; the table pointers are data-dependent, so the compiler cannot infer the space)
+template <int IMM>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0+%1], {%2, %3};" ::"r"(addr), "n"(IMM), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return r;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 
+// one 64-wide K chunk of one r1 row: 8 channels per thread (4g..4g+3 and 32+4g..+3 of the chunk)
+template <int KC>
+__device__ __forceinline__ void produce_chunk(const uint32_t (&ra)[5], uint32_t sa0, uint32_t sa1, bool emit_mask,
+                                              uint32_t& mbits) {
+    constexpr int CB = KC * KCH * 4;               // byte offset of the chunk inside a table row
+    const float4 z0 = lds128<CB>(ra[0]);
+    const float4 z1 = lds128<CB + 128>(ra[0]);
+    float2 a0 = make_float2(z0.x, z0.y), a1 = make_float2(z0.z, z0.w);
+    float2 a2 = make_float2(z1.x, z1.y), a3 = make_float2(z1.z, z1.w);
+#pragma unroll
+    for (int t = 1; t < 5; ++t) {
+        const float4 u0 = lds128<CB>(ra[t]);
+        const float4 u1 = lds128<CB + 128>(ra[t]);
+        a0 = add2(a0, make_float2(u0.x, u0.y)); a1 = add2(a1, make_float2(u0.z, u0.w));
+        a2 = add2(a2, make_float2(u1.x, u1.y)); a3 = add2(a3, make_float2(u1.z, u1.w));
+    }
+    if (emit_mask) {                               // warp-uniform
+        const float v[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+        uint32_t nib = 0u;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) nib |= (__float_as_int(v[e]) > 0 ? 1u : 0u) << e;
+        mbits |= nib << (8 * KC);
+    }
+    float2 x[4] = {a0, a1, a2, a3};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        x[e].x = fmaxf(x[e].x, 0.f); x[e].y = fmaxf(x[e].y, 0.f);
+        const float2 h = make_float2(h_trunc(x[e].x), h_trunc(x[e].y));
+        const float2 l = sub2(x[e], h);
+        hi[e] = pack_h2(h.x, h.y);
+        lo[e] = pack_h2(l.x, l.y);
+    }
+    sts64<0>(sa0, hi[0], hi[1]);
+    sts64<0>(sa1, hi[2], hi[3]);
+    sts64<MAT2_BYTES>(sa0, lo[0], lo[1]);
+    sts64<MAT2_BYTES>(sa1, lo[2], lo[3]);
+}
+
+template <int NCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int C = prm.m.C, P = prm.m.P, J2 = 2 * C;
-    const int KS = prm.nch * KCH;
+    constexpr int KS = NCH * KCH;
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* sT0 = reinterpret_cast<float*>(ring + NSLOT2 * SLOT2_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sT0 + 100 * KS);
-    uint64_t* full = bars;                 // [NSLOT2] (leader's copy is the live one)
-    uint64_t* empty = bars + NSLOT2;       // [NSLOT2] local
-    uint64_t* dfull = empty + NSLOT2;      // [2] local
-    uint64_t* dempty = dfull + 2;          // [2] (leader's copy is the live one)
+    uint64_t* fullL = bars;                // [NSLOT2] local: this CTA's producer warps
+    uint64_t* fullR = fullL + NSLOT2;      // [NSLOT2] leader's copy is live: forwarded "rank 1 is full"
+    uint64_t* empty = fullR + NSLOT2;      // [NSLOT2] local (multicast commit)
+    uint64_t* dfull = empty + NSLOT2;      // [2] local (multicast commit)
+    uint64_t* dempty = dfull + 2;          // [2] leader's copy is live
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
 
     const uint32_t rank = cluster_ctarank();
@@ -474,9 +552,10 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
     const ppde_cnn_net_t net = prm.m.net[k];
     const int b_lo = idle ? 0 : (int)((int64_t)prm.n * within / prm.ctas_per_combo);
     const int b_hi = idle ? 0 : (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_combo);
-    const int ntiles = (b_hi - b_lo) * prm.tiles_per_chain;
+    const int tpc = prm.tiles_per_chain;
+    const int ntiles = (b_hi - b_lo) * tpc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_half = prm.n_tile >> 1;
+    const int n_last = ((P - (tpc - 1) * NT2) + 15) & ~15;   // N of a chain's last tile (multiple of 16, <= 128)
 
     for (int e = threadIdx.x; e < 100 * KS; e += NTHREADS) {
         const int row = e / KS, c = e - row * KS;
@@ -488,8 +567,8 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
         sT0[e] = v * net.r1_scale;
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOT2; ++s) { mbar_init(&full[s], 2 * (NT_PROD / 32)); mbar_init(&empty[s], 1); }
-        for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], 2 * NT_EPI); }
+        for (int s = 0; s < NSLOT2; ++s) { mbar_init(&fullL[s], NT_PROD / 32); mbar_init(&fullR[s], 1); mbar_init(&empty[s], 1); }
+        for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], 2 * (NT_EPI / 32)); }
         fence_barrier_init();
     }
     if (warp == WARP_MMA) {
@@ -529,59 +608,88 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
 
     if (warp < 4) {
         // ===== EPILOGUE (both CTAs): thread = channel j of this CTA's tile =====
+        // running (max, first arg-max) of the RAW accumulator: v = relu(u * unscale + b1) is monotone in u (unscale > 0)
         const int j = mt * 128 + warp * 32 + lane;
         const float bias = (j < J2) ? net.b1[j] : 0.f;
         const float unscale = 1.f / (net.w1_scale * net.r1_scale);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
-        float best = -1.f;
+        float best = -3.0e38f;
         int bp = 0;
+        int b = b_lo, tn = 0;
         for (int it = 0; it < ntiles; ++it) {
             const int buf = it & 1;
-            const int b = b_lo + it / prm.tiles_per_chain;
-            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
-            const int p0 = tn * prm.n_tile;
-            const int valid = min(prm.n_tile, P - p0);
-            if (tn == 0) { best = -1.f; bp = 0; }
+            const int p0 = tn * NT2;
+            const int nt = (tn == tpc - 1) ? n_last : NT2;
+            if (tn == 0) { best = -3.0e38f; bp = 0; }
+            int bl = bp - p0;                                  // arg-max relative to this tile (immediates below)
             mbar_wait(&dfull[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            for (int cg = 0; cg * 32 < valid; ++cg) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + buf * 128 + cg * 32, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t ta = lane_addr + buf * 128;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float v = fmaf(__uint_as_float(r[i]), unscale, bias);
-                    v = v > 0.f ? v : 0.f;
-                    if (cg * 32 + i < valid && v > best) { best = v; bp = p0 + cg * 32 + i; }
+            for (int h = 0; h < 4; ++h) {                      // 32 columns at a time, two x16 loads in flight
+                if (h * 32 < nt) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(ta + h * 32, r0);
+                    const bool second = h * 32 + 16 < nt;
+                    if (second) tmem_ld16(ta + h * 32 + 16, r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float u = __uint_as_float(r0[i]);
+                        if (u > best) { best = u; bl = h * 32 + i; }
+                    }
+                    if (second) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float u = __uint_as_float(r1[i]);
+                            if (u > best) { best = u; bl = h * 32 + 16 + i; }
+                        }
+                    }
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(&dempty[buf], 0);
-            if (tn == prm.tiles_per_chain - 1 && j < J2) {
-                const unsigned long long key =
-                    ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)bp);
-                prm.mkey[((size_t)b * prm.m.n_nets + k) * J2 + j] = key;
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&dempty[buf]); else mbar_arrive_cluster(&dempty[buf], 0);
+            }
+            bp = bl + p0;
+            if (tn == tpc - 1) {
+                if (j < J2) {
+                    float v = fmaf(best, unscale, bias);
+                    int pp = bp;
+                    if (!(v > 0.f)) { v = 0.f; pp = 0; }       // relu; all-nonpositive column -> (0, position 0)
+                    const unsigned long long key =
+                        ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)pp);
+                    prm.mkey[((size_t)b * prm.m.n_nets + k) * J2 + j] = key;
+                }
+                tn = 0; ++b;
+            } else {
+                ++tn;
             }
         }
     } else if (warp == WARP_MMA) {
-        // ===== MMA ISSUER: one lane of the LEADER CTA =====
-        if (rank == 0 && lane == 0) {
-            const uint32_t idesc = make_idesc(256, prm.n_tile);
+        if (lane == 0 && rank == 0) {
+            // ===== MMA ISSUER: one lane of the LEADER CTA =====
+            const uint32_t idesc_full = make_idesc(256, NT2), idesc_last = make_idesc(256, n_last);
             const uint32_t ring_addr = smem_u32(ring);
-            int slot = 0;
+            int slot = 0, tn = 0;
             uint32_t sphase = 0;
-            const int last_ksteps = (prm.kpad - (prm.nch - 1) * KCH) / 16;
+            const int last_ksteps = (prm.kpad - (NCH - 1) * KCH) / 16;
             for (int it = 0; it < ntiles; ++it) {
                 const int buf = it & 1;
+                const uint32_t idesc = (tn == tpc - 1) ? idesc_last : idesc_full;
+                if (++tn == tpc) tn = 0;
                 if (it >= 2) mbar_wait_cluster(&dempty[buf], (uint32_t)(((it >> 1) + 1) & 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
-                for (int kc = 0; kc < prm.nch; ++kc) {
-                    mbar_wait_cluster(&full[slot], sphase);
+#pragma unroll 1
+                for (int kc = 0; kc < NCH; ++kc) {
+                    mbar_wait(&fullL[slot], sphase);
+                    mbar_wait_cluster(&fullR[slot], sphase);
                     tc_fence_after();
                     const uint64_t dhi = make_b_desc(ring_addr + slot * SLOT2_BYTES);
                     const uint64_t dlo = make_b_desc(ring_addr + slot * SLOT2_BYTES + MAT2_BYTES);
-                    const int ksteps = (kc == prm.nch - 1) ? last_ksteps : KCH / 16;
+                    const int ksteps = (kc == NCH - 1) ? last_ksteps : KCH / 16;
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
                         const uint32_t a_lo = a_hi + prm.kpad / 2;
@@ -595,74 +703,74 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
                 }
                 tc_commit2(&dfull[buf]);
             }
+        } else if (lane == 0) {
+            // ===== FORWARDER (rank 1): one remote arrive per chunk instead of one per producer warp =====
+            int slot = 0;
+            uint32_t sphase = 0;
+            for (int c = 0; c < ntiles * NCH; ++c) {
+                mbar_wait(&fullL[slot], sphase);
+                mbar_arrive_cluster(&fullR[slot], 0);
+                if (++slot == NSLOT2) { slot = 0; sphase ^= 1; }
+            }
         }
     } else {
-        // ===== PRODUCERS (both CTAs): rows [rank*n_half, (rank+1)*n_half) of every tile, one row per thread =====
+        // ===== PRODUCERS (both CTAs): one row per thread, rows [rank*N_t/2, (rank+1)*N_t/2) of every tile =====
+        // lane = g + 8q: g = channel group (conflict-free 128-byte LDS phases), q = one of the warp's 4 rows;
+        // rows {x, x+4, x+8, x+12} per warp keep the 8-byte swizzled stores conflict-free.
         const int pw = warp - 5;
         const int g = lane & 7, q = lane >> 3;
         const int r = 16 * (pw >> 2) + (pw & 3) + 4 * q;      // local row 0..63
+        const uint32_t t0addr = smem_u32(sT0) + 16 * g;
+        // element (row r, k) at (r/8)*1024 + (r%8)*128 + ((k/8) ^ (r%8))*16 + (k%8)*2;  k = 4g  and  k = 32 + 4g
+        const uint32_t o0 = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((g >> 1)) ^ (r & 7)) << 4) + ((g & 1) << 3));
+        const uint32_t st0 = smem_u32(ring) + o0, st1 = smem_u32(ring) + (o0 ^ 64u);
         int slot = 0;
         uint32_t phase = 0;
+        int b = b_lo, tn = 0;
+        uint32_t an[5] = {0u, 0u, 0u, 0u, 0u};               // residues of MY row's 5 taps, one tile ahead
+        auto row_pos = [&](int tt) {
+            const int nt = (tt == tpc - 1) ? n_last : NT2;
+            return tt * NT2 + (int)rank * (nt >> 1) + r;
+        };
+        auto load_aa = [&](int bb, int tt) {
+            const int pos = min(row_pos(tt), P - 1);          // rows past the end replicate the last position
+            const uint8_t* ap = prm.aa + (size_t)bb * prm.aa_stride + pos;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) an[t] = ap[t];
+        };
+        if (ntiles > 0) load_aa(b, 0);
+        int emit_ctr = 0;                                     // the MP clusters sharing a chain block take turns with the mask
         for (int it = 0; it < ntiles; ++it) {
-            const int b = b_lo + it / prm.tiles_per_chain;
-            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
-            const int p0 = tn * prm.n_tile + (int)rank * n_half;           // first position of MY half
-            const int valid = min(n_half, P - p0);                         // may be <= 0
-            const bool ok = r < valid;
-            const uint8_t* a = prm.aa + (size_t)b * prm.aa_stride + p0;
-            const float* trow[5];
+            const int nt = (tn == tpc - 1) ? n_last : NT2;
+            const bool active = r < (nt >> 1);
+            const int pos = row_pos(tn);
+            uint32_t ra[5];
 #pragma unroll
-            for (int t = 0; t < 5; ++t) trow[t] = sT0 + (ok ? (t * PPDE_Q + a[r + t]) * KS : 0) + 4 * g;
-            const bool emit_mask = (prm.r1mask != nullptr) && (it % MP == mp);
+            for (int t = 0; t < 5; ++t) ra[t] = t0addr + (uint32_t)((t * PPDE_Q + (int)an[t]) * (KS * 4));
+            const int bcur = b;
+            if (++tn == tpc) { tn = 0; ++b; }
+            if (it + 1 < ntiles) load_aa(b, tn);              // in flight during this tile's chunks
+            const bool emit_mask = (prm.r1mask != nullptr) && (emit_ctr == mp);
+            if (++emit_ctr == MP) emit_ctr = 0;
             uint32_t mbits = 0u;
-            for (int kc = 0; kc < prm.nch; ++kc) {
+#pragma unroll
+            for (int kc = 0; kc < NCH; ++kc) {
                 mbar_wait(&empty[slot], phase ^ 1);
-                unsigned char* mat_hi = ring + slot * SLOT2_BYTES;
-                unsigned char* mat_lo = mat_hi + MAT2_BYTES;
-                const int cb = kc * KCH;
-                if (ok) {
-                    float4 z0 = *reinterpret_cast<const float4*>(trow[0] + cb);
-                    float4 z1 = *reinterpret_cast<const float4*>(trow[0] + cb + 32);
-                    float2 a0 = make_float2(z0.x, z0.y), a1 = make_float2(z0.z, z0.w);
-                    float2 a2 = make_float2(z1.x, z1.y), a3 = make_float2(z1.z, z1.w);
-#pragma unroll
-                    for (int t = 1; t < 5; ++t) {
-                        const float4 u0 = *reinterpret_cast<const float4*>(trow[t] + cb);
-                        const float4 u1 = *reinterpret_cast<const float4*>(trow[t] + cb + 32);
-                        a0 = add2(a0, make_float2(u0.x, u0.y)); a1 = add2(a1, make_float2(u0.z, u0.w));
-                        a2 = add2(a2, make_float2(u1.x, u1.y)); a3 = add2(a3, make_float2(u1.z, u1.w));
-                    }
-                    if (emit_mask) {
-                        const float v[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-                        uint32_t nib = 0u;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) nib |= (__float_as_int(v[e]) > 0 ? 1u : 0u) << e;
-                        mbits |= nib << (8 * kc);
-                    }
-                    float2 x[4] = {a0, a1, a2, a3};
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        x[e].x = fmaxf(x[e].x, 0.f); x[e].y = fmaxf(x[e].y, 0.f);
-                        const float2 h = make_float2(h_trunc(x[e].x), h_trunc(x[e].y));
-                        const float2 l = add2(x[e], make_float2(-h.x, -h.y));
-                        hi[e] = pack_h2(h.x, h.y);
-                        lo[e] = pack_h2(l.x, l.y);
-                    }
-                    const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
-                    const int o0 = rbase + (((g >> 1) ^ (r & 7)) << 4) + ((g & 1) << 3);
-                    const int o1 = rbase + ((((g >> 1) + 4) ^ (r & 7)) << 4) + ((g & 1) << 3);
-                    *reinterpret_cast<uint2*>(mat_hi + o0) = make_uint2(hi[0], hi[1]);
-                    *reinterpret_cast<uint2*>(mat_hi + o1) = make_uint2(hi[2], hi[3]);
-                    *reinterpret_cast<uint2*>(mat_lo + o0) = make_uint2(lo[0], lo[1]);
-                    *reinterpret_cast<uint2*>(mat_lo + o1) = make_uint2(lo[2], lo[3]);
+                if (active) {
+                    const uint32_t so = (uint32_t)(slot * SLOT2_BYTES);
+                    if (kc == 0) produce_chunk<0>(ra, st0 + so, st1 + so, emit_mask, mbits);
+                    if (kc == 1) produce_chunk<1>(ra, st0 + so, st1 + so, emit_mask, mbits);
+                    if (kc == 2) produce_chunk<2>(ra, st0 + so, st1 + so, emit_mask, mbits);
+                    if (kc == 3) produce_chunk<3>(ra, st0 + so, st1 + so, emit_mask, mbits);
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&full[slot], 0);
+                if (lane == 0) mbar_arrive(&fullL[slot]);
                 if (++slot == NSLOT2) { slot = 0; phase ^= 1; }
             }
             if (emit_mask) {
+                // word w of a row's 256 mask bits = channels 32w..32w+31 = nibble w of the row's 8 lanes:
+                // 8x8 nibble transpose across those lanes (3 butterfly stages), then one coalesced 32-byte store per row
                 uint32_t word = mbits;
                 uint32_t o = __shfl_xor_sync(0xffffffffu, word, 4);
                 word = (g & 4) ? ((word & 0xFFFF0000u) | ((o >> 16) & 0x0000FFFFu)) : ((word & 0x0000FFFFu) | ((o << 16) & 0xFFFF0000u));
@@ -670,7 +778,8 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
                 word = (g & 2) ? ((word & 0xFF00FF00u) | ((o >> 8) & 0x00FF00FFu)) : ((word & 0x00FF00FFu) | ((o << 8) & 0xFF00FF00u));
                 o = __shfl_xor_sync(0xffffffffu, word, 1);
                 word = (g & 1) ? ((word & 0xF0F0F0F0u) | ((o >> 4) & 0x0F0F0F0Fu)) : ((word & 0x0F0F0F0Fu) | ((o << 4) & 0xF0F0F0F0u));
-                if (ok) reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)b * prm.m.n_nets + k) * P + p0 + r) * 32)[g] = word;
+                if (active && pos < P)
+                    reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)bcur * prm.m.n_nets + k) * P + pos) * 32)[g] = word;
             }
         }
     }
@@ -1127,17 +1236,6 @@ static int choose_n_tile(int P, int* tiles) {
     return best_n;
 }
 
-// positions-per-tile for the 2-CTA kernel: multiple of 32 (N of a cta_group::2 MMA), split in two halves
-static int choose_n_tile2(int P, int* tiles) {
-    int best_n = 128, best_cost = 1 << 30;
-    for (int nt = 128; nt >= 64; nt -= 32) {
-        const int t = (P + nt - 1) / nt;
-        const int cost = t * nt + 8 * t;
-        if (cost < best_cost) { best_cost = cost; best_n = nt; *tiles = t; }
-    }
-    return best_n;
-}
-
 static int g_forward_variant = -1;         // -1: read PPDE_TC_CTAS once (default 2); 1 or 2
 extern "C" int ppde_set_forward_variant(int ctas) { g_forward_variant = (ctas == 1) ? 1 : 2; return 0; }
 
@@ -1164,7 +1262,8 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     const int MT = (2 * m->C + 127) / 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (g_forward_variant == 2) {
-        prm.n_tile = choose_n_tile2(m->P, &prm.tiles_per_chain);
+        prm.n_tile = tc::NT2;
+        prm.tiles_per_chain = (m->P + tc::NT2 - 1) / tc::NT2;
         prm.MT = (MT + 1) / 2;                                             // channel-tile pairs
         const int combos = m->n_nets * prm.MT;
         prm.ctas_per_combo = (sms / 2) / combos;                           // cluster pairs per combo
@@ -1172,13 +1271,20 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
         if (prm.ctas_per_combo > n) prm.ctas_per_combo = n;
         const size_t smem = (size_t)tc::NSLOT2 * tc::SLOT2_BYTES + (size_t)100 * prm.nch * tc::KCH * sizeof(float) +
                             32 * sizeof(uint64_t) + 1024;
-        static size_t configured2 = 0;
-        if (smem > configured2) {
-            cudaError_t e = cudaFuncSetAttribute(tc::cnn_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            configured2 = smem;
+        void (*kern)(tc::Params) = nullptr;
+        switch (prm.nch) {
+            case 1: kern = tc::cnn_forward_tc2_kernel<1>; break;
+            case 2: kern = tc::cnn_forward_tc2_kernel<2>; break;
+            case 3: kern = tc::cnn_forward_tc2_kernel<3>; break;
+            default: kern = tc::cnn_forward_tc2_kernel<4>; break;
         }
-        tc::cnn_forward_tc2_kernel<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, st>>>(prm);
+        static size_t configured2[5] = {0, 0, 0, 0, 0};
+        if (smem > configured2[prm.nch]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            configured2[prm.nch] = smem;
+        }
+        kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, st>>>(prm);
         return launch_done();
     }
     prm.n_tile = choose_n_tile(m->P, &prm.tiles_per_chain);
