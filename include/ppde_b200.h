@@ -144,6 +144,9 @@ int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_strid
                         unsigned long long* mkey /* [n, n_nets, 2C] */, uint8_t* r1mask, void* stream);
 /* 1 = one CTA per channel tile, 2 = CTA pairs with cta_group::2 MMAs (default; also PPDE_TC_CTAS=1|2 in the environment) */
 int ppde_set_forward_variant(int ctas);
+/* profiling aid: non-NULL device buffer [grid][16] int64 selects an instrumented build of the 2-CTA forward kernel that
+ * accumulates per-role cycle counters (tools/prof_fwd.py); NULL (default) = production kernel. */
+int ppde_set_forward_profile(long long* buf);
 int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                               int32_t n, const unsigned long long* mkey, float lamda,
                               const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,

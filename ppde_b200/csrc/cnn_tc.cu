@@ -138,6 +138,7 @@ struct Params {
     int MT;               // channel tiles of 128
     int nch;              // K chunks of 64
     int kpad;             // K rounded up to 16
+    long long* prof;      // optional [grid][16] cycle counters (PPDE_TC_PROFILE=1 builds of the 2-CTA kernel only)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) cnn_forward_tc_kernel(const __grid_constant__ Params prm) {
@@ -416,6 +417,13 @@ constexpr int NSLOT2 = 6;
 constexpr int MAT2_BYTES = 64 * KCH * 2;          // one [64 x 64] fp16 operand half-matrix (8 KB)
 constexpr int SLOT2_BYTES = 2 * MAT2_BYTES;       // hi + lo
 constexpr int NT2 = 128;                          // positions per full tile
+constexpr int WARP_MMA2 = 20;                     // MMA issuer = highest warp id of its scheduler (top arbitration priority)
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0;
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -525,7 +533,7 @@ __device__ __forceinline__ void produce_chunk(const uint32_t (&ra)[5], uint32_t 
     sts64<MAT2_BYTES>(sa1, lo[2], lo[3]);
 }
 
-template <int NCH>
+template <int NCH, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -571,7 +579,7 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
         for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], 2 * (NT_EPI / 32)); }
         fence_barrier_init();
     }
-    if (warp == WARP_MMA) {
+    if (warp == WARP_MMA2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -616,6 +624,8 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
         float best = -3.0e38f;
         int bp = 0;
         int b = b_lo, tn = 0;
+        long long pc[3] = {0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
         for (int it = 0; it < ntiles; ++it) {
             const int buf = it & 1;
             const int p0 = tn * NT2;
@@ -623,6 +633,7 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
             if (tn == 0) { best = -3.0e38f; bp = 0; }
             int bl = bp - p0;                                  // arg-max relative to this tile (immediates below)
             mbar_wait(&dfull[buf], (uint32_t)((it >> 1) & 1));
+            if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
             tc_fence_after();
             const uint32_t ta = lane_addr + buf * 128;
 #pragma unroll
@@ -649,9 +660,11 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
             }
             tc_fence_before();
             __syncwarp();
+            if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
             if (lane == 0) {
                 if (rank == 0) mbar_arrive(&dempty[buf]); else mbar_arrive_cluster(&dempty[buf], 0);
             }
+            if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
             bp = bl + p0;
             if (tn == tpc - 1) {
                 if (j < J2) {
@@ -667,57 +680,78 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
                 ++tn;
             }
         }
-    } else if (warp == WARP_MMA) {
-        if (lane == 0 && rank == 0) {
-            // ===== MMA ISSUER: one lane of the LEADER CTA =====
+        if (PROF && threadIdx.x == 0 && prm.prof) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; }
+    } else if (warp == WARP_MMA2) {
+        if (rank == 0) {
+            // ===== MMA ISSUER (leader CTA): the whole warp runs the loop warp-uniformly (descriptors live in uniform
+            // registers, no per-MMA broadcasts); one elected lane issues the MMAs and the commits =====
             const uint32_t idesc_full = make_idesc(256, NT2), idesc_last = make_idesc(256, n_last);
             const uint32_t ring_addr = smem_u32(ring);
             int slot = 0, tn = 0;
             uint32_t sphase = 0;
             const int last_ksteps = (prm.kpad - (NCH - 1) * KCH) / 16;
+            const uint32_t a_lo_off = (uint32_t)(prm.kpad / 2);
+            long long pc[4] = {0, 0, 0, 0};
+            long long tp = PROF ? clock64() : 0;
+            const long long tstart = tp;
             for (int it = 0; it < ntiles; ++it) {
                 const int buf = it & 1;
                 const uint32_t idesc = (tn == tpc - 1) ? idesc_last : idesc_full;
                 if (++tn == tpc) tn = 0;
                 if (it >= 2) mbar_wait_cluster(&dempty[buf], (uint32_t)(((it >> 1) + 1) & 1));
+                if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
 #pragma unroll 1
                 for (int kc = 0; kc < NCH; ++kc) {
                     mbar_wait(&fullL[slot], sphase);
+                    if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                     mbar_wait_cluster(&fullR[slot], sphase);
+                    if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
                     tc_fence_after();
                     const uint64_t dhi = make_b_desc(ring_addr + slot * SLOT2_BYTES);
                     const uint64_t dlo = make_b_desc(ring_addr + slot * SLOT2_BYTES + MAT2_BYTES);
                     const int ksteps = (kc == NCH - 1) ? last_ksteps : KCH / 16;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
-                        const uint32_t a_lo = a_hi + prm.kpad / 2;
-                        const uint64_t koff = (uint64_t)(ks * 2);
-                        mma_ts2(d_tmem, a_hi, dhi + koff, idesc, (kc | ks) ? 1u : 0u);
-                        mma_ts2(d_tmem, a_hi, dlo + koff, idesc, 1u);
-                        mma_ts2(d_tmem, a_lo, dhi + koff, idesc, 1u);
+                    const uint32_t a_hi0 = tmem_base + kc * (KCH / 2);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < KCH / 16; ++ks) {
+                            if (ks < ksteps) {
+                                const uint32_t a_hi = a_hi0 + ks * 8;
+                                mma_ts2(d_tmem, a_hi, dhi + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                                mma_ts2(d_tmem, a_hi, dlo + (uint64_t)(ks * 2), idesc, 1u);
+                                mma_ts2(d_tmem, a_hi + a_lo_off, dhi + (uint64_t)(ks * 2), idesc, 1u);
+                            }
+                        }
+                        tc_commit2(&empty[slot]);
+                        if (kc == NCH - 1) tc_commit2(&dfull[buf]);
                     }
-                    tc_commit2(&empty[slot]);
+                    __syncwarp();
+                    if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
                     if (++slot == NSLOT2) { slot = 0; sphase ^= 1; }
                 }
-                tc_commit2(&dfull[buf]);
             }
+            if (PROF && prm.prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[3] = pc[0]; o[4] = pc[1]; o[5] = pc[2]; o[6] = pc[3]; o[7] = clock64() - tstart; }
         } else if (lane == 0) {
             // ===== FORWARDER (rank 1): one remote arrive per chunk instead of one per producer warp =====
             int slot = 0;
             uint32_t sphase = 0;
+            long long pc[2] = {0, 0};
+            long long tp = PROF ? clock64() : 0;
             for (int c = 0; c < ntiles * NCH; ++c) {
                 mbar_wait(&fullL[slot], sphase);
+                if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                 mbar_arrive_cluster(&fullR[slot], 0);
+                if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                 if (++slot == NSLOT2) { slot = 0; sphase ^= 1; }
             }
+            if (PROF && prm.prof) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[3] = pc[0]; o[4] = pc[1]; }
         }
     } else {
         // ===== PRODUCERS (both CTAs): one row per thread, rows [rank*N_t/2, (rank+1)*N_t/2) of every tile =====
         // lane = g + 8q: g = channel group (conflict-free 128-byte LDS phases), q = one of the warp's 4 rows;
         // rows {x, x+4, x+8, x+12} per warp keep the 8-byte swizzled stores conflict-free.
-        const int pw = warp - 5;
+        const int pw = warp - 4;                               // producers are warps 4..19
         const int g = lane & 7, q = lane >> 3;
         const int r = 16 * (pw >> 2) + (pw & 3) + 4 * q;      // local row 0..63
         const uint32_t t0addr = smem_u32(sT0) + 16 * g;
@@ -740,6 +774,8 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
         };
         if (ntiles > 0) load_aa(b, 0);
         int emit_ctr = 0;                                     // the MP clusters sharing a chain block take turns with the mask
+        long long pc[3] = {0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
         for (int it = 0; it < ntiles; ++it) {
             const int nt = (tn == tpc - 1) ? n_last : NT2;
             const bool active = r < (nt >> 1);
@@ -756,6 +792,7 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
 #pragma unroll
             for (int kc = 0; kc < NCH; ++kc) {
                 mbar_wait(&empty[slot], phase ^ 1);
+                if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                 if (active) {
                     const uint32_t so = (uint32_t)(slot * SLOT2_BYTES);
                     if (kc == 0) produce_chunk<0>(ra, st0 + so, st1 + so, emit_mask, mbits);
@@ -763,9 +800,11 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
                     if (kc == 2) produce_chunk<2>(ra, st0 + so, st1 + so, emit_mask, mbits);
                     if (kc == 3) produce_chunk<3>(ra, st0 + so, st1 + so, emit_mask, mbits);
                 }
+                if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&fullL[slot]);
+                if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
                 if (++slot == NSLOT2) { slot = 0; phase ^= 1; }
             }
             if (emit_mask) {
@@ -782,12 +821,15 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
                     reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)bcur * prm.m.n_nets + k) * P + pos) * 32)[g] = word;
             }
         }
+        if (PROF && prm.prof && lane == 0 && (pw == 0 || pw == 15)) {
+            long long* o = prm.prof + (size_t)blockIdx.x * 16 + (pw == 0 ? 8 : 11); o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2];
+        }
     }
 
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                    // the peer may still be reading my smem / signalling my barriers
-    if (warp == WARP_MMA) {
+    if (warp == WARP_MMA2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
@@ -1237,6 +1279,8 @@ static int choose_n_tile(int P, int* tiles) {
 }
 
 static int g_forward_variant = -1;         // -1: read PPDE_TC_CTAS once (default 2); 1 or 2
+static long long* g_forward_prof = nullptr;  // device buffer [grid][16]; non-null selects the instrumented build of the kernel
+extern "C" int ppde_set_forward_profile(long long* buf) { g_forward_prof = buf; return 0; }
 extern "C" int ppde_set_forward_variant(int ctas) { g_forward_variant = (ctas == 1) ? 1 : 2; return 0; }
 
 extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
@@ -1254,6 +1298,7 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     prm.n = n;
     prm.mkey = mkey;
     prm.r1mask = r1mask;
+    prm.prof = nullptr;
     prm.kpad = (m->C + 15) / 16 * 16;
     prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
     int dev = 0, sms = 148;
@@ -1273,16 +1318,19 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
                             32 * sizeof(uint64_t) + 1024;
         void (*kern)(tc::Params) = nullptr;
         switch (prm.nch) {
-            case 1: kern = tc::cnn_forward_tc2_kernel<1>; break;
-            case 2: kern = tc::cnn_forward_tc2_kernel<2>; break;
-            case 3: kern = tc::cnn_forward_tc2_kernel<3>; break;
-            default: kern = tc::cnn_forward_tc2_kernel<4>; break;
+            case 1: kern = tc::cnn_forward_tc2_kernel<1, false>; break;
+            case 2: kern = tc::cnn_forward_tc2_kernel<2, false>; break;
+            case 3: kern = tc::cnn_forward_tc2_kernel<3, false>; break;
+            default: kern = tc::cnn_forward_tc2_kernel<4, false>; break;
         }
+        prm.prof = g_forward_prof;
+        if (g_forward_prof && prm.nch == 4) kern = tc::cnn_forward_tc2_kernel<4, true>;   // role-level cycle counters (tools/prof_fwd.py)
         static size_t configured2[5] = {0, 0, 0, 0, 0};
-        if (smem > configured2[prm.nch]) {
+        const int cfg = (g_forward_prof && prm.nch == 4) ? 0 : prm.nch;
+        if (smem > configured2[cfg]) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            configured2[prm.nch] = smem;
+            configured2[cfg] = smem;
         }
         kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, st>>>(prm);
         return launch_done();
