@@ -907,13 +907,18 @@ __global__ void __launch_bounds__(128) cnn_winner_sort_kernel(int n_nets, int C,
     for (int i = threadIdx.x; i <= P; i += 128) out[i] = (uint16_t)sStart[i];
 }
 
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 constexpr int BW_NT = 64;               // positions per tile (N of the MMA)
-constexpr int BW_NT_PROD = 512;         // 16 producer warps = 8 gather sets of 64 threads
-constexpr int BW_NTHREADS = NT_EPI + 32 + BW_NT_PROD;   // 672
+constexpr int BW_NT_PROD = 512;         // 16 producer warps, 4 tile rows each
+constexpr int BW_NTHREADS = NT_EPI + BW_NT_PROD + 32;   // 672: warps 0-3 epilogue, 4-19 producers, 20 MMA issuer
+constexpr int BW_WARP_MMA = 20;         // highest warp id of its scheduler: top arbitration priority
 constexpr int BW_MAT = BW_NT * KCH * 2; // one [64 x 64] fp16 operand matrix (8 KB)
 constexpr int BW_SLOT = 2 * BW_MAT;     // hi + lo
 constexpr int BW_MAXCH = 4;             // K chunks per tile (kpad <= 256)
-constexpr int YS = 65;                  // sY row stride (floats): 64 columns + 1 (conflict-free column writes)
+constexpr int BW_NDBUF = 4;             // accumulator buffers of 64 TMEM columns
 
 struct BwdParams {
     ppde_cnn_t m;
@@ -927,76 +932,101 @@ struct BwdParams {
     float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
     int ctas_per_net;
     int tiles_per_chain, nch, kpad;
-    int dbg;                            // profiling experiments only (PPDE_BWD_DEBUG): 1 = skip col2im, 2 = skip gathers
+    int dbg;                            // profiling experiments only (PPDE_BWD_DEBUG): 2 = skip gathers
+    long long* prof;                    // optional [grid][16] cycle counters (instrumented build)
 };
 
-__device__ __forceinline__ void named_bar(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
 
-// Producers (16 warps = 8 sets of 64 threads), per tile of 64 positions:
-//   set s owns rows [8s, 8s+8) of the tile, whose winners are one contiguous run of the (position, channel)-sorted
-//   list; thread tl of a set owns channels 4tl..4tl+3 of the whole K extent.  It streams its 16-byte piece of each
-//   winner's W1 row from L2 (two register batches of 4 loads, the next batch in flight while one is consumed, all
-//   lanes useful), accumulates d_j * W1[j, :] in registers in ascending channel order (deterministic), and when a row
-//   is complete applies the relu mask (bits from the forward), the power-of-two scale and the fp16 hi/lo split and
-//   stores its 8 bytes straight into the K-major SW128 operand slot of its K chunk.  No fp32 staging, one fence and
-//   one arrive per slot and warp.  The ring holds two tiles (2 x nch slots); winner lists and mask words of the next
-//   chain / tile are prefetched into the other half of double buffers.
+// Backward of one net for a contiguous block of chains, persistent CTA.
+//
+//   GEMM  Y[m(a,t), p] = sum_c W0[c,a,t] * A[p,c]      M = 128 rows (100 used), N = 64 positions per tile, K = C
+//   A[p,c] = 1[r1[p,c] > 0] * sum_{j in winners(p)} d_j W1[j,c]       (adjoint of the conv output)
+//
+// * A-operand (W0^T, fp16 hi/lo) is resident in tensor memory.  Row order m(a,t) = 32*(a/6) + 5*(a%6) + t puts the 5
+//   taps of a residue in 5 adjacent lanes of one warp, so the col2im below is a warp-shuffle reduction in registers.
+// * Producers: warp w owns rows 4w..4w+3 of every tile, lane l owns channels 8l..8l+7.  The winners of those rows are
+//   one contiguous run of the chain's (position, channel)-sorted list (staged in shared memory by a bulk copy one chain
+//   ahead); a warp streams their W1 rows from L2 in groups of 4 (8 x 16-byte loads in flight per lane), accumulates
+//   d_j * W1[j,:] in registers in list order (deterministic), and on every row boundary applies the relu mask (bits
+//   from the forward), the power-of-two scale and the fp16 hi/lo split and writes 16 + 16 bytes straight into the
+//   K-major SW128 operand ring.  All control flow is warp-uniform.
+// * Epilogue: tcgen05.ld (lane = (a,t) row, 64 columns), then  G[p0+i, a] = sum_t Y[m(a,t), i-t]  by 64 shuffles: lane
+//   d of a residue's 5-lane group accumulates the outputs i = d (mod 5); 4 partial outputs carry into the next tile.
+//   Results go to a shared [20L] row and are flushed per chain with coalesced 16-byte stores.
+template <bool PROF>
 __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
-    const int nslot = 2 * prm.nch;
+    const int nch = prm.nch;
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* sGc = reinterpret_cast<float*>(ring + 2 * BW_MAXCH * BW_SLOT);   // [NE] chain accumulator
-    float* sY = sGc + NE;                                              // [100][YS]
-    float* sDj = sY + 100 * YS;                                        // [J2] decoder weights
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sDj + J2);           // [2][BW_NT][8] relu mask words (double-buffered)
-    // [2] x winner record { start[P+1] | list[J2] | row[J2] } as uint16, `rec` entries each (16-byte multiple)
-    uint16_t* sLists = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sMask + 2 * BW_NT * 8) + 15) & ~(uintptr_t)15);
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sLists + 2 * prm.rec) + 7) & ~(uintptr_t)7);
-    uint64_t* full = bars;                      // [2*BW_MAXCH]
-    uint64_t* empty = bars + 2 * BW_MAXCH;      // [2*BW_MAXCH]
-    uint64_t* dfull = empty + 2 * BW_MAXCH;     // [2]
-    uint64_t* dempty = dfull + 2;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+    float* sGc = reinterpret_cast<float*>(ring + 2 * BW_MAXCH * BW_SLOT);   // [NE] chain gradient row
+    float* sDj = sGc + ((NE + 3) & ~3);                                      // [J2] decoder weights
+    uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sDj + J2) + 15) & ~(uintptr_t)15);   // [2][rec]
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRec + 2 * prm.rec) + 7) & ~(uintptr_t)7);
+    uint64_t* full = bars;                      // [2] tile buffers: producers -> MMA (16 warp arrivals)
+    uint64_t* empty = full + 2;                 // [2] MMA -> producers
+    uint64_t* dfull = empty + 2;                // [BW_NDBUF] MMA -> epilogue
+    uint64_t* dempty = dfull + BW_NDBUF;        // [BW_NDBUF] epilogue -> MMA (4 warp arrivals)
+    uint64_t* recfull = dempty + BW_NDBUF;      // [2] winner record landed (bulk copy, tx bytes)
+    uint64_t* recempty = recfull + 2;           // [2] producers done with the record (16 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recempty + 2);
 
     const int k = blockIdx.x / prm.ctas_per_net;                       // this CTA's net
     const int within = blockIdx.x - k * prm.ctas_per_net;
     if (k >= prm.m.n_nets) return;
     const int b_lo = (int)((int64_t)prm.n * within / prm.ctas_per_net);
     const int b_hi = (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_net);
-    const int ntiles = (b_hi - b_lo) * prm.tiles_per_chain;
+    const int tpc = prm.tiles_per_chain;
+    const int nchains = b_hi - b_lo;
+    const int ntiles = nchains * tpc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ppde_cnn_net_t net = prm.m.net[k];
+    const uint32_t rec_bytes = (uint32_t)prm.rec * 2u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nslot; ++s) { mbar_init(&full[s], BW_NT_PROD / 32); mbar_init(&empty[s], 1); }
-        for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full[s], BW_NT_PROD / 32); mbar_init(&empty[s], 1);
+            mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BW_NT_PROD / 32);
+        }
+        for (int d = 0; d < BW_NDBUF; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI / 32); }
         fence_barrier_init();
     }
-    if (warp == WARP_MMA) {
+    if (warp == BW_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int e = threadIdx.x; e < NE; e += BW_NTHREADS) sGc[e] = 0.f;
     for (int j = threadIdx.x; j < J2; j += BW_NTHREADS) sDj[j] = net.d[j];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {   // A = W0^T (scaled, fp16 hi/lo) -> TMEM: lane = (t,a) row
-        const int nrow = warp * 32 + lane;
+    if (warp < 4) {   // A = W0^T (scaled, fp16 hi/lo) -> TMEM: lane m(a,t) = 32*(a/6) + 5*(a%6) + t
+        const int grp = lane / 5, t = lane - 5 * grp, a = 6 * warp + grp;
+        const bool rowok = lane < 30 && a < PPDE_Q;
+        const int nrow = t * PPDE_Q + a;                                // W0r[c][t][a]
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         for (int ks = 0; ks < prm.kpad / 16; ++ks) {
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int c0 = ks * 16 + 2 * q;
-                const float w0 = (nrow < 100 && c0 < C) ? net.W0r[(size_t)c0 * 100 + nrow] * net.w0_scale : 0.f;
-                const float w1 = (nrow < 100 && c0 + 1 < C) ? net.W0r[(size_t)(c0 + 1) * 100 + nrow] * net.w0_scale : 0.f;
+                const float w0 = (rowok && c0 < C) ? net.W0r[(size_t)c0 * 100 + nrow] * net.w0_scale : 0.f;
+                const float w1 = (rowok && c0 + 1 < C) ? net.W0r[(size_t)(c0 + 1) * 100 + nrow] * net.w0_scale : 0.f;
                 const float h0 = h_round(w0), h1 = h_round(w1);
                 hi[q] = pack_h2(h0, h1);
                 lo[q] = pack_h2(w0 - h0, w1 - h1);
@@ -1011,231 +1041,241 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
     tc_fence_after();
 
     if (warp < 4) {
-        // ===== EPILOGUE: thread = output row (t,a); deterministic col2im into the chain accumulator =====
-        const int nrow = warp * 32 + lane;
+        // ===== EPILOGUE: lane = (a, t); col2im by shuffles inside the residue's 5-lane group =====
+        const int grp = lane / 5, d = lane - 5 * grp, a = 6 * warp + grp;
+        const bool rowok = lane < 30 && a < PPDE_Q;
+        const int gbase = 5 * grp;
         const int tid = threadIdx.x;
         const float unscale = 1.f / (net.w0_scale * net.adj_scale);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+        int srcv[5];                      // source lane of column c = 5u+v: tap t' = (d - v) mod 5 of my group
+#pragma unroll
+        for (int v = 0; v < 5; ++v) srcv[v] = min(gbase + (d - v + 5) % 5, 31);
+        float carry = 0.f;                // partial output i = d (< 4) of the NEXT tile (from this tile's columns 60..63)
+        long long pc[4] = {0, 0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
+        int b = b_lo, tn = 0;
         for (int it = 0; it < ntiles; ++it) {
-            const int buf = it & 1;
-            const int b = b_lo + it / prm.tiles_per_chain;
-            const int tn = it - (it / prm.tiles_per_chain) * prm.tiles_per_chain;
+            const int buf = it & (BW_NDBUF - 1);
             const int p0 = tn * BW_NT;
-            const int valid = min(BW_NT, P - p0);
-            mbar_wait(&dfull[buf], (uint32_t)((it >> 1) & 1));
+            mbar_wait(&dfull[buf], (uint32_t)((it / BW_NDBUF) & 1));
+            if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
             tc_fence_after();
-            {
-                // the whole 64-column accumulator in one go: two TMEM loads in flight, one wait, one hand-back
-                uint32_t r0[32], r1[32];
-                tmem_ld32(lane_addr + buf * 128, r0);
-                if (valid > 32) tmem_ld32(lane_addr + buf * 128 + 32, r1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                mbar_arrive(&dempty[buf]);
-                if (nrow < 100) {
+            uint32_t y[64];
+            tmem_ld32(lane_addr + buf * BW_NT, y);
+            tmem_ld32(lane_addr + buf * BW_NT + 32, y + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dempty[buf]);
+            if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+            // acc[s] = output i = 5 s + d of this tile (relative position), contributions in order of increasing column
+            float acc[14];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) sY[nrow * YS + i] = __uint_as_float(r0[i]) * unscale;
-                    if (valid > 32) {
+            for (int s = 0; s < 14; ++s) acc[s] = 0.f;
+            acc[0] = (tn == 0) ? 0.f : carry;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) sY[nrow * YS + 32 + i] = __uint_as_float(r1[i]) * unscale;
-                    }
-                }
-                named_bar(2, NT_EPI);
-                // col2im, fixed summation order: output (i,a) = sum_t Y[(t,a), i - t]
-                for (int o = tid; o < ((prm.dbg & 1) ? 0 : (valid + 4) * PPDE_Q); o += NT_EPI) {
-                    const int di = o / PPDE_Q, a = o - di * PPDE_Q;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) {
-                        const int pp = di - t;
-                        if (pp >= 0 && pp < valid) acc += sY[(t * PPDE_Q + a) * YS + pp];
-                    }
-                    const int i = p0 + di;
-                    if (i < L) sGc[i * PPDE_Q + a] += acc;
-                }
-                named_bar(2, NT_EPI);
+            for (int c = 0; c < 64; ++c) {
+                const int u = c / 5, v = c - 5 * u;
+                const float x = __shfl_sync(0xffffffffu, __uint_as_float(y[c]), srcv[v]);
+                if (d >= v) acc[u] += x; else acc[u + 1] += x;
             }
-            if (tn == prm.tiles_per_chain - 1) {
-                // flush the chain's partial gradient (streaming float4 stores) and clear the accumulator
-                float4* dst = reinterpret_cast<float4*>(prm.Gc + ((size_t)k * prm.n + b) * NE);
-                float4* src = reinterpret_cast<float4*>(sGc);
-                for (int e = tid; e < NE / 4; e += NT_EPI) {
-                    __stcs(dst + e, src[e]);
-                    src[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // outputs i < 64 are complete; i = 64..67 (lanes d = 4 slot 12; d = 0,1,2 slot 13) carry into the next tile,
+            // where output i - 64 lives in lane d' = i - 64:  d' = 0 <- (lane 4, slot 12),  d' = 1,2,3 <- (lane d'-1, slot 13)
+            {
+                const float c12 = __shfl_sync(0xffffffffu, acc[12], min(gbase + 4, 31));
+                const float c13 = __shfl_sync(0xffffffffu, acc[13], max(gbase + d - 1, 0));
+                carry = (d == 0) ? c12 : ((d < 4) ? c13 : 0.f);
+            }
+            if (rowok) {
+#pragma unroll
+                for (int s = 0; s < 13; ++s) {
+                    const int i = 5 * s + d;
+                    if (i < 64 && p0 + i < L) sGc[(p0 + i) * PPDE_Q + a] = acc[s] * unscale;
                 }
+                if (tn == tpc - 1 && d < 4 && p0 + 64 + d < L) sGc[(p0 + 64 + d) * PPDE_Q + a] = carry * unscale;
+            }
+            if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+            if (tn == tpc - 1) {
+                // flush the chain's partial gradient (streaming 16-byte stores)
                 named_bar(2, NT_EPI);
+                float4* dst = reinterpret_cast<float4*>(prm.Gc + ((size_t)k * prm.n + b) * NE);
+                const float4* src = reinterpret_cast<const float4*>(sGc);
+                for (int e = tid; e < NE / 4; e += NT_EPI) __stcs(dst + e, src[e]);
+                named_bar(2, NT_EPI);
+                if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
+                tn = 0; ++b;
+            } else {
+                ++tn;
             }
         }
-    } else if (warp == WARP_MMA) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, BW_NT);
-            const uint32_t ring_addr = smem_u32(ring);
-            const int last_ksteps = (prm.kpad - (prm.nch - 1) * KCH) / 16;
-            for (int it = 0; it < ntiles; ++it) {
-                const int buf = it & 1;
-                const uint32_t par = (uint32_t)((it >> 1) & 1);
-                if (it >= 2) mbar_wait(&dempty[buf], par ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
-                for (int kc = 0; kc < prm.nch; ++kc) {
-                    const int slot = buf * prm.nch + kc;
-                    mbar_wait(&full[slot], par);
-                    tc_fence_after();
+        if (PROF && prm.prof && threadIdx.x == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3]; }
+    } else if (warp == BW_WARP_MMA) {
+        // ===== MMA ISSUER: warp-uniform loop, one elected lane issues; also stages the winner records (bulk copies) =====
+        const uint32_t idesc = make_idesc(128, BW_NT);
+        const uint32_t ring_addr = smem_u32(ring);
+        const int last_ksteps = (prm.kpad - (nch - 1) * KCH) / 16;
+        const uint32_t a_lo_off = (uint32_t)(prm.kpad / 2);
+        long long pc[3] = {0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
+        auto stage_record = [&](int ci) {      // chain ci of this CTA -> record buffer ci & 1
+            const int rb = ci & 1;
+            if (ci >= 2) mbar_wait(&recempty[rb], (uint32_t)(((ci >> 1) + 1) & 1));
+            if (elect_one()) {
+                mbar_expect_tx(&recfull[rb], rec_bytes);
+                bulk_g2s(sRec + (size_t)rb * prm.rec, prm.wl + ((size_t)(b_lo + ci) * prm.m.n_nets + k) * prm.rec, rec_bytes,
+                         &recfull[rb]);
+            }
+            __syncwarp();
+        };
+        if (nchains > 0) stage_record(0);
+        int tn = 0, ci = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int tb = it & 1;                                   // tile ring buffer
+            const int buf = it & (BW_NDBUF - 1);                      // accumulator buffer
+            if (tn == 0 && ci + 1 < nchains) stage_record(ci + 1);   // one chain ahead
+            if (it >= BW_NDBUF) mbar_wait(&dempty[buf], (uint32_t)(((it / BW_NDBUF) + 1) & 1));
+            if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+            mbar_wait(&full[tb], (uint32_t)((it >> 1) & 1));
+            if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + D_COL0 + buf * BW_NT;
+            if (elect_one()) {
+                for (int kc = 0; kc < nch; ++kc) {
+                    const int slot = tb * BW_MAXCH + kc;
                     const uint64_t dhi = make_b_desc(ring_addr + slot * BW_SLOT);
                     const uint64_t dlo = make_b_desc(ring_addr + slot * BW_SLOT + BW_MAT);
-                    const int ksteps = (kc == prm.nch - 1) ? last_ksteps : KCH / 16;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t a_hi = tmem_base + kc * (KCH / 2) + ks * 8;
-                        const uint32_t a_lo = a_hi + prm.kpad / 2;
-                        const uint64_t koff = (uint64_t)(ks * 2);
-                        mma_ts(d_tmem, a_hi, dhi + koff, idesc, (kc | ks) ? 1u : 0u);
-                        mma_ts(d_tmem, a_hi, dlo + koff, idesc, 1u);
-                        mma_ts(d_tmem, a_lo, dhi + koff, idesc, 1u);
+                    const int ksteps = (kc == nch - 1) ? last_ksteps : KCH / 16;
+                    const uint32_t a_hi0 = tmem_base + kc * (KCH / 2);
+#pragma unroll
+                    for (int ks = 0; ks < KCH / 16; ++ks) {
+                        if (ks < ksteps) {
+                            const uint32_t a_hi = a_hi0 + ks * 8;
+                            mma_ts(d_tmem, a_hi, dhi + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                            mma_ts(d_tmem, a_hi, dlo + (uint64_t)(ks * 2), idesc, 1u);
+                            mma_ts(d_tmem, a_hi + a_lo_off, dhi + (uint64_t)(ks * 2), idesc, 1u);
+                        }
                     }
-                    tc_commit(&empty[slot]);
                 }
+                tc_commit(&empty[tb]);
                 tc_commit(&dfull[buf]);
             }
+            __syncwarp();
+            if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+            if (++tn == tpc) { tn = 0; ++ci; }
         }
+        if (PROF && prm.prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[4] = pc[0]; o[5] = pc[1]; o[6] = pc[2]; }
     } else {
         // ===== PRODUCERS =====
-        const int ptid = threadIdx.x - (WARP_MMA + 1) * 32;           // 0..511
-        const int pw = warp - 5;                                      // 0..15
-        const int ts = pw >> 1;                                       // gather set 0..7: rows [8 ts, 8 ts + 8)
-        const int tl = (pw & 1) * 32 + lane;                          // 0..63: channels 4 tl .. 4 tl + 3
-        const bool gact = 4 * tl < prm.kpad;
+        const int pw = warp - 4;                                      // 0..15: rows 4 pw .. 4 pw + 3 of every tile
+        const int r0 = 4 * pw;
+        const bool lact = 8 * lane < prm.kpad;
         const float adj_scale = net.adj_scale;
-        const int my_kc = tl >> 4;                                    // K chunk of my channels
-        const int my_sw = (tl & 15) >> 1, my_half = (tl & 1) << 3;    // 16-byte chunk index inside the 128-byte row, 8-byte half
-        const float* wbase = net.W1p + 4 * tl;
-        // cp.async prefetches (no register staging): 16-byte pieces of a winner record, 4-byte mask words
-        auto cp16 = [](void* dst, const void* src) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-        };
-        auto cp4 = [](void* dst, const void* src) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-        };
-        auto fetch_lists = [&](int bb, int bufi) {
-            const uint16_t* recp = prm.wl + ((size_t)bb * prm.m.n_nets + k) * prm.rec;
-            for (int i = ptid; i * 8 < prm.rec; i += BW_NT_PROD) cp16(sLists + (size_t)bufi * prm.rec + i * 8, recp + i * 8);
-        };
-        auto fetch_mask = [&](int it2) {        // my word of tile it2's mask rows: (row ptid/8, word ptid%8)
-            const int ci2 = it2 / prm.tiles_per_chain;
-            const int tn2 = it2 - ci2 * prm.tiles_per_chain;
-            const int mr = ptid >> 3, mw = ptid & 7;
-            uint32_t* dst = sMask + (it2 & 1) * BW_NT * 8 + ptid;
-            if (mr < min(BW_NT, P - tn2 * BW_NT))
-                cp4(dst, reinterpret_cast<const uint32_t*>(
-                             prm.r1mask + (((size_t)(b_lo + ci2) * prm.m.n_nets + k) * P + tn2 * BW_NT + mr) * 32) + mw);
-        };
-        if (ntiles > 0) { fetch_lists(b_lo, 0); fetch_mask(0); }
-        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-        named_bar(1, BW_NT_PROD);
+        const float* wbase = net.W1p + 8 * lane;
+        // element (row r, k = 8 lane + e): chunk lane/8, 16-byte unit (lane%8) ^ (r%8) of the row's 128 bytes
+        const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BW_SLOT);
+        const uint32_t unit = (uint32_t)(lane & 7);
+        long long pc[4] = {0, 0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
+        int tn = 0, ci = 0;
         for (int it = 0; it < ntiles; ++it) {
-            const int ci = it / prm.tiles_per_chain;                  // chain index inside this CTA
+            const int tb = it & 1;
             const int b = b_lo + ci;
-            const int tn = it - ci * prm.tiles_per_chain;
             const int p0 = tn * BW_NT;
-            const int valid = min(BW_NT, P - p0);
-            const uint16_t* sStart = sLists + (size_t)(ci & 1) * prm.rec;
+            const int rb = ci & 1;
+            // relu-mask bytes of my 4 rows (independent of the winners: issue first)
+            uint32_t m4 = 0u;
+            {
+                const uint8_t* mrow = prm.r1mask + (((size_t)b * prm.m.n_nets + k) * P + p0 + r0) * 32 + lane;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+                    if (lact && p0 + r0 + rr < P) m4 |= (uint32_t)__ldg(mrow + rr * 32) << (8 * rr);
+            }
+            if (tn == 0) mbar_wait(&recfull[rb], (uint32_t)((ci >> 1) & 1));
+            const uint16_t* sStart = sRec + (size_t)rb * prm.rec;
             const uint16_t* sList = sStart + (P + 1);
-            const uint16_t* sRow = sList + J2;
-            const uint32_t* mcur = sMask + (it & 1) * BW_NT * 8;
-            // prefetch the next tile's mask words (my set's rows: ptid/8 = 8 ts + ...) and, at the first tile of a chain,
-            // the next chain's winner record, straight into the other halves of the double buffers
-            const bool has_next = it + 1 < ntiles;
-            if (has_next) fetch_mask(it + 1);
-            const bool pf_lists = (tn == 0) && (b + 1 < b_hi);
-            if (pf_lists) fetch_lists(b + 1, (ci + 1) & 1);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-
-            // the tile's ring slots must have been drained by the MMAs of tile it-2
-            const int sbase = (it & 1) * prm.nch;
-            const uint32_t par = (uint32_t)((it >> 1) & 1);
-            for (int kc = 0; kc < prm.nch; ++kc) mbar_wait(&empty[sbase + kc], par ^ 1);
-            unsigned char* mat_hi = ring + (sbase + my_kc) * BW_SLOT;
-            unsigned char* mat_lo = mat_hi + BW_MAT;
-
-            if (gact) {
-                const int r0 = 8 * ts, r1 = min(8 * ts + 8, valid);
-                const int eA = (r0 < valid) ? sStart[p0 + r0] : 0;
-                const int eB = (r0 < valid && !(prm.dbg & 2)) ? sStart[p0 + r1] : eA;
-                int next_r = r0, cur = -1;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                auto store_row = [&](int r, const float4& a4, bool zero) {
-                    uint32_t h01 = 0u, h23 = 0u, l01 = 0u, l23 = 0u;
-                    if (!zero) {
-                        const uint32_t nib = (mcur[r * 8 + (tl >> 3)] >> (4 * (tl & 7))) & 15u;
-                        const float x0 = (nib & 1u) ? a4.x * adj_scale : 0.f, x1 = (nib & 2u) ? a4.y * adj_scale : 0.f;
-                        const float x2 = (nib & 4u) ? a4.z * adj_scale : 0.f, x3 = (nib & 8u) ? a4.w * adj_scale : 0.f;
-                        const float h0 = h_round(x0), h1 = h_round(x1), h2 = h_round(x2), h3 = h_round(x3);
-                        h01 = pack_h2(h0, h1); h23 = pack_h2(h2, h3);
-                        l01 = pack_h2(x0 - h0, x1 - h1); l23 = pack_h2(x2 - h2, x3 - h3);
-                    }
-                    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((my_sw ^ (r & 7)) << 4) + my_half;
-                    *reinterpret_cast<uint2*>(mat_hi + off) = make_uint2(h01, h23);
-                    *reinterpret_cast<uint2*>(mat_lo + off) = make_uint2(l01, l23);
-                };
-                float4 wA[4], wB[4];
-                float dA[4], dB[4];
-                int rA_[4], rB_[4];
-                auto issue = [&](float4 (&w)[4], float (&dj)[4], int (&rr)[4], int e0) {
+            mbar_wait(&empty[tb], (uint32_t)(((it >> 1) + 1) & 1));
+            if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+            const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BW_SLOT);
+            int e = sStart[min(p0 + r0, P)];
+            const int eB = (prm.dbg & 2) ? e : (int)sStart[min(p0 + r0 + 4, P)];
+            int cur = 0;
+            int rend = sStart[min(p0 + r0 + 1, P)];
+            float acc[8];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        rr[v] = -1; dj[v] = 0.f; w[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e0 + v < eB) {
-                            const int jn = sList[e0 + v];
-                            rr[v] = sRow[e0 + v] - p0;
-                            dj[v] = sDj[jn];
-                            w[v] = __ldg(reinterpret_cast<const float4*>(wbase + (size_t)jn * prm.kpad));
-                        }
-                    }
-                };
-                auto consume = [&](const float4 (&w)[4], const float (&dj)[4], const int (&rr)[4]) {
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            auto store_row = [&]() {       // row r0 + cur <- mask * scale * acc, fp16 hi (truncated: exact) + lo
+                const int r = r0 + cur;
+                const uint32_t mb = (m4 >> (8 * cur)) & 0xffu;
+                uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const int r = rr[v];
-                        if (r < 0) continue;
-                        if (r != cur) {
-                            if (cur >= 0) { store_row(cur, acc, false); next_r = cur + 1; }
-                            for (; next_r < r; ++next_r) store_row(next_r, acc, true);
-                            cur = r;
-                            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) {
+                    const float s0 = (mb >> (2 * q)) & 1u ? adj_scale : 0.f, s1 = (mb >> (2 * q + 1)) & 1u ? adj_scale : 0.f;
+                    const float2 x = make_float2(acc[2 * q] * s0, acc[2 * q + 1] * s1);
+                    const float2 h = make_float2(h_trunc(x.x), h_trunc(x.y));
+                    const float2 l = sub2(x, h);
+                    hi[q] = pack_h2(h.x, h.y);
+                    lo[q] = pack_h2(l.x, l.y);
+                }
+                const uint32_t addr = tile_addr + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((unit ^ (uint32_t)(r & 7)) << 4);
+                if (lact) {
+                    sts128(addr, hi[0], hi[1], hi[2], hi[3]);
+                    sts128(addr + BW_MAT, lo[0], lo[1], lo[2], lo[3]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                ++cur;
+                rend = sStart[min(p0 + r0 + cur + 1, P)];
+            };
+            for (; e < eB; e += 4) {
+                float4 w[4][2];
+                float dj[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    dj[v] = 0.f;
+                    w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e + v < eB) {
+                        const int jn = sList[e + v];
+                        dj[v] = sDj[jn];
+                        if (lact) {
+                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn * prm.kpad);
+                            w[v][0] = __ldg(src);
+                            w[v][1] = __ldg(src + 1);
                         }
-                        const float d = dj[v];
-                        acc.x = fmaf(d, w[v].x, acc.x); acc.y = fmaf(d, w[v].y, acc.y);
-                        acc.z = fmaf(d, w[v].z, acc.z); acc.w = fmaf(d, w[v].w, acc.w);
-                    }
-                };
-                if (eA < eB) issue(wA, dA, rA_, eA);
-                for (int eb = eA; eb < eB; eb += 8) {
-                    if (eb + 4 < eB) issue(wB, dB, rB_, eb + 4);
-                    consume(wA, dA, rA_);
-                    if (eb + 4 < eB) {
-                        if (eb + 8 < eB) issue(wA, dA, rA_, eb + 8);
-                        consume(wB, dB, rB_);
                     }
                 }
-                if (cur >= 0) { store_row(cur, acc, false); next_r = cur + 1; }
-                for (; next_r < r1; ++next_r) store_row(next_r, acc, true);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (e + v < eB) {
+                        while (e + v >= rend) store_row();
+                        const float dd = dj[v];
+                        acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
+                        acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
+                        acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
+                        acc[6] = fmaf(dd, w[v][1].z, acc[6]); acc[7] = fmaf(dd, w[v][1].w, acc[7]);
+                    }
+                }
             }
+            while (cur < 4) store_row();
+            if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0)
-                for (int kc = 0; kc < prm.nch; ++kc) mbar_arrive(&full[sbase + kc]);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            // mask words of a tile row are fetched by the 8 threads ptid = 8*row + w, i.e. by the set that owns the row:
-            // a 64-thread barrier per set publishes them; sets are otherwise free to run ahead of each other
-            named_bar(3 + ts, 64);
-            if (tn == prm.tiles_per_chain - 1 && has_next)
-                named_bar(1, BW_NT_PROD);  // chain boundary: the next chain's record is complete and nobody reads the old one
+            if (lane == 0) {
+                mbar_arrive(&full[tb]);
+                if (tn == tpc - 1) mbar_arrive(&recempty[rb]);         // this warp is done with the chain's record
+            }
+            if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+            if (++tn == tpc) { tn = 0; ++ci; }
+        }
+        if (PROF && prm.prof && lane == 0 && (pw == 0 || pw == 15)) {
+            long long* o = prm.prof + (size_t)blockIdx.x * 16 + (pw == 0 ? 8 : 12); o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3];
         }
     }
 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == WARP_MMA) {
+    if (warp == BW_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
@@ -1353,6 +1393,9 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     return launch_done();
 }
 
+static long long* g_backward_prof = nullptr;
+extern "C" int ppde_set_backward_profile(long long* buf) { g_backward_prof = buf; return 0; }
+
 extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                                     int32_t n, const unsigned long long* mkey, float lamda,
                                     const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
@@ -1376,14 +1419,15 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
     const int rec_ = ((P + 1) + 2 * J2 + 7) & ~7;
-    const size_t smem = 1024 + (size_t)2 * tc::BW_MAXCH * tc::BW_SLOT +
-                        ((size_t)L * PPDE_Q + 100 * tc::YS + J2 + 2 * tc::BW_NT * 8) * sizeof(float) +
-                        2 * (size_t)rec_ * sizeof(uint16_t) + 16 + 8 + 24 * sizeof(uint64_t);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::cnn_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = 1024 + (size_t)2 * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
+                        2 * (size_t)rec_ * sizeof(uint16_t) + 8 + 32 * sizeof(uint64_t);
+    void (*bkern)(tc::BwdParams) = g_backward_prof ? tc::cnn_backward_tc_kernel<true> : tc::cnn_backward_tc_kernel<false>;
+    prm.prof = g_backward_prof;
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[g_backward_prof ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = smem;
+        configured[g_backward_prof ? 1 : 0] = smem;
     }
     cudaStream_t st = (cudaStream_t)stream;
     // winner records live behind the per-net gradient scratch: [n_nets*n*20L floats][n*n_nets*rec uint16]
@@ -1394,7 +1438,7 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
     tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
     int r0 = launch_done();
     if (r0) return r0;
-    tc::cnn_backward_tc_kernel<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
+    bkern<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
     int r = launch_done();
     if (r) return r;
     tc::cnn_grad_combine_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
