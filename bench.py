@@ -254,8 +254,8 @@ def main():
         roof = {"kernel": ("cnn_forward_tc2_kernel" if os.environ.get("PPDE_TC_CTAS", "2") != "1" else "cnn_forward_tc_kernel") if m.cnn_forward_impl == "tc" else "cnn_forward_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 # dram__bytes_read+write of this kernel from the committed `ncu --set full` capture
-                # (profiles/r01_cnn_forward_tc_v2_summary.txt: 228.5 MB at 8192 chains), scaled to this launch
-                "traffic": (228.5e6 / 8192) * n if m.cnn_forward_impl == "tc" and L == 238 else None,
+                # (profiles/r01_cnn_forward_tc2_v3_summary.txt: 3.7 + 221.8 MB at 8192 chains), scaled to this launch
+                "traffic": (225.5e6 / 8192) * n if m.cnn_forward_impl == "tc" and L == 238 else None,
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": flops_fwd, "avg_launch_ms": breakdown["cnn_forward"]}
         hbm_bytes = (8 * m.D + 2 * L + 16) * n                        # SURVEY.md §8d B_alg per chain-step
