@@ -10,6 +10,7 @@
  *   ppde_potts_symmetrize        PottsModel.__init__ parameter load          ppde/nets.py:245-262
  *   ppde_potts_full              PottsModel.hamiltonian/forward + autograd   ppde/nets.py:282-299, ppde/energy.py:106-108
  *   ppde_potts_incremental       same quantity at y, reusing the field at x  
+ *   ppde_potts_dense_full        same as ppde_potts_full as one tensor-core GEMM  ppde/nets.py:285-290 (the two einsums)
  *   ppde_cnn_forward             OnehotCNN.forward x3, EnsembleProtein mean  ppde/nets.py:363-376,434-442
  *   ppde_cnn_backward_combine    autograd through the CNN + PoE sum          ppde/energy.py:104-108
  *   ppde_pas_propose             PPDE_PAS.run forward path loop              ppde/protein_samplers/ppde.py:67-116
@@ -135,6 +136,14 @@ int ppde_potts_symmetrize(const float* J, int32_t Lp, float* Jsym, void* stream)
 int ppde_potts_full(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                     float* Gp, int64_t Gp_stride, float* Epotts, void* stream);
 int ppde_potts_incremental(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
+/* Dense re-evaluation on the tcgen05 tensor cores: Gp = h + onehot(aa) x Jsym as one [n x D] x [D x D] GEMM (same
+ * quantity and contract as ppde_potts_full; any D).  `Jt` is a tiled fp16 hi/lo image of Jsym * jscale built once by
+ * ppde_potts_dense_pack (ppde_potts_dense_image_bytes(D) bytes, 16-byte aligned); jscale = power of two with
+ * max|Jsym| * jscale in [2^13, 2^14). */
+int64_t ppde_potts_dense_image_bytes(int32_t D);
+int ppde_potts_dense_pack(const ppde_potts_t* m, float jscale, void* Jt, void* stream);
+int ppde_potts_dense_full(const ppde_potts_t* m, const void* Jt, float jscale, const uint8_t* aa, int32_t aa_stride,
+                          int32_t n, float* Gp, int64_t Gp_stride, float* Epotts, void* stream);
 int ppde_cnn_forward(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                      unsigned long long* mkey /* [n, n_nets, 2C] */, void* stream);
 /* same contract as ppde_cnn_forward, on the tcgen05 tensor cores (needs C <= 256); writes every key, no memset.

@@ -54,6 +54,9 @@ SIGNATURES = {
     "ppde_potts_symmetrize": (C.c_int, [vp, C.c_int32, vp, vp]),
     "ppde_potts_full": (C.c_int, [C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp]),
     "ppde_potts_incremental": (C.c_int, [C.POINTER(PottsT), C.POINTER(ChainsT), C.POINTER(PasParamsT), vp]),
+    "ppde_potts_dense_image_bytes": (C.c_int64, [C.c_int32]),
+    "ppde_potts_dense_pack": (C.c_int, [C.POINTER(PottsT), C.c_float, vp, vp]),
+    "ppde_potts_dense_full": (C.c_int, [C.POINTER(PottsT), vp, C.c_float, vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp]),
     "ppde_cnn_forward": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp]),
     "ppde_cnn_forward_tc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, vp]),
     "ppde_set_forward_variant": (C.c_int, [C.c_int]),

@@ -84,6 +84,13 @@ class PoEModel:
                                                     self.D, _ptr(ep), _stream()), "potts_full(wt)")
                 self.wt_H = float(ep.item())
                 self.potts.wt_H = self.wt_H
+                # dense tensor-core path for bulk re-evaluation: tiled fp16 hi/lo image of Jsym * 2^k (built once)
+                jmax = float(self.Jsym.abs().max().item())
+                self.jscale = 2.0 ** (13 - int(np.ceil(np.log2(max(jmax, 1e-30)))))
+                nbytes = int(self.lib.ppde_potts_dense_image_bytes(self.D))
+                self.Jt = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _lib.check(self.lib.ppde_potts_dense_pack(C.byref(self.potts), self.jscale, _ptr(self.Jt), _stream()),
+                           "potts_dense_pack")
             # CNN ensemble
             self.n_nets = len(cnn)
             if self.n_nets > _lib.MAX_NETS:
@@ -134,6 +141,9 @@ class PoEModel:
         self.cnn_forward_impl = "tc" if (want == "tc" and self.C <= 256) else "simt"
         wantb = os.environ.get("PPDE_CNN_BACKWARD", "tc")
         self.cnn_backward_impl = "tc" if (wantb == "tc" and self.C <= 256) else "simt"
+        # full Potts evaluation: "dense" = tcgen05 GEMM for batches of >= dense_min chains, "gather" = row-gather kernel
+        self.potts_full_impl = os.environ.get("PPDE_POTTS_FULL", "dense")
+        self.dense_min = int(os.environ.get("PPDE_POTTS_DENSE_MIN", "512"))
 
     def cnn_forward(self, aa, n, mk, st):
         if self.cnn_forward_impl == "tc":
@@ -190,13 +200,23 @@ class PoEModel:
         gp_ptr, ep_ptr = C.c_void_p(0), C.c_void_p(0)
         if self.has_potts:
             gp_ptr, ep_ptr = C.c_void_p(Gp.data_ptr() + gp_row0 * self.D * 4), _ptr(Epotts)
-            _lib.check(lib.ppde_potts_full(C.byref(self.potts), _ptr(aa), self.aa_stride, n, gp_ptr, self.D,
-                                           ep_ptr, st), "potts_full")
+            self.potts_full(aa, n, gp_ptr, ep_ptr, st)
         mk = self.mkey(n)
         self.cnn_forward(aa, n, mk, st)
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
         self.cnn_backward_combine(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr if want_grad else None,
                                   C.c_void_p(0), E, fit, st)
+
+    def potts_full(self, aa, n, gp_ptr, ep_ptr, st, impl=None):
+        """Potts field rows (contiguous, stride D) + energies of n states: dense tensor-core GEMM for large batches,
+        row gather otherwise (ppde/nets.py:282-299 + autograd)."""
+        impl = impl or (self.potts_full_impl if n >= self.dense_min else "gather")
+        if impl == "dense":
+            _lib.check(self.lib.ppde_potts_dense_full(C.byref(self.potts), _ptr(self.Jt), self.jscale, _ptr(aa),
+                                                      self.aa_stride, n, gp_ptr, self.D, ep_ptr, st), "potts_dense_full")
+        else:
+            _lib.check(self.lib.ppde_potts_full(C.byref(self.potts), _ptr(aa), self.aa_stride, n, gp_ptr, self.D,
+                                                ep_ptr, st), "potts_full")
 
     def onehot_to_aa(self, x):
         n, L, q = x.shape
