@@ -18,6 +18,7 @@
  *   ppde_pas_reverse_accept      reverse proposal, MH accept, reset, history ppde/protein_samplers/ppde.py:122-153,172-183
  *   ppde_onehot_to_aa / ppde_aa_to_onehot   seqs_to_onehot / onehot2seq      ppde/third_party/hsu/data_utils.py:150-175
  *   ppde_population_metrics      mut_distance mean, #accepted (logging)      ppde/protein_samplers/ppde.py:162-168
+ *   ppde_oracle_ridge            AugmentedLinearRegression.forward           ppde/nets.py:315-347 (log_every oracle call)
  *   ppde_sequence_hash           diversity_score (unique sequences)          scripts/make_figures.py:38-49
  *
  * Data layout (all row-major, device memory):
@@ -170,6 +171,14 @@ int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint
                          float* G, int64_t G_stride, const int32_t* g_rows,
                          const uint8_t* r1mask /* from ppde_cnn_forward_tc */,
                          float* scratch /* n_nets*n*20L floats + n*n_nets*roundup8(P+1+4C) uint16 */, void* stream);
+/* dH_potts of n states from field rows already in the pool: Epotts[b] = 1/2 sum_i (Gp[rows[b]][(i,aa_i)] + h) - H(wt);
+ * rows == NULL means row b. */
+int ppde_potts_energy_rows(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n, const float* Gp,
+                           int64_t Gp_stride, const int32_t* rows, float* Epotts, void* stream);
+/* Oracle model = mean of the ridge heads over [sqrt(1/reg) dH_potts, sqrt(1/r_h) onehot]  (ppde/nets.py:315-347), heads
+ * pre-averaged on the host: out[b] = sbar * dH[b] + sum_i wbar[20 i + aa_i] + cbar. */
+int ppde_oracle_ridge(const float* wbar /* [20L] */, float sbar, float cbar, const uint8_t* aa, int32_t aa_stride, int32_t n,
+                      int32_t L, const float* dH /* [n] or NULL */, float* out /* [n] */, void* stream);
 int ppde_step_rows(const ppde_chains_t* c, int32_t* rows_y, void* stream);
 int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);
 int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p, void* stream);

@@ -66,6 +66,8 @@ SIGNATURES = {
                                             C.c_float, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp]),
     "ppde_cnn_backward_tc": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
                                        vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, vp]),
+    "ppde_potts_energy_rows": (C.c_int, [C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp, vp]),
+    "ppde_oracle_ridge": (C.c_int, [vp, C.c_float, C.c_float, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
     "ppde_step_rows": (C.c_int, [C.POINTER(ChainsT), vp, vp]),
     "ppde_pas_propose": (C.c_int, [C.POINTER(PottsT), C.POINTER(ChainsT), C.POINTER(PasParamsT), vp]),
     "ppde_pas_reverse_accept": (C.c_int, [C.POINTER(PottsT), C.POINTER(ChainsT), C.POINTER(PasParamsT), vp]),

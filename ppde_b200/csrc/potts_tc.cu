@@ -249,12 +249,13 @@ __global__ void __launch_bounds__(PD_NTHREADS, 1) potts_dense_tc_kernel(const __
 
 // Epotts[b] = 1/2 sum_i ( Gp[b,(i,aa_i)] + h[(i,aa_i)] ) - wt_H     (one warp per chain)
 __global__ void potts_energy_from_field_kernel(ppde_potts_t m, const uint8_t* __restrict__ aa, int aa_stride, int n,
-                                               const float* __restrict__ Gp, int64_t Gp_stride, float* __restrict__ Epotts) {
+                                               const float* __restrict__ Gp, int64_t Gp_stride,
+                                               const int32_t* __restrict__ rows, float* __restrict__ Epotts) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= n) return;
     const int lane = threadIdx.x & 31;
     const uint8_t* a = aa + (int64_t)b * aa_stride + m.win_lo;
-    const float* g = Gp + (int64_t)b * Gp_stride;
+    const float* g = Gp + (int64_t)(rows ? rows[b] : b) * Gp_stride;
     float part = 0.f;
     for (int i = lane; i < m.Lp; i += 32) {
         const int r = i * PPDE_Q + a[i];
@@ -266,10 +267,41 @@ __global__ void potts_energy_from_field_kernel(ppde_potts_t m, const uint8_t* __
     if (lane == 0) Epotts[b] = 0.5f * part - m.wt_H;
 }
 
+// Oracle model (AugmentedLinearRegression, ppde/nets.py:315-347): mean over the ridge heads of
+//   W_h[0] * sqrt(1/reg_potts) * dH(x) + sqrt(1/r_h) * sum_{(i,a)} W_h[1 + 20 i + a] x[i,a] + b_h .
+// The heads are linear, so their mean is one head with averaged weights (folded on the host in fp64):
+//   y[b] = sbar * dH[b] + sum_i wbar[20 i + aa_i] + cbar          (one warp per chain, fixed-order reduction)
+__global__ void oracle_ridge_kernel(const float* __restrict__ wbar, float sbar, float cbar, const uint8_t* __restrict__ aa,
+                                    int aa_stride, int n, int L, const float* __restrict__ dH, float* __restrict__ out) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n) return;
+    const int lane = threadIdx.x & 31;
+    const uint8_t* a = aa + (int64_t)b * aa_stride;
+    float part = 0.f;
+    for (int i = lane; i < L; i += 32) part += __ldg(wbar + i * PPDE_Q + a[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) out[b] = fmaf(sbar, dH ? dH[b] : 0.f, part) + cbar;
+}
+
 }  // namespace tc
 }  // namespace ppde
 
 using namespace ppde;
+
+extern "C" int ppde_potts_energy_rows(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n, const float* Gp,
+                                      int64_t Gp_stride, const int32_t* rows, float* Epotts, void* stream) {
+    if (n <= 0) return 0;
+    tc::potts_energy_from_field_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*m, aa, aa_stride, n, Gp, Gp_stride, rows, Epotts);
+    return launch_done();
+}
+
+extern "C" int ppde_oracle_ridge(const float* wbar, float sbar, float cbar, const uint8_t* aa, int32_t aa_stride, int32_t n,
+                                 int32_t L, const float* dH, float* out, void* stream) {
+    if (n <= 0) return 0;
+    tc::oracle_ridge_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(wbar, sbar, cbar, aa, aa_stride, n, L, dH, out);
+    return launch_done();
+}
 
 extern "C" int64_t ppde_potts_dense_image_bytes(int32_t D) {
     const int64_t KC = (D + tc::KCH - 1) / tc::KCH, MT = (D + tc::PD_M - 1) / tc::PD_M;
@@ -316,7 +348,7 @@ extern "C" int ppde_potts_dense_full(const ppde_potts_t* m, const void* Jt, floa
     int r = launch_done();
     if (r) return r;
     if (Epotts) {
-        tc::potts_energy_from_field_kernel<<<(n + 7) / 8, 256, 0, st>>>(*m, aa, aa_stride, n, Gp, Gp_stride, Epotts);
+        tc::potts_energy_from_field_kernel<<<(n + 7) / 8, 256, 0, st>>>(*m, aa, aa_stride, n, Gp, Gp_stride, nullptr, Epotts);
         r = launch_done();
     }
     return r;

@@ -77,7 +77,7 @@ class PPDE_PAS:
 
             # iteration-0 report (ppde.py:48-57)
             if oracle is not None:
-                gt = gather_host(oracle(m.aa_to_onehot(eng.aa)).detach().float().reshape(-1))
+                gt = gather_host(self._oracle_scores(oracle, eng, m))
             e0, f0 = gather_host(eng.E_hist[0]), gather_host(eng.fit_hist[0])
             eq, fq = np.quantile(e0, [0.5, 0.9]), np.quantile(f0, [0.5, 0.9])
             self._print(f'[Iteration 0] energy: 50% {eq[0]:.3f}, 90% {eq[1]:.3f}')
@@ -113,6 +113,14 @@ class PPDE_PAS:
             random_traj = list(m.aa_to_onehot(traj).cpu().numpy())
         return best_x, best_e, best_f, e_hist, f_hist, random_traj
 
+    @staticmethod
+    def _oracle_scores(oracle, eng, m):
+        """oracle(cur_x) (ppde.py:48,156): our own model scores the residue states straight from the sampler's
+        field rows; any other callable gets the reference's float one-hot view."""
+        if hasattr(oracle, "score_engine") and getattr(oracle, "model", None) is m:
+            return oracle.score_engine(eng).reshape(-1)
+        return oracle(m.aa_to_onehot(eng.aa)).detach().float().reshape(-1)
+
     def _log(self, eng, m, oracle, i, n, gather_host):
         e = gather_host(eng.E_hist[i + 1]); f = gather_host(eng.fit_hist[i + 1])
         dist_d, hashes = eng.population_metrics()
@@ -120,7 +128,7 @@ class PPDE_PAS:
         acc = gather_host(eng.accept.float())
         gt = None
         if oracle is not None:
-            gt = gather_host(oracle(m.aa_to_onehot(eng.aa)).detach().float().reshape(-1))
+            gt = gather_host(self._oracle_scores(oracle, eng, m))
         rep = D.population_report(e, f, gt, acc, rep_dist, gather_host(hashes))
         self.last_report = rep
         self._print(f'[Iteration {i}] energy: 50% {rep["energy_q"][0]:.3f}, 90% {rep["energy_q"][1]:.3f}', flush=True)

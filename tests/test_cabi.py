@@ -68,11 +68,15 @@ def test_product_fails_loudly_without_cuda():
 
 
 def test_product_never_imports_the_oracle():
+    """The product path must not import, include, load or execute anything under oracle/ (the CPU checker).
+    ("oracle" is also the reference's name for its fitness model, ppde/nets.py:315 - that word is fine.)"""
+    import re
     pkg = os.path.join(REPO, "ppde_b200")
+    bad = re.compile(r"^\s*(from|import)\s+oracle\b|importlib[^\n]*['\"]oracle|#include\s*[\"<][^\n]*oracle/|['\"][^'\"\n]*oracle/[^'\"\n]*['\"]",
+                     re.MULTILINE)
     for root, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
-                assert "oracle" not in text.replace("the oracle", "").replace("oracle model", "").replace("oracle(", "") \
-                    .replace("oracle,", "").replace("oracle is", "").replace("oracle:", "").replace(" oracle ", " ") \
-                    .replace("oracle)", "").replace("oracle_", "").replace("`oracle`", ""), f"{f} mentions the oracle package"
+                m = bad.search(text)
+                assert m is None, f"{f} reaches into the oracle package: {m.group(0)!r}"
