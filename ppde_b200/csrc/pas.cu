@@ -18,29 +18,29 @@ __device__ __forceinline__ int y_row(int row_cur, int b, int n) { return row_cur
 // softmax -> clamp -> renormalise statistics of one logit vector held in shared memory.
 // On return sP[j] = clamp(exp(l_j - m1) / s2) and the function returns s3 = sum_j sP[j].
 // (utils.py:106-111: logits - logsumexp, softmax, clamp_probs; Categorical.__init__: p / p.sum())
+// `mx` is the caller's per-thread running maximum of the logits it wrote (saves one pass).
+// exp through ex2.approx (2^-22 relative) and one reciprocal per vector instead of a division per entry: the
+// probabilities agree with the reference's to ~2e-7 relative, far inside the 1e-4 tolerance; all reductions are
+// fixed-order (deterministic).
 template <int NT>
-__device__ __forceinline__ float softmax_clamp_inplace(float* sP, int n4, float* red) {
+__device__ __forceinline__ float softmax_clamp_inplace(float* sP, int n4, float mx, float* red) {
     float4* p4 = reinterpret_cast<float4*>(sP);
-    float mx = -INFINITY;
-    for (int q = threadIdx.x; q < n4; q += NT) {
-        float4 v = p4[q];
-        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-    }
     const float m1 = block_max<NT>(mx, red);
     const float off = (m1 == -INFINITY) ? 0.f : m1;
     float sum = 0.f;
     for (int q = threadIdx.x; q < n4; q += NT) {
         float4 v = p4[q];
-        v.x = expf(v.x - off); v.y = expf(v.y - off); v.z = expf(v.z - off); v.w = expf(v.w - off);
+        v.x = __expf(v.x - off); v.y = __expf(v.y - off); v.z = __expf(v.z - off); v.w = __expf(v.w - off);
         p4[q] = v;
         sum += (v.x + v.y) + (v.z + v.w);
     }
     const float s2 = block_sum<NT>(sum, red);
+    const float r2 = 1.0f / s2;
     float sum3 = 0.f;
     for (int q = threadIdx.x; q < n4; q += NT) {
         float4 v = p4[q];
-        v.x = clamp_prob(v.x / s2); v.y = clamp_prob(v.y / s2);
-        v.z = clamp_prob(v.z / s2); v.w = clamp_prob(v.w / s2);
+        v.x = clamp_prob(v.x * r2); v.y = clamp_prob(v.y * r2);
+        v.z = clamp_prob(v.z * r2); v.w = clamp_prob(v.w * r2);
         p4[q] = v;
         sum3 += (v.x + v.y) + (v.z + v.w);
     }
@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
     __shared__ float red[33];
     __shared__ int redi[33];
     __shared__ int s_idx;
+    __shared__ int s_best;                                   // bits of the best race quotient so far (positive floats order as ints)
 
     const int b = blockIdx.x;
     const uint32_t gid = (uint32_t)(c.chain_offset + b);
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
         // Taylor logits with the revert-only mask and the window mask (ppde.py:95-104, utils.py:17-28)
         float4* p4 = reinterpret_cast<float4*>(sP);
         const float4* g4 = reinterpret_cast<const float4*>(sG);
+        float lmax = -INFINITY;
         for (int q = threadIdx.x; q < n4; q += NT) {
             const int i = q / 5, a0 = (q - i * 5) * 4;
             float4 g = g4[q];
@@ -106,10 +108,14 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
                 if (a0 + 3 != w) l.w = -INFINITY;
             }
             p4[q] = l;
+            lmax = fmaxf(fmaxf(lmax, fmaxf(l.x, l.y)), fmaxf(l.z, l.w));
         }
-        __syncthreads();
-        const float s3 = softmax_clamp_inplace<NT>(sP, n4, red);
-        // exponential race: argmax_j p_j / E_j, E_j = -log(u_j)  (= torch.multinomial(p, 1, True))
+        if (threadIdx.x == 0) s_best = 0;
+        const float s3 = softmax_clamp_inplace<NT>(sP, n4, lmax, red);     // (its barriers also publish s_best = 0)
+        // exponential race: argmax_j p_j / E_j, E_j = -log(u_j)  (= torch.multinomial(p, 1, True)).
+        // The quotient r_j = (p_j / s3) / (-log u_j) is evaluated exactly as before, but only for entries that can
+        // still win: -log u >= 1 - u, so r_j <= p_j / (s3 (1 - u_j)); an entry whose bound is below the best quotient
+        // seen so far by ANY thread of the block (s_best, monotone) with a 1e-5 margin (>> rounding) is skipped.
         float best = -1.f; int bidx = 0x7fffffff;
         const float* um = p.uniforms ? p.uniforms + ((int64_t)s * c.n + b) * NE : nullptr;
         for (int q = threadIdx.x; q < n4; q += NT) {
@@ -120,15 +126,17 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
                 uint4 w = rng((uint32_t)q, gid, (uint32_t)t, (uint32_t)(s | (KIND_PROPOSAL << 16)));
                 u = make_float4(u32_to_unit(w.x), u32_to_unit(w.y), u32_to_unit(w.z), u32_to_unit(w.w));
             }
-            float4 pr = p4[q];
-            float r0 = (pr.x / s3) / (-logf(u.x));
-            float r1 = (pr.y / s3) / (-logf(u.y));
-            float r2 = (pr.z / s3) / (-logf(u.z));
-            float r3 = (pr.w / s3) / (-logf(u.w));
-            if (r0 > best) { best = r0; bidx = q * 4; }
-            if (r1 > best) { best = r1; bidx = q * 4 + 1; }
-            if (r2 > best) { best = r2; bidx = q * 4 + 2; }
-            if (r3 > best) { best = r3; bidx = q * 4 + 3; }
+            const float4 pr = p4[q];
+            const float thr = fmaxf(best, __int_as_float(*(volatile int*)&s_best)) * s3;
+            const float pv[4] = {pr.x, pr.y, pr.z, pr.w};
+            const float uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (pv[k] * 1.00001f > thr * (1.0f - uv[k])) {           // may still win: exact evaluation
+                    const float r = (pv[k] / s3) / (-logf(uv[k]));
+                    if (r > best) { best = r; bidx = q * 4 + k; atomicMax(&s_best, __float_as_int(r)); }
+                }
+            }
         }
         block_argmax<NT>(best, bidx, red, redi);
         if (threadIdx.x == 0) {
@@ -185,13 +193,15 @@ __global__ void __launch_bounds__(NT) pas_reverse_accept_kernel(ppde_potts_t m, 
         __syncthreads();
         float4* p4 = reinterpret_cast<float4*>(sP);
         const float4* g4 = reinterpret_cast<const float4*>(sG);
+        float lmax = -INFINITY;
         for (int q = threadIdx.x; q < n4; q += NT) {              // NO masks on the reverse path (ppde.py:126-127)
             const float gc = sCur[q / 5];
             float4 g = g4[q];
-            p4[q] = make_float4((g.x - gc) * 0.5f, (g.y - gc) * 0.5f, (g.z - gc) * 0.5f, (g.w - gc) * 0.5f);
+            const float4 l = make_float4((g.x - gc) * 0.5f, (g.y - gc) * 0.5f, (g.z - gc) * 0.5f, (g.w - gc) * 0.5f);
+            p4[q] = l;
+            lmax = fmaxf(fmaxf(lmax, fmaxf(l.x, l.y)), fmaxf(l.z, l.w));
         }
-        __syncthreads();
-        const float s3 = softmax_clamp_inplace<NT>(sP, n4, red);
+        const float s3 = softmax_clamp_inplace<NT>(sP, n4, lmax, red);
         if (threadIdx.x == 0) {
             const float lqr = logf(clamp_prob(sP[cidx] / s3));
             c.lqr[o] = lqr;
