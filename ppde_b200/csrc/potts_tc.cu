@@ -221,9 +221,10 @@ __global__ void __launch_bounds__(PD_NTHREADS, 1) potts_dense_tc_kernel(const __
                 }
                 mbar_wait(&empty[s], ph ^ 1);
                 const uint32_t ra = row_a + (uint32_t)(s * PD_STAGE_BYTES);
+                // zero the row: lane l starts at 16-byte unit l % 8, so the 8 rows of a store phase hit 8 different bank groups
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ra + (u << 4)), "r"(0u) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ra + ((uint32_t)((u + lane) & 7) << 4)), "r"(0u) : "memory");
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (rel[q] >= 0 && rel[q] < KCH) {

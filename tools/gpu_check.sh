@@ -1,17 +1,24 @@
 #!/bin/bash
 # Runs on the B200 box (under gpurun): GPU parity tests, smoke, full default bench, reference arm,
-# ncu launch list and one `--set full` capture of the top kernels. Outputs under gpurun_out/.
-# usage: tools/gpu_check.sh <tag> [kernel-regex for the full capture]
+# ncu launch list and `--set full` captures of the top kernels. Outputs under gpurun_out/.
+# usage: tools/gpu_check.sh <tag>
 TAG=${1:-r01}
-KRE=${2:-cnn_forward_tc2_kernel}
+K="timeout -s KILL"
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/${TAG}_pytest.log
-python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/${TAG}_smoke.log
-python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ref.json
+$K 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest.log
+$K 120 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
+$K 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json
+$K 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ref.json
+$K 200 python bench.py --workload ube4b_potts_poe_4k --no-cpu-baseline > gpurun_out/${TAG}_bench_ube4b.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ube4b.json
+$K 300 python bench.py --workload gfp_paper_pas10 --no-cpu-baseline --steps 5 > gpurun_out/${TAG}_bench_pas10.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_pas10.json
+$K 200 python tools/bench_potts_full.py 64 128 238 512 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
 SMALL="python bench.py --chains 8192 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline"
-$SMALL > gpurun_out/${TAG}_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
-$SMALL > gpurun_out/${TAG}_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s 4 -c 2 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
-tail -2 gpurun_out/${TAG}_ncu_f.log
+$K 200 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 && \
+$K 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
+$K 200 $SMALL > gpurun_out/${TAG}_plain2.log 2>&1 && \
+$K 400 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_tc2_kernel|cnn_backward_tc_kernel|pas_propose_kernel|pas_reverse_accept_kernel|potts_incremental_kernel" -s 12 -c 5 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
+tail -1 gpurun_out/${TAG}_ncu_f.log
+PD="python tools/bench_potts_full.py 238"
+$K 200 $PD > gpurun_out/${TAG}_plain3.log 2>&1 && \
+$K 300 ncu --set full --clock-control none --import-source on -k regex:potts_dense_tc_kernel -s 6 -c 1 -o gpurun_out/${TAG}_potts_dense -f $PD > gpurun_out/${TAG}_ncu_p.log 2>&1
+tail -1 gpurun_out/${TAG}_ncu_p.log
