@@ -59,6 +59,18 @@ def broadcast_from(t, src):
     return t
 
 
+def agree_int(value, src=0, device=None):
+    """The same integer on every rank (rank `src`'s).  Host-side draws such as the reference's
+    `np.random.randint` for the tracked chain (ppde.py:37) differ between processes unless every
+    rank seeded numpy identically; collectives that depend on them (broadcast source) must agree."""
+    _, ws = world()
+    if ws == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.broadcast(t, src=src)
+    return int(t.item())
+
+
 def owner_of(chain, n, world_size):
     for r in range(world_size):
         lo, hi = shard_range(n, r, world_size)

@@ -60,6 +60,7 @@ class PPDE_PAS:
             lo, hi = D.shard_range(n, rank, ws)
             pop_local = initial_population[lo:hi]
         random_idx = np.random.randint(0, n)                  # ppde.py:37 (numpy global generator)
+        random_idx = D.agree_int(random_idx, 0, m.device)     # ranks must track the same chain
         own_rank, own_local = D.owner_of(random_idx, n, ws)
         thr = 0 if self.nmut_threshold == np.iinfo(np.int32).max else self.nmut_threshold
 

@@ -26,6 +26,8 @@ def _worker(rank, ws, port, n, T, out_dir):
     traj = D.broadcast_from(traj, owner)
     ok = (torch.equal(e, glob_e) and torch.equal(hist, glob_hist) and torch.equal(aa, glob_aa)
           and float(acc) == n and torch.equal(traj, torch.full((T + 1, 4), float(owner))))
+    # host-side draws differ between processes; the tracked-chain index must be made to agree (ppde.py:37)
+    ok = ok and D.agree_int(100 + 17 * rank, 0) == 100 and D.agree_int(5 + rank, 1) == 6
     rep = D.population_report(e.numpy(), e.numpy(), None, np.ones(n), np.arange(n), np.arange(n) % 3)
     ok = ok and rep["diversity_pct"] == pytest.approx(300.0 / n) and rep["oracle_q"] is None
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("1" if ok else "0")
