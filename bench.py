@@ -283,11 +283,19 @@ def main():
         best_host = torch.empty(n, L, 20, dtype=torch.float32).pin_memory()    # the caller's result buffer
         barrier()
         t0 = time.perf_counter()
+        trace = os.environ.get("PPDE_TRACE", "0") == "1"
         pop_dev = pop_host.to(dev, non_blocking=True)          # H2D of the call's input, inside the timed region
+        if trace:
+            torch.cuda.synchronize(); t1 = time.perf_counter()
         out = smp.run(pop_dev, K, energy, pr["win_lo"], win_hi, None, log_every=10 ** 9)
+        if trace:
+            torch.cuda.synchronize(); t2 = time.perf_counter()
         best_host.copy_(out[0])                                # D2H of the call's result (histories are host numpy already)
         barrier()
         dt = time.perf_counter() - t0
+        if trace:
+            print(f"[bench trace] h2d={1e3 * (t1 - t0):.1f}ms run={1e3 * (t2 - t1):.1f}ms d2h={1e3 * (t0 + dt - t2):.1f}ms",
+                  file=sys.stderr, flush=True)
         if world > 1:
             tt = torch.tensor([dt], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -14,12 +14,37 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
   * under torch.distributed each rank runs its contiguous block of chains; the returned 6-tuple is
     the whole population on every rank.
 """
+import os
+import time
+
 import numpy as np
 import torch
 
 from . import dist as D
 from .energy import as_b200_energy
 from .engine import ChainEngine
+
+
+class _Phases:
+    """Wall-clock phase times of one `run` call (PPDE_TRACE=1): a device synchronize closes every phase, so it is a
+    diagnostic, not something to leave on when measuring throughput."""
+
+    def __init__(self, device):
+        self.on = os.environ.get("PPDE_TRACE", "0") == "1"
+        self.device = device
+        self.rows = []
+        self.t = time.perf_counter()
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize(self.device)
+            now = time.perf_counter()
+            self.rows.append((name, (now - self.t) * 1e3))
+            self.t = now
+
+    def report(self):
+        if self.on:
+            print("[ppde trace] " + "  ".join(f"{k}={v:.1f}ms" for k, v in self.rows), flush=True)
 
 
 class PPDE_PAS:
@@ -64,14 +89,17 @@ class PPDE_PAS:
         own_rank, own_local = D.owner_of(random_idx, n, ws)
         thr = 0 if self.nmut_threshold == np.iinfo(np.int32).max else self.nmut_threshold
 
+        ph = _Phases(m.device)
         with torch.cuda.device(m.device):
             aa0 = m.onehot_to_aa(pop_local)
+            ph.mark("onehot_to_aa")
             eng = ChainEngine(m, hi - lo, self.ppde_pas_length, thr, self.paper_results, seed=self.seed,
                               chain_offset=lo, num_steps=num_steps,
                               traj_chain=own_local if own_rank == rank else -1,
                               min_pos=int(min_pos), max_pos=int(max_pos))
             eng.init_population(aa0)
             self.engine = eng
+            ph.mark("engine_init")
 
             def gather_host(t):
                 return D.all_gather_cat(t, n).cpu().numpy()
@@ -87,6 +115,7 @@ class PPDE_PAS:
                 gq = np.quantile(gt, [0.5, 0.9])
                 self._print(f'[Iteration 0] oracle fit 50% {gq[0]:.3f}, 90% {gq[1]:.3f}')
             self._print('')
+            ph.mark("report0")
 
             t = 0
             while t < num_steps:
@@ -99,6 +128,7 @@ class PPDE_PAS:
                 if t == i + 1:
                     self._log(eng, m, oracle, i, n, gather_host)
 
+            ph.mark("steps")
             # final 6-tuple (ppde.py:172-192)
             if self.local_population:
                 gat = lambda t, dim=0: t
@@ -112,6 +142,8 @@ class PPDE_PAS:
                 num_steps + 1, m.aa_stride, dtype=torch.uint8, device=m.device)
             traj = D.broadcast_from(traj, own_rank)
             random_traj = list(m.aa_to_onehot(traj).cpu().numpy())
+            ph.mark("results")
+            ph.report()
         return best_x, best_e, best_f, e_hist, f_hist, random_traj
 
     @staticmethod
