@@ -236,10 +236,8 @@ def main():
             _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "propose"); evs[1].record()
             _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "inc")
             _lib.check(lib.ppde_step_rows(C.byref(eng.chains), _ptr(eng.rows_y), st), "rows"); evs[2].record()
-            mk = m.mkey(n)
-            m.cnn_forward(eng.aa_y, n, mk, st); evs[3].record()
-            m.cnn_backward_combine(eng.aa_y, n, mk, _ptr(eng.Gp), _ptr(eng.rows_y), _ptr(eng.Epotts_y), _ptr(eng.G),
-                                   _ptr(eng.rows_y), eng.E_y, eng.fit_y, st)
+            eng.cnn_forward_y(st); evs[3].record()
+            eng.cnn_backward_y(st)
             evs[4].record()
             _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "rev"); evs[5].record()
             torch.cuda.synchronize()

@@ -744,6 +744,515 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
 }
 
 // =====================================================================================================
+// INCREMENTAL forward (same 2-CTA tcgen05 skeleton as cnn_forward_tc2_kernel).
+//
+// A proposal y differs from the chain's current state x in at most S residues, and a residue change at i only moves
+// the conv rows p in [i-4, i]: the max-pool of y over all P positions is re-used from x except for the few 16-position
+// BLOCKS that contain such a row.  Per (pool row, net, block q, channel j) the pool `bkey` holds
+//     key = ordered(raw accumulator max over the block) << 32 | (0xFFFFFFFF - first arg-max position)
+// (ordered() = the usual order-preserving map of fp32 bits, -0 canonicalised), so the chain-level winner - first
+// arg-max of the raw accumulator, the quantity cnn_forward_tc2_kernel tracks - is the 64-bit maximum over the blocks.
+// The kernel recomputes only the dirty blocks of every chain (bit q of dmask[b]; dmask == NULL: every block).  The dirty
+// blocks of a CTA's chains form one sequence (cnn_inc_scan_kernel: exclusive prefix `boff`, compact list `blist`), cut
+// into MMA tiles of 8 blocks = 128 positions REGARDLESS of chain boundaries: a tcgen05.mma costs the same ~60 cycles at
+// N = 32 as at N = 128, so one short tile per chain would be bound by the MMA count, not by the flops.  The epilogue
+// copies the clean blocks' keys from the current row to the proposal row and writes the same `mkey` the full kernel
+// writes, bit for bit: every accumulator element depends only on its own r1 row and W1 row, in the same K order.  The relu-mask rows of the dirty positions go to the proposal
+// row of the r1mask pool (the clean rows were copied there by cnn_dirty_kernel).
+struct IncParams {
+    ppde_cnn_t m;
+    const uint8_t* aa;                  // proposal states [n, aa_stride]
+    int aa_stride;
+    int n;
+    unsigned long long* mkey;           // [n, n_nets, 2C]
+    uint8_t* r1mask;                    // pool [rows, n_nets, P, 32] or NULL
+    const uint32_t* dmask;              // [n] dirty-block bits, NULL = every block is dirty (full evaluation into the pool)
+    unsigned long long* bkey;           // pool [rows, n_nets, NB, 2C]
+    const int32_t* rows_x;              // [n] pool row of the current state (NULL only with dmask == NULL)
+    const int32_t* rows_y;              // [n] pool row of the proposal, NULL = row_base_y + b
+    int row_base_y;
+    const int32_t* boff;                // [n] dirty blocks of the CTA's chains before chain b (cnn_inc_scan_kernel)
+    const int32_t* gtot;                // [ctas_per_combo] dirty blocks per chain range
+    const uint32_t* blist;              // [n * 16] compact (chain << 4 | block) list, range r starts at 16 * b_lo(r)
+    int NB;                             // blocks of 16 positions per chain = ceil(P / 16) <= 16
+    int ctas_per_combo;
+    int MT;                             // channel-tile pairs
+    int kpad;
+    long long* prof;                    // optional [grid][16] role-level cycle counters (ppde_set_forward_profile; tools/prof_inc.py)
+    int dbg;                            // timing experiments only (PPDE_INC_DEBUG): 1 = no key traffic, 2 = no r1 production,
+                                        // 4 = no residue loads (results are wrong with any bit set)
+};
+
+__device__ __forceinline__ int nth_set_bit(uint32_t mask, int k) {
+    for (int i = 0; i < k; ++i) mask &= mask - 1u;
+    return __ffs((int)mask) - 1;
+}
+__device__ __forceinline__ uint32_t f32_ordered(float u) {
+    const uint32_t b = __float_as_uint(u + 0.0f);                  // -0 -> +0
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+
+// Cluster-scope barrier traffic WITHOUT release/acquire fences.  What these barriers order is never generic-proxy global
+// data: (a) "rank 1's operand chunk is in ITS shared memory" - already performed there and fenced to the async proxy by the
+// producers before the forwarder saw the local barrier flip; (b) "my tcgen05.ld of the accumulator has completed" -
+// guaranteed by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.  The default .release.cluster arrive compiles to
+// MEMBAR.ALL.GPU + ERRBAR (and the acquire wait to CCTL.IVALL): ~600 cycles each and, once the thread has global stores
+// in flight, a full write round trip - with one short tile per chain these would bound the incremental kernel.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_relaxed(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_LOOP_R:\n"
+        " mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_R;\n"
+        " bra WAIT_LOOP_R;\n"
+        "DONE_R:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+
+template <int NCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int C = prm.m.C, P = prm.m.P, J2 = 2 * C, NB = prm.NB;
+    constexpr int KS = NCH * KCH;
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* sT0 = reinterpret_cast<float*>(ring + NSLOT2 * SLOT2_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sT0 + 100 * KS);
+    uint64_t* fullL = bars;
+    uint64_t* fullR = fullL + NSLOT2;
+    uint64_t* empty = fullR + NSLOT2;
+    uint64_t* dfull = empty + NSLOT2;
+    uint64_t* dempty = dfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int MP = prm.MT;
+    const int combo = pair / prm.ctas_per_combo;
+    const int within = pair - combo * prm.ctas_per_combo;
+    const bool idle = combo >= prm.m.n_nets * MP;
+    const int k = idle ? 0 : combo / MP, mp = idle ? 0 : combo - k * MP;
+    const int mt = mp * 2 + (int)rank;
+    const ppde_cnn_net_t net = prm.m.net[k];
+    const int b_lo = idle ? 0 : (int)((int64_t)prm.n * within / prm.ctas_per_combo);
+    const int b_hi = idle ? 0 : (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_combo);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t all_blocks = (NB >= 32) ? 0xFFFFFFFFu : ((1u << NB) - 1u);
+    auto ld_mask = [&](int b) -> uint32_t {
+        return (b < b_hi) ? (prm.dmask ? (__ldg(prm.dmask + b) & all_blocks) : all_blocks) : 0u;
+    };
+    const int G = idle ? 0 : __ldg(prm.gtot + within);       // dirty blocks of my chains
+    const int ntiles = (G + 7) >> 3;                         // tiles of 8 blocks (the last one may be shorter)
+    const uint32_t* bl = prm.blist + (size_t)b_lo * 16;
+
+    for (int e = threadIdx.x; e < 100 * KS; e += NTHREADS) {
+        const int row = e / KS, c = e - row * KS;
+        float v = 0.f;
+        if (c < C) {
+            v = net.T0[(size_t)row * C + c];
+            if (row < PPDE_Q) v += net.b0[c];
+        }
+        sT0[e] = v * net.r1_scale;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT2; ++s) { mbar_init(&fullL[s], NT_PROD / 32); mbar_init(&fullR[s], 1); mbar_init(&empty[s], 1); }
+        for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], 2 * (NT_EPI / 32)); }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {      // A = this CTA's W1 tile (fp16 hi/lo) -> tensor memory, as in the full kernel
+        const int j = mt * 128 + warp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int ks = 0; ks < prm.kpad / 16; ++ks) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c0 = ks * 16 + 2 * q;
+                const float w0 = (j < J2 && c0 < C) ? net.W1[(size_t)j * C + c0] * net.w1_scale : 0.f;
+                const float w1 = (j < J2 && c0 + 1 < C) ? net.W1[(size_t)j * C + c0 + 1] * net.w1_scale : 0.f;
+                const float h0 = h_round(w0), h1 = h_round(w1);
+                hi[q] = pack_h2(h0, h1);
+                lo[q] = pack_h2(w0 - h0, w1 - h1);
+            }
+            tmem_st8(lane_addr + ks * 8, hi);
+            tmem_st8(lane_addr + prm.kpad / 2 + ks * 8, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+
+    if (warp < 4) {
+        // ===== EPILOGUE (both CTAs): thread = channel j; per TILE: the 8 blocks' keys go straight to their final place in
+        // the proposal rows of the pool (no per-chain work here: cnn_inc_merge_kernel copies the clean keys and forms mkey) =====
+        const int j = mt * 128 + warp * 32 + lane;
+        const bool jok = j < J2;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+        const size_t row_keys = (size_t)prm.m.n_nets * NB * J2;            // keys per pool row
+        const size_t koff = ((size_t)k * NB) * J2 + j;
+        // lane l (mod 8) holds block l of the tile: entry (chain << 4 | block) two tiles ahead, its pool row one tile ahead
+        auto ld_ent = [&](int T) -> uint32_t {
+            const int g = 8 * T + (lane & 7);
+            return (g < G) ? __ldg(bl + g) : 0u;
+        };
+        auto ld_row = [&](int T, uint32_t ent) -> int {
+            const int g = 8 * T + (lane & 7);
+            const int b = (int)(ent >> 4);
+            return (g < G) ? (prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b) : 0;
+        };
+        uint32_t ent_a = ld_ent(0);
+        int row_a = ld_row(0, ent_a);
+        uint32_t ent_b = ld_ent(1);
+        const bool prof = prm.prof != nullptr;
+        long long pc[4] = {0, 0, 0, 0};
+        long long tp = prof ? clock64() : 0;
+        for (int T = 0; T < ntiles; ++T) {
+            const int cnt = min(8, G - 8 * T);
+            const int buf = T & 1;
+            const uint32_t ent = ent_a;
+            const int row = row_a;
+            ent_a = ent_b;
+            row_a = ld_row(T + 1, ent_a);
+            ent_b = ld_ent(T + 2);
+            if (prof) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+            mbar_wait(&dfull[buf], (uint32_t)((T >> 1) & 1));
+            tc_fence_after();
+            if (prof) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s < cnt) {                                              // warp-uniform
+                    uint32_t r[16];
+                    tmem_ld16(lane_addr + buf * 128 + 16 * s, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float bu = __uint_as_float(r[0]);
+                    int bi = 0;
+#pragma unroll
+                    for (int i = 1; i < 16; ++i) {
+                        const float u = __uint_as_float(r[i]);
+                        if (u > bu) { bu = u; bi = i; }
+                    }
+                    const uint32_t e_s = __shfl_sync(0xffffffffu, ent, s);
+                    const int r_s = __shfl_sync(0xffffffffu, row, s);
+                    const int q = (int)(e_s & 15u);
+                    const unsigned long long key = ((unsigned long long)f32_ordered(bu) << 32) |
+                                                   (unsigned long long)(0xFFFFFFFFu - (unsigned)(16 * q + bi));
+                    if (jok && !(prm.dbg & 1)) __stcg(prm.bkey + (size_t)r_s * row_keys + koff + (size_t)q * J2, key);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&dempty[buf]); else mbar_arrive_cluster_relaxed(&dempty[buf], 0);
+            }
+            if (prof) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+        }
+        if (prof && threadIdx.x == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3]; }
+    } else if (warp == WARP_MMA2) {
+        if (rank == 0) {
+            // ===== MMA ISSUER (leader CTA) =====
+            const uint32_t ring_addr = smem_u32(ring);
+            int slot = 0;
+            uint32_t sphase = 0;
+            const int last_ksteps = (prm.kpad - (NCH - 1) * KCH) / 16;
+            const uint32_t a_lo_off = (uint32_t)(prm.kpad / 2);
+            const bool prof = prm.prof != nullptr;
+            long long pc[4] = {0, 0, 0, 0};
+            long long tp = prof ? clock64() : 0;
+            const long long tstart = tp;
+            for (int it = 0; it < ntiles; ++it) {
+                const int cnt = min(8, G - 8 * it);
+                const uint32_t idesc = make_idesc(256, 16 * cnt);
+                const int buf = it & 1;
+                if (it >= 2) mbar_wait_cluster_relaxed(&dempty[buf], (uint32_t)(((it >> 1) + 1) & 1));
+                if (prof) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + D_COL0 + buf * 128;
+#pragma unroll 1
+                for (int kc = 0; kc < NCH; ++kc) {
+                    mbar_wait(&fullL[slot], sphase);
+                    if (prof) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                    mbar_wait_cluster_relaxed(&fullR[slot], sphase);
+                    if (prof) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+                    tc_fence_after();
+                    const uint64_t dhi = make_b_desc(ring_addr + slot * SLOT2_BYTES);
+                    const uint64_t dlo = make_b_desc(ring_addr + slot * SLOT2_BYTES + MAT2_BYTES);
+                    const int ksteps = (kc == NCH - 1) ? last_ksteps : KCH / 16;
+                    const uint32_t a_hi0 = tmem_base + kc * (KCH / 2);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < KCH / 16; ++ks) {
+                            if (ks < ksteps) {
+                                const uint32_t a_hi = a_hi0 + ks * 8;
+                                mma_ts2(d_tmem, a_hi, dhi + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                                mma_ts2(d_tmem, a_hi, dlo + (uint64_t)(ks * 2), idesc, 1u);
+                                mma_ts2(d_tmem, a_hi + a_lo_off, dhi + (uint64_t)(ks * 2), idesc, 1u);
+                            }
+                        }
+                        tc_commit2(&empty[slot]);
+                        if (kc == NCH - 1) tc_commit2(&dfull[buf]);
+                    }
+                    __syncwarp();
+                    if (prof) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
+                    if (++slot == NSLOT2) { slot = 0; sphase ^= 1; }
+                }
+            }
+            if (prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[4] = pc[0]; o[5] = pc[1]; o[6] = pc[2]; o[7] = pc[3]; o[8] = clock64() - tstart; o[9] = ntiles; o[10] = b_hi - b_lo; }
+        } else if (lane == 0) {
+            // ===== FORWARDER (rank 1): one remote arrive per chunk =====
+            int slot = 0;
+            uint32_t sphase = 0;
+            for (int c = 0; c < ntiles * NCH; ++c) {
+                mbar_wait(&fullL[slot], sphase);
+                mbar_arrive_cluster_relaxed(&fullR[slot], 0);
+                if (++slot == NSLOT2) { slot = 0; sphase ^= 1; }
+            }
+        }
+    } else {
+        // ===== PRODUCERS (both CTAs): one row per thread; a tile = 8 consecutive dirty blocks of the CTA.s sequence, this CTA.s half =====
+        const int pw = warp - 4;
+        const int g = lane & 7, q = lane >> 3;
+        const int r = 16 * (pw >> 2) + (pw & 3) + 4 * q;      // local row 0..63
+        const uint32_t t0addr = smem_u32(sT0) + 16 * g;
+        const uint32_t o0 = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((g >> 1)) ^ (r & 7)) << 4) + ((g & 1) << 3));
+        const uint32_t st0 = smem_u32(ring) + o0, st1 = smem_u32(ring) + (o0 ^ 64u);
+        int slot = 0;
+        uint32_t phase = 0;
+        // my row of tile T: block entry (chain << 4 | block) from the compact list two tiles ahead, residues one tile ahead
+        auto my_row = [&](int T, bool& act, int& gr) {
+            const int half = 8 * min(8, G - 8 * T);
+            act = r < half;
+            gr = (int)rank * half + (act ? r : 0);
+        };
+        auto ld_entry = [&](int T) -> uint32_t {
+            if (T >= ntiles) return 0u;
+            bool act; int gr;
+            my_row(T, act, gr);
+            return __ldg(bl + 8 * T + (gr >> 4));
+        };
+        uint32_t an[5] = {0u, 0u, 0u, 0u, 0u};
+        bool nact = false;
+        int npos = 0, nb = 0;
+        auto prep = [&](int T, uint32_t ent) {   // decode my row of tile T and put the loads of its 5 residues in flight
+            nact = false;
+            if (T >= ntiles) return;
+            int gr;
+            my_row(T, nact, gr);
+            nb = (int)(ent >> 4);
+            npos = 16 * (int)(ent & 15u) + (gr & 15);
+            const uint8_t* ap = prm.aa + (size_t)nb * prm.aa_stride + min(npos, P - 1);   // rows past the end replicate P-1
+            if (!(prm.dbg & 4)) {
+#pragma unroll
+                for (int t = 0; t < 5; ++t) an[t] = ap[t];
+            }
+        };
+        prep(0, ld_entry(0));
+        uint32_t ent_next = ld_entry(1);
+        int emit_ctr = 0;
+        const bool prof = prm.prof != nullptr;
+        long long pce = 0;
+        const long long tstart = prof ? clock64() : 0;
+        for (int T = 0; T < ntiles; ++T) {
+            const bool active = nact;
+            const int pos = npos;
+            const int bcur = nb;
+            uint32_t ra[5];
+#pragma unroll
+            for (int t = 0; t < 5; ++t) ra[t] = t0addr + (uint32_t)((t * PPDE_Q + (int)an[t]) * (KS * 4));
+            prep(T + 1, ent_next);                             // next tile's residues in flight during this tile's chunks
+            ent_next = ld_entry(T + 2);
+            const bool emit_mask = (prm.r1mask != nullptr) && (emit_ctr == mp);
+            if (++emit_ctr == MP) emit_ctr = 0;
+            uint32_t mbits = 0u;
+#pragma unroll
+            for (int kc = 0; kc < NCH; ++kc) {
+                const long long tw = prof ? clock64() : 0;
+                mbar_wait(&empty[slot], phase ^ 1);
+                if (prof) pce += clock64() - tw;
+                if (active && !(prm.dbg & 2)) {
+                    const uint32_t so = (uint32_t)(slot * SLOT2_BYTES);
+                    if (kc == 0) produce_chunk<0>(ra, st0 + so, st1 + so, emit_mask, mbits);
+                    if (kc == 1) produce_chunk<1>(ra, st0 + so, st1 + so, emit_mask, mbits);
+                    if (kc == 2) produce_chunk<2>(ra, st0 + so, st1 + so, emit_mask, mbits);
+                    if (kc == 3) produce_chunk<3>(ra, st0 + so, st1 + so, emit_mask, mbits);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&fullL[slot]);
+                if (++slot == NSLOT2) { slot = 0; phase ^= 1; }
+            }
+            if (emit_mask) {
+                uint32_t word = mbits;
+                uint32_t o = __shfl_xor_sync(0xffffffffu, word, 4);
+                word = (g & 4) ? ((word & 0xFFFF0000u) | ((o >> 16) & 0x0000FFFFu)) : ((word & 0x0000FFFFu) | ((o << 16) & 0xFFFF0000u));
+                o = __shfl_xor_sync(0xffffffffu, word, 2);
+                word = (g & 2) ? ((word & 0xFF00FF00u) | ((o >> 8) & 0x00FF00FFu)) : ((word & 0x00FF00FFu) | ((o << 8) & 0xFF00FF00u));
+                o = __shfl_xor_sync(0xffffffffu, word, 1);
+                word = (g & 1) ? ((word & 0xF0F0F0F0u) | ((o >> 4) & 0x0F0F0F0Fu)) : ((word & 0x0F0F0F0Fu) | ((o << 4) & 0xF0F0F0F0u));
+                if (active && pos < P) {
+                    const int mrow = prm.rows_y ? __ldg(prm.rows_y + bcur) : prm.row_base_y + bcur;
+                    reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)mrow * prm.m.n_nets + k) * P + pos) * 32)[g] = word;
+                }
+            }
+        }
+        if (prof && lane == 0 && pw == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[12] = pce; o[13] = clock64() - tstart; }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == WARP_MMA2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// Dirty blocks of every proposal (bit q of dmask[b]: some conv row of block q reads a residue where y differs from x) and
+// the copy of the current state's relu-mask rows into the proposal's pool row (the forward overwrites the dirty ones).
+__global__ void __launch_bounds__(128) cnn_dirty_kernel(int n, int L, int P, int aa_stride, const uint8_t* __restrict__ aa_x,
+                                                        const uint8_t* __restrict__ aa_y, uint32_t* __restrict__ dmask,
+                                                        uint8_t* r1mask, const int32_t* __restrict__ rows_x,
+                                                        const int32_t* __restrict__ rows_y, size_t mask_row_bytes) {
+    const int b = blockIdx.x;
+    if (b >= n) return;
+    __shared__ uint32_t smask;
+    if (threadIdx.x == 0) smask = 0u;
+    __syncthreads();
+    uint32_t m = 0u;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        if (aa_x[(size_t)b * aa_stride + i] != aa_y[(size_t)b * aa_stride + i]) {
+            const int p_lo = max(i - 4, 0), p_hi = min(i, P - 1);
+            if (p_lo <= p_hi) m |= (1u << (p_lo >> 4)) | (1u << (p_hi >> 4));
+        }
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(&smask, m);
+    if (r1mask) {
+        const uint4* src = reinterpret_cast<const uint4*>(r1mask + (size_t)rows_x[b] * mask_row_bytes);
+        uint4* dst = reinterpret_cast<uint4*>(r1mask + (size_t)rows_y[b] * mask_row_bytes);
+        for (size_t e = threadIdx.x; e < mask_row_bytes / 16; e += blockDim.x) __stcg(dst + e, __ldcg(src + e));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) dmask[b] = smask;
+}
+
+// Second half of the incremental forward, one thread per (chain, net, channel): the clean blocks' keys are copied from
+// the current row to the proposal row (the dirty ones were written there by cnn_forward_inc_kernel), and the chain-level
+// winner - the 64-bit maximum over the blocks - becomes the same `mkey` the full forward kernel writes.
+__global__ void __launch_bounds__(256) cnn_inc_merge_kernel(const __grid_constant__ IncParams prm) {
+    const int b = blockIdx.x;
+    const int J2 = 2 * prm.m.C, NB = prm.NB, nets = prm.m.n_nets;
+    const uint32_t all_blocks = (NB >= 32) ? 0xFFFFFFFFu : ((1u << NB) - 1u);
+    const uint32_t mask = prm.dmask ? (__ldg(prm.dmask + b) & all_blocks) : all_blocks;
+    const size_t row_keys = (size_t)nets * NB * J2;
+    const int rx = prm.rows_x ? __ldg(prm.rows_x + b) : 0;
+    const int ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
+    const unsigned long long* kx = prm.bkey + (size_t)rx * row_keys;
+    unsigned long long* ky = prm.bkey + (size_t)ry * row_keys;
+    for (int e = threadIdx.x; e < nets * J2; e += blockDim.x) {
+        const int k = e / J2, j = e - k * J2;
+        const size_t base = ((size_t)k * NB) * J2 + j;
+        unsigned long long key[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            key[q] = (q < NB) ? (((mask >> q) & 1u) ? __ldcg(ky + base + (size_t)q * J2) : __ldcg(kx + base + (size_t)q * J2)) : 0ull;
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (q < NB) {
+                if (!((mask >> q) & 1u)) __stcg(ky + base + (size_t)q * J2, key[q]);
+                best = (key[q] > best) ? key[q] : best;
+            }
+        }
+        const ppde_cnn_net_t& net = prm.m.net[k];
+        const float unscale = 1.f / (net.w1_scale * net.r1_scale);
+        const float u = f32_unordered((uint32_t)(best >> 32));
+        int pp = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
+        float v = fmaf(u, unscale, __ldg(net.b1 + j));
+        if (!(v > 0.f)) { v = 0.f; pp = 0; }                // relu; all-nonpositive column -> (0, position 0)
+        prm.mkey[((size_t)b * nets + k) * J2 + j] =
+            ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)pp);
+    }
+}
+
+// Dirty-block bookkeeping of the incremental forward: for chain range r = [n r / R, n (r+1) / R) (R = clusters per
+// (net, channel-tile pair), the forward kernel's partition) an exclusive prefix of the chains' dirty-block counts, the
+// range total, and the compact list of (chain << 4 | block) entries in sequence order.
+__global__ void __launch_bounds__(1024) cnn_inc_scan_kernel(int n, int R, int NB, const uint32_t* __restrict__ dmask,
+                                                            int32_t* __restrict__ boff, int32_t* __restrict__ gtot,
+                                                            uint32_t* __restrict__ blist) {
+    const int range = blockIdx.x;
+    const int b_lo = (int)((int64_t)n * range / R), b_hi = (int)((int64_t)n * (range + 1) / R);
+    const uint32_t all_blocks = (NB >= 32) ? 0xFFFFFFFFu : ((1u << NB) - 1u);
+    __shared__ int wsum[32];
+    __shared__ int running;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    uint32_t* out = blist + (size_t)b_lo * 16;
+    for (int base = b_lo; base < b_hi; base += 1024) {
+        const int b = base + (int)threadIdx.x;
+        uint32_t mask = 0u;
+        if (b < b_hi) mask = dmask ? (dmask[b] & all_blocks) : all_blocks;
+        const int c = __popc(mask);
+        int incl = c;                                           // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = wsum[lane], iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, iv, o);
+                if (lane >= o) iv += u;
+            }
+            wsum[lane] = iv - v;                                // exclusive prefix of the warp sums
+        }
+        __syncthreads();
+        const int start = running;
+        int off = start + wsum[warp] + incl - c;
+        if (b < b_hi) {
+            boff[b] = off;
+            while (mask) {
+                const int q = __ffs((int)mask) - 1;
+                mask &= mask - 1u;
+                out[off++] = ((uint32_t)b << 4) | (uint32_t)q;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) running = start + wsum[31] + incl;   // last thread: total of this batch
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) gtot[range] = running;
+}
+
+// =====================================================================================================
 // Backward of the CNN ensemble on the tensor cores (same skeleton as the forward kernel).
 //
 //   dfit_k/dx[i,a] = sum_t sum_c A[i-t,c] W0[c,a,t],   A[p,c] = 1[r1[p,c]>0] * sum_{j: p*_j=p, m_j>0} d_j W1[j,c]
@@ -835,7 +1344,9 @@ struct BwdParams {
     int aa_stride;
     int n;
     const unsigned long long* mkey;
-    const uint8_t* r1mask;              // [n, n_nets, P, 32] relu mask bits written by the forward kernel
+    const uint8_t* r1mask;              // [rows, n_nets, P, 32] relu mask bits written by the forward kernel
+    const int32_t* mask_rows;           // [n] row of chain b in r1mask, NULL = mask_row_base + b
+    int mask_row_base;
     const uint16_t* wl; int rec;        // winner records from cnn_winner_sort_kernel
     float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
     int ctas_per_net;
@@ -1085,7 +1596,8 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
             // relu-mask bytes of my 4 rows (independent of the winners: issue first)
             uint32_t m4 = 0u;
             {
-                const uint8_t* mrow = prm.r1mask + (((size_t)b * prm.m.n_nets + k) * P + p0 + r0) * 32 + lane;
+                const int mr = prm.mask_rows ? __ldg(prm.mask_rows + b) : prm.mask_row_base + b;
+                const uint8_t* mrow = prm.r1mask + (((size_t)mr * prm.m.n_nets + k) * P + p0 + r0) * 32 + lane;
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr)
                     if (lact && p0 + r0 + rr < P) m4 |= (uint32_t)__ldg(mrow + rr * 32) << (8 * rr);
@@ -1292,20 +1804,99 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     return launch_done();
 }
 
+extern "C" int ppde_cnn_dirty(const ppde_cnn_t* m, const uint8_t* aa_x, const uint8_t* aa_y, int32_t aa_stride, int32_t n,
+                              uint32_t* dmask, uint8_t* r1mask, const int32_t* rows_x, const int32_t* rows_y, void* stream) {
+    if (n <= 0) return 0;
+    if (!aa_x || !aa_y || !dmask || (r1mask && (!rows_x || !rows_y))) return (int)cudaErrorInvalidValue;
+    tc::cnn_dirty_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, m->L, m->P, aa_stride, aa_x, aa_y, dmask, r1mask, rows_x, rows_y,
+                                                              (size_t)m->n_nets * m->P * 32);
+    return launch_done();
+}
+
+extern "C" int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n) { return ((int64_t)n + 256 + (int64_t)n * 16) * 4; }
+
+extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
+                                    unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask,
+                                    unsigned long long* bkey, const int32_t* rows_x, const int32_t* rows_y,
+                                    int32_t row_base_y, void* ws, void* stream) {
+    if (n <= 0) return 0;
+    const int NB = (m->P + 15) / 16;
+    if (m->C > 256 || m->P < 1 || NB > 16 || !bkey || !mkey || !ws || (dmask && !rows_x)) return (int)cudaErrorInvalidValue;
+    tc::IncParams prm;
+    prm.m = *m; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey; prm.r1mask = r1mask; prm.dmask = dmask;
+    prm.bkey = bkey;
+    prm.rows_x = dmask ? rows_x : nullptr;   // full evaluation: nothing is read from a current row
+    prm.rows_y = rows_y; prm.row_base_y = row_base_y; prm.NB = NB;
+    prm.kpad = (m->C + 15) / 16 * 16;
+    { const char* e = getenv("PPDE_INC_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
+    prm.prof = g_forward_prof;
+    const int nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int MT = (2 * m->C + 127) / 128;
+    prm.MT = (MT + 1) / 2;
+    const int combos = m->n_nets * prm.MT;
+    prm.ctas_per_combo = (sms / 2) / combos;
+    if (prm.ctas_per_combo < 1) prm.ctas_per_combo = 1;
+    if (prm.ctas_per_combo > n) prm.ctas_per_combo = n;
+    if (prm.ctas_per_combo > 256) prm.ctas_per_combo = 256;
+    int32_t* boff = reinterpret_cast<int32_t*>(ws);
+    int32_t* gtot = boff + n;
+    uint32_t* blist = reinterpret_cast<uint32_t*>(gtot + 256);
+    prm.boff = boff; prm.gtot = gtot; prm.blist = blist;
+    tc::cnn_inc_scan_kernel<<<prm.ctas_per_combo, 1024, 0, (cudaStream_t)stream>>>(n, prm.ctas_per_combo, NB, dmask, boff, gtot, blist);
+    { int r0 = launch_done(); if (r0) return r0; }
+    const size_t smem = (size_t)tc::NSLOT2 * tc::SLOT2_BYTES + (size_t)100 * nch * tc::KCH * sizeof(float) +
+                        32 * sizeof(uint64_t) + 1024;
+    void (*kern)(tc::IncParams) = nullptr;
+    switch (nch) {
+        case 1: kern = tc::cnn_forward_inc_kernel<1>; break;
+        case 2: kern = tc::cnn_forward_inc_kernel<2>; break;
+        case 3: kern = tc::cnn_forward_inc_kernel<3>; break;
+        default: kern = tc::cnn_forward_inc_kernel<4>; break;
+    }
+    static size_t configured[5] = {0, 0, 0, 0, 0};
+    if (smem > configured[nch]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured[nch] = smem;
+    }
+    kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
+    { int r1 = launch_done(); if (r1) return r1; }
+    tc::cnn_inc_merge_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(prm);
+    return launch_done();
+}
+
 static long long* g_backward_prof = nullptr;
 extern "C" int ppde_set_backward_profile(long long* buf) { g_backward_prof = buf; return 0; }
 
+extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
+                                         int32_t n, const unsigned long long* mkey, float lamda,
+                                         const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
+                                         float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
+                                         const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream);
 extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                                     int32_t n, const unsigned long long* mkey, float lamda,
                                     const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                                     float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
                                     float* scratch, void* stream) {
+    return ppde_cnn_backward_tc_rows(m, pm, aa, aa_stride, n, mkey, lamda, Gp, Gp_stride, gp_rows, G, G_stride, g_rows, r1mask,
+                                     nullptr, 0, scratch, stream);
+}
+extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
+                                         int32_t n, const unsigned long long* mkey, float lamda,
+                                         const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
+                                         float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
+                                         const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream) {
     if (n <= 0) return 0;
     if (m->C > 256 || m->P < 1 || !scratch || !r1mask) return (int)cudaErrorInvalidValue;
     tc::BwdParams prm;
     prm.m = *m; prm.pm = *pm; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey;
     prm.Gc = scratch;
     prm.r1mask = r1mask;
+    prm.mask_rows = mask_rows;
+    prm.mask_row_base = mask_row_base;
     { const char* e = getenv("PPDE_BWD_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
     prm.tiles_per_chain = (m->P + tc::BW_NT - 1) / tc::BW_NT;
     prm.kpad = (m->C + 15) / 16 * 16;

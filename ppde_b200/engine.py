@@ -5,6 +5,7 @@ Host mirror of the reference's hot loop (ppde/protein_samplers/ppde.py:65-153) a
 and streams only; every arithmetic step is a kernel of libppde_b200.so.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -136,11 +137,15 @@ class PoEModel:
         self._mkey = None
         # CNN forward implementation: tcgen05 tensor-core kernel (needs the W1 tile in 256 TMEM columns,
         # i.e. C <= 256) or the fp32 SIMT kernel.  PPDE_CNN_FORWARD=simt forces the latter (A/B tests).
-        import os
         want = os.environ.get("PPDE_CNN_FORWARD", "tc")
         self.cnn_forward_impl = "tc" if (want == "tc" and self.C <= 256) else "simt"
         wantb = os.environ.get("PPDE_CNN_BACKWARD", "tc")
         self.cnn_backward_impl = "tc" if (wantb == "tc" and self.C <= 256) else "simt"
+        # incremental CNN forward (block-wise max-pool cache in the chain engine's row pools); needs both tensor-core
+        # kernels and <= 16 blocks of 16 positions.  PPDE_CNN_INC=0 re-evaluates every position of every proposal.
+        self.NB = (self.P + 15) // 16
+        self.cnn_inc = (os.environ.get("PPDE_CNN_INC", "1") != "0" and self.cnn_forward_impl == "tc"
+                        and self.cnn_backward_impl == "tc" and self.NB <= 16)
         # full Potts evaluation: "dense" = tcgen05 GEMM for batches of >= dense_min chains, "gather" = row-gather kernel
         self.potts_full_impl = os.environ.get("PPDE_POTTS_FULL", "dense")
         self.dense_min = int(os.environ.get("PPDE_POTTS_DENSE_MIN", "512"))
@@ -171,6 +176,25 @@ class PoEModel:
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
                 gp_ptr, self.D, gp_rows, ep_ptr, g_ptr, self.NE, g_rows, _ptr(E), _ptr(fit), st), "cnn_backward_combine")
 
+    # -- CNN with the block-key / relu-mask POOLS of a chain engine (incremental path) -----------------
+    def cnn_forward_pool(self, aa, n, mk, bkey, r1pool, dmask, rows_x, rows_y, row_base_y, st):
+        """Forward of n states into pool rows rows_y (None: row_base_y + b).  dmask None: every block is evaluated;
+        otherwise only the dirty blocks, the others come from rows_x (ppde_cnn_forward_inc)."""
+        _lib.check(self.lib.ppde_cnn_forward_inc(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), _ptr(r1pool),
+                                                 _ptr(dmask), _ptr(bkey), _ptr(rows_x), _ptr(rows_y), int(row_base_y),
+                                                 _ptr(self.inc_ws(n)), st), "cnn_forward_inc")
+
+    def cnn_backward_pool(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, r1pool, mask_rows, mask_row_base, st):
+        lib = self.lib
+        null = C.c_void_p(0)
+        _lib.check(lib.ppde_cnn_backward_combine(
+            C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+            null, self.D, null, ep_ptr, null, self.NE, null, _ptr(E), _ptr(fit), st), "cnn_fit")
+        _lib.check(lib.ppde_cnn_backward_tc_rows(
+            C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+            gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(r1pool), _ptr(mask_rows), int(mask_row_base),
+            _ptr(self.grad_scratch(n)), st), "cnn_backward_tc_rows")
+
     # -- scratch ------------------------------------------------------------------------------
     def grad_scratch(self, n):
         rec = ((self.P + 1) + 4 * self.C + 7) // 8 * 8                      # winner records (uint16) behind the floats
@@ -178,6 +202,12 @@ class PoEModel:
         if getattr(self, "_gscratch", None) is None or self._gscratch.numel() < need:
             self._gscratch = torch.empty(need, dtype=torch.float32, device=self.device)
         return self._gscratch
+
+    def inc_ws(self, n):
+        need = int(self.lib.ppde_cnn_forward_inc_ws_bytes(n))
+        if getattr(self, "_inc_ws", None) is None or self._inc_ws.numel() < need:
+            self._inc_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._inc_ws
 
     def r1mask(self, n):
         need = n * self.n_nets * self.P * 32
@@ -192,9 +222,10 @@ class PoEModel:
         return self._mkey
 
     # -- full evaluation ------------------------------------------------------------------------
-    def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True):
+    def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True, bkey=None, r1pool=None):
         """Energy (+ gradient field) of n states `aa` [n, aa_stride] written into pool rows
-        g_row0.. / gp_row0.. (contiguous). E, fit, Epotts: float tensors [n]."""
+        g_row0.. / gp_row0.. (contiguous). E, fit, Epotts: float tensors [n].
+        bkey / r1pool: the engine's block-key and relu-mask pools (rows g_row0.. are filled too)."""
         lib = self.lib
         st = _stream()
         gp_ptr, ep_ptr = C.c_void_p(0), C.c_void_p(0)
@@ -202,8 +233,13 @@ class PoEModel:
             gp_ptr, ep_ptr = C.c_void_p(Gp.data_ptr() + gp_row0 * self.D * 4), _ptr(Epotts)
             self.potts_full(aa, n, gp_ptr, ep_ptr, st)
         mk = self.mkey(n)
-        self.cnn_forward(aa, n, mk, st)
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
+        if bkey is not None and want_grad:
+            self.cnn_forward_pool(aa, n, mk, bkey, r1pool, None, None, None, g_row0, st)
+            self.cnn_backward_pool(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr, C.c_void_p(0), E, fit,
+                                   r1pool, None, g_row0, st)
+            return
+        self.cnn_forward(aa, n, mk, st)
         self.cnn_backward_combine(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr if want_grad else None,
                                   C.c_void_p(0), E, fit, st)
 
@@ -309,6 +345,13 @@ class ChainEngine:
         local_traj = (T is not None and 0 <= self.traj_chain < n)
         self.traj_aa = torch.zeros(T + 1, m.aa_stride, dtype=u8, device=dev) if local_traj else None
         self.t_dev = torch.zeros(1, dtype=i32, device=dev)
+        # incremental CNN forward: per-row block keys of the max-pool and relu-mask rows, indexed like G / Gp
+        self.inc = bool(m.cnn_inc)
+        self.bkey = self.r1pool = self.dmask = None
+        if self.inc:
+            self.bkey = torch.empty(rows * m.n_nets * m.NB * 2 * m.C, dtype=torch.int64, device=dev)
+            self.r1pool = torch.empty(rows * m.n_nets * m.P * 32, dtype=u8, device=dev)
+            self.dmask = torch.zeros(n, dtype=i32, device=dev)
         self._allocated = True
 
     def _struct(self):
@@ -344,13 +387,14 @@ class ChainEngine:
                 self.aa_fixed[1:].copy_(anchor)
                 self.anchor_fixed = torch.arange(1, n + 1, dtype=torch.int32, device=m.device)
             ep = torch.empty(self.n_fixed, dtype=torch.float32, device=m.device)
-            m.evaluate_into(self.aa_fixed, self.n_fixed, self.G, 2 * n, self.Gp, 2 * n, self.E_fixed, self.fit_fixed, ep)
+            m.evaluate_into(self.aa_fixed, self.n_fixed, self.G, 2 * n, self.Gp, 2 * n, self.E_fixed, self.fit_fixed, ep,
+                            bkey=self.bkey, r1pool=self.r1pool)
             if all_wt:
                 self.row_cur.fill_(2 * n)
                 self.E.copy_(self.E_fixed[0].expand(n)); self.fit.copy_(self.fit_fixed[0].expand(n))
             else:
                 epn = torch.empty(n, dtype=torch.float32, device=m.device)
-                m.evaluate_into(self.aa, n, self.G, 0, self.Gp, 0, self.E, self.fit, epn)
+                m.evaluate_into(self.aa, n, self.G, 0, self.Gp, 0, self.E, self.fit, epn, bkey=self.bkey, r1pool=self.r1pool)
                 self.row_cur.copy_(torch.arange(n, dtype=torch.int32, device=m.device))
             self.best_E.copy_(self.E); self.best_fit.copy_(self.fit); self.best_aa.copy_(self.aa)
             if self.E_hist is not None:
@@ -376,12 +420,33 @@ class ChainEngine:
         if m.has_potts:
             _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(c), C.byref(p), st), "potts_incremental")
         _lib.check(lib.ppde_step_rows(C.byref(c), _ptr(self.rows_y), st), "step_rows")
-        mk = m.mkey(n)
-        m.cnn_forward(self.aa_y, n, mk, st)
-        m.cnn_backward_combine(self.aa_y, n, mk, _ptr(self.Gp) if m.has_potts else C.c_void_p(0), _ptr(self.rows_y),
-                               _ptr(self.Epotts_y) if m.has_potts else C.c_void_p(0), _ptr(self.G), _ptr(self.rows_y),
-                               self.E_y, self.fit_y, st)
+        self.cnn_forward_y(st)
+        self.cnn_backward_y(st)
         _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_reverse_accept")
+
+    def cnn_forward_y(self, st):
+        """CNN ensemble at the proposals aa_y: max-pool winners -> mkey (only the dirty blocks on the incremental path)."""
+        m, n = self.m, self.n
+        mk = m.mkey(n)
+        if self.inc:
+            _lib.check(self.lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(self.aa), _ptr(self.aa_y), m.aa_stride, n, _ptr(self.dmask),
+                                               _ptr(self.r1pool), _ptr(self.row_cur), _ptr(self.rows_y), st), "cnn_dirty")
+            m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st)
+        else:
+            m.cnn_forward(self.aa_y, n, mk, st)
+
+    def cnn_backward_y(self, st):
+        """fit_y / E_y and the gradient rows of the proposals from the winners in mkey."""
+        m, n = self.m, self.n
+        mk = m.mkey(n)
+        gp = _ptr(self.Gp) if m.has_potts else C.c_void_p(0)
+        ep = _ptr(self.Epotts_y) if m.has_potts else C.c_void_p(0)
+        if self.inc:
+            m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
+                                self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st)
+        else:
+            m.cnn_backward_combine(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
+                                   self.E_y, self.fit_y, st)
 
     def step(self, uniforms=None):
         """One MCMC iteration (eager launches). `uniforms`: optional float32 device tensor
@@ -401,7 +466,10 @@ class ChainEngine:
             if self._graph is None:
                 self.m.mkey(self.n)
                 self.m.grad_scratch(self.n)
-                self.m.r1mask(self.n)
+                if not self.inc:
+                    self.m.r1mask(self.n)
+                else:
+                    self.m.inc_ws(self.n)
                 self.t_dev.fill_(self.t)
                 p = self._params(0, None, use_t_dev=True)
                 self._graph_params = p
