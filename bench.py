@@ -224,39 +224,83 @@ def main():
     if not args.no_breakdown:
         import ctypes as C
         from ppde_b200.engine import _ptr, _stream
-        names = ["pas_propose", "potts_incremental", "cnn_forward", "cnn_backward_combine", "pas_reverse_accept"]
-        tot = {k: 0.0 for k in names}
+        st = _stream()
+        p_holder = {}
+        seq = [("pas_propose", lambda: _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(eng.chains), C.byref(p_holder["p"]), st), "propose")),
+               ("potts_incremental", lambda: (_lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(eng.chains), C.byref(p_holder["p"]), st), "inc"),
+                                              _lib.check(lib.ppde_step_rows(C.byref(eng.chains), _ptr(eng.rows_y), st), "rows")))]
+        if eng.inc:
+            seq += [("cnn_dirty", lambda: eng.cnn_forward_y(st, dirty=True, parts=0)),
+                    ("cnn_inc_scan", lambda: eng.cnn_forward_y(st, dirty=False, parts=1)),
+                    ("cnn_forward_inc_tc", lambda: eng.cnn_forward_y(st, dirty=False, parts=2)),
+                    ("cnn_inc_merge", lambda: eng.cnn_forward_y(st, dirty=False, parts=4)),
+                    ("cnn_fit", lambda: eng.cnn_backward_y(st, do_fit=True, parts=0)),
+                    ("cnn_winner_sort", lambda: eng.cnn_backward_y(st, do_fit=False, parts=1)),
+                    ("cnn_backward_tc", lambda: eng.cnn_backward_y(st, do_fit=False, parts=2)),
+                    ("cnn_grad_combine", lambda: eng.cnn_backward_y(st, do_fit=False, parts=4))]
+        else:
+            seq += [("cnn_forward", lambda: eng.cnn_forward_y(st)), ("cnn_backward_combine", lambda: eng.cnn_backward_y(st))]
+        seq += [("pas_reverse_accept", lambda: _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(eng.chains), C.byref(p_holder["p"]), st), "rev"))]
+        tot = {k: 0.0 for k, _ in seq}
         reps = min(K, 5)
-        c_before = lib.ppde_last_launch_count()
-        for _ in range(reps):
-            p = eng._params(eng.t)
-            st = _stream()
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        launches_per_step, dirty_blocks = 0, None
+        for rep in range(reps):
+            p_holder["p"] = eng._params(eng.t)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(seq) + 1)]
+            c_before = lib.ppde_last_launch_count()
             evs[0].record()
-            _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "propose"); evs[1].record()
-            _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "inc")
-            _lib.check(lib.ppde_step_rows(C.byref(eng.chains), _ptr(eng.rows_y), st), "rows"); evs[2].record()
-            eng.cnn_forward_y(st); evs[3].record()
-            eng.cnn_backward_y(st)
-            evs[4].record()
-            _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "rev"); evs[5].record()
+            for i, (_, fn) in enumerate(seq):
+                fn()
+                evs[i + 1].record()
             torch.cuda.synchronize()
+            launches_per_step = lib.ppde_last_launch_count() - c_before
             eng.t += 1
-            for i, k in enumerate(names):
+            for i, (k, _) in enumerate(seq):
                 tot[k] += evs[i].elapsed_time(evs[i + 1])
-        launches_per_step = (lib.ppde_last_launch_count() - c_before) // reps
+            if eng.inc and rep == reps - 1:
+                dm = eng.dmask.to(torch.int64) & 0xFFFF
+                dirty_blocks = float(sum(((dm >> q) & 1).sum() for q in range(16)).item())
         breakdown = {k: v / reps for k, v in tot.items()}
         P, Cc = L - 4, L
-        flops_fwd = 3 * 2 * P * Cc * 2 * Cc * n                    # 3*2*P*C*2C per chain
-        t_fwd = breakdown["cnn_forward"] * 1e-3
-        achieved = flops_fwd / t_fwd / 1e12
-        roof = {"kernel": ("cnn_forward_tc2_kernel" if os.environ.get("PPDE_TC_CTAS", "2") != "1" else "cnn_forward_tc_kernel") if m.cnn_forward_impl == "tc" else "cnn_forward_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                # dram__bytes_read+write of this kernel from the committed `ncu --set full` capture
-                # (profiles/r01_cnn_forward_tc2_v3_summary.txt: 3.7 + 221.8 MB at 8192 chains), scaled to this launch
-                "traffic": (225.5e6 / 8192) * n if m.cnn_forward_impl == "tc" and L == 238 else None,
-                "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
-                "algorithmic_flops_per_launch": flops_fwd, "avg_launch_ms": breakdown["cnn_forward"]}
+        per_sum = " (every kernel timed alone with CUDA events inside an eager replay of the step)"
+        if eng.inc:
+            # dominant kernel of the step: the tensor-core CNN backward (3*(4C^2 + 200*P*C) flops per chain)
+            flops = 3 * (4 * Cc * Cc + 200 * P * Cc) * n
+            t_k = breakdown["cnn_backward_tc"] * 1e-3
+            achieved = flops / t_k / 1e12
+            roof = {"kernel": "cnn_backward_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                    # dram__bytes_read+write from the committed `ncu --set full` capture (profiles/r01_cnn_backward_tc_v7_summary.txt:
+                    # 244.7 + 414.2 MB at 8192 chains), scaled to this launch
+                    "traffic": (658.9e6 / 8192) * n if L == 238 else None,
+                    "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "algorithmic_flops_per_launch": flops, "avg_launch_ms": breakdown["cnn_backward_tc"],
+                    "note": "fp32-faithful fp16 hi/lo split = 3 tensor-core passes per algorithmic flop; the kernel is limited by the "
+                            "L2->SM gather of the max-pool winners' W1 rows (422 KB per chain and net), not by the tensor pipe" + per_sum}
+            # the incremental forward computes only the dirty 16-position blocks: 3 nets * 2*16*C*2C flops per block
+            if dirty_blocks is not None:
+                f_inc = dirty_blocks * 3 * 2 * 16 * Cc * 2 * Cc
+                t_inc = breakdown["cnn_forward_inc_tc"] * 1e-3
+                roof["forward_incremental"] = {
+                    "kernel": "cnn_forward_inc_kernel", "dirty_blocks_per_chain": dirty_blocks / n, "blocks_per_chain": (P + 15) // 16,
+                    "executed_algorithmic_tflops": f_inc / t_inc / 1e12, "avg_launch_ms": breakdown["cnn_forward_inc_tc"],
+                    "full_evaluation_equivalent_tflops": 3 * 2 * P * Cc * 2 * Cc * n / ((breakdown["cnn_dirty"] + breakdown["cnn_inc_scan"]
+                                                         + breakdown["cnn_forward_inc_tc"] + breakdown["cnn_inc_merge"]) * 1e-3) / 1e12}
+                mbytes = n * 3 * 2 * Cc * (((P + 15) // 16) * 8 * 2 + 8)
+                roof["merge_kernel"] = {"kernel": "cnn_inc_merge_kernel", "bound": "hbm", "algorithmic_bytes": mbytes,
+                                        "achieved_gbs": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
+                                        "frac": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9 / pk["hbm_gbs"]}
+        else:
+            flops_fwd = 3 * 2 * P * Cc * 2 * Cc * n                    # 3*2*P*C*2C per chain
+            t_fwd = breakdown["cnn_forward"] * 1e-3
+            achieved = flops_fwd / t_fwd / 1e12
+            roof = {"kernel": ("cnn_forward_tc2_kernel" if os.environ.get("PPDE_TC_CTAS", "2") != "1" else "cnn_forward_tc_kernel") if m.cnn_forward_impl == "tc" else "cnn_forward_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                    # dram__bytes_read+write of this kernel from the committed `ncu --set full` capture
+                    # (profiles/r01_cnn_forward_tc2_v3_summary.txt: 3.7 + 221.8 MB at 8192 chains), scaled to this launch
+                    "traffic": (225.5e6 / 8192) * n if m.cnn_forward_impl == "tc" and L == 238 else None,
+                    "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "algorithmic_flops_per_launch": flops_fwd, "avg_launch_ms": breakdown["cnn_forward"]}
         hbm_bytes = (8 * m.D + 2 * L + 16) * n                        # SURVEY.md §8d B_alg per chain-step
         t_hbm = (breakdown["pas_propose"] + breakdown["potts_incremental"] + breakdown["pas_reverse_accept"]) * 1e-3
         roof["hbm_kernels"] = {"achieved_gbs": hbm_bytes / t_hbm / 1e9, "peak_gbs": pk["hbm_gbs"],
@@ -264,7 +308,7 @@ def main():
                                "kernels": "pas_propose + potts_incremental + pas_reverse_accept",
                                "algorithmic_bytes_per_step": hbm_bytes}
     if launches_per_step is None:
-        launches_per_step = 8
+        launches_per_step = 12 if m.cnn_inc else 9
 
     # ---- end to end through the reference-facing API, host buffers in / out ----------------------
     e2e = None

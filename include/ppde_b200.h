@@ -157,7 +157,10 @@ int ppde_set_forward_variant(int ctas);
 /* profiling aid: non-NULL device buffer [grid][16] int64 selects an instrumented build of the 2-CTA forward kernel that
  * accumulates per-role cycle counters (tools/prof_fwd.py); NULL (default) = production kernel. */
 int ppde_set_forward_profile(long long* buf);
-int ppde_set_backward_profile(long long* buf);   /* same, for the tensor-core backward kernel (tools/prof_bwd.py) */
+int ppde_set_backward_profile(long long* buf);
+/* measurement aid for per-kernel timing: bit masks of the kernels the composite launchers run (default 7 = all).
+ * ppde_cnn_forward_inc: 1 scan, 2 tensor-core kernel, 4 merge; ppde_cnn_backward_tc[_rows]: 1 winner sort, 2 tensor-core kernel, 4 combine. */
+int ppde_set_profile_parts(int forward_inc_parts, int backward_parts);   /* same, for the tensor-core backward kernel (tools/prof_bwd.py) */
 int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                               int32_t n, const unsigned long long* mkey, float lamda,
                               const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,

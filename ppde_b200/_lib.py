@@ -62,6 +62,7 @@ SIGNATURES = {
     "ppde_set_forward_variant": (C.c_int, [C.c_int]),
     "ppde_set_forward_profile": (C.c_int, [vp]),
     "ppde_set_backward_profile": (C.c_int, [vp]),
+    "ppde_set_profile_parts": (C.c_int, [C.c_int, C.c_int]),
     "ppde_cnn_backward_combine": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp,
                                             C.c_float, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp]),
     "ppde_cnn_backward_tc": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,

@@ -1804,6 +1804,15 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     return launch_done();
 }
 
+// measurement aid (bench.py's per-kernel breakdown): which kernels the composite launchers run.
+// forward_inc: 1 = scan, 2 = tensor-core kernel, 4 = merge; backward_tc: 1 = winner sort, 2 = tensor-core kernel, 4 = combine.
+static int g_inc_parts = 7, g_bwd_parts = 7;
+extern "C" int ppde_set_profile_parts(int forward_inc_parts, int backward_parts) {
+    g_inc_parts = forward_inc_parts & 7;
+    g_bwd_parts = backward_parts & 7;
+    return 0;
+}
+
 extern "C" int ppde_cnn_dirty(const ppde_cnn_t* m, const uint8_t* aa_x, const uint8_t* aa_y, int32_t aa_stride, int32_t n,
                               uint32_t* dmask, uint8_t* r1mask, const int32_t* rows_x, const int32_t* rows_y, void* stream) {
     if (n <= 0) return 0;
@@ -1845,8 +1854,11 @@ extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int3
     int32_t* gtot = boff + n;
     uint32_t* blist = reinterpret_cast<uint32_t*>(gtot + 256);
     prm.boff = boff; prm.gtot = gtot; prm.blist = blist;
-    tc::cnn_inc_scan_kernel<<<prm.ctas_per_combo, 1024, 0, (cudaStream_t)stream>>>(n, prm.ctas_per_combo, NB, dmask, boff, gtot, blist);
-    { int r0 = launch_done(); if (r0) return r0; }
+    if (g_inc_parts & 1) {
+        tc::cnn_inc_scan_kernel<<<prm.ctas_per_combo, 1024, 0, (cudaStream_t)stream>>>(n, prm.ctas_per_combo, NB, dmask, boff, gtot, blist);
+        int r0 = launch_done();
+        if (r0) return r0;
+    }
     const size_t smem = (size_t)tc::NSLOT2 * tc::SLOT2_BYTES + (size_t)100 * nch * tc::KCH * sizeof(float) +
                         32 * sizeof(uint64_t) + 1024;
     void (*kern)(tc::IncParams) = nullptr;
@@ -1862,10 +1874,16 @@ extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int3
         if (e != cudaSuccess) return (int)e;
         configured[nch] = smem;
     }
-    kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
-    { int r1 = launch_done(); if (r1) return r1; }
-    tc::cnn_inc_merge_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(prm);
-    return launch_done();
+    if (g_inc_parts & 2) {
+        kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
+        int r1 = launch_done();
+        if (r1) return r1;
+    }
+    if (g_inc_parts & 4) {
+        tc::cnn_inc_merge_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(prm);
+        return launch_done();
+    }
+    return 0;
 }
 
 static long long* g_backward_prof = nullptr;
@@ -1925,13 +1943,20 @@ extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t
     uint16_t* wl = reinterpret_cast<uint16_t*>(scratch + (size_t)m->n_nets * n * L * PPDE_Q);
     prm.wl = wl;
     prm.rec = rec;
-    tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
-    int r0 = launch_done();
-    if (r0) return r0;
-    bkern<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
-    int r = launch_done();
-    if (r) return r;
-    tc::cnn_grad_combine_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
-                                                   Gp, Gp_stride, gp_rows, G, G_stride, g_rows);
-    return launch_done();
+    if (g_bwd_parts & 1) {
+        tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
+        int r0 = launch_done();
+        if (r0) return r0;
+    }
+    if (g_bwd_parts & 2) {
+        bkern<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
+        int r = launch_done();
+        if (r) return r;
+    }
+    if (g_bwd_parts & 4) {
+        tc::cnn_grad_combine_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
+                                                       Gp, Gp_stride, gp_rows, G, G_stride, g_rows);
+        return launch_done();
+    }
+    return 0;
 }

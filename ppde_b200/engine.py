@@ -184,16 +184,19 @@ class PoEModel:
                                                  _ptr(dmask), _ptr(bkey), _ptr(rows_x), _ptr(rows_y), int(row_base_y),
                                                  _ptr(self.inc_ws(n)), st), "cnn_forward_inc")
 
-    def cnn_backward_pool(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, r1pool, mask_rows, mask_row_base, st):
+    def cnn_backward_pool(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, r1pool, mask_rows, mask_row_base, st,
+                          do_fit=True, do_grad=True):
         lib = self.lib
         null = C.c_void_p(0)
-        _lib.check(lib.ppde_cnn_backward_combine(
-            C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
-            null, self.D, null, ep_ptr, null, self.NE, null, _ptr(E), _ptr(fit), st), "cnn_fit")
-        _lib.check(lib.ppde_cnn_backward_tc_rows(
-            C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
-            gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(r1pool), _ptr(mask_rows), int(mask_row_base),
-            _ptr(self.grad_scratch(n)), st), "cnn_backward_tc_rows")
+        if do_fit:
+            _lib.check(lib.ppde_cnn_backward_combine(
+                C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+                null, self.D, null, ep_ptr, null, self.NE, null, _ptr(E), _ptr(fit), st), "cnn_fit")
+        if do_grad:
+            _lib.check(lib.ppde_cnn_backward_tc_rows(
+                C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
+                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(r1pool), _ptr(mask_rows), int(mask_row_base),
+                _ptr(self.grad_scratch(n)), st), "cnn_backward_tc_rows")
 
     # -- scratch ------------------------------------------------------------------------------
     def grad_scratch(self, n):
@@ -424,27 +427,39 @@ class ChainEngine:
         self.cnn_backward_y(st)
         _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_reverse_accept")
 
-    def cnn_forward_y(self, st):
-        """CNN ensemble at the proposals aa_y: max-pool winners -> mkey (only the dirty blocks on the incremental path)."""
+    def cnn_forward_y(self, st, dirty=True, parts=7):
+        """CNN ensemble at the proposals aa_y: max-pool winners -> mkey (only the dirty blocks on the incremental path).
+        dirty / parts select sub-kernels for per-kernel timing (bench.py); the defaults run everything."""
         m, n = self.m, self.n
         mk = m.mkey(n)
         if self.inc:
-            _lib.check(self.lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(self.aa), _ptr(self.aa_y), m.aa_stride, n, _ptr(self.dmask),
-                                               _ptr(self.r1pool), _ptr(self.row_cur), _ptr(self.rows_y), st), "cnn_dirty")
-            m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st)
-        else:
+            if dirty:
+                _lib.check(self.lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(self.aa), _ptr(self.aa_y), m.aa_stride, n,
+                                                   _ptr(self.dmask), _ptr(self.r1pool), _ptr(self.row_cur), _ptr(self.rows_y), st),
+                           "cnn_dirty")
+            if parts:
+                self.lib.ppde_set_profile_parts(parts, 7)
+                try:
+                    m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st)
+                finally:
+                    self.lib.ppde_set_profile_parts(7, 7)
+        elif parts == 7:
             m.cnn_forward(self.aa_y, n, mk, st)
 
-    def cnn_backward_y(self, st):
+    def cnn_backward_y(self, st, do_fit=True, parts=7):
         """fit_y / E_y and the gradient rows of the proposals from the winners in mkey."""
         m, n = self.m, self.n
         mk = m.mkey(n)
         gp = _ptr(self.Gp) if m.has_potts else C.c_void_p(0)
         ep = _ptr(self.Epotts_y) if m.has_potts else C.c_void_p(0)
         if self.inc:
-            m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
-                                self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st)
-        else:
+            self.lib.ppde_set_profile_parts(7, parts if parts else 7)
+            try:
+                m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
+                                    self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st, do_fit=do_fit, do_grad=bool(parts))
+            finally:
+                self.lib.ppde_set_profile_parts(7, 7)
+        elif do_fit and parts == 7:
             m.cnn_backward_combine(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
                                    self.E_y, self.fit_y, st)
 
