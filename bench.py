@@ -286,7 +286,8 @@ def main():
                     "executed_algorithmic_tflops": f_inc / t_inc / 1e12, "avg_launch_ms": breakdown["cnn_forward_inc_tc"],
                     "full_evaluation_equivalent_tflops": 3 * 2 * P * Cc * 2 * Cc * n / ((breakdown["cnn_dirty"] + breakdown["cnn_inc_scan"]
                                                          + breakdown["cnn_forward_inc_tc"] + breakdown["cnn_inc_merge"]) * 1e-3) / 1e12}
-                mbytes = n * 3 * 2 * Cc * (((P + 15) // 16) * 8 * 2 + 8)
+                nb_ = (P + 15) // 16                # per channel: NB keys read, the clean ones written to the proposal row, mkey written
+                mbytes = int(n * 3 * 2 * Cc * 8 * (nb_ + (nb_ - dirty_blocks / n) + 1))
                 roof["merge_kernel"] = {"kernel": "cnn_inc_merge_kernel", "bound": "hbm", "algorithmic_bytes": mbytes,
                                         "achieved_gbs": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
                                         "frac": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9 / pk["hbm_gbs"]}
