@@ -219,7 +219,7 @@ def main():
     mean_dist = float(eng.population_metrics()[0].float().mean().item())
 
     # ---- per-kernel durations, live (eager launches bracketed by CUDA events on the launch stream) ----
-    breakdown, roof = {}, None
+    breakdown, roof, refresh_ms = {}, None, None
     pk = peaks()
     if not args.no_breakdown:
         import ctypes as C
@@ -234,10 +234,10 @@ def main():
                     ("cnn_inc_scan", lambda: eng.cnn_forward_y(st, dirty=False, parts=1)),
                     ("cnn_forward_inc_tc", lambda: eng.cnn_forward_y(st, dirty=False, parts=2)),
                     ("cnn_inc_merge", lambda: eng.cnn_forward_y(st, dirty=False, parts=4)),
-                    ("cnn_fit", lambda: eng.cnn_backward_y(st, do_fit=True, parts=0)),
-                    ("cnn_winner_sort", lambda: eng.cnn_backward_y(st, do_fit=False, parts=1)),
-                    ("cnn_backward_tc", lambda: eng.cnn_backward_y(st, do_fit=False, parts=2)),
-                    ("cnn_grad_combine", lambda: eng.cnn_backward_y(st, do_fit=False, parts=4))]
+                    ("cnn_fit", lambda: eng.cnn_backward_y(st, do_fit=True, parts=0, full=not eng.delta)),
+                    ("cnn_winner_sort", lambda: eng.cnn_backward_y(st, do_fit=False, parts=1, full=not eng.delta)),
+                    ("cnn_backward_tc", lambda: eng.cnn_backward_y(st, do_fit=False, parts=2, full=not eng.delta)),
+                    ("cnn_grad_combine", lambda: eng.cnn_backward_y(st, do_fit=False, parts=4, full=not eng.delta))]
         else:
             seq += [("cnn_forward", lambda: eng.cnn_forward_y(st)), ("cnn_backward_combine", lambda: eng.cnn_backward_y(st))]
         seq += [("pas_reverse_accept", lambda: _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(eng.chains), C.byref(p_holder["p"]), st), "rev"))]
@@ -261,22 +261,53 @@ def main():
                 dm = eng.dmask.to(torch.int64) & 0xFFFF
                 dirty_blocks = float(sum(((dm >> q) & 1).sum() for q in range(16)).item())
         breakdown = {k: v / reps for k, v in tot.items()}
+        if eng.inc and eng.delta:
+            # the exact backward that replaces the delta backward every bwd_refresh-th iteration (same inputs, same outputs)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(); eng.cnn_backward_y(st, do_fit=False, parts=7, full=True); ev1.record()
+            torch.cuda.synchronize()
+            refresh_ms = ev0.elapsed_time(ev1)
         P, Cc = L - 4, L
         per_sum = " (every kernel timed alone with CUDA events inside an eager replay of the step)"
         if eng.inc:
-            # dominant kernel of the step: the tensor-core CNN backward (3*(4C^2 + 200*P*C) flops per chain)
-            flops = 3 * (4 * Cc * Cc + 200 * P * Cc) * n
-            t_k = breakdown["cnn_backward_tc"] * 1e-3
-            achieved = flops / t_k / 1e12
-            roof = {"kernel": "cnn_backward_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                    # dram__bytes_read+write from the committed `ncu --set full` capture (profiles/r01_cnn_backward_tc_v7_summary.txt:
-                    # 244.7 + 414.2 MB at 8192 chains), scaled to this launch
-                    "traffic": (658.9e6 / 8192) * n if L == 238 else None,
-                    "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)",
-                    "algorithmic_flops_per_launch": flops, "avg_launch_ms": breakdown["cnn_backward_tc"],
-                    "note": "fp32-faithful fp16 hi/lo split = 3 tensor-core passes per algorithmic flop; the kernel is limited by the "
-                            "L2->SM gather of the max-pool winners' W1 rows (422 KB per chain and net), not by the tensor pipe" + per_sum}
+            # roofline of the DOMINANT kernel of the step (largest live duration); algorithmic work per SURVEY.md §8d
+            NE = 20 * L
+            tflop = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12
+            gbs = lambda by, ms_: by / (ms_ * 1e-3) / 1e9
+            cand = {
+                "cnn_backward_tc": dict(kernel="cnn_backward_tc_kernel" + ("<delta>" if eng.delta else ""), bound="tensor", unit="TFLOP/s",
+                                        work=3 * (4 * Cc * Cc + 200 * P * Cc) * n, peak=pk["bf16_sustained"],
+                                        # dram bytes of the full backward from the committed ncu capture (244.6 + 415.9 MB at 8192 chains)
+                                        traffic=(660.6e6 / 8192) * n if (L == 238 and not eng.delta) else None,
+                                        note="gradient of the CNN ensemble for every proposal: 3*(4C^2+200PC) algorithmic flops per chain; "
+                                             "fp16 hi/lo split = 3 tensor-core passes per flop; " +
+                                             ("delta mode gathers only the adjoint rows that differ from the current state" if eng.delta else
+                                              "limited by the L2->SM gather of the winners' W1 rows (422 KB per chain and net)")),
+                "cnn_forward_inc_tc": dict(kernel="cnn_forward_inc_kernel", bound="tensor", unit="TFLOP/s",
+                                           work=3 * 2 * P * Cc * 2 * Cc * n, peak=pk["bf16_sustained"], traffic=(190.96e6 / 8192) * n if L == 238 else None,
+                                           note="max-pool winners of every proposal: 3*2*P*C*2C algorithmic flops per chain, of which only the dirty "
+                                                "16-position blocks are executed (3 fp16 passes per flop)"),
+                "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s", work=None, peak=pk["hbm_gbs"],
+                                      traffic=(2654.2e6 / 8192) * n if L == 238 else None, note="clean block keys copied to the proposal row + chain-level winner"),
+                "pas_propose": dict(kernel="pas_propose_kernel", bound="hbm", unit="GB/s", work=(4 * NE + L) * n, peak=pk["hbm_gbs"],
+                                    traffic=(164.9e6 / 8192) * n if L == 238 else None,
+                                    note="reads one gradient row per chain; bound by the per-entry Philox + softmax arithmetic "
+                                         "(one uniform per entry of [n, 20L] per sub-step), not by bytes"),
+            }
+            dom = max(cand, key=lambda k_: breakdown[k_])
+            cd = cand[dom]
+            if dom == "cnn_inc_merge":
+                nb_ = (P + 15) // 16
+                cd["work"] = int(n * 3 * 2 * Cc * 8 * (nb_ + (nb_ - (dirty_blocks or 0) / n) + 1))
+            ach = tflop(cd["work"], breakdown[dom]) if cd["unit"] == "TFLOP/s" else gbs(cd["work"], breakdown[dom])
+            roof = {"kernel": cd["kernel"], "bound": cd["bound"], "achieved": ach, "peak": cd["peak"], "unit": cd["unit"],
+                    "frac": ach / cd["peak"], "traffic": cd["traffic"],
+                    "peak_source": pk["src"] + (", sustained bf16 (kernel timed inside a long step)" if cd["bound"] == "tensor" else ", HBM copy"),
+                    ("algorithmic_flops_per_launch" if cd["bound"] == "tensor" else "algorithmic_bytes_per_launch"): cd["work"],
+                    "avg_launch_ms": breakdown[dom], "note": cd["note"] + per_sum}
+            if eng.delta:
+                roof["backward"] = {"mode": "delta", "exact_refresh_every": m.bwd_refresh, "exact_backward_ms": refresh_ms,
+                                    "delta_backward_ms": breakdown["cnn_winner_sort"] + breakdown["cnn_backward_tc"] + breakdown["cnn_grad_combine"]}
             # the incremental forward computes only the dirty 16-position blocks: 3 nets * 2*16*C*2C flops per block
             if dirty_blocks is not None:
                 f_inc = dirty_blocks * 3 * 2 * 16 * Cc * 2 * Cc

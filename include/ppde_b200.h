@@ -198,7 +198,19 @@ int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n);   /* workspace of ppde_cnn_for
 int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                          unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask, unsigned long long* bkey,
                          const int32_t* rows_x, const int32_t* rows_y, int32_t row_base_y,
+                         unsigned long long* mkey_pool /* optional [rows, n_nets, 2C]: row of the proposal also gets mkey */,
                          void* ws /* ppde_cnn_forward_inc_ws_bytes(n) bytes */, void* stream);
+/* DELTA backward: the CNN part of the gradient changes between the current state x and the proposal y only through the
+ * conv rows whose relu mask changed and the channels whose max-pool winner moved (a few percent of the winners), so
+ *     G[rows_y[b]] = G[rows_x[b]] + (Gp[rows_y[b]] - Gp[rows_x[b]])(window) + lamda/n_nets * sum_k d(dfit_k/dx)
+ * with only those adjoint rows gathered (same tensor-core kernel, signed winner records).  Rounding differences accumulate
+ * (~1e-7 of max|G| per update): callers refresh with ppde_cnn_backward_tc_rows periodically.  mkey_pool holds the winners
+ * of every pool row (ppde_cnn_forward_inc), r1mask the relu-mask pool; same scratch as ppde_cnn_backward_tc. */
+int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa_x, const uint8_t* aa_y,
+                            int32_t aa_stride, int32_t n, const unsigned long long* mkey_y,
+                            const unsigned long long* mkey_pool, float lamda, const float* Gp, int64_t Gp_stride,
+                            float* G, int64_t G_stride, const int32_t* rows_x, const int32_t* rows_y,
+                            const uint8_t* r1mask, float* scratch, void* stream);
 /* dH_potts of n states from field rows already in the pool: Epotts[b] = 1/2 sum_i (Gp[rows[b]][(i,aa_i)] + h) - H(wt);
  * rows == NULL means row b. */
 int ppde_potts_energy_rows(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n, const float* Gp,

@@ -767,6 +767,7 @@ struct IncParams {
     unsigned long long* mkey;           // [n, n_nets, 2C]
     uint8_t* r1mask;                    // pool [rows, n_nets, P, 32] or NULL
     const uint32_t* dmask;              // [n] dirty-block bits, NULL = every block is dirty (full evaluation into the pool)
+    unsigned long long* mkey_pool;      // optional pool [rows, n_nets, 2C]: the proposal row also gets mkey (delta backward)
     unsigned long long* bkey;           // pool [rows, n_nets, NB, 2C]
     const int32_t* rows_x;              // [n] pool row of the current state (NULL only with dmask == NULL)
     const int32_t* rows_y;              // [n] pool row of the proposal, NULL = row_base_y + b
@@ -1192,8 +1193,9 @@ __global__ void __launch_bounds__(256) cnn_inc_merge_kernel(const __grid_constan
         int pp = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
         float v = fmaf(u, unscale, __ldg(net.b1 + j));
         if (!(v > 0.f)) { v = 0.f; pp = 0; }                // relu; all-nonpositive column -> (0, position 0)
-        prm.mkey[((size_t)b * nets + k) * J2 + j] =
-            ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)pp);
+        const unsigned long long mk = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)pp);
+        prm.mkey[((size_t)b * nets + k) * J2 + j] = mk;
+        if (prm.mkey_pool) prm.mkey_pool[((size_t)ry * nets + k) * J2 + j] = mk;
     }
 }
 
@@ -1328,6 +1330,117 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Winner records of the DELTA backward.  For chain b and net k the per-net gradient changes between the current state x
+// and the proposal y only through
+//   * the conv rows whose relu mask changed: p in D0 = U_{i: x_i != y_i} [i-4, i], and
+//   * the channels whose arg-max position (or liveness) changed.
+// Entries (channel | side << 15; side 0 = y, 1 = x), counting-sorted by position and ordered by (side, channel) inside a
+// position: every winner sitting on a position of D0 (both sides), and both ends of every moved winner.  Same record layout
+// as cnn_winner_sort_kernel (start[P+1] | list[<= 2*J2]).
+__global__ void __launch_bounds__(128) cnn_winner_delta_kernel(int n_nets, int C, int P, int L, int aa_stride,
+                                                               const uint8_t* __restrict__ aa_x, const uint8_t* __restrict__ aa_y,
+                                                               const unsigned long long* __restrict__ mkey_y,
+                                                               const unsigned long long* __restrict__ mkey_pool,
+                                                               const int32_t* __restrict__ rows_x,
+                                                               uint16_t* __restrict__ wl, int rec) {
+    extern __shared__ int sw[];
+    const int J2 = 2 * C;
+    int* sStart = sw;                 // [P+1]
+    int* sFill = sStart + (P + 1);    // [P]
+    int* sD0 = sFill + P;             // [P]
+    int* sPy = sD0 + P;               // [J2] position of the y-side entry or -1
+    int* sPx = sPy + J2;              // [J2]
+    int* sList = sPx + J2;            // [2 J2]
+    const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
+    const unsigned long long* ky = mkey_y + (size_t)bk * J2;
+    const unsigned long long* kx = mkey_pool + ((size_t)rows_x[b] * n_nets + k) * J2;
+    for (int i = threadIdx.x; i <= P; i += 128) { sStart[i] = 0; if (i < P) { sFill[i] = 0; sD0[i] = 0; } }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += 128) {
+        if (aa_x[(size_t)b * aa_stride + i] != aa_y[(size_t)b * aa_stride + i])
+            for (int p = max(i - 4, 0); p <= min(i, P - 1); ++p) sD0[p] = 1;
+    }
+    __syncthreads();
+    auto decode = [&](unsigned long long key) -> int {
+        const float mj = __uint_as_float((unsigned)(key >> 32));
+        const int pst = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
+        return ((mj > 0.f) && pst >= 0 && pst < P) ? pst : -1;
+    };
+    for (int j = threadIdx.x; j < J2; j += 128) {
+        const int py = decode(ky[j]), px = decode(kx[j]);
+        const bool moved = py != px;
+        const int ey = (py >= 0 && (moved || sD0[py])) ? py : -1;
+        const int ex = (px >= 0 && (moved || sD0[px])) ? px : -1;
+        sPy[j] = ey; sPx[j] = ex;
+        if (ey >= 0) atomicAdd(&sStart[ey + 1], 1);
+        if (ex >= 0) atomicAdd(&sStart[ex + 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = (P + 1 + 31) / 32;
+        int run = 0;
+        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) run += sStart[i];
+        int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int base = incl - run;
+        for (int i = lane * per; i < min((lane + 1) * per, P + 1); ++i) { base += sStart[i]; sStart[i] = base; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < J2; j += 128) {
+        const int ey = sPy[j], ex = sPx[j];
+        if (ey >= 0) sList[sStart[ey] + atomicAdd(&sFill[ey], 1)] = j;
+        if (ex >= 0) sList[sStart[ex] + atomicAdd(&sFill[ex], 1)] = j | 0x8000;
+    }
+    __syncthreads();
+    uint16_t* out = wl + (size_t)bk * rec;
+    for (int pp = threadIdx.x; pp < P; pp += 128) {
+        const int s0 = sStart[pp], s1 = sStart[pp + 1];
+        for (int u = s0 + 1; u < s1; ++u) {           // insertion sort: y side first, channels ascending (deterministic sums)
+            const int v = sList[u];
+            int w = u - 1;
+            while (w >= s0 && sList[w] > v) { sList[w + 1] = sList[w]; --w; }
+            sList[w + 1] = v;
+        }
+        for (int u = s0; u < s1; ++u) out[(P + 1) + u] = (uint16_t)sList[u];
+    }
+    for (int i = threadIdx.x; i <= P; i += 128) out[i] = (uint16_t)sStart[i];
+}
+
+// G_y = G_x + (Gp_y - Gp_x)(window) + lamda / n_nets * (dGc_0 + dGc_1 + dGc_2)   (delta backward; fixed summation order)
+__global__ void cnn_grad_combine_delta_kernel(int n, int NE, int n_nets, float scale, ppde_potts_t pm,
+                                              const float* __restrict__ Gc, const float* __restrict__ Gp, int64_t Gp_stride,
+                                              float* __restrict__ G, int64_t G_stride,
+                                              const int32_t* __restrict__ rows_x, const int32_t* __restrict__ rows_y) {
+    const int b = blockIdx.x;
+    const int wlo = pm.win_lo * PPDE_Q, whi = (pm.win_lo + pm.Lp) * PPDE_Q;     // multiples of 4
+    const int rx = rows_x[b], ry = rows_y[b];
+    const float4* gx = reinterpret_cast<const float4*>(G + (int64_t)rx * G_stride);
+    float4* gy = reinterpret_cast<float4*>(G + (int64_t)ry * G_stride);
+    const float* px = Gp ? Gp + (int64_t)rx * Gp_stride : nullptr;
+    const float* py = Gp ? Gp + (int64_t)ry * Gp_stride : nullptr;
+    for (int q = threadIdx.x; q < NE / 4; q += blockDim.x) {
+        float4 acc = __ldcs(reinterpret_cast<const float4*>(Gc + (size_t)b * NE) + q);
+        for (int k = 1; k < n_nets; ++k) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(Gc + ((size_t)k * n + b) * NE) + q);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float4 base = gx[q];
+        const int e = q * 4;
+        if (Gp && e >= wlo && e < whi) {
+            const float4 a = *reinterpret_cast<const float4*>(py + (e - wlo));
+            const float4 c = *reinterpret_cast<const float4*>(px + (e - wlo));
+            base.x += a.x - c.x; base.y += a.y - c.y; base.z += a.z - c.z; base.w += a.w - c.w;
+        }
+        gy[q] = make_float4(fmaf(scale, acc.x, base.x), fmaf(scale, acc.y, base.y), fmaf(scale, acc.z, base.z),
+                            fmaf(scale, acc.w, base.w));
+    }
+}
+
 constexpr int BW_NT = 64;               // positions per tile (N of the MMA)
 constexpr int BW_NT_PROD = 512;         // 16 producer warps, 4 tile rows each
 constexpr int BW_NTHREADS = NT_EPI + BW_NT_PROD + 32;   // 672: warps 0-3 epilogue, 4-19 producers, 20 MMA issuer
@@ -1347,6 +1460,7 @@ struct BwdParams {
     const uint8_t* r1mask;              // [rows, n_nets, P, 32] relu mask bits written by the forward kernel
     const int32_t* mask_rows;           // [n] row of chain b in r1mask, NULL = mask_row_base + b
     int mask_row_base;
+    const int32_t* mask_rows_x;         // delta mode only: [n] r1mask row of the chain's CURRENT state
     const uint16_t* wl; int rec;        // winner records from cnn_winner_sort_kernel
     float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
     int ctas_per_net;
@@ -1359,6 +1473,18 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
+// explicit shared-space scalar loads (32-bit addresses; the record / decoder pointers lose their address space through
+// the alignment casts and would otherwise compile to generic LD with 64-bit address math and long-scoreboard waits)
+__device__ __forceinline__ int lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (int)v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 
 // Backward of one net for a contiguous block of chains, persistent CTA.
 //
@@ -1369,14 +1495,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) { 
 //   taps of a residue in 5 adjacent lanes of one warp, so the col2im below is a warp-shuffle reduction in registers.
 // * Producers: warp w owns rows 4w..4w+3 of every tile, lane l owns channels 8l..8l+7.  The winners of those rows are
 //   one contiguous run of the chain's (position, channel)-sorted list (staged in shared memory by a bulk copy one chain
-//   ahead); a warp streams their W1 rows from L2 in groups of 4 (8 x 16-byte loads in flight per lane), accumulates
+//   ahead, read with explicit ld.shared); a warp streams their W1 rows from L2 in groups of 4 (8 x 16-byte loads in
+//   flight per lane, the first group issued BEFORE the tile buffer is waited for; mask bytes one tile ahead), accumulates
 //   d_j * W1[j,:] in registers in list order (deterministic), and on every row boundary applies the relu mask (bits
 //   from the forward), the power-of-two scale and the fp16 hi/lo split and writes 16 + 16 bytes straight into the
 //   K-major SW128 operand ring.  All control flow is warp-uniform.
 // * Epilogue: tcgen05.ld (lane = (a,t) row, 64 columns), then  G[p0+i, a] = sum_t Y[m(a,t), i-t]  by 64 shuffles: lane
 //   d of a residue's 5-lane group accumulates the outputs i = d (mod 5); 4 partial outputs carry into the next tile.
 //   Results go to a shared [20L] row and are flushed per chain with coalesced 16-byte stores.
-template <bool PROF>
+// DELTA = true: the records come from cnn_winner_delta_kernel (bit 15 of an entry = side: 0 proposal y, 1 current state x) and
+// the operand rows are  dA[p,:] = mask_y[p] . sum_{y-side} d_j W1[j,:] - mask_x[p] . sum_{x-side} d_j W1[j,:]  (mask applied per
+// entry, one accumulator), so the kernel produces the CHANGE of the per-net gradient between the current state and the proposal.
+template <bool PROF, bool DELTA>
 __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
@@ -1585,39 +1715,61 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         // element (row r, k = 8 lane + e): chunk lane/8, 16-byte unit (lane%8) ^ (r%8) of the row's 128 bytes
         const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BW_SLOT);
         const uint32_t unit = (uint32_t)(lane & 7);
+        const uint32_t rec_a = smem_u32(sRec), dj_a = smem_u32(sDj);
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
+        // relu-mask bytes of my 4 rows of tile (ci, tn): proposal rows and, in delta mode, the current state's rows
+        auto load_masks = [&](int ci_, int tn_, uint32_t& my, uint32_t& mx) {
+            my = 0u; mx = 0u;
+            const int bb = b_lo + ci_, pp0 = tn_ * BW_NT;
+            const int mr = prm.mask_rows ? __ldg(prm.mask_rows + bb) : prm.mask_row_base + bb;
+            const uint8_t* mrow = prm.r1mask + (((size_t)mr * prm.m.n_nets + k) * P + pp0 + r0) * 32 + lane;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+                if (lact && pp0 + r0 + rr < P) my |= (uint32_t)__ldg(mrow + rr * 32) << (8 * rr);
+            if (DELTA) {
+                const int mxr = __ldg(prm.mask_rows_x + bb);
+                const uint8_t* xrow = prm.r1mask + (((size_t)mxr * prm.m.n_nets + k) * P + pp0 + r0) * 32 + lane;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+                    if (lact && pp0 + r0 + rr < P) mx |= (uint32_t)__ldg(xrow + rr * 32) << (8 * rr);
+            }
+        };
+        uint32_t m4n = 0u, m4xn = 0u;                                  // one tile ahead
+        if (ntiles > 0) load_masks(0, 0, m4n, m4xn);
         int tn = 0, ci = 0;
         for (int it = 0; it < ntiles; ++it) {
             const int tb = it & 1;
-            const int b = b_lo + ci;
             const int p0 = tn * BW_NT;
             const int rb = ci & 1;
-            // relu-mask bytes of my 4 rows (independent of the winners: issue first)
-            uint32_t m4 = 0u;
-            {
-                const int mr = prm.mask_rows ? __ldg(prm.mask_rows + b) : prm.mask_row_base + b;
-                const uint8_t* mrow = prm.r1mask + (((size_t)mr * prm.m.n_nets + k) * P + p0 + r0) * 32 + lane;
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr)
-                    if (lact && p0 + r0 + rr < P) m4 |= (uint32_t)__ldg(mrow + rr * 32) << (8 * rr);
+            const uint32_t m4 = m4n, m4x = m4xn;
+            if (it + 1 < ntiles) {
+                int ntn = tn + 1, nci = ci;
+                if (ntn == tpc) { ntn = 0; ++nci; }
+                load_masks(nci, ntn, m4n, m4xn);
             }
             if (tn == 0) mbar_wait(&recfull[rb], (uint32_t)((ci >> 1) & 1));
-            const uint16_t* sStart = sRec + (size_t)rb * prm.rec;
-            const uint16_t* sList = sStart + (P + 1);
-            mbar_wait(&empty[tb], (uint32_t)(((it >> 1) + 1) & 1));
-            if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+            const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;         // this chain's record: start[P+1] | list
+            const uint32_t ls = rs + 2u * (uint32_t)(P + 1);
             const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BW_SLOT);
-            int e = sStart[min(p0 + r0, P)];
-            const int eB = (prm.dbg & 2) ? e : (int)sStart[min(p0 + r0 + 4, P)];
+            int e = lds_u16(rs + 2u * (uint32_t)min(p0 + r0, P));
+            const int eB = (prm.dbg & 2) ? e : lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + 4, P));
             int cur = 0;
-            int rend = sStart[min(p0 + r0 + 1, P)];
+            int rend = lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + 1, P));
+            bool have_buf = false;          // the tile buffer is waited for at the first row store: the W1 loads of the first
+                                            // group are already in flight by then
             float acc[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] = 0.f;
             auto store_row = [&]() {       // row r0 + cur <- mask * scale * acc, fp16 hi (truncated: exact) + lo
+                if (!have_buf) {
+                    if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                    mbar_wait(&empty[tb], (uint32_t)(((it >> 1) + 1) & 1));
+                    have_buf = true;
+                    if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+                }
                 const int r = r0 + cur;
-                const uint32_t mb = (m4 >> (8 * cur)) & 0xffu;
+                const uint32_t mb = DELTA ? 0xffu : ((m4 >> (8 * cur)) & 0xffu);   // delta mode: masks were applied per entry
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1636,18 +1788,22 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] = 0.f;
                 ++cur;
-                rend = sStart[min(p0 + r0 + cur + 1, P)];
+                rend = lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + cur + 1, P));
             };
             for (; e < eB; e += 4) {
                 float4 w[4][2];
                 float dj[4];
+                bool sd[4];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     dj[v] = 0.f;
+                    sd[v] = false;
                     w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (e + v < eB) {
-                        const int jn = sList[e + v];
-                        dj[v] = sDj[jn];
+                        int jn = lds_u16(ls + 2u * (uint32_t)(e + v));
+                        if (DELTA) { sd[v] = (jn >> 15) != 0; jn &= 0x7FFF; }
+                        const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn);
+                        dj[v] = sd[v] ? -d0 : d0;
                         if (lact) {
                             const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn * prm.kpad);
                             w[v][0] = __ldg(src);
@@ -1660,6 +1816,13 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
                     if (e + v < eB) {
                         while (e + v >= rend) store_row();
                         const float dd = dj[v];
+                        if (DELTA) {                                   // relu mask of the entry's side, per channel
+                            const uint32_t mb = ((sd[v] ? m4x : m4) >> (8 * cur)) & 0xffu;
+                            w[v][0].x = (mb & 1u) ? w[v][0].x : 0.f;   w[v][0].y = (mb & 2u) ? w[v][0].y : 0.f;
+                            w[v][0].z = (mb & 4u) ? w[v][0].z : 0.f;   w[v][0].w = (mb & 8u) ? w[v][0].w : 0.f;
+                            w[v][1].x = (mb & 16u) ? w[v][1].x : 0.f;  w[v][1].y = (mb & 32u) ? w[v][1].y : 0.f;
+                            w[v][1].z = (mb & 64u) ? w[v][1].z : 0.f;  w[v][1].w = (mb & 128u) ? w[v][1].w : 0.f;
+                        }
                         acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
                         acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
                         acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
@@ -1827,13 +1990,13 @@ extern "C" int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n) { return ((int64_t)n
 extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                                     unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask,
                                     unsigned long long* bkey, const int32_t* rows_x, const int32_t* rows_y,
-                                    int32_t row_base_y, void* ws, void* stream) {
+                                    int32_t row_base_y, unsigned long long* mkey_pool, void* ws, void* stream) {
     if (n <= 0) return 0;
     const int NB = (m->P + 15) / 16;
     if (m->C > 256 || m->P < 1 || NB > 16 || !bkey || !mkey || !ws || (dmask && !rows_x)) return (int)cudaErrorInvalidValue;
     tc::IncParams prm;
     prm.m = *m; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey; prm.r1mask = r1mask; prm.dmask = dmask;
-    prm.bkey = bkey;
+    prm.bkey = bkey; prm.mkey_pool = mkey_pool;
     prm.rows_x = dmask ? rows_x : nullptr;   // full evaluation: nothing is read from a current row
     prm.rows_y = rows_y; prm.row_base_y = row_base_y; prm.NB = NB;
     prm.kpad = (m->C + 15) / 16 * 16;
@@ -1902,19 +2065,27 @@ extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm,
     return ppde_cnn_backward_tc_rows(m, pm, aa, aa_stride, n, mkey, lamda, Gp, Gp_stride, gp_rows, G, G_stride, g_rows, r1mask,
                                      nullptr, 0, scratch, stream);
 }
-extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
-                                         int32_t n, const unsigned long long* mkey, float lamda,
-                                         const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
-                                         float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
-                                         const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream) {
+struct BwdDelta {                 // delta backward: gradient of the proposal = gradient of the current state + change
+    const uint8_t* aa_x;          // current states [n, aa_stride]
+    const unsigned long long* mkey_pool;   // [rows, n_nets, 2C] winners of every pool row
+    const int32_t* rows_x;        // [n] pool row of the current state (G, Gp, r1mask, mkey_pool)
+    const int32_t* rows_y;        // [n] pool row of the proposal
+};
+
+static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
+                           int32_t n, const unsigned long long* mkey, float lamda,
+                           const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
+                           float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
+                           const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream, const BwdDelta* dl) {
     if (n <= 0) return 0;
     if (m->C > 256 || m->P < 1 || !scratch || !r1mask) return (int)cudaErrorInvalidValue;
     tc::BwdParams prm;
     prm.m = *m; prm.pm = *pm; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey;
     prm.Gc = scratch;
     prm.r1mask = r1mask;
-    prm.mask_rows = mask_rows;
+    prm.mask_rows = dl ? dl->rows_y : mask_rows;
     prm.mask_row_base = mask_row_base;
+    prm.mask_rows_x = dl ? dl->rows_x : nullptr;
     { const char* e = getenv("PPDE_BWD_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
     prm.tiles_per_chain = (m->P + tc::BW_NT - 1) / tc::BW_NT;
     prm.kpad = (m->C + 15) / 16 * 16;
@@ -1926,25 +2097,31 @@ extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t
     if (prm.ctas_per_net < 1) prm.ctas_per_net = 1;
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
-    const int rec_ = ((P + 1) + 2 * J2 + 7) & ~7;
+    const int rec = ((P + 1) + 2 * J2 + 7) & ~7;
     const size_t smem = 1024 + (size_t)2 * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
-                        2 * (size_t)rec_ * sizeof(uint16_t) + 8 + 32 * sizeof(uint64_t);
-    void (*bkern)(tc::BwdParams) = g_backward_prof ? tc::cnn_backward_tc_kernel<true> : tc::cnn_backward_tc_kernel<false>;
-    prm.prof = g_backward_prof;
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[g_backward_prof ? 1 : 0]) {
+                        2 * (size_t)rec * sizeof(uint16_t) + 8 + 32 * sizeof(uint64_t);
+    const bool prof = g_backward_prof != nullptr && !dl;
+    void (*bkern)(tc::BwdParams) = dl ? tc::cnn_backward_tc_kernel<false, true>
+                                      : (prof ? tc::cnn_backward_tc_kernel<true, false> : tc::cnn_backward_tc_kernel<false, false>);
+    prm.prof = prof ? g_backward_prof : nullptr;
+    static size_t configured[3] = {0, 0, 0};
+    const int cfg = dl ? 2 : (prof ? 1 : 0);
+    if (smem > configured[cfg]) {
         cudaError_t e = cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured[g_backward_prof ? 1 : 0] = smem;
+        configured[cfg] = smem;
     }
     cudaStream_t st = (cudaStream_t)stream;
     // winner records live behind the per-net gradient scratch: [n_nets*n*20L floats][n*n_nets*rec uint16]
-    const int rec = ((P + 1) + 2 * J2 + 7) & ~7;
     uint16_t* wl = reinterpret_cast<uint16_t*>(scratch + (size_t)m->n_nets * n * L * PPDE_Q);
     prm.wl = wl;
     prm.rec = rec;
     if (g_bwd_parts & 1) {
-        tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
+        if (dl)
+            tc::cnn_winner_delta_kernel<<<n * m->n_nets, 128, ((P + 1) + 2 * P + 4 * J2) * sizeof(int), st>>>(
+                m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec);
+        else
+            tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
         int r0 = launch_done();
         if (r0) return r0;
     }
@@ -1954,9 +2131,33 @@ extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t
         if (r) return r;
     }
     if (g_bwd_parts & 4) {
-        tc::cnn_grad_combine_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
-                                                       Gp, Gp_stride, gp_rows, G, G_stride, g_rows);
+        if (dl)
+            tc::cnn_grad_combine_delta_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
+                                                                 Gp, Gp_stride, G, G_stride, dl->rows_x, dl->rows_y);
+        else
+            tc::cnn_grad_combine_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
+                                                           Gp, Gp_stride, gp_rows, G, G_stride, g_rows);
         return launch_done();
     }
     return 0;
+}
+
+extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
+                                         int32_t n, const unsigned long long* mkey, float lamda,
+                                         const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
+                                         float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
+                                         const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream) {
+    return backward_launch(m, pm, aa, aa_stride, n, mkey, lamda, Gp, Gp_stride, gp_rows, G, G_stride, g_rows, r1mask, mask_rows,
+                           mask_row_base, scratch, stream, nullptr);
+}
+
+extern "C" int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa_x, const uint8_t* aa_y,
+                                       int32_t aa_stride, int32_t n, const unsigned long long* mkey_y,
+                                       const unsigned long long* mkey_pool, float lamda, const float* Gp, int64_t Gp_stride,
+                                       float* G, int64_t G_stride, const int32_t* rows_x, const int32_t* rows_y,
+                                       const uint8_t* r1mask, float* scratch, void* stream) {
+    if (!aa_x || !mkey_pool || !rows_x || !rows_y || !G) return (int)cudaErrorInvalidValue;
+    BwdDelta dl{aa_x, mkey_pool, rows_x, rows_y};
+    return backward_launch(m, pm, aa_y, aa_stride, n, mkey_y, lamda, Gp, Gp_stride, rows_y, G, G_stride, rows_y, r1mask, rows_y, 0,
+                           scratch, stream, &dl);
 }

@@ -146,6 +146,11 @@ class PoEModel:
         self.NB = (self.P + 15) // 16
         self.cnn_inc = (os.environ.get("PPDE_CNN_INC", "1") != "0" and self.cnn_forward_impl == "tc"
                         and self.cnn_backward_impl == "tc" and self.NB <= 16)
+        # delta backward on top of the incremental forward: gradient rows updated by the change of the few adjoint rows that
+        # differ between the current state and the proposal; an exact (full) backward every `bwd_refresh` iterations bounds the
+        # accumulated rounding.  PPDE_CNN_BWD_DELTA=0 always runs the full backward.
+        self.cnn_bwd_delta = self.cnn_inc and os.environ.get("PPDE_CNN_BWD_DELTA", "1") != "0"
+        self.bwd_refresh = max(1, int(os.environ.get("PPDE_BWD_REFRESH", "32")))
         # full Potts evaluation: "dense" = tcgen05 GEMM for batches of >= dense_min chains, "gather" = row-gather kernel
         self.potts_full_impl = os.environ.get("PPDE_POTTS_FULL", "dense")
         self.dense_min = int(os.environ.get("PPDE_POTTS_DENSE_MIN", "512"))
@@ -177,12 +182,12 @@ class PoEModel:
                 gp_ptr, self.D, gp_rows, ep_ptr, g_ptr, self.NE, g_rows, _ptr(E), _ptr(fit), st), "cnn_backward_combine")
 
     # -- CNN with the block-key / relu-mask POOLS of a chain engine (incremental path) -----------------
-    def cnn_forward_pool(self, aa, n, mk, bkey, r1pool, dmask, rows_x, rows_y, row_base_y, st):
+    def cnn_forward_pool(self, aa, n, mk, bkey, r1pool, dmask, rows_x, rows_y, row_base_y, st, mkpool=None):
         """Forward of n states into pool rows rows_y (None: row_base_y + b).  dmask None: every block is evaluated;
         otherwise only the dirty blocks, the others come from rows_x (ppde_cnn_forward_inc)."""
         _lib.check(self.lib.ppde_cnn_forward_inc(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), _ptr(r1pool),
                                                  _ptr(dmask), _ptr(bkey), _ptr(rows_x), _ptr(rows_y), int(row_base_y),
-                                                 _ptr(self.inc_ws(n)), st), "cnn_forward_inc")
+                                                 _ptr(mkpool), _ptr(self.inc_ws(n)), st), "cnn_forward_inc")
 
     def cnn_backward_pool(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, r1pool, mask_rows, mask_row_base, st,
                           do_fit=True, do_grad=True):
@@ -197,6 +202,21 @@ class PoEModel:
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
                 gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(r1pool), _ptr(mask_rows), int(mask_row_base),
                 _ptr(self.grad_scratch(n)), st), "cnn_backward_tc_rows")
+
+    def cnn_backward_delta(self, aa_x, aa_y, n, mk, mkpool, gp_ptr, ep_ptr, g_ptr, rows_x, rows_y, E, fit, r1pool, st,
+                           do_fit=True, do_grad=True):
+        """fit / E of the proposals, and their gradient rows as  G[rows_y] = G[rows_x] + change  (ppde_cnn_backward_delta)."""
+        lib = self.lib
+        null = C.c_void_p(0)
+        if do_fit:
+            _lib.check(lib.ppde_cnn_backward_combine(
+                C.byref(self.cnn), C.byref(self.potts), _ptr(aa_y), self.aa_stride, n, _ptr(mk), self.lamda,
+                null, self.D, null, ep_ptr, null, self.NE, null, _ptr(E), _ptr(fit), st), "cnn_fit")
+        if do_grad:
+            _lib.check(lib.ppde_cnn_backward_delta(
+                C.byref(self.cnn), C.byref(self.potts), _ptr(aa_x), _ptr(aa_y), self.aa_stride, n, _ptr(mk), _ptr(mkpool),
+                self.lamda, gp_ptr, self.D, g_ptr, self.NE, _ptr(rows_x), _ptr(rows_y), _ptr(r1pool),
+                _ptr(self.grad_scratch(n)), st), "cnn_backward_delta")
 
     # -- scratch ------------------------------------------------------------------------------
     def grad_scratch(self, n):
@@ -225,7 +245,7 @@ class PoEModel:
         return self._mkey
 
     # -- full evaluation ------------------------------------------------------------------------
-    def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True, bkey=None, r1pool=None):
+    def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True, bkey=None, r1pool=None, mkpool=None):
         """Energy (+ gradient field) of n states `aa` [n, aa_stride] written into pool rows
         g_row0.. / gp_row0.. (contiguous). E, fit, Epotts: float tensors [n].
         bkey / r1pool: the engine's block-key and relu-mask pools (rows g_row0.. are filled too)."""
@@ -238,7 +258,7 @@ class PoEModel:
         mk = self.mkey(n)
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
         if bkey is not None and want_grad:
-            self.cnn_forward_pool(aa, n, mk, bkey, r1pool, None, None, None, g_row0, st)
+            self.cnn_forward_pool(aa, n, mk, bkey, r1pool, None, None, None, g_row0, st, mkpool=mkpool)
             self.cnn_backward_pool(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr, C.c_void_p(0), E, fit,
                                    r1pool, None, g_row0, st)
             return
@@ -350,8 +370,10 @@ class ChainEngine:
         self.t_dev = torch.zeros(1, dtype=i32, device=dev)
         # incremental CNN forward: per-row block keys of the max-pool and relu-mask rows, indexed like G / Gp
         self.inc = bool(m.cnn_inc)
-        self.bkey = self.r1pool = self.dmask = None
+        self.bkey = self.r1pool = self.dmask = self.mkpool = None
+        self.delta = bool(m.cnn_bwd_delta)
         if self.inc:
+            self.mkpool = torch.empty(rows * m.n_nets * 2 * m.C, dtype=torch.int64, device=dev)
             self.bkey = torch.empty(rows * m.n_nets * m.NB * 2 * m.C, dtype=torch.int64, device=dev)
             self.r1pool = torch.empty(rows * m.n_nets * m.P * 32, dtype=u8, device=dev)
             self.dmask = torch.zeros(n, dtype=i32, device=dev)
@@ -391,13 +413,14 @@ class ChainEngine:
                 self.anchor_fixed = torch.arange(1, n + 1, dtype=torch.int32, device=m.device)
             ep = torch.empty(self.n_fixed, dtype=torch.float32, device=m.device)
             m.evaluate_into(self.aa_fixed, self.n_fixed, self.G, 2 * n, self.Gp, 2 * n, self.E_fixed, self.fit_fixed, ep,
-                            bkey=self.bkey, r1pool=self.r1pool)
+                            bkey=self.bkey, r1pool=self.r1pool, mkpool=self.mkpool)
             if all_wt:
                 self.row_cur.fill_(2 * n)
                 self.E.copy_(self.E_fixed[0].expand(n)); self.fit.copy_(self.fit_fixed[0].expand(n))
             else:
                 epn = torch.empty(n, dtype=torch.float32, device=m.device)
-                m.evaluate_into(self.aa, n, self.G, 0, self.Gp, 0, self.E, self.fit, epn, bkey=self.bkey, r1pool=self.r1pool)
+                m.evaluate_into(self.aa, n, self.G, 0, self.Gp, 0, self.E, self.fit, epn, bkey=self.bkey, r1pool=self.r1pool,
+                                mkpool=self.mkpool)
                 self.row_cur.copy_(torch.arange(n, dtype=torch.int32, device=m.device))
             self.best_E.copy_(self.E); self.best_fit.copy_(self.fit); self.best_aa.copy_(self.aa)
             if self.E_hist is not None:
@@ -416,7 +439,7 @@ class ChainEngine:
                           uniforms=uniforms.data_ptr() if uniforms is not None else None,
                           t_dev=self.t_dev.data_ptr() if use_t_dev else None)
 
-    def _launch_step(self, p):
+    def _launch_step(self, p, full=True):
         m, lib, c, n = self.m, self.lib, self.chains, self.n
         st = _stream()
         _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_propose")
@@ -424,7 +447,7 @@ class ChainEngine:
             _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(c), C.byref(p), st), "potts_incremental")
         _lib.check(lib.ppde_step_rows(C.byref(c), _ptr(self.rows_y), st), "step_rows")
         self.cnn_forward_y(st)
-        self.cnn_backward_y(st)
+        self.cnn_backward_y(st, full=full)
         _lib.check(lib.ppde_pas_reverse_accept(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_reverse_accept")
 
     def cnn_forward_y(self, st, dirty=True, parts=7):
@@ -440,14 +463,16 @@ class ChainEngine:
             if parts:
                 self.lib.ppde_set_profile_parts(parts, 7)
                 try:
-                    m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st)
+                    m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st,
+                                       mkpool=self.mkpool)
                 finally:
                     self.lib.ppde_set_profile_parts(7, 7)
         elif parts == 7:
             m.cnn_forward(self.aa_y, n, mk, st)
 
-    def cnn_backward_y(self, st, do_fit=True, parts=7):
-        """fit_y / E_y and the gradient rows of the proposals from the winners in mkey."""
+    def cnn_backward_y(self, st, do_fit=True, parts=7, full=True):
+        """fit_y / E_y and the gradient rows of the proposals from the winners in mkey.  full=False (incremental path
+        only): the rows are updated from the current state's rows by the delta backward."""
         m, n = self.m, self.n
         mk = m.mkey(n)
         gp = _ptr(self.Gp) if m.has_potts else C.c_void_p(0)
@@ -455,19 +480,27 @@ class ChainEngine:
         if self.inc:
             self.lib.ppde_set_profile_parts(7, parts if parts else 7)
             try:
-                m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
-                                    self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st, do_fit=do_fit, do_grad=bool(parts))
+                if self.delta and not full:
+                    m.cnn_backward_delta(self.aa, self.aa_y, n, mk, self.mkpool, gp, ep, _ptr(self.G), self.row_cur, self.rows_y,
+                                         self.E_y, self.fit_y, self.r1pool, st, do_fit=do_fit, do_grad=bool(parts))
+                else:
+                    m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
+                                        self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st, do_fit=do_fit, do_grad=bool(parts))
             finally:
                 self.lib.ppde_set_profile_parts(7, 7)
         elif do_fit and parts == 7:
             m.cnn_backward_combine(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
                                    self.E_y, self.fit_y, st)
 
+    def full_backward_at(self, t):
+        """Iteration t runs the exact backward (always without the delta path; every bwd_refresh-th iteration with it)."""
+        return (not self.delta) or (t % self.m.bwd_refresh == self.m.bwd_refresh - 1)
+
     def step(self, uniforms=None):
         """One MCMC iteration (eager launches). `uniforms`: optional float32 device tensor
         [S, n, 20L] replacing the in-kernel Philox proposal stream (parity mode)."""
         with torch.cuda.device(self.m.device):
-            self._launch_step(self._params(self.t, uniforms))
+            self._launch_step(self._params(self.t, uniforms), full=self.full_backward_at(self.t))
         self.t += 1
 
     def run_steps(self, k, use_graph=True):
@@ -488,17 +521,21 @@ class ChainEngine:
                 self.t_dev.fill_(self.t)
                 p = self._params(0, None, use_t_dev=True)
                 self._graph_params = p
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    self._launch_step(p)
-                    _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
-                self._graph = g
+                self._graph = {}
             else:
                 self.t_dev.fill_(self.t)
-            for _ in range(k):
-                self._graph.replay()
+            for i in range(k):
+                full = self.full_backward_at(self.t + i)
+                if full not in self._graph:                    # captured once per variant (exact / delta backward)
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        self._launch_step(self._graph_params, full=full)
+                        _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
+                    self._graph[full] = g
+                    torch.cuda.current_stream().wait_stream(side)
+                self._graph[full].replay()
         self.t += k
 
     # -- results ------------------------------------------------------------------------------------

@@ -105,3 +105,69 @@ def test_incremental_forward_is_bit_identical(L, n):
     torch.cuda.synchronize()
     assert torch.equal(mk_b, mk_fx), "second incremental step (y -> x) differs from the full kernel"
     assert torch.equal(pool[rows_x.long()], rm_fx.view(n, -1))
+
+
+@pytest.mark.parametrize("L,n", [(40, 24), (104, 40), (238, 96)])
+def test_delta_backward_matches_full_backward(L, n):
+    """G(y) = G(x) + change of the few adjoint rows that differ (delta backward) against the full backward of y."""
+    from ppde_b200 import _lib
+    from ppde_b200.engine import PoEModel, _ptr, _stream
+    w = port.synthetic_weights(L, seed=L + 3, lamda=4.0, window=(1, L - 2))
+    m = PoEModel(w.wt, w.J, w.h, w.win_lo, w.cnn, w.lamda, device="cuda:0")
+    if not m.cnn_bwd_delta:
+        pytest.skip("delta backward disabled")
+    lib, dev = m.lib, m.device
+    rng = np.random.default_rng(L + 1)
+    x = np.tile(w.wt, (n, 1)).astype(np.uint8)
+    for b in range(n):
+        pos = rng.integers(0, L, size=b % 13)
+        x[b, pos] = rng.integers(0, 20, size=pos.shape[0])
+    y = _mutants(rng, x, L)
+    y[n - 1, 5:11] = y[n - 1, 20:26]                     # repeated 5-mers: exact max-pool ties
+
+    def dev_aa(a):
+        pad = np.zeros((n, m.aa_stride), dtype=np.uint8); pad[:, :L] = a
+        return torch.from_numpy(pad).to(dev)
+    ax, ay = dev_aa(x), dev_aa(y)
+    J2, nets, P, NB = 2 * m.C, m.n_nets, m.P, m.NB
+    rows = 2 * n + 1
+    f32 = torch.float32
+    G = torch.full((rows, m.NE), float("nan"), dtype=f32, device=dev)
+    Gp = torch.zeros(rows, m.D, dtype=f32, device=dev)
+    bkey = torch.zeros(rows * nets * NB * J2, dtype=torch.int64, device=dev)
+    r1pool = torch.zeros(rows * nets * P * 32, dtype=torch.uint8, device=dev)
+    mkpool = torch.zeros(rows * nets * J2, dtype=torch.int64, device=dev)
+    E = torch.zeros(n, dtype=f32, device=dev); fit = torch.zeros_like(E); Ep = torch.zeros_like(E)
+    st = _stream()
+    m.evaluate_into(ax, n, G, 0, Gp, 0, E, fit, Ep, bkey=bkey, r1pool=r1pool, mkpool=mkpool)      # rows 0..n-1 = states x
+    rows_x = torch.arange(n, dtype=torch.int32, device=dev)
+    rows_y = rows_x + n
+    Ep_y = torch.zeros_like(E); E_y = torch.zeros_like(E); fit_y = torch.zeros_like(E)
+    m.potts_full(ay, n, C.c_void_p(Gp.data_ptr() + n * m.D * 4), _ptr(Ep_y), st)
+    dmask = torch.zeros(n, dtype=torch.int32, device=dev)
+    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay), m.aa_stride, n, _ptr(dmask), _ptr(r1pool),
+                                  _ptr(rows_x), _ptr(rows_y), st), "dirty")
+    mk = m.mkey(n)
+    m.cnn_forward_pool(ay, n, mk, bkey, r1pool, dmask, rows_x, rows_y, 0, st, mkpool=mkpool)
+    m.cnn_backward_delta(ax, ay, n, mk, mkpool, _ptr(Gp), _ptr(Ep_y), _ptr(G), rows_x, rows_y, E_y, fit_y, r1pool, st)
+    torch.cuda.synchronize()
+    g_delta = G[n:2 * n].cpu().numpy()
+    e_delta, f_delta = E_y.cpu().numpy(), fit_y.cpu().numpy()
+    E2, fit2, G2, _ = m.energy(ay)                        # full forward + full backward of y
+    torch.cuda.synchronize()
+    g_full = G2.reshape(n, -1).cpu().numpy()
+    assert np.isfinite(g_delta).all()
+    scale = np.abs(g_full).max(axis=1, keepdims=True)
+    err = np.max(np.abs(g_delta - g_full) / scale)
+    assert err < 2e-6, f"delta vs full gradient, relative to each chain's max |g|: {err:.3e}"
+    assert np.array_equal(f_delta, fit2.cpu().numpy()) and np.array_equal(e_delta, E2.cpu().numpy())
+    # a second delta step back to x (rows swap roles) stays within rounding of the exact gradient of x
+    Gx_exact = G[:n].clone()
+    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ay), _ptr(ax), m.aa_stride, n, _ptr(dmask), _ptr(r1pool),
+                                  _ptr(rows_y), _ptr(rows_x), st), "dirty back")
+    m.cnn_forward_pool(ax, n, mk, bkey, r1pool, dmask, rows_y, rows_x, 0, st, mkpool=mkpool)
+    m.cnn_backward_delta(ay, ax, n, mk, mkpool, _ptr(Gp), _ptr(Ep), _ptr(G), rows_y, rows_x, E, fit, r1pool, st)
+    torch.cuda.synchronize()
+    gx = G[:n].cpu().numpy(); gx0 = Gx_exact.cpu().numpy()
+    err = np.max(np.abs(gx - gx0) / np.abs(gx0).max(axis=1, keepdims=True))
+    assert err < 4e-6, f"x -> y -> x round trip of the delta backward: {err:.3e}"
