@@ -1442,7 +1442,7 @@ __global__ void cnn_grad_combine_delta_kernel(int n, int NE, int n_nets, float s
 }
 
 constexpr int BW_NT = 64;               // positions per tile (N of the MMA)
-constexpr int BW_NT_PROD = 512;         // 16 producer warps, 4 tile rows each
+constexpr int BW_NT_PROD = 512;         // 16 producer warps in two sets of 8: set s builds the tiles with it % 2 == s, 8 rows per warp
 constexpr int BW_NTHREADS = NT_EPI + BW_NT_PROD + 32;   // 672: warps 0-3 epilogue, 4-19 producers, 20 MMA issuer
 constexpr int BW_WARP_MMA = 20;         // highest warp id of its scheduler: top arbitration priority
 constexpr int BW_MAT = BW_NT * KCH * 2; // one [64 x 64] fp16 operand matrix (8 KB)
@@ -1493,10 +1493,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 //
 // * A-operand (W0^T, fp16 hi/lo) is resident in tensor memory.  Row order m(a,t) = 32*(a/6) + 5*(a%6) + t puts the 5
 //   taps of a residue in 5 adjacent lanes of one warp, so the col2im below is a warp-shuffle reduction in registers.
-// * Producers: warp w owns rows 4w..4w+3 of every tile, lane l owns channels 8l..8l+7.  The winners of those rows are
-//   one contiguous run of the chain's (position, channel)-sorted list (staged in shared memory by a bulk copy one chain
-//   ahead, read with explicit ld.shared); a warp streams their W1 rows from L2 in groups of 4 (8 x 16-byte loads in
-//   flight per lane, the first group issued BEFORE the tile buffer is waited for; mask bytes one tile ahead), accumulates
+// * Producers: two sets of 8 warps alternate over the tiles (set s <-> ring buffer s); a warp owns 8 rows of its set's
+//   tile, lane l owns channels 8l..8l+7.  The winners of those rows are one contiguous run of the chain's (position,
+//   channel)-sorted list (staged in shared memory by a bulk copy one chain ahead, read with explicit ld.shared); a warp
+//   streams their W1 rows from L2 in groups of 4 (8 x 16-byte loads in flight per lane, the first group issued BEFORE the
+//   tile buffer is waited for), rows without winners are stored as zeros without arithmetic, accumulates
 //   d_j * W1[j,:] in registers in list order (deterministic), and on every row boundary applies the relu mask (bits
 //   from the forward), the power-of-two scale and the fp16 hi/lo split and writes 16 + 16 bytes straight into the
 //   K-major SW128 operand ring.  All control flow is warp-uniform.
@@ -1538,7 +1539,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&full[s], BW_NT_PROD / 32); mbar_init(&empty[s], 1);
+            mbar_init(&full[s], BW_NT_PROD / 64); mbar_init(&empty[s], 1);       // 8 warps of one producer set per tile
             mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BW_NT_PROD / 32);
         }
         for (int d = 0; d < BW_NDBUF; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI / 32); }
@@ -1707,8 +1708,12 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         if (PROF && prm.prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[4] = pc[0]; o[5] = pc[1]; o[6] = pc[2]; }
     } else {
         // ===== PRODUCERS =====
-        const int pw = warp - 4;                                      // 0..15: rows 4 pw .. 4 pw + 3 of every tile
-        const int r0 = 4 * pw;
+        // Two sets of 8 warps; set s = pw / 8 builds the tiles with it % 2 == s (always in ring buffer s), warp pw % 8 owns rows
+        // 8 (pw % 8) .. + 7 of them.  A warp's work on one tile is a latency chain (record reads -> W1 rows from L2 -> row
+        // stores); with each set working on its own tile two such chains overlap per SM.
+        const int pw = warp - 4;
+        const int pset = pw >> 3;
+        const int r0 = 8 * (pw & 7);
         const bool lact = 8 * lane < prm.kpad;
         const float adj_scale = net.adj_scale;
         const float* wbase = net.W1p + 8 * lane;
@@ -1718,127 +1723,137 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         const uint32_t rec_a = smem_u32(sRec), dj_a = smem_u32(sDj);
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
-        // relu-mask bytes of my 4 rows of tile (ci, tn): proposal rows and, in delta mode, the current state's rows
-        auto load_masks = [&](int ci_, int tn_, uint32_t& my, uint32_t& mx) {
-            my = 0u; mx = 0u;
-            const int bb = b_lo + ci_, pp0 = tn_ * BW_NT;
+        // relu-mask bytes of my 8 rows of a tile (byte rr of the 64-bit word = row r0 + rr): proposal rows and, in delta mode,
+        // the current state's rows
+        auto load_masks = [&](int bb, int pp0, unsigned long long& my, unsigned long long& mx) {
+            my = 0ull; mx = 0ull;
             const int mr = prm.mask_rows ? __ldg(prm.mask_rows + bb) : prm.mask_row_base + bb;
             const uint8_t* mrow = prm.r1mask + (((size_t)mr * prm.m.n_nets + k) * P + pp0 + r0) * 32 + lane;
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr)
-                if (lact && pp0 + r0 + rr < P) my |= (uint32_t)__ldg(mrow + rr * 32) << (8 * rr);
+            for (int rr = 0; rr < 8; ++rr)
+                if (lact && pp0 + r0 + rr < P) my |= (unsigned long long)__ldg(mrow + rr * 32) << (8 * rr);
             if (DELTA) {
                 const int mxr = __ldg(prm.mask_rows_x + bb);
                 const uint8_t* xrow = prm.r1mask + (((size_t)mxr * prm.m.n_nets + k) * P + pp0 + r0) * 32 + lane;
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr)
-                    if (lact && pp0 + r0 + rr < P) mx |= (uint32_t)__ldg(xrow + rr * 32) << (8 * rr);
+                for (int rr = 0; rr < 8; ++rr)
+                    if (lact && pp0 + r0 + rr < P) mx |= (unsigned long long)__ldg(xrow + rr * 32) << (8 * rr);
             }
         };
-        uint32_t m4n = 0u, m4xn = 0u;                                  // one tile ahead
-        if (ntiles > 0) load_masks(0, 0, m4n, m4xn);
+        // masks of my NEXT tile (it + 2) are requested while the current one is built: they come from HBM
+        unsigned long long m8n = 0ull, m8xn = 0ull;
+        if (pset < ntiles) load_masks(b_lo + pset / tpc, (pset % tpc) * BW_NT, m8n, m8xn);
         int tn = 0, ci = 0;
         for (int it = 0; it < ntiles; ++it) {
-            const int tb = it & 1;
-            const int p0 = tn * BW_NT;
             const int rb = ci & 1;
-            const uint32_t m4 = m4n, m4x = m4xn;
-            if (it + 1 < ntiles) {
-                int ntn = tn + 1, nci = ci;
-                if (ntn == tpc) { ntn = 0; ++nci; }
-                load_masks(nci, ntn, m4n, m4xn);
-            }
-            if (tn == 0) mbar_wait(&recfull[rb], (uint32_t)((ci >> 1) & 1));
-            const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;         // this chain's record: start[P+1] | list
-            const uint32_t ls = rs + 2u * (uint32_t)(P + 1);
-            const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BW_SLOT);
-            int e = lds_u16(rs + 2u * (uint32_t)min(p0 + r0, P));
-            const int eB = (prm.dbg & 2) ? e : lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + 4, P));
-            int cur = 0;
-            int rend = lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + 1, P));
-            bool have_buf = false;          // the tile buffer is waited for at the first row store: the W1 loads of the first
+            if ((it & 1) == pset) {
+                const int tb = pset;
+                const int p0 = tn * BW_NT;
+                const unsigned long long m8 = m8n, m8x = m8xn;
+                if (it + 2 < ntiles) {
+                    int tn2 = tn + 2, ci2 = ci;
+                    while (tn2 >= tpc) { tn2 -= tpc; ++ci2; }
+                    load_masks(b_lo + ci2, tn2 * BW_NT, m8n, m8xn);
+                }
+                mbar_wait(&recfull[rb], (uint32_t)((ci >> 1) & 1));
+                const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;         // this chain's record: start[P+1] | list
+                const uint32_t ls = rs + 2u * (uint32_t)(P + 1);
+                const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BW_SLOT);
+                int e = lds_u16(rs + 2u * (uint32_t)min(p0 + r0, P));
+                const int eB = (prm.dbg & 2) ? e : lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + 8, P));
+                int cur = 0;
+                int rend = lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + 1, P));
+                bool have_buf = false;      // the tile buffer is waited for at the first row store: the W1 loads of the first
                                             // group are already in flight by then
-            float acc[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-            auto store_row = [&]() {       // row r0 + cur <- mask * scale * acc, fp16 hi (truncated: exact) + lo
-                if (!have_buf) {
-                    if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-                    mbar_wait(&empty[tb], (uint32_t)(((it >> 1) + 1) & 1));
-                    have_buf = true;
-                    if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
-                }
-                const int r = r0 + cur;
-                const uint32_t mb = DELTA ? 0xffu : ((m4 >> (8 * cur)) & 0xffu);   // delta mode: masks were applied per entry
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float s0 = (mb >> (2 * q)) & 1u ? adj_scale : 0.f, s1 = (mb >> (2 * q + 1)) & 1u ? adj_scale : 0.f;
-                    const float2 x = make_float2(acc[2 * q] * s0, acc[2 * q + 1] * s1);
-                    const float2 h = make_float2(h_trunc(x.x), h_trunc(x.y));
-                    const float2 l = sub2(x, h);
-                    hi[q] = pack_h2(h.x, h.y);
-                    lo[q] = pack_h2(l.x, l.y);
-                }
-                const uint32_t addr = tile_addr + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((unit ^ (uint32_t)(r & 7)) << 4);
-                if (lact) {
-                    sts128(addr, hi[0], hi[1], hi[2], hi[3]);
-                    sts128(addr + BW_MAT, lo[0], lo[1], lo[2], lo[3]);
-                }
+                bool dirty_row = false;     // the current row received an entry
+                float acc[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-                ++cur;
-                rend = lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + cur + 1, P));
-            };
-            for (; e < eB; e += 4) {
-                float4 w[4][2];
-                float dj[4];
-                bool sd[4];
+                auto store_row = [&]() {   // row r0 + cur <- mask * scale * acc, fp16 hi (truncated: exact) + lo
+                    if (!have_buf) {
+                        if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                        mbar_wait(&empty[tb], (uint32_t)(((it >> 1) + 1) & 1));
+                        have_buf = true;
+                        if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+                    }
+                    const int r = r0 + cur;
+                    const uint32_t addr = tile_addr + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((unit ^ (uint32_t)(r & 7)) << 4);
+                    if (!dirty_row) {                                   // no winner on this position: a zero operand row
+                        if (lact) { sts128(addr, 0u, 0u, 0u, 0u); sts128(addr + BW_MAT, 0u, 0u, 0u, 0u); }
+                    } else {
+                        const uint32_t mb = DELTA ? 0xffu : (uint32_t)((m8 >> (8 * cur)) & 0xffull);   // delta: masks applied per entry
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    dj[v] = 0.f;
-                    sd[v] = false;
-                    w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e + v < eB) {
-                        int jn = lds_u16(ls + 2u * (uint32_t)(e + v));
-                        if (DELTA) { sd[v] = (jn >> 15) != 0; jn &= 0x7FFF; }
-                        const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn);
-                        dj[v] = sd[v] ? -d0 : d0;
+                        for (int q = 0; q < 4; ++q) {
+                            const float s0 = (mb >> (2 * q)) & 1u ? adj_scale : 0.f, s1 = (mb >> (2 * q + 1)) & 1u ? adj_scale : 0.f;
+                            const float2 x = make_float2(acc[2 * q] * s0, acc[2 * q + 1] * s1);
+                            const float2 h = make_float2(h_trunc(x.x), h_trunc(x.y));
+                            const float2 l = sub2(x, h);
+                            hi[q] = pack_h2(h.x, h.y);
+                            lo[q] = pack_h2(l.x, l.y);
+                        }
                         if (lact) {
-                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn * prm.kpad);
+                            sts128(addr, hi[0], hi[1], hi[2], hi[3]);
+                            sts128(addr + BW_MAT, lo[0], lo[1], lo[2], lo[3]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                        dirty_row = false;
+                    }
+                    ++cur;
+                    rend = lds_u16(rs + 2u * (uint32_t)min(p0 + r0 + cur + 1, P));
+                };
+                for (; e < eB; e += 4) {
+                    float4 w[4][2];
+                    float dj[4];
+                    bool sd[4];
+                    int jn[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) jn[v] = (e + v < eB) ? lds_u16(ls + 2u * (uint32_t)(e + v)) : 0;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        sd[v] = false;
+                        if (DELTA) { sd[v] = (jn[v] >> 15) != 0; jn[v] &= 0x7FFF; }
+                        w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e + v < eB && lact) {
+                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn[v] * prm.kpad);
                             w[v][0] = __ldg(src);
                             w[v][1] = __ldg(src + 1);
                         }
                     }
-                }
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    if (e + v < eB) {
-                        while (e + v >= rend) store_row();
-                        const float dd = dj[v];
-                        if (DELTA) {                                   // relu mask of the entry's side, per channel
-                            const uint32_t mb = ((sd[v] ? m4x : m4) >> (8 * cur)) & 0xffu;
-                            w[v][0].x = (mb & 1u) ? w[v][0].x : 0.f;   w[v][0].y = (mb & 2u) ? w[v][0].y : 0.f;
-                            w[v][0].z = (mb & 4u) ? w[v][0].z : 0.f;   w[v][0].w = (mb & 8u) ? w[v][0].w : 0.f;
-                            w[v][1].x = (mb & 16u) ? w[v][1].x : 0.f;  w[v][1].y = (mb & 32u) ? w[v][1].y : 0.f;
-                            w[v][1].z = (mb & 64u) ? w[v][1].z : 0.f;  w[v][1].w = (mb & 128u) ? w[v][1].w : 0.f;
+                    for (int v = 0; v < 4; ++v) {
+                        const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn[v]);
+                        dj[v] = sd[v] ? -d0 : d0;
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (e + v < eB) {
+                            while (e + v >= rend) store_row();
+                            dirty_row = true;
+                            const float dd = dj[v];
+                            if (DELTA) {                               // relu mask of the entry's side, per channel
+                                const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);
+                                w[v][0].x = (mb & 1u) ? w[v][0].x : 0.f;   w[v][0].y = (mb & 2u) ? w[v][0].y : 0.f;
+                                w[v][0].z = (mb & 4u) ? w[v][0].z : 0.f;   w[v][0].w = (mb & 8u) ? w[v][0].w : 0.f;
+                                w[v][1].x = (mb & 16u) ? w[v][1].x : 0.f;  w[v][1].y = (mb & 32u) ? w[v][1].y : 0.f;
+                                w[v][1].z = (mb & 64u) ? w[v][1].z : 0.f;  w[v][1].w = (mb & 128u) ? w[v][1].w : 0.f;
+                            }
+                            acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
+                            acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
+                            acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
+                            acc[6] = fmaf(dd, w[v][1].z, acc[6]); acc[7] = fmaf(dd, w[v][1].w, acc[7]);
                         }
-                        acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
-                        acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
-                        acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
-                        acc[6] = fmaf(dd, w[v][1].z, acc[6]); acc[7] = fmaf(dd, w[v][1].w, acc[7]);
                     }
                 }
+                while (cur < 8) store_row();
+                if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[tb]);
+                if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
             }
-            while (cur < 4) store_row();
-            if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&full[tb]);
-                if (tn == tpc - 1) mbar_arrive(&recempty[rb]);         // this warp is done with the chain's record
-            }
-            if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+            if (tn == tpc - 1 && lane == 0) mbar_arrive(&recempty[rb]);   // past the chain's last tile: done with its record
             if (++tn == tpc) { tn = 0; ++ci; }
         }
         if (PROF && prm.prof && lane == 0 && (pw == 0 || pw == 15)) {
@@ -2100,12 +2115,12 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     const int rec = ((P + 1) + 2 * J2 + 7) & ~7;
     const size_t smem = 1024 + (size_t)2 * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
                         2 * (size_t)rec * sizeof(uint16_t) + 8 + 32 * sizeof(uint64_t);
-    const bool prof = g_backward_prof != nullptr && !dl;
-    void (*bkern)(tc::BwdParams) = dl ? tc::cnn_backward_tc_kernel<false, true>
+    const bool prof = g_backward_prof != nullptr;
+    void (*bkern)(tc::BwdParams) = dl ? (prof ? tc::cnn_backward_tc_kernel<true, true> : tc::cnn_backward_tc_kernel<false, true>)
                                       : (prof ? tc::cnn_backward_tc_kernel<true, false> : tc::cnn_backward_tc_kernel<false, false>);
     prm.prof = prof ? g_backward_prof : nullptr;
-    static size_t configured[3] = {0, 0, 0};
-    const int cfg = dl ? 2 : (prof ? 1 : 0);
+    static size_t configured[4] = {0, 0, 0, 0};
+    const int cfg = (dl ? 2 : 0) + (prof ? 1 : 0);
     if (smem > configured[cfg]) {
         cudaError_t e = cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
