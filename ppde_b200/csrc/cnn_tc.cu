@@ -1449,6 +1449,8 @@ constexpr int BW_MAT = BW_NT * KCH * 2; // one [64 x 64] fp16 operand matrix (8 
 constexpr int BW_SLOT = 2 * BW_MAT;     // hi + lo
 constexpr int BW_MAXCH = 4;             // K chunks per tile (kpad <= 256)
 constexpr int BW_NDBUF = 4;             // accumulator buffers of 64 TMEM columns
+constexpr int BW_NBUF = 3;              // operand tile buffers in shared memory (3 x 64 KB): a producer set starts storing its next
+                                        // tile while the MMA still reads the set's previous one
 
 struct BwdParams {
     ppde_cnn_t m;
@@ -1513,13 +1515,13 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
     const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
     const int nch = prm.nch;
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* sGc = reinterpret_cast<float*>(ring + 2 * BW_MAXCH * BW_SLOT);   // [NE] chain gradient row
+    float* sGc = reinterpret_cast<float*>(ring + BW_NBUF * BW_MAXCH * BW_SLOT);   // [NE] chain gradient row
     float* sDj = sGc + ((NE + 3) & ~3);                                      // [J2] decoder weights
     uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sDj + J2) + 15) & ~(uintptr_t)15);   // [2][rec]
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRec + 2 * prm.rec) + 7) & ~(uintptr_t)7);
-    uint64_t* full = bars;                      // [2] tile buffers: producers -> MMA (16 warp arrivals)
-    uint64_t* empty = full + 2;                 // [2] MMA -> producers
-    uint64_t* dfull = empty + 2;                // [BW_NDBUF] MMA -> epilogue
+    uint64_t* full = bars;                      // [BW_NBUF] tile buffers: producers -> MMA (8 warp arrivals: one producer set)
+    uint64_t* empty = full + BW_NBUF;           // [BW_NBUF] MMA -> producers
+    uint64_t* dfull = empty + BW_NBUF;          // [BW_NDBUF] MMA -> epilogue
     uint64_t* dempty = dfull + BW_NDBUF;        // [BW_NDBUF] epilogue -> MMA (4 warp arrivals)
     uint64_t* recfull = dempty + BW_NDBUF;      // [2] winner record landed (bulk copy, tx bytes)
     uint64_t* recempty = recfull + 2;           // [2] producers done with the record (16 warp arrivals)
@@ -1538,10 +1540,8 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
     const uint32_t rec_bytes = (uint32_t)prm.rec * 2u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&full[s], BW_NT_PROD / 64); mbar_init(&empty[s], 1);       // 8 warps of one producer set per tile
-            mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BW_NT_PROD / 32);
-        }
+        for (int s = 0; s < BW_NBUF; ++s) { mbar_init(&full[s], BW_NT_PROD / 64); mbar_init(&empty[s], 1); }   // 8 warps of one set per tile
+        for (int s = 0; s < 2; ++s) { mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BW_NT_PROD / 32); }
         for (int d = 0; d < BW_NDBUF; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI / 32); }
         fence_barrier_init();
     }
@@ -1672,12 +1672,12 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         if (nchains > 0) stage_record(0);
         int tn = 0, ci = 0;
         for (int it = 0; it < ntiles; ++it) {
-            const int tb = it & 1;                                   // tile ring buffer
+            const int tb = it % BW_NBUF;                             // tile ring buffer
             const int buf = it & (BW_NDBUF - 1);                      // accumulator buffer
             if (tn == 0 && ci + 1 < nchains) stage_record(ci + 1);   // one chain ahead
             if (it >= BW_NDBUF) mbar_wait(&dempty[buf], (uint32_t)(((it / BW_NDBUF) + 1) & 1));
             if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
-            mbar_wait(&full[tb], (uint32_t)((it >> 1) & 1));
+            mbar_wait(&full[tb], (uint32_t)((it / BW_NBUF) & 1));
             if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + D_COL0 + buf * BW_NT;
@@ -1740,21 +1740,14 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
                     if (lact && pp0 + r0 + rr < P) mx |= (unsigned long long)__ldg(xrow + rr * 32) << (8 * rr);
             }
         };
-        // masks of my NEXT tile (it + 2) are requested while the current one is built: they come from HBM
-        unsigned long long m8n = 0ull, m8xn = 0ull;
-        if (pset < ntiles) load_masks(b_lo + pset / tpc, (pset % tpc) * BW_NT, m8n, m8xn);
         int tn = 0, ci = 0;
         for (int it = 0; it < ntiles; ++it) {
             const int rb = ci & 1;
             if ((it & 1) == pset) {
-                const int tb = pset;
+                const int tb = it % BW_NBUF;
                 const int p0 = tn * BW_NT;
-                const unsigned long long m8 = m8n, m8x = m8xn;
-                if (it + 2 < ntiles) {
-                    int tn2 = tn + 2, ci2 = ci;
-                    while (tn2 >= tpc) { tn2 -= tpc; ++ci2; }
-                    load_masks(b_lo + ci2, tn2 * BW_NT, m8n, m8xn);
-                }
+                unsigned long long m8 = 0ull, m8x = 0ull;
+                load_masks(b_lo + ci, p0, m8, m8x);                    // independent of the winners: in flight during the record reads
                 mbar_wait(&recfull[rb], (uint32_t)((ci >> 1) & 1));
                 const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;         // this chain's record: start[P+1] | list
                 const uint32_t ls = rs + 2u * (uint32_t)(P + 1);
@@ -1772,7 +1765,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
                 auto store_row = [&]() {   // row r0 + cur <- mask * scale * acc, fp16 hi (truncated: exact) + lo
                     if (!have_buf) {
                         if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-                        mbar_wait(&empty[tb], (uint32_t)(((it >> 1) + 1) & 1));
+                        mbar_wait(&empty[tb], (uint32_t)(((it / BW_NBUF) + 1) & 1));
                         have_buf = true;
                         if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                     }
@@ -2113,7 +2106,7 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
     const int rec = ((P + 1) + 2 * J2 + 7) & ~7;
-    const size_t smem = 1024 + (size_t)2 * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
+    const size_t smem = 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
                         2 * (size_t)rec * sizeof(uint16_t) + 8 + 32 * sizeof(uint64_t);
     const bool prof = g_backward_prof != nullptr;
     void (*bkern)(tc::BwdParams) = dl ? (prof ? tc::cnn_backward_tc_kernel<true, true> : tc::cnn_backward_tc_kernel<false, true>)
