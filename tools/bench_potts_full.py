@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Full Potts re-evaluation: dense tcgen05 GEMM vs row-gather kernel (BASELINE.json configs[4]-style sweep).
+"""Potts expert alone (BASELINE.json configs[4]-style sweep): full re-evaluation as a dense tcgen05 GEMM vs the row-gather
+kernel, and the sampler's incremental field update (k <= S gathered J row differences per chain) for the same chains.
 usage (GPU box): python tools/bench_potts_full.py [L ...]   (Potts-only: lamda = 0, synthetic couplings)"""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from ppde_b200.engine import PoEModel, _ptr, _stream
+from ppde_b200 import _lib
+from ppde_b200.engine import ChainEngine, PoEModel, _ptr, _stream
 from ppde_b200.synthetic import synthetic_problem
 
 Ls = [int(a) for a in sys.argv[1:]] or [64, 128, 238, 512]
@@ -12,7 +14,7 @@ peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.absp
 for L in Ls:
     pr = synthetic_problem(L, seed=0)
     m = PoEModel(pr["wt"], pr["J"], pr["h"], pr["win_lo"], pr["cnn"], 0.0, device="cuda:0")
-    for n in ([1024, 16384, 65536] if L <= 512 else [1024, 16384]):
+    for n in ([1024, 16384, 65536, 262144] if L <= 238 else ([1024, 16384, 65536] if L <= 512 else [1024, 16384])):
         rng = np.random.default_rng(0)
         aa = np.tile(pr["wt"], (n, 1)).astype(np.uint8)
         idx = rng.integers(0, L, size=(n, 8)); val = rng.integers(0, 20, size=(n, 8))
@@ -31,9 +33,30 @@ for L in Ls:
             for _ in range(reps): m.potts_full(aad, n, _ptr(Gp), _ptr(Ep), _stream(), impl=impl)
             e1.record(); torch.cuda.synchronize()
             res[impl] = e0.elapsed_time(e1) / reps
+        res["incremental"] = float("nan")
+        if m.C <= 512:        # the engine evaluates the CNN of the wild type once; the fp32 SIMT CNN (C > 256) needs C*68*4 B of smem
+            # the sampler's incremental path on the same population size: propose (pas=2, up to 3 moves) then update the field
+            del Gp
+            eng = ChainEngine(m, n, 2, 0, False, seed=0)
+            wt = np.zeros((n, m.aa_stride), dtype=np.uint8); wt[:, :L] = pr["wt"]
+            eng.init_population(torch.from_numpy(wt).to(m.device))
+            st = _stream()
+            inc = []
+            for rep in range(4):
+                p = eng._params(rep)
+                _lib.check(m.lib.ppde_pas_propose(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "propose")
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(m.lib.ppde_potts_incremental(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "inc")
+                e1.record(); torch.cuda.synchronize()
+                inc.append(e0.elapsed_time(e1))
+            res["incremental"] = min(inc[1:])
+            del eng
         flops = 2.0 * n * m.D * m.D
         tf = flops / (res["dense"] * 1e-3) / 1e12
         print(json.dumps({"L": L, "D": m.D, "chains": n, "gather_ms": round(res["gather"], 3), "dense_ms": round(res["dense"], 3),
+                          "incremental_ms": None if res["incremental"] != res["incremental"] else round(res["incremental"], 3),
+                          "incremental_GBs": None if res["incremental"] != res["incremental"] else round((8 * m.D + L) * n / (res["incremental"] * 1e-3) / 1e9, 1),
                           "dense_alg_TFLOPs": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / peaks["bf16_tflops"], 3),
                           "note": "2 fp16 passes per algorithmic flop (hi/lo split): executed = 2x"}))
     del m

@@ -11,7 +11,7 @@ $K 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench
 $K 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ref.json
 $K 200 python bench.py --workload ube4b_potts_poe_4k --no-cpu-baseline > gpurun_out/${TAG}_bench_ube4b.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ube4b.json
 $K 300 python bench.py --workload gfp_paper_pas10 --no-cpu-baseline --steps 5 > gpurun_out/${TAG}_bench_pas10.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_pas10.json
-$K 200 python tools/bench_potts_full.py 64 128 238 512 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
+$K 200 python tools/bench_potts_full.py 64 128 238 512 1024 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
 SMALL="python bench.py --chains 8192 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline"
 $K 200 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 && \
 $K 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
