@@ -128,6 +128,10 @@ typedef struct ppde_pas_params {
     uint64_t seed;
     const float* uniforms; /* optional materialised proposal uniforms [S, n, 20L]; NULL = Philox in-kernel */
     const int32_t* t_dev;  /* optional device-resident iteration counter (CUDA-graph replay); NULL = use t */
+    int32_t full_trace;    /* 1: evaluate all S sub-steps of every chain (the reference computes, then masks, the sub-steps
+                            * s >= U[b], ppde.py:83,111-115,132); 0: skip those dead sub-steps - nothing they produce reaches
+                            * the state, the log-ratio or the accept decision - and record idx = -1, lqf = lqr = 0 for them */
+    int32_t _pad;
 } ppde_pas_params_t;
 
 const char* ppde_version(void);

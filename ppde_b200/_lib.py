@@ -44,7 +44,8 @@ class ChainsT(C.Structure):
 
 class PasParamsT(C.Structure):
     _fields_ = [("S", C.c_int32), ("nmut_threshold", C.c_int32), ("paper_results", C.c_int32), ("t", C.c_int32),
-                ("min_pos", C.c_int32), ("max_pos", C.c_int32), ("seed", C.c_uint64), ("uniforms", vp), ("t_dev", vp)]
+                ("min_pos", C.c_int32), ("max_pos", C.c_int32), ("seed", C.c_uint64), ("uniforms", vp), ("t_dev", vp),
+                ("full_trace", C.c_int32), ("_pad", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/ppde_b200.h

@@ -78,8 +78,14 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
     const int U = 1 + (int)(rng(0u, gid, (uint32_t)t, (uint32_t)(KIND_PATHLEN << 16)).x % (uint32_t)span);
     if (threadIdx.x == 0) c.U[b] = U;
     __syncthreads();
+    // sub-steps s >= U are masked out by the reference (u_mask, ppde.py:111-115,132): they are evaluated only on request
+    const int S_eff = p.full_trace ? p.S : U;
+    for (int s = S_eff + (int)threadIdx.x; s < p.S; s += NT) {
+        const int64_t o = (int64_t)s * c.n + b;
+        c.idx[o] = -1; c.old_aa[o] = 0; c.lqf[o] = 0.f;
+    }
 
-    for (int s = 0; s < p.S; ++s) {
+    for (int s = 0; s < S_eff; ++s) {
         // edit distance to WT and the threshold flag (utils.py:5-14, ppde.py:86-91)
         int dpart = 0;
         for (int i = threadIdx.x; i < L; i += NT) {
@@ -184,7 +190,9 @@ __global__ void __launch_bounds__(NT) pas_reverse_accept_kernel(ppde_potts_t m, 
     __syncthreads();
 
     float log_ratio = 0.f;
-    for (int s = 0; s < p.S; ++s) {
+    const int S_eff = p.full_trace ? p.S : U;                      // dead sub-steps (s >= U) only on request
+    for (int s = S_eff + (int)threadIdx.x; s < p.S; s += NT) c.lqr[(int64_t)s * n + b] = 0.f;
+    for (int s = 0; s < S_eff; ++s) {
         const int64_t o = (int64_t)s * n + b;
         const int cidx = c.idx[o];
         if (threadIdx.x == 0 && s < U) sZ[cidx / PPDE_Q] = (uint8_t)(cidx % PPDE_Q);   // state AFTER move s

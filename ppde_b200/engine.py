@@ -329,6 +329,9 @@ class ChainEngine:
             model.win_lo + model.Lp - 1 if model.has_potts else model.L - 1)
         self._allocated = False
         self._graph = None
+        # True: also evaluate the sub-steps s >= U[b] that the reference computes and then masks (complete idx / lqf / lqr
+        # trace, as the golden comparisons read it); False: skip them (same states, energies and accept decisions)
+        self.full_trace = False
 
     # -- allocation ------------------------------------------------------------------------------
     def _alloc(self, n_fixed):
@@ -437,7 +440,7 @@ class ChainEngine:
         return PasParamsT(S=self.S, nmut_threshold=self.thr, paper_results=int(self.paper), t=int(t),
                           min_pos=self.min_pos, max_pos=self.max_pos, seed=self.seed,
                           uniforms=uniforms.data_ptr() if uniforms is not None else None,
-                          t_dev=self.t_dev.data_ptr() if use_t_dev else None)
+                          t_dev=self.t_dev.data_ptr() if use_t_dev else None, full_trace=int(self.full_trace))
 
     def _launch_step(self, p, full=True):
         m, lib, c, n = self.m, self.lib, self.chains, self.n

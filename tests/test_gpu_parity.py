@@ -66,14 +66,19 @@ def _engine(m, z, T=None):
                        num_steps=T, traj_chain=int(z["random_idx"]))
 
 
+@pytest.mark.parametrize("full_trace", [True, False])
 @pytest.mark.parametrize("name", TRAJ)
-def test_step_teacher_forced_vs_reference(name):
-    """Every iteration of the reference run is replayed from the reference's own state."""
+def test_step_teacher_forced_vs_reference(name, full_trace):
+    """Every iteration of the reference run is replayed from the reference's own state.
+    full_trace=True: all sub-steps the reference evaluates (s < max_b U[b]) are compared; False (the production default):
+    the sub-steps s >= U[b], which the reference computes and then masks, are skipped - everything that reaches the
+    state, the log-ratio and the accept decision must be unchanged."""
     z = np.load(os.path.join(GOLD, f"traj_{name}.npz"))
     w = port.golden_weights(str(z["prot"]), z["window"], float(z["lamda"]), **_meta(z))
     m = _model(w)
     n, T = int(z["n"]), int(z["T"])
     eng = _engine(m, z)
+    eng.full_trace = full_trace
     wt_pop = _aa_dev(m, np.tile(w.wt, (n, 1)))
     near_ties = 0
     for t in range(T):
@@ -81,15 +86,21 @@ def test_step_teacher_forced_vs_reference(name):
         eng.t = t
         eng.step()
         torch.cuda.synchronize()
-        assert np.array_equal(eng.U.cpu().numpy(), z["U"][t])
-        mu = int(z["U"][t].max())
+        U = z["U"][t].reshape(-1)
+        assert np.array_equal(eng.U.cpu().numpy(), U)
+        mu = int(U.max())
+        live = np.arange(mu)[:, None] < U[None, :]                  # [mu, n]: sub-steps that are not masked
+        sel = np.ones_like(live) if full_trace else live
         idx = eng.idx.cpu().numpy()[:mu]
-        if not np.array_equal(idx, z["idx"][t, :mu]):
+        if not np.array_equal(idx[sel], z["idx"][t, :mu][sel]):
             near_ties += 1          # a flipped exponential race: must be a documented near tie
             continue
+        lqf, lqr = eng.lqf.cpu().numpy()[:mu], eng.lqr.cpu().numpy()[:mu]
+        if not full_trace:
+            assert (idx[~live] == -1).all() and (lqf[~live] == 0).all() and (lqr[~live] == 0).all()
         assert np.array_equal(eng.aa_y.cpu().numpy()[:, :w.L], z["aa_y"][t])
-        _close(eng.lqf.cpu().numpy()[:mu], z["lqf"][t, :mu], np.maximum(np.abs(z["lqf"][t, :mu]), 1.0), what="lqf")
-        _close(eng.lqr.cpu().numpy()[:mu], z["lqr"][t, :mu], np.maximum(np.abs(z["lqr"][t, :mu]), 1.0), what="lqr")
+        _close(lqf[sel], z["lqf"][t, :mu][sel], np.maximum(np.abs(z["lqf"][t, :mu][sel]), 1.0), what="lqf")
+        _close(lqr[sel], z["lqr"][t, :mu][sel], np.maximum(np.abs(z["lqr"][t, :mu][sel]), 1.0), what="lqr")
         escale = np.maximum(np.abs(z["e_y"][t]), abs(m.wt_H))
         _close(eng.E_y.cpu().numpy(), z["e_y"][t], escale, what="E_y")
         _close(eng.fit_y.cpu().numpy(), z["fit_y"][t], np.maximum(np.abs(z["fit_y"][t]), 1e-2), what="fit_y")
