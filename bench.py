@@ -289,7 +289,7 @@ def main():
                                            note="max-pool winners of every proposal: 3*2*P*C*2C algorithmic flops per chain, of which only the dirty "
                                                 "16-position blocks are executed (3 fp16 passes per flop)"),
                 "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s", work=None, peak=pk["hbm_gbs"],
-                                      traffic=(2748.5e6 / 8192) * n if L == 238 else None, note="clean block keys copied to the proposal row + chain-level winner"),
+                                      traffic=(2748.5e6 / 8192) * n if L == 238 else None, note="chain-level winner = max over the NB block keys read through the block table"),
                 "pas_propose": dict(kernel="pas_propose_kernel", bound="hbm", unit="GB/s", work=(4 * NE + L) * n, peak=pk["hbm_gbs"],
                                     traffic=(164.4e6 / 8192) * n if L == 238 else None,
                                     note="reads one gradient row per chain; bound by the per-entry Philox + softmax arithmetic "
@@ -299,7 +299,7 @@ def main():
             cd = cand[dom]
             if dom == "cnn_inc_merge":
                 nb_ = (P + 15) // 16
-                cd["work"] = int(n * 3 * 2 * Cc * 8 * (nb_ + (nb_ - (dirty_blocks or 0) / n) + 1))
+                cd["work"] = int(n * 3 * 2 * Cc * 8 * (nb_ + 2))
             ach = tflop(cd["work"], breakdown[dom]) if cd["unit"] == "TFLOP/s" else gbs(cd["work"], breakdown[dom])
             roof = {"kernel": cd["kernel"], "bound": cd["bound"], "achieved": ach, "peak": cd["peak"], "unit": cd["unit"],
                     "frac": ach / cd["peak"], "traffic": cd["traffic"],
@@ -318,8 +318,8 @@ def main():
                     "executed_algorithmic_tflops": f_inc / t_inc / 1e12, "avg_launch_ms": breakdown["cnn_forward_inc_tc"],
                     "full_evaluation_equivalent_tflops": 3 * 2 * P * Cc * 2 * Cc * n / ((breakdown["cnn_dirty"] + breakdown["cnn_inc_scan"]
                                                          + breakdown["cnn_forward_inc_tc"] + breakdown["cnn_inc_merge"]) * 1e-3) / 1e12}
-                nb_ = (P + 15) // 16                # per channel: NB keys read, the clean ones written to the proposal row, mkey written
-                mbytes = int(n * 3 * 2 * Cc * 8 * (nb_ + (nb_ - dirty_blocks / n) + 1))
+                nb_ = (P + 15) // 16                # per channel: NB block keys read through the block table; mkey and its pool copy written
+                mbytes = int(n * 3 * 2 * Cc * 8 * (nb_ + 2))
                 roof["merge_kernel"] = {"kernel": "cnn_inc_merge_kernel", "bound": "hbm", "algorithmic_bytes": mbytes,
                                         "achieved_gbs": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
                                         "frac": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9 / pk["hbm_gbs"]}

@@ -185,23 +185,26 @@ int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const
                               const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                               float* G, int64_t G_stride, const int32_t* g_rows,
                               const uint8_t* r1mask, const int32_t* mask_rows, int32_t mask_row_base,
+                              const int32_t* btab /* optional block table of the pools, see ppde_cnn_forward_inc */,
                               float* scratch, void* stream);
 /* Incremental CNN forward (same quantity as ppde_cnn_forward_tc, bit for bit; OnehotCNN.forward, ppde/nets.py:363-376).
  * A proposal differs from the chain's current state in a few residues, and a residue only moves the 5 conv rows that
  * read it, so the max-pool over positions is kept per BLOCK of 16 positions in a pool
  *     bkey [rows, n_nets, NB = ceil(P/16), 2C] uint64   (rows indexed like the G / Gp pools)
  * and only the dirty blocks of every chain are recomputed on the tensor cores.
- *   ppde_cnn_dirty        dmask[b] = dirty-block bits of proposal aa_y[b] against the current state aa_x[b]; also copies
- *                         the current row of the relu-mask pool r1mask [rows, n_nets, P, 32] to the proposal row.
- *   ppde_cnn_forward_inc  recomputes the dirty blocks of aa[b] (dmask == NULL: all blocks = full evaluation), merges them
- *                         with the clean blocks of row rows_x[b], writes row rows_y[b] (NULL: row_base_y + b) of bkey,
- *                         the dirty rows of r1mask (same row) and mkey [n, n_nets, 2C] as ppde_cnn_forward_tc does. */
+ * A proposal row does not copy the clean blocks of the current state, it POINTS at them:
+ *     btab [rows, NB] int32   btab[r][q] = the pool row whose slot holds block q of row r (its keys in bkey and its 16
+ *                             relu-mask rows in r1mask [rows, n_nets, P, 32]); a fully evaluated row points at itself.
+ *   ppde_cnn_dirty        dmask[b] = dirty-block bits of proposal aa_y[b] against the current state aa_x[b].
+ *   ppde_cnn_forward_inc  recomputes the dirty blocks of aa[b] (dmask == NULL: all blocks = full evaluation) into free
+ *                         slots, writes row rows_y[b] (NULL: row_base_y + b) of btab (clean blocks: the entries of row
+ *                         rows_x[b]) and mkey [n, n_nets, 2C] as ppde_cnn_forward_tc does. */
 int ppde_cnn_dirty(const ppde_cnn_t* m, const uint8_t* aa_x, const uint8_t* aa_y, int32_t aa_stride, int32_t n,
-                   uint32_t* dmask /* [n] */, uint8_t* r1mask, const int32_t* rows_x, const int32_t* rows_y, void* stream);
+                   uint32_t* dmask /* [n] */, void* stream);
 int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n);   /* workspace of ppde_cnn_forward_inc (block prefix sums and lists) */
 int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                          unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask, unsigned long long* bkey,
-                         const int32_t* rows_x, const int32_t* rows_y, int32_t row_base_y,
+                         int32_t* btab, const int32_t* rows_x, const int32_t* rows_y, int32_t row_base_y,
                          unsigned long long* mkey_pool /* optional [rows, n_nets, 2C]: row of the proposal also gets mkey */,
                          void* ws /* ppde_cnn_forward_inc_ws_bytes(n) bytes */, void* stream);
 /* DELTA backward: the CNN part of the gradient changes between the current state x and the proposal y only through the
@@ -214,7 +217,7 @@ int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const u
                             int32_t aa_stride, int32_t n, const unsigned long long* mkey_y,
                             const unsigned long long* mkey_pool, float lamda, const float* Gp, int64_t Gp_stride,
                             float* G, int64_t G_stride, const int32_t* rows_x, const int32_t* rows_y,
-                            const uint8_t* r1mask, float* scratch, void* stream);
+                            const uint8_t* r1mask, const int32_t* btab, float* scratch, void* stream);
 /* dH_potts of n states from field rows already in the pool: Epotts[b] = 1/2 sum_i (Gp[rows[b]][(i,aa_i)] + h) - H(wt);
  * rows == NULL means row b. */
 int ppde_potts_energy_rows(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n, const float* Gp,

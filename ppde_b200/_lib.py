@@ -69,12 +69,12 @@ SIGNATURES = {
     "ppde_cnn_backward_tc": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
                                        vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, vp]),
     "ppde_cnn_backward_tc_rows": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
-                                            vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp]),
-    "ppde_cnn_dirty": (C.c_int, [C.POINTER(CnnT), vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]),
+                                            vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, vp]),
+    "ppde_cnn_dirty": (C.c_int, [C.POINTER(CnnT), vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "ppde_cnn_forward_inc_ws_bytes": (C.c_int64, [C.c_int32]),
-    "ppde_cnn_forward_inc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp]),
+    "ppde_cnn_forward_inc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp]),
     "ppde_cnn_backward_delta": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_float,
-                                          vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, vp]),
+                                          vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
     "ppde_potts_energy_rows": (C.c_int, [C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp, vp]),
     "ppde_oracle_ridge": (C.c_int, [vp, C.c_float, C.c_float, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
     "ppde_step_rows": (C.c_int, [C.POINTER(ChainsT), vp, vp]),

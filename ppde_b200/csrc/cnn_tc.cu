@@ -769,6 +769,8 @@ struct IncParams {
     const uint32_t* dmask;              // [n] dirty-block bits, NULL = every block is dirty (full evaluation into the pool)
     unsigned long long* mkey_pool;      // optional pool [rows, n_nets, 2C]: the proposal row also gets mkey (delta backward)
     unsigned long long* bkey;           // pool [rows, n_nets, NB, 2C]
+    int32_t* btab;                      // pool [rows, NB]: the pool row whose slot holds block q of this row (keys AND relu-mask rows):
+                                        // a proposal row only POINTS at the clean blocks of the current state instead of copying them
     const int32_t* rows_x;              // [n] pool row of the current state (NULL only with dmask == NULL)
     const int32_t* rows_y;              // [n] pool row of the proposal, NULL = row_base_y + b
     int row_base_y;
@@ -919,10 +921,16 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
             const int g = 8 * T + (lane & 7);
             return (g < G) ? __ldg(bl + g) : 0u;
         };
+        // slot that receives block (b, q): the proposal row's own, unless the current row still points at it (then the current
+        // row's own slot is free: it is referenced by neither row) - see cnn_inc_merge_kernel for the table update
         auto ld_row = [&](int T, uint32_t ent) -> int {
             const int g = 8 * T + (lane & 7);
-            const int b = (int)(ent >> 4);
-            return (g < G) ? (prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b) : 0;
+            if (g >= G) return 0;
+            const int b = (int)(ent >> 4), q = (int)(ent & 15u);
+            const int ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
+            if (!prm.rows_x) return ry;
+            const int rx = __ldg(prm.rows_x + b);
+            return (__ldg(prm.btab + (size_t)rx * NB + q) == ry) ? rx : ry;
         };
         uint32_t ent_a = ld_ent(0);
         int row_a = ld_row(0, ent_a);
@@ -1113,7 +1121,11 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
                 o = __shfl_xor_sync(0xffffffffu, word, 1);
                 word = (g & 1) ? ((word & 0xF0F0F0F0u) | ((o >> 4) & 0x0F0F0F0Fu)) : ((word & 0x0F0F0F0Fu) | ((o << 4) & 0xF0F0F0F0u));
                 if (active && pos < P) {
-                    const int mrow = prm.rows_y ? __ldg(prm.rows_y + bcur) : prm.row_base_y + bcur;
+                    int mrow = prm.rows_y ? __ldg(prm.rows_y + bcur) : prm.row_base_y + bcur;
+                    if (prm.rows_x) {                          // same slot rule as the block keys
+                        const int rx = __ldg(prm.rows_x + bcur);
+                        if (__ldg(prm.btab + (size_t)rx * NB + (pos >> 4)) == mrow) mrow = rx;
+                    }
                     reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)mrow * prm.m.n_nets + k) * P + pos) * 32)[g] = word;
                 }
             }
@@ -1130,12 +1142,9 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
     }
 }
 
-// Dirty blocks of every proposal (bit q of dmask[b]: some conv row of block q reads a residue where y differs from x) and
-// the copy of the current state's relu-mask rows into the proposal's pool row (the forward overwrites the dirty ones).
+// Dirty blocks of every proposal: bit q of dmask[b] is set when some conv row of block q reads a residue where y differs from x.
 __global__ void __launch_bounds__(128) cnn_dirty_kernel(int n, int L, int P, int aa_stride, const uint8_t* __restrict__ aa_x,
-                                                        const uint8_t* __restrict__ aa_y, uint32_t* __restrict__ dmask,
-                                                        uint8_t* r1mask, const int32_t* __restrict__ rows_x,
-                                                        const int32_t* __restrict__ rows_y, size_t mask_row_bytes) {
+                                                        const uint8_t* __restrict__ aa_y, uint32_t* __restrict__ dmask) {
     const int b = blockIdx.x;
     if (b >= n) return;
     __shared__ uint32_t smask;
@@ -1150,43 +1159,44 @@ __global__ void __launch_bounds__(128) cnn_dirty_kernel(int n, int L, int P, int
     }
     m = __reduce_or_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0 && m) atomicOr(&smask, m);
-    if (r1mask) {
-        const uint4* src = reinterpret_cast<const uint4*>(r1mask + (size_t)rows_x[b] * mask_row_bytes);
-        uint4* dst = reinterpret_cast<uint4*>(r1mask + (size_t)rows_y[b] * mask_row_bytes);
-        for (size_t e = threadIdx.x; e < mask_row_bytes / 16; e += blockDim.x) __stcg(dst + e, __ldcg(src + e));
-    }
     __syncthreads();
     if (threadIdx.x == 0) dmask[b] = smask;
 }
 
-// Second half of the incremental forward, one thread per (chain, net, channel): the clean blocks' keys are copied from
-// the current row to the proposal row (the dirty ones were written there by cnn_forward_inc_kernel), and the chain-level
-// winner - the 64-bit maximum over the blocks - becomes the same `mkey` the full forward kernel writes.
+// Second half of the incremental forward, one thread per (chain, net, channel).  Nothing is copied: the proposal row's
+// block table points at the current row's slots for the clean blocks and at the slots cnn_forward_inc_kernel just wrote
+// for the dirty ones; the chain-level winner - the 64-bit maximum over the blocks - becomes the same `mkey` the full
+// forward kernel writes.  Slot rule for a dirty block q of proposal row Y built from current row X: Y's own slot, unless
+// X's table points at it (X inherited that block from an earlier state that lived in Y) - then X's own slot, which neither
+// row references.  Only the two private rows of a chain and read-only fixed rows ever appear in its tables.
 __global__ void __launch_bounds__(256) cnn_inc_merge_kernel(const __grid_constant__ IncParams prm) {
     const int b = blockIdx.x;
     const int J2 = 2 * prm.m.C, NB = prm.NB, nets = prm.m.n_nets;
     const uint32_t all_blocks = (NB >= 32) ? 0xFFFFFFFFu : ((1u << NB) - 1u);
     const uint32_t mask = prm.dmask ? (__ldg(prm.dmask + b) & all_blocks) : all_blocks;
     const size_t row_keys = (size_t)nets * NB * J2;
-    const int rx = prm.rows_x ? __ldg(prm.rows_x + b) : 0;
     const int ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
-    const unsigned long long* kx = prm.bkey + (size_t)rx * row_keys;
-    unsigned long long* ky = prm.bkey + (size_t)ry * row_keys;
+    const int rx = prm.rows_x ? __ldg(prm.rows_x + b) : ry;
+    int slot[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        slot[q] = ry;
+        if (q < NB && prm.rows_x) {
+            const int tx = __ldg(prm.btab + (size_t)rx * NB + q);
+            slot[q] = ((mask >> q) & 1u) ? ((tx == ry) ? rx : ry) : tx;
+        }
+    }
     for (int e = threadIdx.x; e < nets * J2; e += blockDim.x) {
         const int k = e / J2, j = e - k * J2;
         const size_t base = ((size_t)k * NB) * J2 + j;
         unsigned long long key[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-            key[q] = (q < NB) ? (((mask >> q) & 1u) ? __ldcg(ky + base + (size_t)q * J2) : __ldcg(kx + base + (size_t)q * J2)) : 0ull;
+            key[q] = (q < NB) ? __ldcg(prm.bkey + (size_t)slot[q] * row_keys + base + (size_t)q * J2) : 0ull;
         unsigned long long best = 0ull;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            if (q < NB) {
-                if (!((mask >> q) & 1u)) __stcg(ky + base + (size_t)q * J2, key[q]);
-                best = (key[q] > best) ? key[q] : best;
-            }
-        }
+        for (int q = 0; q < 16; ++q)
+            if (q < NB) best = (key[q] > best) ? key[q] : best;
         const ppde_cnn_net_t& net = prm.m.net[k];
         const float unscale = 1.f / (net.w1_scale * net.r1_scale);
         const float u = f32_unordered((uint32_t)(best >> 32));
@@ -1196,6 +1206,12 @@ __global__ void __launch_bounds__(256) cnn_inc_merge_kernel(const __grid_constan
         const unsigned long long mk = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)pp);
         prm.mkey[((size_t)b * nets + k) * J2 + j] = mk;
         if (prm.mkey_pool) prm.mkey_pool[((size_t)ry * nets + k) * J2 + j] = mk;
+    }
+    __syncthreads();                                        // every thread has read the current row's table (rx may equal ry never)
+    if (threadIdx.x < NB) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (q == (int)threadIdx.x) prm.btab[(size_t)ry * NB + q] = slot[q];
     }
 }
 
@@ -1463,6 +1479,7 @@ struct BwdParams {
     const int32_t* mask_rows;           // [n] row of chain b in r1mask, NULL = mask_row_base + b
     int mask_row_base;
     const int32_t* mask_rows_x;         // delta mode only: [n] r1mask row of the chain's CURRENT state
+    const int32_t* btab; int NB;        // optional block table of the pools [rows, NB]: the mask rows of block q of row r live in row btab[r][q]
     const uint16_t* wl; int rec;        // winner records from cnn_winner_sort_kernel
     float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
     int ctas_per_net;
@@ -1727,13 +1744,16 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         // the current state's rows
         auto load_masks = [&](int bb, int pp0, unsigned long long& my, unsigned long long& mx) {
             my = 0ull; mx = 0ull;
-            const int mr = prm.mask_rows ? __ldg(prm.mask_rows + bb) : prm.mask_row_base + bb;
+            int mr = prm.mask_rows ? __ldg(prm.mask_rows + bb) : prm.mask_row_base + bb;
+            const int blk = min((pp0 + r0) >> 4, prm.NB - 1);            // my 8 rows lie in one 16-position block
+            if (prm.btab) mr = __ldg(prm.btab + (size_t)mr * prm.NB + blk);
             const uint8_t* mrow = prm.r1mask + (((size_t)mr * prm.m.n_nets + k) * P + pp0 + r0) * 32 + lane;
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr)
                 if (lact && pp0 + r0 + rr < P) my |= (unsigned long long)__ldg(mrow + rr * 32) << (8 * rr);
             if (DELTA) {
-                const int mxr = __ldg(prm.mask_rows_x + bb);
+                int mxr = __ldg(prm.mask_rows_x + bb);
+                if (prm.btab) mxr = __ldg(prm.btab + (size_t)mxr * prm.NB + blk);
                 const uint8_t* xrow = prm.r1mask + (((size_t)mxr * prm.m.n_nets + k) * P + pp0 + r0) * 32 + lane;
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr)
@@ -1985,11 +2005,10 @@ extern "C" int ppde_set_profile_parts(int forward_inc_parts, int backward_parts)
 }
 
 extern "C" int ppde_cnn_dirty(const ppde_cnn_t* m, const uint8_t* aa_x, const uint8_t* aa_y, int32_t aa_stride, int32_t n,
-                              uint32_t* dmask, uint8_t* r1mask, const int32_t* rows_x, const int32_t* rows_y, void* stream) {
+                              uint32_t* dmask, void* stream) {
     if (n <= 0) return 0;
-    if (!aa_x || !aa_y || !dmask || (r1mask && (!rows_x || !rows_y))) return (int)cudaErrorInvalidValue;
-    tc::cnn_dirty_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, m->L, m->P, aa_stride, aa_x, aa_y, dmask, r1mask, rows_x, rows_y,
-                                                              (size_t)m->n_nets * m->P * 32);
+    if (!aa_x || !aa_y || !dmask) return (int)cudaErrorInvalidValue;
+    tc::cnn_dirty_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, m->L, m->P, aa_stride, aa_x, aa_y, dmask);
     return launch_done();
 }
 
@@ -1997,14 +2016,14 @@ extern "C" int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n) { return ((int64_t)n
 
 extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                                     unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask,
-                                    unsigned long long* bkey, const int32_t* rows_x, const int32_t* rows_y,
+                                    unsigned long long* bkey, int32_t* btab, const int32_t* rows_x, const int32_t* rows_y,
                                     int32_t row_base_y, unsigned long long* mkey_pool, void* ws, void* stream) {
     if (n <= 0) return 0;
     const int NB = (m->P + 15) / 16;
-    if (m->C > 256 || m->P < 1 || NB > 16 || !bkey || !mkey || !ws || (dmask && !rows_x)) return (int)cudaErrorInvalidValue;
+    if (m->C > 256 || m->P < 1 || NB > 16 || !bkey || !btab || !mkey || !ws || (dmask && !rows_x)) return (int)cudaErrorInvalidValue;
     tc::IncParams prm;
     prm.m = *m; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey; prm.r1mask = r1mask; prm.dmask = dmask;
-    prm.bkey = bkey; prm.mkey_pool = mkey_pool;
+    prm.bkey = bkey; prm.btab = btab; prm.mkey_pool = mkey_pool;
     prm.rows_x = dmask ? rows_x : nullptr;   // full evaluation: nothing is read from a current row
     prm.rows_y = rows_y; prm.row_base_y = row_base_y; prm.NB = NB;
     prm.kpad = (m->C + 15) / 16 * 16;
@@ -2064,14 +2083,15 @@ extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t
                                          int32_t n, const unsigned long long* mkey, float lamda,
                                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                                          float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
-                                         const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream);
+                                         const int32_t* mask_rows, int32_t mask_row_base, const int32_t* btab, float* scratch,
+                                         void* stream);
 extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                                     int32_t n, const unsigned long long* mkey, float lamda,
                                     const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                                     float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
                                     float* scratch, void* stream) {
     return ppde_cnn_backward_tc_rows(m, pm, aa, aa_stride, n, mkey, lamda, Gp, Gp_stride, gp_rows, G, G_stride, g_rows, r1mask,
-                                     nullptr, 0, scratch, stream);
+                                     nullptr, 0, nullptr, scratch, stream);
 }
 struct BwdDelta {                 // delta backward: gradient of the proposal = gradient of the current state + change
     const uint8_t* aa_x;          // current states [n, aa_stride]
@@ -2084,7 +2104,8 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
                            int32_t n, const unsigned long long* mkey, float lamda,
                            const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                            float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
-                           const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream, const BwdDelta* dl) {
+                           const int32_t* mask_rows, int32_t mask_row_base, const int32_t* btab, float* scratch, void* stream,
+                           const BwdDelta* dl) {
     if (n <= 0) return 0;
     if (m->C > 256 || m->P < 1 || !scratch || !r1mask) return (int)cudaErrorInvalidValue;
     tc::BwdParams prm;
@@ -2094,6 +2115,7 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     prm.mask_rows = dl ? dl->rows_y : mask_rows;
     prm.mask_row_base = mask_row_base;
     prm.mask_rows_x = dl ? dl->rows_x : nullptr;
+    prm.btab = btab; prm.NB = (m->P + 15) / 16;
     { const char* e = getenv("PPDE_BWD_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
     prm.tiles_per_chain = (m->P + tc::BW_NT - 1) / tc::BW_NT;
     prm.kpad = (m->C + 15) / 16 * 16;
@@ -2154,18 +2176,19 @@ extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t
                                          int32_t n, const unsigned long long* mkey, float lamda,
                                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                                          float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
-                                         const int32_t* mask_rows, int32_t mask_row_base, float* scratch, void* stream) {
+                                         const int32_t* mask_rows, int32_t mask_row_base, const int32_t* btab, float* scratch,
+                                         void* stream) {
     return backward_launch(m, pm, aa, aa_stride, n, mkey, lamda, Gp, Gp_stride, gp_rows, G, G_stride, g_rows, r1mask, mask_rows,
-                           mask_row_base, scratch, stream, nullptr);
+                           mask_row_base, btab, scratch, stream, nullptr);
 }
 
 extern "C" int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa_x, const uint8_t* aa_y,
                                        int32_t aa_stride, int32_t n, const unsigned long long* mkey_y,
                                        const unsigned long long* mkey_pool, float lamda, const float* Gp, int64_t Gp_stride,
                                        float* G, int64_t G_stride, const int32_t* rows_x, const int32_t* rows_y,
-                                       const uint8_t* r1mask, float* scratch, void* stream) {
+                                       const uint8_t* r1mask, const int32_t* btab, float* scratch, void* stream) {
     if (!aa_x || !mkey_pool || !rows_x || !rows_y || !G) return (int)cudaErrorInvalidValue;
     BwdDelta dl{aa_x, mkey_pool, rows_x, rows_y};
     return backward_launch(m, pm, aa_y, aa_stride, n, mkey_y, lamda, Gp, Gp_stride, rows_y, G, G_stride, rows_y, r1mask, rows_y, 0,
-                           scratch, stream, &dl);
+                           btab, scratch, stream, &dl);
 }

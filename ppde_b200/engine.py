@@ -182,15 +182,15 @@ class PoEModel:
                 gp_ptr, self.D, gp_rows, ep_ptr, g_ptr, self.NE, g_rows, _ptr(E), _ptr(fit), st), "cnn_backward_combine")
 
     # -- CNN with the block-key / relu-mask POOLS of a chain engine (incremental path) -----------------
-    def cnn_forward_pool(self, aa, n, mk, bkey, r1pool, dmask, rows_x, rows_y, row_base_y, st, mkpool=None):
+    def cnn_forward_pool(self, aa, n, mk, bkey, r1pool, dmask, rows_x, rows_y, row_base_y, st, mkpool=None, btab=None):
         """Forward of n states into pool rows rows_y (None: row_base_y + b).  dmask None: every block is evaluated;
         otherwise only the dirty blocks, the others come from rows_x (ppde_cnn_forward_inc)."""
         _lib.check(self.lib.ppde_cnn_forward_inc(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), _ptr(r1pool),
-                                                 _ptr(dmask), _ptr(bkey), _ptr(rows_x), _ptr(rows_y), int(row_base_y),
+                                                 _ptr(dmask), _ptr(bkey), _ptr(btab), _ptr(rows_x), _ptr(rows_y), int(row_base_y),
                                                  _ptr(mkpool), _ptr(self.inc_ws(n)), st), "cnn_forward_inc")
 
     def cnn_backward_pool(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, r1pool, mask_rows, mask_row_base, st,
-                          do_fit=True, do_grad=True):
+                          do_fit=True, do_grad=True, btab=None):
         lib = self.lib
         null = C.c_void_p(0)
         if do_fit:
@@ -200,11 +200,11 @@ class PoEModel:
         if do_grad:
             _lib.check(lib.ppde_cnn_backward_tc_rows(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
-                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(r1pool), _ptr(mask_rows), int(mask_row_base),
+                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(r1pool), _ptr(mask_rows), int(mask_row_base), _ptr(btab),
                 _ptr(self.grad_scratch(n)), st), "cnn_backward_tc_rows")
 
     def cnn_backward_delta(self, aa_x, aa_y, n, mk, mkpool, gp_ptr, ep_ptr, g_ptr, rows_x, rows_y, E, fit, r1pool, st,
-                           do_fit=True, do_grad=True):
+                           do_fit=True, do_grad=True, btab=None):
         """fit / E of the proposals, and their gradient rows as  G[rows_y] = G[rows_x] + change  (ppde_cnn_backward_delta)."""
         lib = self.lib
         null = C.c_void_p(0)
@@ -215,7 +215,7 @@ class PoEModel:
         if do_grad:
             _lib.check(lib.ppde_cnn_backward_delta(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa_x), _ptr(aa_y), self.aa_stride, n, _ptr(mk), _ptr(mkpool),
-                self.lamda, gp_ptr, self.D, g_ptr, self.NE, _ptr(rows_x), _ptr(rows_y), _ptr(r1pool),
+                self.lamda, gp_ptr, self.D, g_ptr, self.NE, _ptr(rows_x), _ptr(rows_y), _ptr(r1pool), _ptr(btab),
                 _ptr(self.grad_scratch(n)), st), "cnn_backward_delta")
 
     # -- scratch ------------------------------------------------------------------------------
@@ -245,7 +245,8 @@ class PoEModel:
         return self._mkey
 
     # -- full evaluation ------------------------------------------------------------------------
-    def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True, bkey=None, r1pool=None, mkpool=None):
+    def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True, bkey=None, r1pool=None, mkpool=None,
+                      btab=None):
         """Energy (+ gradient field) of n states `aa` [n, aa_stride] written into pool rows
         g_row0.. / gp_row0.. (contiguous). E, fit, Epotts: float tensors [n].
         bkey / r1pool: the engine's block-key and relu-mask pools (rows g_row0.. are filled too)."""
@@ -258,9 +259,9 @@ class PoEModel:
         mk = self.mkey(n)
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
         if bkey is not None and want_grad:
-            self.cnn_forward_pool(aa, n, mk, bkey, r1pool, None, None, None, g_row0, st, mkpool=mkpool)
+            self.cnn_forward_pool(aa, n, mk, bkey, r1pool, None, None, None, g_row0, st, mkpool=mkpool, btab=btab)
             self.cnn_backward_pool(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr, C.c_void_p(0), E, fit,
-                                   r1pool, None, g_row0, st)
+                                   r1pool, None, g_row0, st, btab=btab)
             return
         self.cnn_forward(aa, n, mk, st)
         self.cnn_backward_combine(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr if want_grad else None,
@@ -373,10 +374,12 @@ class ChainEngine:
         self.t_dev = torch.zeros(1, dtype=i32, device=dev)
         # incremental CNN forward: per-row block keys of the max-pool and relu-mask rows, indexed like G / Gp
         self.inc = bool(m.cnn_inc)
-        self.bkey = self.r1pool = self.dmask = self.mkpool = None
+        self.bkey = self.r1pool = self.dmask = self.mkpool = self.btab = None
         self.delta = bool(m.cnn_bwd_delta)
         if self.inc:
             self.mkpool = torch.empty(rows * m.n_nets * 2 * m.C, dtype=torch.int64, device=dev)
+            # block table: btab[r][q] = the pool row whose slot holds block q (keys and relu-mask rows) of row r
+            self.btab = torch.arange(rows, dtype=i32, device=dev).repeat_interleave(m.NB).contiguous()
             self.bkey = torch.empty(rows * m.n_nets * m.NB * 2 * m.C, dtype=torch.int64, device=dev)
             self.r1pool = torch.empty(rows * m.n_nets * m.P * 32, dtype=u8, device=dev)
             self.dmask = torch.zeros(n, dtype=i32, device=dev)
@@ -416,14 +419,14 @@ class ChainEngine:
                 self.anchor_fixed = torch.arange(1, n + 1, dtype=torch.int32, device=m.device)
             ep = torch.empty(self.n_fixed, dtype=torch.float32, device=m.device)
             m.evaluate_into(self.aa_fixed, self.n_fixed, self.G, 2 * n, self.Gp, 2 * n, self.E_fixed, self.fit_fixed, ep,
-                            bkey=self.bkey, r1pool=self.r1pool, mkpool=self.mkpool)
+                            bkey=self.bkey, r1pool=self.r1pool, mkpool=self.mkpool, btab=self.btab)
             if all_wt:
                 self.row_cur.fill_(2 * n)
                 self.E.copy_(self.E_fixed[0].expand(n)); self.fit.copy_(self.fit_fixed[0].expand(n))
             else:
                 epn = torch.empty(n, dtype=torch.float32, device=m.device)
                 m.evaluate_into(self.aa, n, self.G, 0, self.Gp, 0, self.E, self.fit, epn, bkey=self.bkey, r1pool=self.r1pool,
-                                mkpool=self.mkpool)
+                                mkpool=self.mkpool, btab=self.btab)
                 self.row_cur.copy_(torch.arange(n, dtype=torch.int32, device=m.device))
             self.best_E.copy_(self.E); self.best_fit.copy_(self.fit); self.best_aa.copy_(self.aa)
             if self.E_hist is not None:
@@ -461,13 +464,12 @@ class ChainEngine:
         if self.inc:
             if dirty:
                 _lib.check(self.lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(self.aa), _ptr(self.aa_y), m.aa_stride, n,
-                                                   _ptr(self.dmask), _ptr(self.r1pool), _ptr(self.row_cur), _ptr(self.rows_y), st),
-                           "cnn_dirty")
+                                                   _ptr(self.dmask), st), "cnn_dirty")
             if parts:
                 self.lib.ppde_set_profile_parts(parts, 7)
                 try:
                     m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st,
-                                       mkpool=self.mkpool)
+                                       mkpool=self.mkpool, btab=self.btab)
                 finally:
                     self.lib.ppde_set_profile_parts(7, 7)
         elif parts == 7:
@@ -485,10 +487,11 @@ class ChainEngine:
             try:
                 if self.delta and not full:
                     m.cnn_backward_delta(self.aa, self.aa_y, n, mk, self.mkpool, gp, ep, _ptr(self.G), self.row_cur, self.rows_y,
-                                         self.E_y, self.fit_y, self.r1pool, st, do_fit=do_fit, do_grad=bool(parts))
+                                         self.E_y, self.fit_y, self.r1pool, st, do_fit=do_fit, do_grad=bool(parts), btab=self.btab)
                 else:
                     m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
-                                        self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st, do_fit=do_fit, do_grad=bool(parts))
+                                        self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st, do_fit=do_fit, do_grad=bool(parts),
+                                        btab=self.btab)
             finally:
                 self.lib.ppde_set_profile_parts(7, 7)
         elif do_fit and parts == 7:

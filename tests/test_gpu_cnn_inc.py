@@ -12,6 +12,16 @@ from oracle import ppde_port as port
 pytestmark = pytest.mark.gpu
 
 
+def _mask_rows(r1pool, btab, rows, nets, P, NB):
+    """Relu-mask rows [n, nets, P, 32] of the pool rows `rows`, read through the block table."""
+    n_rows = btab.numel() // NB
+    pool = r1pool.view(n_rows, nets, P, 32)
+    tab = btab.view(n_rows, NB).long()[rows.long()]                    # [n, NB]
+    src = tab[:, (torch.arange(P, device=tab.device) >> 4)]            # [n, P] source row of every position
+    pidx = torch.arange(P, device=tab.device)[None, :].expand_as(src)
+    return pool[src, :, pidx, :].permute(0, 2, 1, 3).contiguous()      # [n, P, nets, 32] -> [n, nets, P, 32]
+
+
 def _mutants(rng, x, L):
     """One proposal per chain: a mix of the patterns the sampler produces and the edge cases."""
     n = x.shape[0]
@@ -63,12 +73,13 @@ def test_incremental_forward_is_bit_identical(L, n):
     rows = 2 * n + 1
     bkey = torch.full((rows * nets * NB * J2,), -1, dtype=torch.int64, device=dev)
     r1pool = torch.full((rows * nets * P * 32,), 0xAB, dtype=torch.uint8, device=dev)
+    btab = torch.full((rows * NB,), -1, dtype=torch.int32, device=dev)
     st = _stream()
     # current states: private row b for even chains, row n + b for odd ones (both halves of the pool get used)
     rows_x = torch.tensor([b if b % 2 == 0 else n + b for b in range(n)], dtype=torch.int32, device=dev)
     rows_y = torch.tensor([n + b if b % 2 == 0 else b for b in range(n)], dtype=torch.int32, device=dev)
     mk_x = torch.zeros(n * nets * J2, dtype=torch.int64, device=dev)
-    m.cnn_forward_pool(ax, n, mk_x, bkey, r1pool, None, None, rows_x, 0, st)         # full evaluation into rows_x
+    m.cnn_forward_pool(ax, n, mk_x, bkey, r1pool, None, None, rows_x, 0, st, btab=btab)         # full evaluation into rows_x
     # full tensor-core kernel on x and y (the reference for bit-exactness)
     mk_fx = torch.zeros_like(mk_x); mk_fy = torch.zeros_like(mk_x)
     rm_fx = torch.zeros(n * nets * P * 32, dtype=torch.uint8, device=dev); rm_fy = torch.zeros_like(rm_fx)
@@ -76,15 +87,15 @@ def test_incremental_forward_is_bit_identical(L, n):
     _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ay), m.aa_stride, n, _ptr(mk_fy), _ptr(rm_fy), st), "tc y")
     torch.cuda.synchronize()
     assert torch.equal(mk_x, mk_fx), "full evaluation through the block-key kernel differs from the full kernel"
-    pool = r1pool.view(rows, nets * P * 32)
-    assert torch.equal(pool[rows_x.long()], rm_fx.view(n, -1)), "relu-mask rows of the full evaluation differ"
+    tab = btab.view(rows, NB)
+    assert torch.equal(tab[rows_x.long()], rows_x[:, None].expand(n, NB)), "a fully evaluated row must point at itself"
+    assert torch.equal(_mask_rows(r1pool, btab, rows_x, nets, P, NB), rm_fx.view(n, nets, P, 32)), "relu-mask rows of the full evaluation differ"
 
     # incremental: dirty blocks of y against x
     dmask = torch.zeros(n, dtype=torch.int32, device=dev)
-    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay), m.aa_stride, n, _ptr(dmask), _ptr(r1pool),
-                                  _ptr(rows_x), _ptr(rows_y), st), "dirty")
+    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay), m.aa_stride, n, _ptr(dmask), st), "dirty")
     mk_y = torch.zeros_like(mk_x)
-    m.cnn_forward_pool(ay, n, mk_y, bkey, r1pool, dmask, rows_x, rows_y, 0, st)
+    m.cnn_forward_pool(ay, n, mk_y, bkey, r1pool, dmask, rows_x, rows_y, 0, st, btab=btab)
     torch.cuda.synchronize()
     # dirty masks against a host restatement
     dm = dmask.cpu().numpy().astype(np.uint32)
@@ -96,15 +107,34 @@ def test_incremental_forward_is_bit_identical(L, n):
         assert dm[b] == want, f"chain {b}: dirty mask {dm[b]:#x} != {want:#x}"
     assert (dm[::8] == 0).all() and (dm[6::8] == (1 << NB) - 1).all()
     assert torch.equal(mk_y, mk_fy), "incremental winners differ from the full kernel"
-    assert torch.equal(pool[rows_y.long()], rm_fy.view(n, -1)), "incremental relu-mask rows differ"
+    assert torch.equal(_mask_rows(r1pool, btab, rows_y, nets, P, NB), rm_fy.view(n, nets, P, 32)), "incremental relu-mask rows differ"
+    # table of the proposal rows: own slot for the dirty blocks, the current row's entry for the clean ones
+    dmt = torch.from_numpy(dm.astype(np.int64)).to(dev)
+    dirty = ((dmt[:, None] >> torch.arange(NB, device=dev)[None, :]) & 1).bool()
+    want_tab = torch.where(dirty, rows_y[:, None].expand(n, NB), tab[rows_x.long()])
+    assert torch.equal(tab[rows_y.long()], want_tab)
+    # the current rows are untouched: x can still be read back exactly
+    assert torch.equal(_mask_rows(r1pool, btab, rows_x, nets, P, NB), rm_fx.view(n, nets, P, 32))
     # the proposal rows now hold a complete cache: a second incremental step from y back to x reproduces x
-    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ay), _ptr(ax), m.aa_stride, n, _ptr(dmask), _ptr(r1pool),
-                                  _ptr(rows_y), _ptr(rows_x), st), "dirty back")
+    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ay), _ptr(ax), m.aa_stride, n, _ptr(dmask), st), "dirty back")
     mk_b = torch.zeros_like(mk_x)
-    m.cnn_forward_pool(ax, n, mk_b, bkey, r1pool, dmask, rows_y, rows_x, 0, st)
+    m.cnn_forward_pool(ax, n, mk_b, bkey, r1pool, dmask, rows_y, rows_x, 0, st, btab=btab)
     torch.cuda.synchronize()
     assert torch.equal(mk_b, mk_fx), "second incremental step (y -> x) differs from the full kernel"
-    assert torch.equal(pool[rows_x.long()], rm_fx.view(n, -1))
+    assert torch.equal(_mask_rows(r1pool, btab, rows_x, nets, P, NB), rm_fx.view(n, nets, P, 32))
+    assert torch.equal(_mask_rows(r1pool, btab, rows_y, nets, P, NB), rm_fy.view(n, nets, P, 32)), "y (now the current rows) was damaged"
+    # a third step x -> y2 exercises slots that the other row still points at
+    y2 = _mutants(np.random.default_rng(L + 99), x, L)
+    ay2 = dev_aa(y2)
+    mk_fy2 = torch.zeros_like(mk_x); rm_fy2 = torch.zeros_like(rm_fx)
+    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ay2), m.aa_stride, n, _ptr(mk_fy2), _ptr(rm_fy2), st), "tc y2")
+    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay2), m.aa_stride, n, _ptr(dmask), st), "dirty 3")
+    mk_y2 = torch.zeros_like(mk_x)
+    m.cnn_forward_pool(ay2, n, mk_y2, bkey, r1pool, dmask, rows_x, rows_y, 0, st, btab=btab)
+    torch.cuda.synchronize()
+    assert torch.equal(mk_y2, mk_fy2), "third incremental step differs from the full kernel"
+    assert torch.equal(_mask_rows(r1pool, btab, rows_y, nets, P, NB), rm_fy2.view(n, nets, P, 32))
+    assert torch.equal(_mask_rows(r1pool, btab, rows_x, nets, P, NB), rm_fx.view(n, nets, P, 32)), "the current rows were damaged"
 
 
 @pytest.mark.parametrize("L,n", [(40, 24), (104, 40), (238, 96)])
@@ -137,19 +167,19 @@ def test_delta_backward_matches_full_backward(L, n):
     bkey = torch.zeros(rows * nets * NB * J2, dtype=torch.int64, device=dev)
     r1pool = torch.zeros(rows * nets * P * 32, dtype=torch.uint8, device=dev)
     mkpool = torch.zeros(rows * nets * J2, dtype=torch.int64, device=dev)
+    btab = torch.full((rows * NB,), -1, dtype=torch.int32, device=dev)
     E = torch.zeros(n, dtype=f32, device=dev); fit = torch.zeros_like(E); Ep = torch.zeros_like(E)
     st = _stream()
-    m.evaluate_into(ax, n, G, 0, Gp, 0, E, fit, Ep, bkey=bkey, r1pool=r1pool, mkpool=mkpool)      # rows 0..n-1 = states x
+    m.evaluate_into(ax, n, G, 0, Gp, 0, E, fit, Ep, bkey=bkey, r1pool=r1pool, mkpool=mkpool, btab=btab)      # rows 0..n-1 = states x
     rows_x = torch.arange(n, dtype=torch.int32, device=dev)
     rows_y = rows_x + n
     Ep_y = torch.zeros_like(E); E_y = torch.zeros_like(E); fit_y = torch.zeros_like(E)
     m.potts_full(ay, n, C.c_void_p(Gp.data_ptr() + n * m.D * 4), _ptr(Ep_y), st)
     dmask = torch.zeros(n, dtype=torch.int32, device=dev)
-    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay), m.aa_stride, n, _ptr(dmask), _ptr(r1pool),
-                                  _ptr(rows_x), _ptr(rows_y), st), "dirty")
+    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay), m.aa_stride, n, _ptr(dmask), st), "dirty")
     mk = m.mkey(n)
-    m.cnn_forward_pool(ay, n, mk, bkey, r1pool, dmask, rows_x, rows_y, 0, st, mkpool=mkpool)
-    m.cnn_backward_delta(ax, ay, n, mk, mkpool, _ptr(Gp), _ptr(Ep_y), _ptr(G), rows_x, rows_y, E_y, fit_y, r1pool, st)
+    m.cnn_forward_pool(ay, n, mk, bkey, r1pool, dmask, rows_x, rows_y, 0, st, mkpool=mkpool, btab=btab)
+    m.cnn_backward_delta(ax, ay, n, mk, mkpool, _ptr(Gp), _ptr(Ep_y), _ptr(G), rows_x, rows_y, E_y, fit_y, r1pool, st, btab=btab)
     torch.cuda.synchronize()
     g_delta = G[n:2 * n].cpu().numpy()
     e_delta, f_delta = E_y.cpu().numpy(), fit_y.cpu().numpy()
@@ -163,10 +193,9 @@ def test_delta_backward_matches_full_backward(L, n):
     assert np.array_equal(f_delta, fit2.cpu().numpy()) and np.array_equal(e_delta, E2.cpu().numpy())
     # a second delta step back to x (rows swap roles) stays within rounding of the exact gradient of x
     Gx_exact = G[:n].clone()
-    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ay), _ptr(ax), m.aa_stride, n, _ptr(dmask), _ptr(r1pool),
-                                  _ptr(rows_y), _ptr(rows_x), st), "dirty back")
-    m.cnn_forward_pool(ax, n, mk, bkey, r1pool, dmask, rows_y, rows_x, 0, st, mkpool=mkpool)
-    m.cnn_backward_delta(ay, ax, n, mk, mkpool, _ptr(Gp), _ptr(Ep), _ptr(G), rows_y, rows_x, E, fit, r1pool, st)
+    _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ay), _ptr(ax), m.aa_stride, n, _ptr(dmask), st), "dirty back")
+    m.cnn_forward_pool(ax, n, mk, bkey, r1pool, dmask, rows_y, rows_x, 0, st, mkpool=mkpool, btab=btab)
+    m.cnn_backward_delta(ay, ax, n, mk, mkpool, _ptr(Gp), _ptr(Ep), _ptr(G), rows_y, rows_x, E, fit, r1pool, st, btab=btab)
     torch.cuda.synchronize()
     gx = G[:n].cpu().numpy(); gx0 = Gx_exact.cpu().numpy()
     err = np.max(np.abs(gx - gx0) / np.abs(gx0).max(axis=1, keepdims=True))
