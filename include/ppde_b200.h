@@ -177,7 +177,7 @@ int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint
                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                          float* G, int64_t G_stride, const int32_t* g_rows,
                          const uint8_t* r1mask /* from ppde_cnn_forward_tc */,
-                         float* scratch /* n_nets*n*20L floats + n*n_nets*roundup8(P+1+4C) uint16 */, void* stream);
+                         float* scratch /* n_nets*n*20L floats + n*n_nets*roundup8(2P+2+4C) uint16 */, void* stream);
 /* same as ppde_cnn_backward_tc with the relu-mask rows taken from a POOL: chain b's mask lives in row
  * mask_rows[b] (NULL: mask_row_base + b) of r1mask [rows, n_nets, P, 32]. */
 int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,

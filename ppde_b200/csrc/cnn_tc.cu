@@ -1358,12 +1358,12 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(int n_nets, int C
                                                                const unsigned long long* __restrict__ mkey_y,
                                                                const unsigned long long* __restrict__ mkey_pool,
                                                                const int32_t* __restrict__ rows_x,
-                                                               uint16_t* __restrict__ wl, int rec) {
+                                                               uint16_t* __restrict__ wl, int rec, int compact) {
     extern __shared__ int sw[];
     const int J2 = 2 * C;
     int* sStart = sw;                 // [P+1]
     int* sFill = sStart + (P + 1);    // [P]
-    int* sD0 = sFill + P;             // [P]
+    int* sD0 = sFill + P;             // [P]   (compact mode: re-used for the compact index of a position)
     int* sPy = sD0 + P;               // [J2] position of the y-side entry or -1
     int* sPx = sPy + J2;              // [J2]
     int* sList = sPx + J2;            // [2 J2]
@@ -1422,9 +1422,42 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(int n_nets, int C
             while (w >= s0 && sList[w] > v) { sList[w + 1] = sList[w]; --w; }
             sList[w + 1] = v;
         }
-        for (int u = s0; u < s1; ++u) out[(P + 1) + u] = (uint16_t)sList[u];
     }
-    for (int i = threadIdx.x; i <= P; i += 128) out[i] = (uint16_t)sStart[i];
+    if (!compact) {                                   // start[P+1] | list
+        __syncthreads();
+        for (int u = threadIdx.x; u < sStart[P]; u += 128) out[(P + 1) + u] = (uint16_t)sList[u];
+        for (int i = threadIdx.x; i <= P; i += 128) out[i] = (uint16_t)sStart[i];
+        return;
+    }
+    // compact record: npos | pos[npos] | start[npos+1] | list   (only the positions that received an entry)
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = (P + 31) / 32;
+        int run = 0;
+        for (int i = lane * per; i < min((lane + 1) * per, P); ++i) run += (sStart[i + 1] > sStart[i]);
+        int incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int base = incl - run;
+        for (int i = lane * per; i < min((lane + 1) * per, P); ++i) {
+            const bool has = sStart[i + 1] > sStart[i];
+            sD0[i] = has ? base : -1;
+            base += has;
+        }
+        if (lane == 31) sFill[0] = incl;              // npos (sFill is free now)
+    }
+    __syncthreads();
+    const int npos = sFill[0];
+    for (int pp = threadIdx.x; pp < P; pp += 128) {
+        const int c = sD0[pp];
+        if (c >= 0) { out[1 + c] = (uint16_t)pp; out[1 + npos + c] = (uint16_t)sStart[pp]; }
+    }
+    if (threadIdx.x == 0) { out[0] = (uint16_t)npos; out[1 + 2 * npos] = (uint16_t)sStart[P]; }
+    for (int u = threadIdx.x; u < sStart[P]; u += 128) out[2 + 2 * npos + u] = (uint16_t)sList[u];
 }
 
 // G_y = G_x + (Gp_y - Gp_x)(window) + lamda / n_nets * (dGc_0 + dGc_1 + dGc_2)   (delta backward; fixed summation order)
@@ -1479,6 +1512,7 @@ struct BwdParams {
     const int32_t* mask_rows;           // [n] row of chain b in r1mask, NULL = mask_row_base + b
     int mask_row_base;
     const int32_t* mask_rows_x;         // delta mode only: [n] r1mask row of the chain's CURRENT state
+    int nrec;                           // compact delta kernel: record buffers in shared memory
     const int32_t* btab; int NB;        // optional block table of the pools [rows, NB]: the mask rows of block q of row r live in row btab[r][q]
     const uint16_t* wl; int rec;        // winner records from cnn_winner_sort_kernel
     float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
@@ -1498,6 +1532,9 @@ __device__ __forceinline__ int lds_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return (int)v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
@@ -1882,6 +1919,384 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
     }
 }
 
+// =====================================================================================================
+// COMPACT delta backward.  The change of the adjoint rows between the current state and the proposal is non-zero on a few
+// dozen positions only (cnn_winner_delta_kernel, compact record: npos | pos[npos] | start[npos+1] | list).  Instead of four
+// mostly-zero 64-position tiles per (chain, net) the kernel builds ceil(npos / 64) tiles - normally ONE - whose columns are
+// the touched positions, and scatters the product into the chain's gradient row:
+//     dGc[(pos[c] + t), a] += Y[(t,a), c]        (shared-memory float adds; columns in order: deterministic)
+// Roles and barriers as in cnn_backward_tc_kernel; differences: every role reads npos from the chain's record (three record
+// buffers; the epilogue releases them too, it needs pos[]), the global tile counter advances by the chain's own tile count.
+constexpr int BD_NREC_MAX = 6;          // record buffers: as many as fit in shared memory (BwdParams.nrec, >= 3)
+template <bool PROF>
+__global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(const __grid_constant__ BwdParams prm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
+    const int nch = prm.nch;
+    const int BD_NREC = prm.nrec;
+    unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* sGc = reinterpret_cast<float*>(ring + BW_NBUF * BW_MAXCH * BW_SLOT);   // [NE] chain gradient row
+    float* sDj = sGc + ((NE + 3) & ~3);                                      // [J2] decoder weights
+    uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sDj + J2) + 15) & ~(uintptr_t)15);   // [BD_NREC][rec]
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRec + BD_NREC * prm.rec) + 7) & ~(uintptr_t)7);
+    uint64_t* full = bars;                      // [BW_NBUF] tile buffers: producers -> MMA (8 warp arrivals: one producer set)
+    uint64_t* empty = full + BW_NBUF;           // [BW_NBUF] MMA -> producers
+    uint64_t* dfull = empty + BW_NBUF;          // [BW_NDBUF] MMA -> epilogue
+    uint64_t* dempty = dfull + BW_NDBUF;        // [BW_NDBUF] epilogue -> MMA (4 warp arrivals)
+    uint64_t* recfull = dempty + BW_NDBUF;      // [BD_NREC] record landed (bulk copy, tx bytes)
+    uint64_t* recempty = recfull + BD_NREC_MAX; // [BD_NREC] producers and epilogue done with the record (20 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recempty + BD_NREC_MAX);
+
+    const int k = blockIdx.x / prm.ctas_per_net;                       // this CTA's net
+    const int within = blockIdx.x - k * prm.ctas_per_net;
+    if (k >= prm.m.n_nets) return;
+    const int b_lo = (int)((int64_t)prm.n * within / prm.ctas_per_net);
+    const int b_hi = (int)((int64_t)prm.n * (within + 1) / prm.ctas_per_net);
+    const int nchains = b_hi - b_lo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ppde_cnn_net_t net = prm.m.net[k];
+    const uint32_t rec_bytes = (uint32_t)prm.rec * 2u;
+    const uint32_t rec_a = smem_u32(sRec);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BW_NBUF; ++s) { mbar_init(&full[s], BW_NT_PROD / 64); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < BD_NREC; ++s) { mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BW_NT_PROD / 32 + NT_EPI / 32); }
+        for (int d = 0; d < BW_NDBUF; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI / 32); }
+        fence_barrier_init();
+    }
+    if (warp == BW_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int j = threadIdx.x; j < J2; j += BW_NTHREADS) sDj[j] = net.d[j];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {   // A = W0^T (scaled, fp16 hi/lo) -> TMEM: lane m(a,t) = 32*(a/6) + 5*(a%6) + t
+        const int grp = lane / 5, t = lane - 5 * grp, a = 6 * warp + grp;
+        const bool rowok = lane < 30 && a < PPDE_Q;
+        const int nrow = t * PPDE_Q + a;                                // W0r[c][t][a]
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int ks = 0; ks < prm.kpad / 16; ++ks) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c0 = ks * 16 + 2 * q;
+                const float w0 = (rowok && c0 < C) ? net.W0r[(size_t)c0 * 100 + nrow] * net.w0_scale : 0.f;
+                const float w1 = (rowok && c0 + 1 < C) ? net.W0r[(size_t)(c0 + 1) * 100 + nrow] * net.w0_scale : 0.f;
+                const float h0 = h_round(w0), h1 = h_round(w1);
+                hi[q] = pack_h2(h0, h1);
+                lo[q] = pack_h2(w0 - h0, w1 - h1);
+            }
+            tmem_st8(lane_addr + ks * 8, hi);
+            tmem_st8(lane_addr + prm.kpad / 2 + ks * 8, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 4) {
+        // ===== EPILOGUE: lane = (a, t); column c of a tile is position pos[c]: scatter-add into the chain's row =====
+        const int grp = lane / 5, d = lane - 5 * grp, a = 6 * warp + grp;
+        const bool rowok = lane < 30 && a < PPDE_Q;
+        const int tid = threadIdx.x;
+        const float unscale = 1.f / (net.w0_scale * net.adj_scale);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+        const uint32_t gc_a = smem_u32(sGc);
+        long long pc[4] = {0, 0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
+        int it = 0;
+        {   // the row accumulates changes: zero once, every flush leaves it zeroed again
+            float4* z = reinterpret_cast<float4*>(sGc);
+            for (int e = tid; e < NE / 4; e += NT_EPI) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        named_bar(2, NT_EPI);
+        const uint32_t my_a = gc_a + 4u * (uint32_t)(d * PPDE_Q + a);     // (p + d) * 20 + a  =  p * 20 + (d * 20 + a)
+        for (int ci = 0; ci < nchains; ++ci) {
+            const int rb = ci % BD_NREC;
+            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
+            const int npos = lds_u16(rs);
+            const int tiles = (npos + BW_NT - 1) / BW_NT;
+            if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
+            for (int t = 0; t < tiles; ++t, ++it) {
+                const int buf = it & (BW_NDBUF - 1);
+                mbar_wait(&dfull[buf], (uint32_t)((it / BW_NDBUF) & 1));
+                if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+                tc_fence_after();
+                uint32_t y[64];
+                tmem_ld32(lane_addr + buf * BW_NT, y);
+                tmem_ld32(lane_addr + buf * BW_NT + 32, y + 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&dempty[buf]);
+                if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                const int ncol = min(BW_NT, npos - t * BW_NT);
+                const uint32_t pa = rs + 2u * (uint32_t)(1 + t * BW_NT);
+                // column c = position pos[c]: lane (a, tap d) adds to G[(pos + d), a].  Within a column the 30 lanes hit 30
+                // different words; across columns (ascending positions, taps overlap when positions are < 5 apart) the
+                // read-modify-writes are ordered by the warp barrier: plain shared-memory adds, deterministic order.
+                int pn = lds_u16(pa);                                      // position of the next column, one ahead
+#pragma unroll
+                for (int c = 0; c < BW_NT; ++c) {
+                    if (c < ncol) {                                        // warp-uniform
+                        const uint32_t addr = my_a + 80u * (uint32_t)pn;
+                        if (c + 1 < BW_NT) pn = lds_u16(pa + 2u * (uint32_t)min(c + 1, BW_NT - 1));
+                        if (rowok) sts_f32(addr, lds_f32(addr) + __uint_as_float(y[c]) * unscale);
+                        __syncwarp();
+                    }
+                }
+                if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+            }
+            // flush the chain's change of the per-net gradient (streaming 16-byte stores) and leave the row zeroed
+            named_bar(2, NT_EPI);
+            float4* dst = reinterpret_cast<float4*>(prm.Gc + ((size_t)k * prm.n + (b_lo + ci)) * NE);
+            float4* src = reinterpret_cast<float4*>(sGc);
+            for (int e = tid; e < NE / 4; e += NT_EPI) { __stcs(dst + e, src[e]); src[e] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            named_bar(2, NT_EPI);
+            if (lane == 0) mbar_arrive(&recempty[rb]);
+            if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
+        }
+        if (PROF && prm.prof && threadIdx.x == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3]; }
+    } else if (warp == BW_WARP_MMA) {
+        // ===== MMA ISSUER: warp-uniform loop, one elected lane issues; also stages the records (bulk copies) =====
+        const uint32_t idesc = make_idesc(128, BW_NT);
+        const uint32_t ring_addr = smem_u32(ring);
+        const int last_ksteps = (prm.kpad - (nch - 1) * KCH) / 16;
+        const uint32_t a_lo_off = (uint32_t)(prm.kpad / 2);
+        long long pc[3] = {0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
+        // Records are staged up to BD_NREC chains ahead, OPPORTUNISTICALLY: buffer c % BD_NREC is free once the producers and
+        // the epilogue have released chain c - BD_NREC; blocking on that here would serialise the MMAs of a chain behind the
+        // epilogue of an earlier one, so the release is only polled (and waited for when the record is needed right now).
+        int staged = 0;
+        int nread = 0;                         // chains whose npos THIS warp has read: their buffers may be reused, not before
+                                               // (a chain without tiles is released by the other roles without waiting for the MMAs)
+        auto stage_records = [&](int need) {   // stage what is free; block until chains < need are staged
+            while (staged < nchains) {
+                const int c = staged, rb = c % BD_NREC;
+                if (c >= BD_NREC) {
+                    if (c - BD_NREC >= nread) break;
+                    const uint32_t par = (uint32_t)(((c / BD_NREC) + 1) & 1);
+                    if (c < need) mbar_wait(&recempty[rb], par);
+                    else if (!mbar_test(&recempty[rb], par)) break;
+                }
+                if (elect_one()) {
+                    mbar_expect_tx(&recfull[rb], rec_bytes);
+                    bulk_g2s(sRec + (size_t)rb * prm.rec, prm.wl + ((size_t)(b_lo + c) * prm.m.n_nets + k) * prm.rec, rec_bytes,
+                             &recfull[rb]);
+                }
+                __syncwarp();
+                ++staged;
+            }
+        };
+        int it = 0;
+        for (int ci = 0; ci < nchains; ++ci) {
+            stage_records(ci + 1);
+            const int rb = ci % BD_NREC;
+            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            const int npos = lds_u16(rec_a + (uint32_t)rb * rec_bytes);
+            nread = ci + 1;
+            const int tiles = (npos + BW_NT - 1) / BW_NT;
+            for (int t = 0; t < tiles; ++t, ++it) {
+                const int tb = it % BW_NBUF;
+                const int buf = it & (BW_NDBUF - 1);
+                if (it >= BW_NDBUF) mbar_wait(&dempty[buf], (uint32_t)(((it / BW_NDBUF) + 1) & 1));
+                if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+                while (!mbar_test(&full[tb], (uint32_t)((it / BW_NBUF) & 1))) stage_records(0);   // keep the records flowing meanwhile
+                if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + D_COL0 + buf * BW_NT;
+                if (elect_one()) {
+                    for (int kc = 0; kc < nch; ++kc) {
+                        const int slot = tb * BW_MAXCH + kc;
+                        const uint64_t dhi = make_b_desc(ring_addr + slot * BW_SLOT);
+                        const uint64_t dlo = make_b_desc(ring_addr + slot * BW_SLOT + BW_MAT);
+                        const int ksteps = (kc == nch - 1) ? last_ksteps : KCH / 16;
+                        const uint32_t a_hi0 = tmem_base + kc * (KCH / 2);
+#pragma unroll
+                        for (int ks = 0; ks < KCH / 16; ++ks) {
+                            if (ks < ksteps) {
+                                const uint32_t a_hi = a_hi0 + ks * 8;
+                                mma_ts(d_tmem, a_hi, dhi + (uint64_t)(ks * 2), idesc, (kc | ks) ? 1u : 0u);
+                                mma_ts(d_tmem, a_hi, dlo + (uint64_t)(ks * 2), idesc, 1u);
+                                mma_ts(d_tmem, a_hi + a_lo_off, dhi + (uint64_t)(ks * 2), idesc, 1u);
+                            }
+                        }
+                    }
+                    tc_commit(&empty[tb]);
+                    tc_commit(&dfull[buf]);
+                }
+                __syncwarp();
+                if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+                stage_records(0);
+            }
+        }
+        if (PROF && prm.prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[4] = pc[0]; o[5] = pc[1]; o[6] = pc[2]; o[7] = it; }
+    } else {
+        // ===== PRODUCERS: two sets of 8 warps alternate over the tiles.  A tile has ncol <= 64 live columns (touched positions, in
+        // order) and 64 - ncol zero columns: the live ones are split evenly over the set's 8 warps (rpw = ceil(ncol / 8) adjacent
+        // columns each, so a warp's entries are one run of the list), the dead ones likewise =====
+        const int pw = warp - 4;
+        const int pset = pw >> 3, w8 = pw & 7;
+        const bool lact = 8 * lane < prm.kpad;
+        const float adj_scale = net.adj_scale;
+        const float* wbase = net.W1p + 8 * lane;
+        const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BW_SLOT);
+        const uint32_t unit = (uint32_t)(lane & 7);
+        const uint32_t dj_a = smem_u32(sDj);
+        const int NB = prm.NB;
+        long long pc[4] = {0, 0, 0, 0};
+        long long tp = PROF ? clock64() : 0;
+        int it = 0;
+        for (int ci = 0; ci < nchains; ++ci) {
+            const int rb = ci % BD_NREC;
+            const int bb = b_lo + ci;
+            const int mry = __ldg(prm.mask_rows + bb), mrx = __ldg(prm.mask_rows_x + bb);     // pool rows of the proposal / current state
+            if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
+            const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
+            const int npos = lds_u16(rs);
+            const int tiles = (npos + BW_NT - 1) / BW_NT;
+            const uint32_t ps = rs + 2u;                                   // pos[c]
+            const uint32_t ss = rs + 2u * (uint32_t)(1 + npos);            // start[c]
+            const uint32_t ls = rs + 2u * (uint32_t)(2 + 2 * npos);        // list
+            for (int t = 0; t < tiles; ++t, ++it) {
+                if ((it & 1) != pset) continue;
+                const int tb = it % BW_NBUF;
+                const int ncol = min(BW_NT, npos - t * BW_NT);
+                const int rpw = (ncol + 7) >> 3;                           // live columns per warp
+                const int rl0 = w8 * rpw;                                  // my first live row of the tile
+                const int rd0 = 8 * rpw + w8 * (8 - rpw) - rpw;            // my dead rows: rd0 + cur for cur = rpw .. 7
+                const int c0 = t * BW_NT + rl0;                            // my first column (compact position index)
+                // relu-mask bytes of my live columns, both sides (byte rr of the 64-bit words): two dependent global loads per byte
+                // (block table -> mask row), requested right AFTER the first group of W1 rows so that the two latencies overlap
+                unsigned long long m8 = 0ull, m8x = 0ull;
+                auto load_masks = [&]() {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        if (rr < rpw && c0 + rr < npos && lact) {
+                            const int p = lds_u16(ps + 2u * (uint32_t)(c0 + rr));
+                            int ry = mry, rx = mrx;
+                            if (prm.btab) { ry = __ldg(prm.btab + (size_t)mry * NB + (p >> 4)); rx = __ldg(prm.btab + (size_t)mrx * NB + (p >> 4)); }
+                            m8 |= (unsigned long long)__ldg(prm.r1mask + (((size_t)ry * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * rr);
+                            m8x |= (unsigned long long)__ldg(prm.r1mask + (((size_t)rx * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * rr);
+                        }
+                    }
+                };
+                bool need_masks = true;
+                const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BW_SLOT);
+                int e = lds_u16(ss + 2u * (uint32_t)min(c0, npos));
+                const int eB = lds_u16(ss + 2u * (uint32_t)min(c0 + rpw, npos));
+                int cur = 0;
+                int rend = lds_u16(ss + 2u * (uint32_t)min(c0 + 1, npos));
+                bool have_buf = false, dirty_row = false;
+                float acc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                auto store_row = [&]() {   // column r0 + cur <- scale * acc (masks were applied per entry), fp16 hi + lo
+                    if (!have_buf) {
+                        if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                        mbar_wait(&empty[tb], (uint32_t)(((it / BW_NBUF) + 1) & 1));
+                        have_buf = true;
+                        if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
+                    }
+                    const int r = (cur < rpw) ? rl0 + cur : rd0 + cur;
+                    const uint32_t addr = tile_addr + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((unit ^ (uint32_t)(r & 7)) << 4);
+                    if (!dirty_row) {
+                        if (lact) { sts128(addr, 0u, 0u, 0u, 0u); sts128(addr + BW_MAT, 0u, 0u, 0u, 0u); }
+                    } else {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 x = make_float2(acc[2 * q] * adj_scale, acc[2 * q + 1] * adj_scale);
+                            const float2 h = make_float2(h_trunc(x.x), h_trunc(x.y));
+                            const float2 l = sub2(x, h);
+                            hi[q] = pack_h2(h.x, h.y);
+                            lo[q] = pack_h2(l.x, l.y);
+                        }
+                        if (lact) {
+                            sts128(addr, hi[0], hi[1], hi[2], hi[3]);
+                            sts128(addr + BW_MAT, lo[0], lo[1], lo[2], lo[3]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                        dirty_row = false;
+                    }
+                    ++cur;
+                    rend = lds_u16(ss + 2u * (uint32_t)min(c0 + min(cur + 1, rpw), npos));
+                };
+                for (; e < eB; e += 4) {
+                    float4 w[4][2];
+                    float dj[4];
+                    bool sd[4];
+                    int jn[4];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) jn[v] = (e + v < eB) ? lds_u16(ls + 2u * (uint32_t)(e + v)) : 0;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        sd[v] = (jn[v] >> 15) != 0;
+                        jn[v] &= 0x7FFF;
+                        w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e + v < eB && lact) {
+                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn[v] * prm.kpad);
+                            w[v][0] = __ldg(src);
+                            w[v][1] = __ldg(src + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn[v]);
+                        dj[v] = sd[v] ? -d0 : d0;
+                    }
+                    if (need_masks) { load_masks(); need_masks = false; }
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (e + v < eB) {
+                            while (e + v >= rend) store_row();
+                            dirty_row = true;
+                            const float dd = dj[v];
+                            const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
+                            w[v][0].x = (mb & 1u) ? w[v][0].x : 0.f;   w[v][0].y = (mb & 2u) ? w[v][0].y : 0.f;
+                            w[v][0].z = (mb & 4u) ? w[v][0].z : 0.f;   w[v][0].w = (mb & 8u) ? w[v][0].w : 0.f;
+                            w[v][1].x = (mb & 16u) ? w[v][1].x : 0.f;  w[v][1].y = (mb & 32u) ? w[v][1].y : 0.f;
+                            w[v][1].z = (mb & 64u) ? w[v][1].z : 0.f;  w[v][1].w = (mb & 128u) ? w[v][1].w : 0.f;
+                            acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
+                            acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
+                            acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
+                            acc[6] = fmaf(dd, w[v][1].z, acc[6]); acc[7] = fmaf(dd, w[v][1].w, acc[7]);
+                        }
+                    }
+                }
+                while (cur < 8) store_row();
+                if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[tb]);
+                if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
+            }
+            if (lane == 0) mbar_arrive(&recempty[rb]);                     // done with this chain's record
+        }
+        if (PROF && prm.prof && lane == 0 && (pw == 0 || pw == 15)) {
+            long long* o = prm.prof + (size_t)blockIdx.x * 16 + (pw == 0 ? 8 : 12); o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == BW_WARP_MMA) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
 __global__ void cnn_grad_combine_kernel(int n, int NE, int n_nets, float scale, ppde_potts_t pm,
                                         const float* __restrict__ Gc, const float* __restrict__ Gp, int64_t Gp_stride,
                                         const int32_t* __restrict__ gp_rows, float* __restrict__ G, int64_t G_stride,
@@ -2127,15 +2542,29 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     if (prm.ctas_per_net < 1) prm.ctas_per_net = 1;
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
-    const int rec = ((P + 1) + 2 * J2 + 7) & ~7;
-    const size_t smem = 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
-                        2 * (size_t)rec * sizeof(uint16_t) + 8 + 32 * sizeof(uint64_t);
+    // delta mode, compact records (default; PPDE_BWD_DELTA_COMPACT=0 keeps one column per position): npos | pos | start | list
+    static int compact_env = -1;
+    if (compact_env < 0) { const char* e = getenv("PPDE_BWD_DELTA_COMPACT"); compact_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool compact = dl && compact_env;
+    const int rec = compact ? ((2 * P + 2 + 2 * J2 + 7) & ~7) : (((P + 1) + 2 * J2 + 7) & ~7);
+    const size_t smem_fixed = 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
+                              8 + 32 * sizeof(uint64_t);
+    int nrec = 2;
+    if (compact) {                                   // as many record buffers as fit under the 227 KB limit (3 .. BD_NREC_MAX)
+        nrec = (int)((232448 - smem_fixed) / ((size_t)rec * sizeof(uint16_t)));
+        if (nrec > tc::BD_NREC_MAX) nrec = tc::BD_NREC_MAX;
+        if (nrec < 3) return (int)cudaErrorInvalidValue;
+    }
+    prm.nrec = nrec;
+    const size_t smem = smem_fixed + (size_t)nrec * rec * sizeof(uint16_t);
     const bool prof = g_backward_prof != nullptr;
-    void (*bkern)(tc::BwdParams) = dl ? (prof ? tc::cnn_backward_tc_kernel<true, true> : tc::cnn_backward_tc_kernel<false, true>)
-                                      : (prof ? tc::cnn_backward_tc_kernel<true, false> : tc::cnn_backward_tc_kernel<false, false>);
+    void (*bkern)(tc::BwdParams) =
+        compact ? (prof ? tc::cnn_backward_delta_kernel<true> : tc::cnn_backward_delta_kernel<false>)
+                : (dl ? (prof ? tc::cnn_backward_tc_kernel<true, true> : tc::cnn_backward_tc_kernel<false, true>)
+                      : (prof ? tc::cnn_backward_tc_kernel<true, false> : tc::cnn_backward_tc_kernel<false, false>));
     prm.prof = prof ? g_backward_prof : nullptr;
-    static size_t configured[4] = {0, 0, 0, 0};
-    const int cfg = (dl ? 2 : 0) + (prof ? 1 : 0);
+    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+    const int cfg = (compact ? 4 : (dl ? 2 : 0)) + (prof ? 1 : 0);
     if (smem > configured[cfg]) {
         cudaError_t e = cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -2149,7 +2578,7 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     if (g_bwd_parts & 1) {
         if (dl)
             tc::cnn_winner_delta_kernel<<<n * m->n_nets, 128, ((P + 1) + 2 * P + 4 * J2) * sizeof(int), st>>>(
-                m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec);
+                m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, compact ? 1 : 0);
         else
             tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
         int r0 = launch_done();

@@ -220,7 +220,7 @@ class PoEModel:
 
     # -- scratch ------------------------------------------------------------------------------
     def grad_scratch(self, n):
-        rec = ((self.P + 1) + 4 * self.C + 7) // 8 * 8                      # winner records (uint16) behind the floats
+        rec = (2 * self.P + 2 + 4 * self.C + 7) // 8 * 8                    # winner records (uint16) behind the floats (compact delta layout is the larger)
         need = self.n_nets * n * self.NE + (n * self.n_nets * rec + 1) // 2
         if getattr(self, "_gscratch", None) is None or self._gscratch.numel() < need:
             self._gscratch = torch.empty(need, dtype=torch.float32, device=self.device)

@@ -42,10 +42,13 @@ lib.ppde_set_backward_profile(None)
 c = buf.cpu().numpy().reshape(grid, 16)[:147]
 P = L - 4; tpc = (P + 63) // 64
 tiles = n / 49 * tpc
+compact = (not full) and os.environ.get("PPDE_BWD_DELTA_COMPACT", "1") != "0" and eng.delta
+if compact:
+    tiles = float(c[:, 7].mean())          # the compact delta kernel counts its own tiles (normally one per chain and net)
 print(f"backward tensor-core kernel ({'exact' if full else 'delta'}), {n} chains: {min(ts):.3f} ms; instrumented {t_inst:.3f} ms; tiles per CTA {tiles:.0f}")
 def pt(x): return f"{x.mean() / tiles:8.0f}"
-print("cycles per 64-position tile (mean over CTAs)")
+print(f"cycles per 64-column tile (mean over CTAs); chains per CTA {n / 49:.0f}")
 print(" epilogue t0 : wait dfull", pt(c[:, 0]), " tmem ld", pt(c[:, 1]), " col2im", pt(c[:, 2]), " flush (per tile avg)", pt(c[:, 3]))
 print(" MMA thread  : wait dempty", pt(c[:, 4]), " wait full", pt(c[:, 5]), " issue+commit", pt(c[:, 6]))
-print(" producer w0 : wait empty", pt(c[:, 8]), " gather+rows", pt(c[:, 9]), " fence+arrive", pt(c[:, 10]))
-print(" producer w15: wait empty", pt(c[:, 12]), " gather+rows", pt(c[:, 13]), " fence+arrive", pt(c[:, 14]))
+print(" producer w0 : wait empty", pt(c[:, 8]), " gather+rows", pt(c[:, 9]), " fence+arrive", pt(c[:, 10]), " wait record", pt(c[:, 11]))
+print(" producer w15: wait empty", pt(c[:, 12]), " gather+rows", pt(c[:, 13]), " fence+arrive", pt(c[:, 14]), " wait record", pt(c[:, 15]))
