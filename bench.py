@@ -275,14 +275,14 @@ def main():
             tflop = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12
             gbs = lambda by, ms_: by / (ms_ * 1e-3) / 1e9
             cand = {
-                "cnn_backward_tc": dict(kernel="cnn_backward_tc_kernel" + ("<delta>" if eng.delta else ""), bound="tensor", unit="TFLOP/s",
+                "cnn_backward_tc": dict(kernel=("cnn_backward_delta_kernel" if eng.delta else "cnn_backward_tc_kernel"), bound="tensor", unit="TFLOP/s",
                                         work=3 * (4 * Cc * Cc + 200 * P * Cc) * n, peak=pk["bf16_sustained"],
                                         # dram read+write bytes from the committed ncu captures at 8192 chains (profiles/r01_v12_ncu_full_summary.txt:
                                         # delta 427.8 + 425.8 MB; profiles/r01_v10_ncu_full_summary.txt: exact 244.6 + 415.9 MB)
                                         traffic=((853.6e6 if eng.delta else 660.6e6) / 8192) * n if L == 238 else None,
                                         note="gradient of the CNN ensemble for every proposal: 3*(4C^2+200PC) algorithmic flops per chain; "
                                              "fp16 hi/lo split = 3 tensor-core passes per flop; " +
-                                             ("delta mode gathers only the adjoint rows that differ from the current state" if eng.delta else
+                                             ("delta mode: one tile of the touched positions per chain and net, only the adjoint rows that differ are gathered" if eng.delta else
                                               "limited by the L2->SM gather of the winners' W1 rows (422 KB per chain and net)")),
                 "cnn_forward_inc_tc": dict(kernel="cnn_forward_inc_kernel", bound="tensor", unit="TFLOP/s",
                                            work=3 * 2 * P * Cc * 2 * Cc * n, peak=pk["bf16_sustained"], traffic=(188.9e6 / 8192) * n if L == 238 else None,

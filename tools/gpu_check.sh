@@ -16,7 +16,7 @@ SMALL="python bench.py --chains 8192 --steps 3 --warmup 3 --no-e2e --no-cpu-base
 $K 200 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 && \
 $K 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
 $K 200 $SMALL > gpurun_out/${TAG}_plain2.log 2>&1 && \
-$K 400 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_dirty_kernel|cnn_backward_tc_kernel|cnn_winner_delta_kernel|cnn_grad_combine_delta_kernel|pas_propose_kernel|pas_reverse_accept_kernel|potts_incremental_kernel" -s 27 -c 9 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
+$K 400 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_dirty_kernel|cnn_backward_tc_kernel|cnn_backward_delta_kernel|cnn_winner_delta_kernel|cnn_grad_combine_delta_kernel|pas_propose_kernel|pas_reverse_accept_kernel|potts_incremental_kernel" -s 27 -c 9 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_f.log
 PD="python tools/bench_potts_full.py 238"
 $K 200 $PD > gpurun_out/${TAG}_plain3.log 2>&1 && \
