@@ -359,15 +359,21 @@ def main():
         barrier()
         t0 = time.perf_counter()
         trace = os.environ.get("PPDE_TRACE", "0") == "1"
+        trace2 = os.environ.get("PPDE_TRACE", "0") == "2"
         pop_dev = pop_host.to(dev, non_blocking=True)          # H2D of the call's input, inside the timed region
         if trace:
             torch.cuda.synchronize(); t1 = time.perf_counter()
         out = smp.run(pop_dev, K, energy, pr["win_lo"], win_hi, None, log_every=10 ** 9)
         if trace:
             torch.cuda.synchronize(); t2 = time.perf_counter()
+        t_run = time.perf_counter() - t0
+        if trace2:
+            print(f"[bench trace2] run returned after {1e3 * t_run:.1f}ms", file=sys.stderr, flush=True)
         best_host.copy_(out[0])                                # D2H of the call's result (histories are host numpy already)
         barrier()
         dt = time.perf_counter() - t0
+        if trace2:
+            print(f"[bench trace2] total {1e3 * dt:.1f}ms", file=sys.stderr, flush=True)
         if trace:
             print(f"[bench trace] h2d={1e3 * (t1 - t0):.1f}ms run={1e3 * (t2 - t1):.1f}ms d2h={1e3 * (t0 + dt - t2):.1f}ms",
                   file=sys.stderr, flush=True)
@@ -379,7 +385,9 @@ def main():
         d2h = (best_host.numel() * 4 + out[3].nbytes + out[4].nbytes + out[1].nbytes + out[2].nbytes) * world
         e2e = {"value": n * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                "what": "PPDE_PAS.run(pinned host one-hot population -> device, K iterations incl. t=0 evaluation, "
-                       "6-tuple back on host); wall clock"}
+                       "6-tuple back on host); wall clock",
+               "host_phases_ms": {"run_returned": 1e3 * t_run, "total": 1e3 * dt,
+                                  **{k_: round(v_, 2) for k_, v_ in getattr(smp, "last_phases", {}).items()}}}
 
     # ---- CPU baseline (oracle port on host cores), rank 0, N=1 only ---------------------------------
     cpu = None

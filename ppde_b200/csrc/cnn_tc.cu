@@ -2109,7 +2109,9 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 const int buf = it & (BW_NDBUF - 1);
                 if (it >= BW_NDBUF) mbar_wait(&dempty[buf], (uint32_t)(((it / BW_NDBUF) + 1) & 1));
                 if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
-                while (!mbar_test(&full[tb], (uint32_t)((it / BW_NBUF) & 1))) stage_records(0);   // keep the records flowing meanwhile
+                // keep the records flowing while the tile is being built: bounded SUSPENDING waits, not a spin (this is the
+                // top-priority warp of its scheduler: spinning here starves four producer warps, measured as a 10x slower kernel)
+                while (!mbar_try_wait_for(&full[tb], (uint32_t)((it / BW_NBUF) & 1), 2000u)) stage_records(0);
                 if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + D_COL0 + buf * BW_NT;

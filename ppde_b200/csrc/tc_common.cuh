@@ -43,6 +43,19 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return __shfl_sync(0xffffffffu, ok, 0) != 0;
 }
+// one bounded, SUSPENDING wait: true if the phase completed, false after at most ~`ns` nanoseconds.  Unlike a test_wait spin the
+// warp is descheduled while it waits (a spinning top-priority warp starves the other warps of its scheduler); lane 0's answer
+// is broadcast so that the callers stay converged.
+__device__ __forceinline__ bool mbar_try_wait_for(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -533,14 +533,23 @@ class ChainEngine:
             for i in range(k):
                 full = self.full_backward_at(self.t + i)
                 if full not in self._graph:                    # captured once per variant (exact / delta backward)
+                    # capture_begin / capture_end directly: the `torch.cuda.graph` context manager also runs gc.collect(),
+                    # a device synchronize and torch.cuda.empty_cache() on entry (measured: 3 .. 650 ms of host time when
+                    # another engine's pools sit in the allocator cache); nothing is allocated while these launches are
+                    # recorded, every buffer was created above
+                    cur = torch.cuda.current_stream()
                     side = torch.cuda.Stream()
-                    side.wait_stream(torch.cuda.current_stream())
+                    side.wait_stream(cur)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=side):
-                        self._launch_step(self._graph_params, full=full)
-                        _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
+                    with torch.cuda.stream(side):
+                        g.capture_begin()
+                        try:
+                            self._launch_step(self._graph_params, full=full)
+                            _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
+                        finally:
+                            g.capture_end()
+                    cur.wait_stream(side)
                     self._graph[full] = g
-                    torch.cuda.current_stream().wait_stream(side)
                 self._graph[full].replay()
         self.t += k
 

@@ -30,20 +30,22 @@ class _Phases:
     diagnostic, not something to leave on when measuring throughput."""
 
     def __init__(self, device):
-        self.on = os.environ.get("PPDE_TRACE", "0") == "1"
+        self.mode = os.environ.get("PPDE_TRACE", "0")          # "1": synchronize at every mark and print; "2": print host-side times
+        self.on = True                                         # host-side times are always recorded (PPDE_PAS.last_phases)
         self.device = device
         self.rows = []
         self.t = time.perf_counter()
 
     def mark(self, name):
         if self.on:
-            torch.cuda.synchronize(self.device)
+            if self.mode == "1":
+                torch.cuda.synchronize(self.device)
             now = time.perf_counter()
             self.rows.append((name, (now - self.t) * 1e3))
             self.t = now
 
     def report(self):
-        if self.on:
+        if self.mode in ("1", "2"):
             print("[ppde trace] " + "  ".join(f"{k}={v:.1f}ms" for k, v in self.rows), flush=True)
 
 
@@ -144,6 +146,7 @@ class PPDE_PAS:
             random_traj = list(m.aa_to_onehot(traj).cpu().numpy())
             ph.mark("results")
             ph.report()
+            self.last_phases = dict(ph.rows)
         return best_x, best_e, best_f, e_hist, f_hist, random_traj
 
     @staticmethod
