@@ -356,6 +356,10 @@ def main():
         del eng          # its pools return to torch's caching allocator and are reused by the run below (warm allocator, as in
                          # any long-lived process); every copy and every kernel of the call stays inside the timed region
         best_host = torch.empty(n, L, 20, dtype=torch.float32).pin_memory()    # the caller's result buffer
+        import gc
+        gc.collect()
+        gc.disable()     # no generational collection in the middle of the timed call (a gen-2 pass over this process' heap
+                         # costs up to ~0.2 s: it would be timed as if it were part of the 20 ms .. 250 ms call)
         barrier()
         t0 = time.perf_counter()
         trace = os.environ.get("PPDE_TRACE", "0") == "1"
@@ -372,6 +376,7 @@ def main():
         best_host.copy_(out[0])                                # D2H of the call's result (histories are host numpy already)
         barrier()
         dt = time.perf_counter() - t0
+        gc.enable()
         if trace2:
             print(f"[bench trace2] total {1e3 * dt:.1f}ms", file=sys.stderr, flush=True)
         if trace:
