@@ -277,21 +277,21 @@ def main():
             cand = {
                 "cnn_backward_tc": dict(kernel=("cnn_backward_delta_kernel" if eng.delta else "cnn_backward_tc_kernel"), bound="tensor", unit="TFLOP/s",
                                         work=3 * (4 * Cc * Cc + 200 * P * Cc) * n, peak=pk["bf16_sustained"],
-                                        # dram read+write bytes from the committed ncu captures at 8192 chains (profiles/r01_v12_ncu_full_summary.txt:
-                                        # delta 427.8 + 425.8 MB; profiles/r01_v10_ncu_full_summary.txt: exact 244.6 + 415.9 MB)
-                                        traffic=((853.6e6 if eng.delta else 660.6e6) / 8192) * n if L == 238 else None,
+                                        # dram read+write bytes from the committed ncu captures at 8192 chains (profiles/r01_v16_ncu_full_summary.txt:
+                                        # compact delta 109.6 + 413.2 MB; profiles/r01_v10_ncu_full_summary.txt: exact 244.6 + 415.9 MB)
+                                        traffic=((522.8e6 if eng.delta else 660.6e6) / 8192) * n if L == 238 else None,
                                         note="gradient of the CNN ensemble for every proposal: 3*(4C^2+200PC) algorithmic flops per chain; "
                                              "fp16 hi/lo split = 3 tensor-core passes per flop; " +
                                              ("delta mode: one tile of the touched positions per chain and net, only the adjoint rows that differ are gathered" if eng.delta else
                                               "limited by the L2->SM gather of the winners' W1 rows (422 KB per chain and net)")),
                 "cnn_forward_inc_tc": dict(kernel="cnn_forward_inc_kernel", bound="tensor", unit="TFLOP/s",
-                                           work=3 * 2 * P * Cc * 2 * Cc * n, peak=pk["bf16_sustained"], traffic=(188.9e6 / 8192) * n if L == 238 else None,
+                                           work=3 * 2 * P * Cc * 2 * Cc * n, peak=pk["bf16_sustained"], traffic=(190.6e6 / 8192) * n if L == 238 else None,
                                            note="max-pool winners of every proposal: 3*2*P*C*2C algorithmic flops per chain, of which only the dirty "
                                                 "16-position blocks are executed (3 fp16 passes per flop)"),
                 "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s", work=None, peak=pk["hbm_gbs"],
-                                      traffic=(2748.5e6 / 8192) * n if L == 238 else None, note="chain-level winner = max over the NB block keys read through the block table"),
+                                      traffic=(833.2e6 / 8192) * n if L == 238 else None, note="chain-level winner = max over the NB block keys read through the block table"),
                 "pas_propose": dict(kernel="pas_propose_kernel", bound="hbm", unit="GB/s", work=(4 * NE + L) * n, peak=pk["hbm_gbs"],
-                                    traffic=(164.4e6 / 8192) * n if L == 238 else None,
+                                    traffic=(163.3e6 / 8192) * n if L == 238 else None,
                                     note="reads one gradient row per chain; bound by the per-entry Philox + softmax arithmetic "
                                          "(one uniform per entry of [n, 20L] per sub-step), not by bytes"),
             }
