@@ -128,6 +128,11 @@ def run_reference(args, wl, pr):
     if rank != 0:
         return
     n_cpu = args.cpu_chains
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     val, ms = cpu_port_throughput(wl, pr, n_cpu, args.steps, args.warmup)
     cores = torch.get_num_threads()
     sample = f"{n_cpu} chains x {args.steps} iterations of the same workload (L={wl['L']}, pas={wl['pas']})"
