@@ -312,8 +312,14 @@ def main():
                     ("algorithmic_flops_per_launch" if cd["bound"] == "tensor" else "algorithmic_bytes_per_launch"): cd["work"],
                     "avg_launch_ms": breakdown[dom], "note": cd["note"] + per_sum}
             if eng.delta:
+                delta_ms = breakdown["cnn_winner_sort"] + breakdown["cnn_backward_tc"] + breakdown["cnn_grad_combine"]
+                extra = (refresh_ms - delta_ms) / m.bwd_refresh          # ms per iteration, averaged over a refresh period
                 roof["backward"] = {"mode": "delta", "exact_refresh_every": m.bwd_refresh, "exact_backward_ms": refresh_ms,
-                                    "delta_backward_ms": breakdown["cnn_winner_sort"] + breakdown["cnn_backward_tc"] + breakdown["cnn_grad_combine"]}
+                                    "delta_backward_ms": delta_ms,
+                                    # the K timed iterations contain an exact-refresh iteration only when K reaches the period;
+                                    # averaged over a whole period the step costs this much more than ms_per_step:
+                                    "refresh_ms_per_step_amortized": extra,
+                                    "value_amortized_over_refresh_period": n * world / ((ms / K + extra) * 1e-3)}
             # the incremental forward computes only the dirty 16-position blocks: 3 nets * 2*16*C*2C flops per block
             if dirty_blocks is not None:
                 f_inc = dirty_blocks * 3 * 2 * 16 * Cc * 2 * Cc

@@ -97,3 +97,68 @@ def test_sampler_constructor_flag_semantics():
     s = PPDE_PAS(argparse.Namespace(ppde_pas_length=3, nmut_threshold=0, paper_results=True))
     assert s.nmut_threshold == np.iinfo(np.int32).max and s.ppde_temp == 2 and s.paper_results   # ppde.py:9-17
     assert s.approximate_energy_change(4.0) == 2.0
+
+
+def test_block_table_slot_rule_never_overwrites_a_live_slot():
+    """Host restatement of the pool-row block tables of the incremental CNN forward (cnn_inc_merge_kernel /
+    cnn_forward_inc_kernel in ppde_b200/csrc/cnn_tc.cu).  A chain owns two private rows (b, n + b) and may point at
+    read-only fixed rows; a proposal row Y built from the current row X takes, for a dirty block q, Y's own slot unless
+    X's table points at it - then X's own slot.  Whatever the sequence of accepts, rejects and resets to a fixed row,
+    (a) the slot written is referenced by neither the current row's table nor a fixed row, and (b) reading a live row
+    through its table returns exactly the blocks of the state it represents.  (Inside the step loop the forward is always
+    incremental; full evaluations only fill rows at t = 0, where every row points at itself.)"""
+    rng = np.random.default_rng(7)
+    NB, FIX = 7, 2                      # rows: 0 = A, 1 = B (private), 2.. = fixed
+    A, B = 0, 1
+    for trial in range(200):
+        content = {}                     # (row, q) -> version stored in that slot
+        tab = {}                         # row -> source row of every block
+        truth = {}                       # row -> versions of the state the row represents
+        ver = 0
+        for f in range(FIX):             # fixed rows: fully evaluated, point at themselves
+            r = 2 + f
+            tab[r] = [r] * NB
+            truth[r] = []
+            for q in range(NB):
+                ver += 1; content[(r, q)] = ver; truth[r].append(ver)
+        cur = 2                          # the chain starts on a fixed row (wild type)
+        for step in range(80):
+            Y = A if cur != A else B     # engine rule: the private row that is not the current one (ppde::y_row)
+            X = cur
+            dirty = [bool(rng.random() < 0.3) for _ in range(NB)]
+            new_tab, new_truth = [], []
+            for q in range(NB):
+                if dirty[q]:
+                    target = X if tab[X][q] == Y else Y
+                    assert target in (A, B), "fixed rows are read-only"
+                    assert tab[X][q] != target, "the slot written is still referenced by the current row"
+                    ver += 1
+                    content[(target, q)] = ver
+                    new_tab.append(target); new_truth.append(ver)
+                else:
+                    new_tab.append(tab[X][q]); new_truth.append(truth[X][q])
+            tab[Y], truth[Y] = new_tab, new_truth
+            for r in (X, Y):             # both live rows read back correctly through their tables
+                assert [content[(tab[r][q], q)] for q in range(NB)] == truth[r], (trial, step, r)
+            u = rng.random()
+            if u < 0.7:
+                cur = Y                  # accept
+            elif u < 0.85:
+                cur = 2 + int(rng.integers(FIX))   # hard reset / paper-mode reject: back to a fixed row
+            # else: reject, keep X
+
+
+def test_exact_backward_schedule():
+    """Delta backward with a periodic exact refresh: which iterations run the exact backward."""
+    from ppde_b200.engine import ChainEngine
+
+    class _M:                            # the two attributes full_backward_at reads
+        bwd_refresh = 32
+
+    e = ChainEngine.__new__(ChainEngine)
+    e.m = _M()
+    e.delta = True
+    full = [t for t in range(100) if e.full_backward_at(t)]
+    assert full == [31, 63, 95]
+    e.delta = False
+    assert all(e.full_backward_at(t) for t in range(5))
