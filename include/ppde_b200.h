@@ -13,6 +13,10 @@
  *   ppde_potts_dense_full        same as ppde_potts_full as one tensor-core GEMM  ppde/nets.py:285-290 (the two einsums)
  *   ppde_cnn_forward             OnehotCNN.forward x3, EnsembleProtein mean  ppde/nets.py:363-376,434-442
  *   ppde_cnn_backward_combine    autograd through the CNN + PoE sum          ppde/energy.py:104-108
+ *   ppde_cnn_dirty / ppde_cnn_forward_inc   the same forward for a proposal that differs from a cached state in a few
+ *                                residues (sampler loop, energy at y)         ppde/protein_samplers/ppde.py:116-120, nets.py:363-376
+ *   ppde_cnn_backward_tc[_rows] / ppde_cnn_backward_delta   the same gradient, exact or as (gradient at the current
+ *                                state) + change                              ppde/energy.py:108
  *   ppde_pas_propose             PPDE_PAS.run forward path loop              ppde/protein_samplers/ppde.py:67-116
  *                                 + mut_distance / mutation_mask / safe_logits_to_probs  ppde/utils.py:5-28,106-111
  *   ppde_pas_reverse_accept      reverse proposal, MH accept, reset, history ppde/protein_samplers/ppde.py:122-153,172-183
