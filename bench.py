@@ -202,6 +202,7 @@ def main():
     # ---- device-resident throughput (inputs already in HBM) -------------------------------------
     c0 = lib.ppde_last_launch_count()
     eng.run_steps(max(Wm, 3), use_graph=True)              # warm-up (captures the CUDA graph once)
+    eng.prepare_graphs()                                   # ... and the exact-refresh variant, should K reach a refresh iteration
     launches_per_step = None
     barrier()
     clocks = ClockSampler(local)

@@ -517,41 +517,53 @@ class ChainEngine:
                 self.step()
             return
         with torch.cuda.device(self.m.device):
-            if self._graph is None:
-                self.m.mkey(self.n)
-                self.m.grad_scratch(self.n)
-                if not self.inc:
-                    self.m.r1mask(self.n)
-                else:
-                    self.m.inc_ws(self.n)
-                self.t_dev.fill_(self.t)
-                p = self._params(0, None, use_t_dev=True)
-                self._graph_params = p
-                self._graph = {}
-            else:
-                self.t_dev.fill_(self.t)
+            self._graph_setup()
+            self.t_dev.fill_(self.t)
             for i in range(k):
                 full = self.full_backward_at(self.t + i)
                 if full not in self._graph:                    # captured once per variant (exact / delta backward)
-                    # capture_begin / capture_end directly: the `torch.cuda.graph` context manager also runs gc.collect(),
-                    # a device synchronize and torch.cuda.empty_cache() on entry (measured: 3 .. 650 ms of host time when
-                    # another engine's pools sit in the allocator cache); nothing is allocated while these launches are
-                    # recorded, every buffer was created above
-                    cur = torch.cuda.current_stream()
-                    side = torch.cuda.Stream()
-                    side.wait_stream(cur)
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.stream(side):
-                        g.capture_begin()
-                        try:
-                            self._launch_step(self._graph_params, full=full)
-                            _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
-                        finally:
-                            g.capture_end()
-                    cur.wait_stream(side)
-                    self._graph[full] = g
+                    self._capture(full)
                 self._graph[full].replay()
         self.t += k
+
+    def _graph_setup(self):
+        if self._graph is None:
+            self.m.mkey(self.n)
+            self.m.grad_scratch(self.n)
+            if not self.inc:
+                self.m.r1mask(self.n)
+            else:
+                self.m.inc_ws(self.n)
+            self._graph_params = self._params(0, None, use_t_dev=True)
+            self._graph = {}
+
+    def _capture(self, full):
+        """Record one iteration (exact or delta backward) into a CUDA graph; nothing is executed."""
+        # capture_begin / capture_end directly: the `torch.cuda.graph` context manager also runs gc.collect(), a device
+        # synchronize and torch.cuda.empty_cache() on entry (measured: 3 .. 650 ms of host time when another engine's pools
+        # sit in the allocator cache); nothing is allocated while these launches are recorded, every buffer exists already
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            g.capture_begin()
+            try:
+                self._launch_step(self._graph_params, full=full)
+                _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
+            finally:
+                g.capture_end()
+        cur.wait_stream(side)
+        self._graph[full] = g
+
+    def prepare_graphs(self):
+        """Capture every graph variant run_steps can need (delta and exact backward), so that no capture falls into a timed
+        region later."""
+        with torch.cuda.device(self.m.device):
+            self._graph_setup()
+            for full in ({True, False} if self.delta else {True}):
+                if full not in self._graph:
+                    self._capture(full)
 
     # -- results ------------------------------------------------------------------------------------
     def population_metrics(self):
