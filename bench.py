@@ -123,24 +123,43 @@ def cpu_port_throughput(wl, pr, n_chains, steps, warmup):
     return n_chains * steps / dt, dt / steps * 1e3
 
 
+def use_all_host_threads():
+    """all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)"""
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
+    return torch.get_num_threads()
+
+
+def cpu_reference_throughput(wl, pr, n_chains, steps, warmup):
+    """CPU arm: the UNMODIFIED reference (oracle/_ref, staged by oracle/stage_ref.py: PPDE_PAS.run + ProteinProductOfExperts,
+    ppde/protein_samplers/ppde.py:24-192, ppde/energy.py:72-108) when it is there, else the oracle port.
+    -> (chain-steps/s, ms per step, kind, what)"""
+    from oracle import ref_arm
+    if ref_arm.available() and os.environ.get("PPDE_BENCH_CPU", "reference") != "port":
+        dt, _ = ref_arm.time_steps(pr, n_chains, wl["lamda"], wl["pas"], wl["nmut"], wl["paper"], steps, warmup)
+        return n_chains * steps / dt, dt / steps * 1e3, "reference", \
+            "unmodified reference PPDE_PAS.run + ProteinProductOfExperts (oracle/_ref), device cpu, steady-state iterations"
+    v, ms = cpu_port_throughput(wl, pr, n_chains, steps, warmup)
+    return v, ms, "port", "oracle port (torch CPU ops in the reference's order)"
+
+
 def run_reference(args, wl, pr):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_cpu = args.cpu_chains
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
-    try:
-        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
-    except Exception:
-        pass
-    val, ms = cpu_port_throughput(wl, pr, n_cpu, args.steps, args.warmup)
-    cores = torch.get_num_threads()
-    sample = f"{n_cpu} chains x {args.steps} iterations of the same workload (L={wl['L']}, pas={wl['pas']})"
+    cores = use_all_host_threads()
+    val, ms, kind, what = cpu_reference_throughput(wl, pr, n_cpu, args.steps, args.warmup)
+    sample = (f"{n_cpu} chains x {args.steps} iterations of the same workload (L={wl['L']}, pas={wl['pas']}, lambda={wl['lamda']}, "
+              f"nmut={wl['nmut']}, same synthetic weights); the GPU arm runs {wl['chains']} chains per GPU: chain-steps/s is per chain, "
+              f"the CPU is saturated at this batch; {what}")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "desc": wl["desc"],
                                                              "cpu_sample_chains": n_cpu},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -154,11 +173,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gfp_potts_poe_64k", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: the workload's)")
-    ap.add_argument("--cpu-chains", type=int, default=128, help="bounded CPU sample size")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-chains", type=int, default=1024, help="bounded CPU sample size (>= 1024 saturates the host cores)")
+    ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's chains are the GLOBAL population, "
+                                                          "sharded over the ranks (default: that many chains PER GPU, weak)")
+    ap.add_argument("--log-every", type=int, default=0, help="e2e leg: run the log_every population report (device kernels + "
+                                                             "NCCL all-gathers) every this many iterations (0 = never)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.chains:
@@ -185,6 +208,10 @@ def main():
     lib = _lib.load()
 
     n = wl["chains"]                                       # per GPU (weak scaling: per-GPU work fixed)
+    if args.strong:                                        # strong scaling: the workload's chains are the global population
+        if n % world:
+            raise SystemExit("--strong needs chains divisible by the number of GPUs")
+        n //= world
     L = wl["L"]
     energy = ProteinProductOfExperts.from_arrays(pr["wt"], pr["J"], pr["h"], pr["win_lo"], pr["cnn"], wl["lamda"], device=dev)
     m = energy.model
@@ -202,7 +229,17 @@ def main():
     # ---- device-resident throughput (inputs already in HBM) -------------------------------------
     c0 = lib.ppde_last_launch_count()
     eng.run_steps(max(Wm, 3), use_graph=True)              # warm-up (captures the CUDA graph once)
-    eng.prepare_graphs()                                   # ... and the exact-refresh variant, should K reach a refresh iteration
+    eng.prepare_graphs()                                   # ... and the exact-refresh variant
+    # The delta backward is refreshed by an exact backward every `bwd_refresh`-th iteration (t % R == R-1).  The timed K
+    # iterations must carry their share of that work: the iteration counter is placed so that they contain exactly
+    # ceil(K / R) refresh iterations (>= the long-run average of K / R; never fewer).
+    refreshes = 0
+    if eng.delta:
+        R = m.bwd_refresh
+        r_ = -(-K // R)
+        eng.t = (eng.t // R + 1) * R + max(0, R * r_ - K)
+        refreshes = sum(1 for i in range(K) if eng.full_backward_at(eng.t + i))
+        assert refreshes == r_, (refreshes, r_)
     launches_per_step = None
     barrier()
     clocks = ClockSampler(local)
@@ -314,13 +351,13 @@ def main():
                     "avg_launch_ms": breakdown[dom], "note": cd["note"] + per_sum}
             if eng.delta:
                 delta_ms = breakdown["cnn_winner_sort"] + breakdown["cnn_backward_tc"] + breakdown["cnn_grad_combine"]
-                extra = (refresh_ms - delta_ms) / m.bwd_refresh          # ms per iteration, averaged over a refresh period
-                roof["backward"] = {"mode": "delta", "exact_refresh_every": m.bwd_refresh, "exact_backward_ms": refresh_ms,
-                                    "delta_backward_ms": delta_ms,
-                                    # the K timed iterations contain an exact-refresh iteration only when K reaches the period;
-                                    # averaged over a whole period the step costs this much more than ms_per_step:
-                                    "refresh_ms_per_step_amortized": extra,
-                                    "value_amortized_over_refresh_period": n * world / ((ms / K + extra) * 1e-3)}
+                R_ = m.bwd_refresh
+                # the timed K iterations contain ceil(K / R) exact-refresh iterations (see above); the long-run share is K / R
+                over = (refreshes / K - 1.0 / R_) * (refresh_ms - delta_ms)          # ms per step charged beyond the long-run share
+                roof["backward"] = {"mode": "delta", "exact_refresh_every": R_, "exact_backward_ms": refresh_ms,
+                                    "delta_backward_ms": delta_ms, "refresh_iterations_in_timed_region": refreshes,
+                                    "refresh_ms_per_step_long_run": (refresh_ms - delta_ms) / R_,
+                                    "value_at_long_run_refresh_share": n * world / ((ms / K - over) * 1e-3)}
             # the incremental forward computes only the dirty 16-position blocks: 3 nets * 2*16*C*2C flops per block
             if dirty_blocks is not None:
                 f_inc = dirty_blocks * 3 * 2 * 16 * Cc * 2 * Cc
@@ -359,78 +396,80 @@ def main():
     e2e = None
     if not args.no_e2e:
         import argparse as ap_
-        sargs = ap_.Namespace(ppde_pas_length=wl["pas"], nmut_threshold=wl["nmut"], paper_results=wl["paper"], seed=0,
-                              ppde_verbose=False, ppde_local_population=True)
-        smp = PPDE_PAS(sargs)
-        pop_host = torch.nn.functional.one_hot(torch.from_numpy(pr["wt"].astype(np.int64)), 20).float()[None] \
-            .repeat(n, 1, 1).pin_memory()   # this rank's shard
-        win_hi = pr["win_lo"] + pr["J"].shape[0] - 1
-        del eng          # its pools return to torch's caching allocator and are reused by the run below (warm allocator, as in
-                         # any long-lived process); every copy and every kernel of the call stays inside the timed region
-        best_host = torch.empty(n, L, 20, dtype=torch.float32).pin_memory()    # the caller's result buffer
         import gc
+        win_hi = pr["win_lo"] + pr["J"].shape[0] - 1
+        log_every = args.log_every if args.log_every > 0 else 10 ** 9
+        del eng          # its pools return to torch's caching allocator and are reused by the runs below (warm allocator, as in
+                         # any long-lived process); every copy and every kernel of a call stays inside its timed region
         gc.collect()
-        gc.disable()     # no generational collection in the middle of the timed call (a gen-2 pass over this process' heap
-                         # costs up to ~0.2 s: it would be timed as if it were part of the 20 ms .. 250 ms call)
-        # the same call twice, the faster one is reported (both are recorded): the host side of a single call depends on what
-        # the allocator cache holds at that moment (engine set-up measured between 3 and 220 ms for identical calls)
-        calls = []
-        for call in range(2):
+
+        def e2e_call(residue_io):
+            """One PPDE_PAS.run from HOST buffers to HOST results; returns (seconds, bytes in, bytes out, phases, reports)."""
+            sargs = ap_.Namespace(ppde_pas_length=wl["pas"], nmut_threshold=wl["nmut"], paper_results=wl["paper"], seed=0,
+                                  ppde_verbose=False, ppde_local_population=True, ppde_residue_io=residue_io)
             smp = PPDE_PAS(sargs)
+            if residue_io:   # opt-in boundary format (INTEGRATION.md): uint8 residue indices [n, L], 1 byte per residue
+                pop_host = torch.from_numpy(np.tile(pr["wt"], (n, 1))).pin_memory()
+            else:            # the reference's format: float one-hot [n, L, 20] in host memory
+                pop_host = torch.nn.functional.one_hot(torch.from_numpy(pr["wt"].astype(np.int64)), 20).float()[None] \
+                    .repeat(n, 1, 1).pin_memory()
             gc.collect()
+            gc.disable()     # no generational collection in the middle of the timed call
             barrier()
             t0 = time.perf_counter()
-            trace = os.environ.get("PPDE_TRACE", "0") == "1"
-            trace2 = os.environ.get("PPDE_TRACE", "0") == "2"
-            pop_dev = pop_host.to(dev, non_blocking=True)          # H2D of the call's input, inside the timed region
-            if trace:
-                torch.cuda.synchronize(); t1 = time.perf_counter()
-            out = smp.run(pop_dev, K, energy, pr["win_lo"], win_hi, None, log_every=10 ** 9)
-            if trace:
-                torch.cuda.synchronize(); t2 = time.perf_counter()
-            t_run = time.perf_counter() - t0
-            if trace2:
-                print(f"[bench trace2] run returned after {1e3 * t_run:.1f}ms", file=sys.stderr, flush=True)
-            best_host.copy_(out[0])                                # D2H of the call's result (histories are host numpy already)
+            out = smp.run(pop_host, K, energy, pr["win_lo"], win_hi, None, log_every=log_every)
+            best = out[0]                                          # host tensor already (same device as the input)
+            assert best.device.type == "cpu"
             barrier()
             dt = time.perf_counter() - t0
-            if trace2:
-                print(f"[bench trace2] total {1e3 * dt:.1f}ms", file=sys.stderr, flush=True)
-            if trace:
-                print(f"[bench trace] h2d={1e3 * (t1 - t0):.1f}ms run={1e3 * (t2 - t1):.1f}ms d2h={1e3 * (t0 + dt - t2):.1f}ms",
-                      file=sys.stderr, flush=True)
-            calls.append((dt, t_run, dict(getattr(smp, "last_phases", {})), out))
-            pop_dev = None
-        gc.enable()
-        dt, t_run, phases, out = min(calls, key=lambda c_: c_[0])
-        call_ms = [round(1e3 * c_[0], 1) for c_ in calls]
-        if world > 1:
-            tt = torch.tensor([dt], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        h2d = pop_host.numel() * 4 * world
-        d2h = (best_host.numel() * 4 + out[3].nbytes + out[4].nbytes + out[1].nbytes + out[2].nbytes) * world
-        e2e = {"value": n * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
-               "what": "PPDE_PAS.run(pinned host one-hot population -> device, K iterations incl. t=0 evaluation, "
-                       "6-tuple back on host); wall clock; faster of two identical calls (calls_ms)",
-               "calls_ms": call_ms,
-               "host_phases_ms": {"run_returned": 1e3 * t_run, "total": 1e3 * dt, **{k_: round(v_, 2) for k_, v_ in phases.items()}}}
+            gc.enable()
+            if world > 1:
+                tt = torch.tensor([dt], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            # bytes that actually crossed PCIe: residues in, residues + histories + best energies out
+            h2d = n * m.aa_stride * world
+            d2h = (n * m.aa_stride + out[3].nbytes + out[4].nbytes + out[1].nbytes + out[2].nbytes) * world
+            return dt, h2d, d2h, dict(getattr(smp, "last_phases", {})), len(smp.reports)
 
-    # ---- CPU baseline (oracle port on host cores), rank 0, N=1 only ---------------------------------
+        # FIRST call of each variant is the reported one (no best-of); a second call is recorded beside it
+        calls = {}
+        for variant, rio in (("residue_io", True), ("onehot_host", False)):
+            r1 = e2e_call(rio)
+            r2 = e2e_call(rio)
+            calls[variant] = (r1, r2)
+        dt, h2d, d2h, phases, nrep = calls["residue_io"][0]
+        dt_oh = calls["onehot_host"][0][0]
+        e2e = {"value": n * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+               "what": "PPDE_PAS.run(host population -> 6-tuple on the host), K iterations incl. engine set-up and the t=0 "
+                       "evaluation; wall clock of the FIRST call; population crosses the API as uint8 residue indices "
+                       "(args.ppde_residue_io, INTEGRATION.md)",
+               "calls_ms": [round(1e3 * c_[0], 1) for c_ in calls["residue_io"]],
+               "log_reports_in_call": nrep,
+               "host_phases_ms": {k_: round(v_, 2) for k_, v_ in phases.items()},
+               # the reference's own boundary format: float one-hot [n, L, 20] in HOST memory in and out; the host cores reduce it to
+               # residues before the copy and expand best_x after it (ppde_host_onehot_to_aa / ppde_host_aa_to_onehot)
+               "onehot_host_api": {"value": n * world * K / dt_oh, "calls_ms": [round(1e3 * c_[0], 1) for c_ in calls["onehot_host"]],
+                                   "host_onehot_bytes_per_call": 2 * n * L * 20 * 4 * world,
+                                   "host_phases_ms": {k_: round(v_, 2) for k_, v_ in calls["onehot_host"][0][3].items()}}}
+
+    # ---- CPU baseline (the unmodified reference on host cores when staged, else the port), rank 0, N=1 only -----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, _ = cpu_port_throughput(wl, pr, args.cpu_chains, args.cpu_steps, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        cores = use_all_host_threads()
+        v, _, kind, what = cpu_reference_throughput(wl, pr, args.cpu_chains, args.cpu_steps, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{args.cpu_chains} chains x {args.cpu_steps} iterations of the same workload "
-                         f"(L={L}, pas={wl['pas']}), torch CPU ops as in the reference"}
+                         f"(L={L}, pas={wl['pas']}); {what}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "desc": wl["desc"], "chains_per_gpu": n, "L": L,
                            "sub_steps": 2 * wl["pas"] - 1, "lamda": wl["lamda"], "nmut_threshold": wl["nmut"],
                            "l2": "per-step working set (gradient rows, >2 GB at 64k chains) exceeds the 126 MB L2; no flush needed",
+                           "exact_refresh_iterations_in_timed_region": refreshes,
                            "parallelism": f"chains sharded x{world}, weights replicated, no collective in the step"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches_per_step * K,
                 "roofline": roof, "cpu_baseline": cpu,

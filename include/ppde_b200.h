@@ -4,7 +4,10 @@
  * Python protocol.  This header is the boundary a maintainer binds under
  * that protocol (ctypes stub in INTEGRATION.md).  Every entry point is a stateless launcher:
  * plain device pointers + sizes + a cudaStream_t (passed as void*), returns 0 or a
- * cudaError_t value, never aborts, allocates nothing.
+ * cudaError_t value (cudaErrorInvalidValue for NULL / inconsistent arguments), never aborts,
+ * allocates nothing and keeps no state between calls except a launch counter and a per-device
+ * cache of "dynamic shared memory limit already raised for this kernel" (profiling and tuning
+ * switches are per-call arguments, ppde_tune_t).
  *
  * Reference interfaces each entry point replaces (paths relative to the reference root):
  *   ppde_potts_symmetrize        PottsModel.__init__ parameter load          ppde/nets.py:245-262
@@ -21,9 +24,8 @@
  *                                 + mut_distance / mutation_mask / safe_logits_to_probs  ppde/utils.py:5-28,106-111
  *   ppde_pas_reverse_accept      reverse proposal, MH accept, reset, history ppde/protein_samplers/ppde.py:122-153,172-183
  *   ppde_onehot_to_aa / ppde_aa_to_onehot   seqs_to_onehot / onehot2seq      ppde/third_party/hsu/data_utils.py:150-175
- *   ppde_population_metrics      mut_distance mean, #accepted (logging)      ppde/protein_samplers/ppde.py:162-168
+ *   ppde_population_metrics      mut_distance (n_hops) + sequence hash       ppde/utils.py:5-14, scripts/make_figures.py:29-36
  *   ppde_oracle_ridge            AugmentedLinearRegression.forward           ppde/nets.py:315-347 (log_every oracle call)
- *   ppde_sequence_hash           diversity_score (unique sequences)          scripts/make_figures.py:38-49
  *
  * Data layout (all row-major, device memory):
  *   residues     uint8  [n, aa_stride]   aa_stride >= L, multiple of 16; alphabet ACDEFGHIKLMNPQRSTVWY = 0..19
@@ -138,6 +140,18 @@ typedef struct ppde_pas_params {
     int32_t _pad;
 } ppde_pas_params_t;
 
+/* Per-call tuning / measurement switches of the tensor-core CNN entry points (NULL = defaults = production behaviour).
+ * No process-global state: two engines, streams or devices can use different settings concurrently. */
+typedef struct ppde_tune {
+    int32_t parts;        /* bit mask of the kernels a composite launcher runs (0 = all; per-kernel timing in bench.py):
+                           * ppde_cnn_forward_inc: 1 scan, 2 tensor-core kernel, 4 merge;
+                           * ppde_cnn_backward_tc[_rows] / ppde_cnn_backward_delta: 1 winner records, 2 tensor-core kernel, 4 combine */
+    int32_t forward_ctas; /* ppde_cnn_forward_tc: 1 = one CTA per channel tile, 0 / 2 = CTA pairs with cta_group::2 MMAs */
+    int32_t delta_layout; /* ppde_cnn_backward_delta: 0 = compact tiles of the touched positions, 1 = one column per position */
+    int32_t dbg;          /* timing experiments only, results are WRONG with any bit set (tools/prof_*.py) */
+    long long* prof;      /* non-NULL device buffer [grid][16] int64: instrumented build with per-role cycle counters */
+} ppde_tune_t;
+
 const char* ppde_version(void);
 int ppde_last_launch_count(void);   /* kernels launched by this library since load (bench's gpu_launches) */
 
@@ -159,16 +173,8 @@ int ppde_cnn_forward(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, 
  * r1mask (optional, [n, n_nets, P, 32] bytes): bit c of a position's 32 bytes = relu mask of the conv layer, consumed
  * by ppde_cnn_backward_tc. */
 int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
-                        unsigned long long* mkey /* [n, n_nets, 2C] */, uint8_t* r1mask, void* stream);
-/* 1 = one CTA per channel tile, 2 = CTA pairs with cta_group::2 MMAs (default; also PPDE_TC_CTAS=1|2 in the environment) */
-int ppde_set_forward_variant(int ctas);
-/* profiling aid: non-NULL device buffer [grid][16] int64 selects an instrumented build of the 2-CTA forward kernel that
- * accumulates per-role cycle counters (tools/prof_fwd.py); NULL (default) = production kernel. */
-int ppde_set_forward_profile(long long* buf);
-int ppde_set_backward_profile(long long* buf);
-/* measurement aid for per-kernel timing: bit masks of the kernels the composite launchers run (default 7 = all).
- * ppde_cnn_forward_inc: 1 scan, 2 tensor-core kernel, 4 merge; ppde_cnn_backward_tc[_rows]: 1 winner sort, 2 tensor-core kernel, 4 combine. */
-int ppde_set_profile_parts(int forward_inc_parts, int backward_parts);   /* same, for the tensor-core backward kernel (tools/prof_bwd.py) */
+                        unsigned long long* mkey /* [n, n_nets, 2C] */, uint8_t* r1mask, const ppde_tune_t* tune,
+                        void* stream);
 int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                               int32_t n, const unsigned long long* mkey, float lamda,
                               const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
@@ -181,7 +187,8 @@ int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint
                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                          float* G, int64_t G_stride, const int32_t* g_rows,
                          const uint8_t* r1mask /* from ppde_cnn_forward_tc */,
-                         float* scratch /* n_nets*n*20L floats + n*n_nets*roundup8(2P+2+4C) uint16 */, void* stream);
+                         float* scratch /* n_nets*n*20L floats + n*n_nets*roundup8(2P+2+4C) uint16 */,
+                         const ppde_tune_t* tune, void* stream);
 /* same as ppde_cnn_backward_tc with the relu-mask rows taken from a POOL: chain b's mask lives in row
  * mask_rows[b] (NULL: mask_row_base + b) of r1mask [rows, n_nets, P, 32]. */
 int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
@@ -190,7 +197,7 @@ int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const
                               float* G, int64_t G_stride, const int32_t* g_rows,
                               const uint8_t* r1mask, const int32_t* mask_rows, int32_t mask_row_base,
                               const int32_t* btab /* optional block table of the pools, see ppde_cnn_forward_inc */,
-                              float* scratch, void* stream);
+                              float* scratch, const ppde_tune_t* tune, void* stream);
 /* Incremental CNN forward (same quantity as ppde_cnn_forward_tc, bit for bit; OnehotCNN.forward, ppde/nets.py:363-376).
  * A proposal differs from the chain's current state in a few residues, and a residue only moves the 5 conv rows that
  * read it, so the max-pool over positions is kept per BLOCK of 16 positions in a pool
@@ -209,8 +216,10 @@ int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n);   /* workspace of ppde_cnn_for
 int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                          unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask, unsigned long long* bkey,
                          int32_t* btab, const int32_t* rows_x, const int32_t* rows_y, int32_t row_base_y,
-                         unsigned long long* mkey_pool /* optional [rows, n_nets, 2C]: row of the proposal also gets mkey */,
-                         void* ws /* ppde_cnn_forward_inc_ws_bytes(n) bytes */, void* stream);
+                         unsigned long long* mkey_pool /* optional [rows, n_nets, 2C]: RAW winner of every pool row (64-bit maximum
+                                                          over its block keys); with it the merge reads the current row's winner
+                                                          and the dirty blocks' keys instead of all NB keys per channel */,
+                         void* ws /* ppde_cnn_forward_inc_ws_bytes(n) bytes */, const ppde_tune_t* tune, void* stream);
 /* DELTA backward: the CNN part of the gradient changes between the current state x and the proposal y only through the
  * conv rows whose relu mask changed and the channels whose max-pool winner moved (a few percent of the winners), so
  *     G[rows_y[b]] = G[rows_x[b]] + (Gp[rows_y[b]] - Gp[rows_x[b]])(window) + lamda/n_nets * sum_k d(dfit_k/dx)
@@ -221,7 +230,8 @@ int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const u
                             int32_t aa_stride, int32_t n, const unsigned long long* mkey_y,
                             const unsigned long long* mkey_pool, float lamda, const float* Gp, int64_t Gp_stride,
                             float* G, int64_t G_stride, const int32_t* rows_x, const int32_t* rows_y,
-                            const uint8_t* r1mask, const int32_t* btab, float* scratch, void* stream);
+                            const uint8_t* r1mask, const int32_t* btab, float* scratch, const ppde_tune_t* tune,
+                            void* stream);
 /* dH_potts of n states from field rows already in the pool: Epotts[b] = 1/2 sum_i (Gp[rows[b]][(i,aa_i)] + h) - H(wt);
  * rows == NULL means row b. */
 int ppde_potts_energy_rows(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n, const float* Gp,
@@ -236,9 +246,39 @@ int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_t* c, const
 
 int ppde_onehot_to_aa(const float* x, int32_t n, int32_t L, uint8_t* aa, int32_t aa_stride, void* stream);
 int ppde_aa_to_onehot(const uint8_t* aa, int32_t aa_stride, int32_t n, int32_t L, float* x, void* stream);
+/* the same two conversions on HOST buffers with `nthreads` host threads (no CUDA call): a host one-hot population is reduced
+ * to 1 byte per residue before it crosses PCIe, and expanded after the copy back (80x fewer bytes than the float one-hot) */
+int ppde_host_onehot_to_aa(const float* x, int64_t n, int32_t L, uint8_t* aa, int64_t aa_stride, int32_t nthreads);
+int ppde_host_aa_to_onehot(const uint8_t* aa, int64_t aa_stride, int64_t n, int32_t L, float* x, int32_t nthreads);
 int ppde_population_metrics(const uint8_t* aa, int32_t aa_stride, int32_t n, int32_t L, const uint8_t* wt,
                             int32_t* dist /* [n] */, unsigned long long* hash /* [n] */, void* stream);
 int ppde_counter_add(int32_t* t_dev, int32_t inc, void* stream);
+
+/* ---- log_every population report on the device (ppde/protein_samplers/ppde.py:155-170; scripts/make_figures.py:29-49;
+ * torch.topk as in ppde/protein_samplers/cmaes.py:39).  Exact: radix select, integer sums, whole-sequence comparison.
+ * Under torch.distributed the inputs are the all-gathered vectors; these kernels are single-GPU. */
+/* out[j] = np.quantile(x[0..n), q[j]) (default 'linear' method, evaluated in double); x, q, out on the device */
+int ppde_quantiles(const float* x, int64_t n, const double* q, int32_t nq, double* out, void* stream);
+/* out = { sum accept, sum dist, sum dist^2, n } (int64, device); accept / dist may be NULL */
+int ppde_population_sums(const uint8_t* accept, const int32_t* dist, int64_t n, long long* out, void* stream);
+/* number of distinct sequences (diversity_score * K / 100): table = int32 workspace of ppde_unique_count_table_entries(n)
+ * entries (a power of two >= 2n); count = one int32 on the device */
+int64_t ppde_unique_count_table_entries(int64_t n);
+int ppde_unique_count(const uint8_t* aa, int64_t aa_stride, int64_t n, int32_t L, int32_t* table, int64_t table_entries,
+                      int32_t* count, void* stream);
+/* torch.topk(x, k): k <= 1024 largest values, descending, ties by lowest id; id of element i = ids[i] (ids != NULL) or
+ * index_base + i */
+int ppde_topk(const float* x, int64_t n, int32_t k, int64_t index_base, const long long* ids, float* vals, long long* idx,
+              void* stream);
+/* out[j, :] = aa[idx[j] - index_base, :]   (sequences of the top-k chains) */
+int ppde_gather_rows(const uint8_t* aa, int64_t aa_stride, const long long* idx, int32_t k, int64_t index_base, uint8_t* out,
+                     void* stream);
+/* Known-answer entry point of the proposal arithmetic (tests): the device functions of ppde_pas_propose /
+ * ppde_pas_reverse_accept on caller-provided logits.  dist [n] (mut_distance, ppde/utils.py:5-14); mask u8 [n, 20L] (mutation_mask,
+ * utils.py:17-28); probs [n, 20L] = clamp(softmax(logits - LSE)) / sum (utils.py:106-111 + Categorical.__init__);
+ * logp [n] = log(clamp(probs))[idx] (Categorical.log_prob).  logits / idx / dist / mask / logp may be NULL. */
+int ppde_pas_kat(const uint8_t* aa, int32_t aa_stride, const uint8_t* wt, int32_t n, int32_t L, const float* logits,
+                 const int32_t* idx, int32_t* dist, uint8_t* mask, float* probs, float* logp, void* stream);
 
 #ifdef __cplusplus
 }

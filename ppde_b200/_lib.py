@@ -42,6 +42,12 @@ class ChainsT(C.Structure):
                 ("traj_aa", vp), ("traj_chain", C.c_int32), ("_pad", C.c_int32)]
 
 
+class TuneT(C.Structure):
+    """ppde_tune_t: per-call tuning / measurement switches (NULL = production defaults)."""
+    _fields_ = [("parts", C.c_int32), ("forward_ctas", C.c_int32), ("delta_layout", C.c_int32), ("dbg", C.c_int32),
+                ("prof", vp)]
+
+
 class PasParamsT(C.Structure):
     _fields_ = [("S", C.c_int32), ("nmut_threshold", C.c_int32), ("paper_results", C.c_int32), ("t", C.c_int32),
                 ("min_pos", C.c_int32), ("max_pos", C.c_int32), ("seed", C.c_uint64), ("uniforms", vp), ("t_dev", vp),
@@ -59,22 +65,20 @@ SIGNATURES = {
     "ppde_potts_dense_pack": (C.c_int, [C.POINTER(PottsT), C.c_float, vp, vp]),
     "ppde_potts_dense_full": (C.c_int, [C.POINTER(PottsT), vp, C.c_float, vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp]),
     "ppde_cnn_forward": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp]),
-    "ppde_cnn_forward_tc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, vp]),
-    "ppde_set_forward_variant": (C.c_int, [C.c_int]),
-    "ppde_set_forward_profile": (C.c_int, [vp]),
-    "ppde_set_backward_profile": (C.c_int, [vp]),
-    "ppde_set_profile_parts": (C.c_int, [C.c_int, C.c_int]),
+    "ppde_cnn_forward_tc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, C.POINTER(TuneT), vp]),
     "ppde_cnn_backward_combine": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp,
                                             C.c_float, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp]),
     "ppde_cnn_backward_tc": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
-                                       vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, vp]),
+                                       vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.POINTER(TuneT), vp]),
     "ppde_cnn_backward_tc_rows": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
-                                            vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, vp]),
+                                            vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp,
+                                            C.POINTER(TuneT), vp]),
     "ppde_cnn_dirty": (C.c_int, [C.POINTER(CnnT), vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "ppde_cnn_forward_inc_ws_bytes": (C.c_int64, [C.c_int32]),
-    "ppde_cnn_forward_inc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp]),
+    "ppde_cnn_forward_inc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp,
+                                       C.POINTER(TuneT), vp]),
     "ppde_cnn_backward_delta": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_float,
-                                          vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
+                                          vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(TuneT), vp]),
     "ppde_potts_energy_rows": (C.c_int, [C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp, vp]),
     "ppde_oracle_ridge": (C.c_int, [vp, C.c_float, C.c_float, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
     "ppde_step_rows": (C.c_int, [C.POINTER(ChainsT), vp, vp]),
@@ -82,8 +86,17 @@ SIGNATURES = {
     "ppde_pas_reverse_accept": (C.c_int, [C.POINTER(PottsT), C.POINTER(ChainsT), C.POINTER(PasParamsT), vp]),
     "ppde_onehot_to_aa": (C.c_int, [vp, C.c_int32, C.c_int32, vp, C.c_int32, vp]),
     "ppde_aa_to_onehot": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "ppde_host_onehot_to_aa": (C.c_int, [vp, C.c_int64, C.c_int32, vp, C.c_int64, C.c_int32]),
+    "ppde_host_aa_to_onehot": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int32]),
     "ppde_population_metrics": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp]),
     "ppde_counter_add": (C.c_int, [vp, C.c_int32, vp]),
+    "ppde_quantiles": (C.c_int, [vp, C.c_int64, vp, C.c_int32, vp, vp]),
+    "ppde_population_sums": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "ppde_unique_count_table_entries": (C.c_int64, [C.c_int64]),
+    "ppde_unique_count": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, vp, vp]),
+    "ppde_topk": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, vp, vp]),
+    "ppde_gather_rows": (C.c_int, [vp, C.c_int64, vp, C.c_int32, C.c_int64, vp, vp]),
+    "ppde_pas_kat": (C.c_int, [vp, C.c_int32, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "../../include/ppde_b200.h"
 #include "launch.cuh"
+#include <thread>
+#include <vector>
 
 namespace ppde {
 int g_launch_count = 0;
@@ -83,4 +85,60 @@ extern "C" int ppde_population_metrics(const uint8_t* aa, int32_t aa_stride, int
 extern "C" int ppde_counter_add(int32_t* t_dev, int32_t inc, void* stream) {
     counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, inc);
     return launch_done();
+}
+
+// ---- host side of the boundary: the reference API hands over a float one-hot [n, L, 20] (80 bytes per residue).  When that
+// buffer lives in HOST memory it is reduced to residue indices (1 byte per residue) by the host cores BEFORE the copy, and the
+// result is expanded after the copy back: 80x fewer bytes cross PCIe (seqs_to_onehot / onehot2seq,
+// ppde/third_party/hsu/data_utils.py:150-175, first maximum as torch.argmax).
+static void run_threads(int64_t n, int nthreads, void (*fn)(int64_t, int64_t, void*), void* ctx) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if (n < 4096 || nthreads == 1) { fn(0, n, ctx); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t lo = (int64_t)t * per, hi = lo + per < n ? lo + per : n;
+        if (lo < hi) th.emplace_back(fn, lo, hi, ctx);
+    }
+    for (auto& t : th) t.join();
+}
+struct HostCodec { const float* x; uint8_t* aa; float* xo; const uint8_t* aai; int64_t L, stride; };
+
+extern "C" int ppde_host_onehot_to_aa(const float* x, int64_t n, int32_t L, uint8_t* aa, int64_t aa_stride, int32_t nthreads) {
+    if (n <= 0) return 0;
+    if (!x || !aa || L <= 0 || aa_stride < L) return (int)cudaErrorInvalidValue;
+    HostCodec c{x, aa, nullptr, nullptr, L, aa_stride};
+    run_threads(n, nthreads, [](int64_t lo, int64_t hi, void* p) {
+        const HostCodec& c = *static_cast<HostCodec*>(p);
+        for (int64_t b = lo; b < hi; ++b) {
+            const float* r = c.x + b * c.L * PPDE_Q;
+            uint8_t* o = c.aa + b * c.stride;
+            for (int64_t i = 0; i < c.L; ++i, r += PPDE_Q) {
+                int best = 0; float bv = r[0];
+                for (int a = 1; a < PPDE_Q; ++a) if (r[a] > bv) { bv = r[a]; best = a; }
+                o[i] = (uint8_t)best;
+            }
+            for (int64_t i = c.L; i < c.stride; ++i) o[i] = 0;
+        }
+    }, &c);
+    return 0;
+}
+
+extern "C" int ppde_host_aa_to_onehot(const uint8_t* aa, int64_t aa_stride, int64_t n, int32_t L, float* x, int32_t nthreads) {
+    if (n <= 0) return 0;
+    if (!x || !aa || L <= 0 || aa_stride < L) return (int)cudaErrorInvalidValue;
+    HostCodec c{nullptr, nullptr, x, aa, L, aa_stride};
+    run_threads(n, nthreads, [](int64_t lo, int64_t hi, void* p) {
+        const HostCodec& c = *static_cast<HostCodec*>(p);
+        for (int64_t b = lo; b < hi; ++b) {
+            float* r = c.xo + b * c.L * PPDE_Q;
+            const uint8_t* a = c.aai + b * c.stride;
+            for (int64_t i = 0; i < c.L; ++i, r += PPDE_Q) {
+                for (int q = 0; q < PPDE_Q; ++q) r[q] = 0.f;
+                r[a[i] < PPDE_Q ? a[i] : 0] = 1.f;
+            }
+        }
+    }, &c);
+    return 0;
 }

@@ -290,12 +290,9 @@ extern "C" int ppde_cnn_forward(const ppde_cnn_t* m, const uint8_t* aa, int32_t 
     cudaError_t e = cudaMemsetAsync(mkey, 0, keys * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return (int)e;
     const size_t smem = ((size_t)m->C * FW_RS + FW_KC * FW_TJ) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        e = cudaFuncSetAttribute(cnn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static SmemCache configured;
+    e = ensure_dynamic_smem(cnn_forward_kernel, smem, configured);
+    if (e != cudaSuccess) return (int)e;
     // grid.z is limited to 65535: split the chains over several launches if needed
     const int tiles = (m->P + FW_TP - 1) / FW_TP;
     for (int b0 = 0; b0 < n; b0 += 65535) {
@@ -323,12 +320,8 @@ extern "C" int ppde_cnn_backward_combine(const ppde_cnn_t* m, const ppde_potts_t
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
     const size_t smem = ((size_t)L * PPDE_Q + (size_t)C * BW_AS + BW_PB * 100 + J2) * sizeof(float) +
                         ((size_t)J2 + (P + 1) + J2 + P) * sizeof(int) + ((L + 15) & ~15);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(cnn_backward_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static SmemCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(cnn_backward_combine_kernel, smem, configured)) return (int)e;
     cnn_backward_combine_kernel<<<n, BW_NT, smem, st>>>(*m, *pm, aa, aa_stride, mkey, lamda, Gp, Gp_stride, gp_rows,
                                                        Epotts, G, G_stride, g_rows, E, fit);
     return launch_done();

@@ -767,7 +767,8 @@ struct IncParams {
     unsigned long long* mkey;           // [n, n_nets, 2C]
     uint8_t* r1mask;                    // pool [rows, n_nets, P, 32] or NULL
     const uint32_t* dmask;              // [n] dirty-block bits, NULL = every block is dirty (full evaluation into the pool)
-    unsigned long long* mkey_pool;      // optional pool [rows, n_nets, 2C]: the proposal row also gets mkey (delta backward)
+    unsigned long long* mkey_pool;      // optional pool [rows, n_nets, 2C]: RAW winner of every pool row (64-bit maximum over its block
+                                        // keys); read for the current row by the merge kernel, written for the proposal row
     unsigned long long* bkey;           // pool [rows, n_nets, NB, 2C]
     int32_t* btab;                      // pool [rows, NB]: the pool row whose slot holds block q of this row (keys AND relu-mask rows):
                                         // a proposal row only POINTS at the clean blocks of the current state instead of copying them
@@ -796,6 +797,15 @@ __device__ __forceinline__ uint32_t f32_ordered(float u) {
 }
 __device__ __forceinline__ float f32_unordered(uint32_t o) {
     return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+// chain-level winner key as the full forward kernel writes it (relu'd maximum << 32 | 0xFFFFFFFF - first arg-max) from the
+// RAW winner of a pool row (ordered raw accumulator maximum << 32 | 0xFFFFFFFF - first arg-max)
+__device__ __forceinline__ unsigned long long winner_from_raw(unsigned long long raw, float unscale, float bias) {
+    const float u = f32_unordered((uint32_t)(raw >> 32));
+    int pp = (int)(0xFFFFFFFFu - (uint32_t)(raw & 0xFFFFFFFFull));
+    float v = fmaf(u, unscale, bias);
+    if (!(v > 0.f)) { v = 0.f; pp = 0; }                    // relu; all-nonpositive column -> (0, position 0)
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)pp);
 }
 
 // Cluster-scope barrier traffic WITHOUT release/acquire fences.  What these barriers order is never generic-proxy global
@@ -950,25 +960,37 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
             mbar_wait(&dfull[buf], (uint32_t)((T >> 1) & 1));
             tc_fence_after();
             if (prof) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
+            // two blocks per tcgen05.wait::ld: the two 16-deep compare chains are independent (ILP) and the TMEM load latency is
+            // paid 4 times per tile instead of 8 (the serial per-block epilogue was at the tile period)
+            auto emit = [&](int s, float bu, int bi) {
+                const uint32_t e_s = __shfl_sync(0xffffffffu, ent, s);
+                const int r_s = __shfl_sync(0xffffffffu, row, s);
+                const int q = (int)(e_s & 15u);
+                const unsigned long long key = ((unsigned long long)f32_ordered(bu) << 32) |
+                                               (unsigned long long)(0xFFFFFFFFu - (unsigned)(16 * q + bi));
+                if (jok && !(prm.dbg & 1)) __stcg(prm.bkey + (size_t)r_s * row_keys + koff + (size_t)q * J2, key);
+            };
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < 8; s += 2) {
                 if (s < cnt) {                                              // warp-uniform
-                    uint32_t r[16];
-                    tmem_ld16(lane_addr + buf * 128 + 16 * s, r);
+                    uint32_t ra[16], rb[16];
+                    const bool two = s + 1 < cnt;
+                    tmem_ld16(lane_addr + buf * 128 + 16 * s, ra);
+                    if (two) tmem_ld16(lane_addr + buf * 128 + 16 * (s + 1), rb);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float bu = __uint_as_float(r[0]);
-                    int bi = 0;
+                    float bu0 = __uint_as_float(ra[0]), bu1 = two ? __uint_as_float(rb[0]) : 0.f;
+                    int bi0 = 0, bi1 = 0;
 #pragma unroll
                     for (int i = 1; i < 16; ++i) {
-                        const float u = __uint_as_float(r[i]);
-                        if (u > bu) { bu = u; bi = i; }
+                        const float u0 = __uint_as_float(ra[i]);
+                        if (u0 > bu0) { bu0 = u0; bi0 = i; }
+                        if (two) {
+                            const float u1 = __uint_as_float(rb[i]);
+                            if (u1 > bu1) { bu1 = u1; bi1 = i; }
+                        }
                     }
-                    const uint32_t e_s = __shfl_sync(0xffffffffu, ent, s);
-                    const int r_s = __shfl_sync(0xffffffffu, row, s);
-                    const int q = (int)(e_s & 15u);
-                    const unsigned long long key = ((unsigned long long)f32_ordered(bu) << 32) |
-                                                   (unsigned long long)(0xFFFFFFFFu - (unsigned)(16 * q + bi));
-                    if (jok && !(prm.dbg & 1)) __stcg(prm.bkey + (size_t)r_s * row_keys + koff + (size_t)q * J2, key);
+                    emit(s, bu0, bi0);
+                    if (two) emit(s + 1, bu1, bi1);
                 }
             }
             tc_fence_before();
@@ -1169,7 +1191,14 @@ __global__ void __launch_bounds__(128) cnn_dirty_kernel(int n, int L, int P, int
 // forward kernel writes.  Slot rule for a dirty block q of proposal row Y built from current row X: Y's own slot, unless
 // X's table points at it (X inherited that block from an earlier state that lived in Y) - then X's own slot, which neither
 // row references.  Only the two private rows of a chain and read-only fixed rows ever appear in its tables.
-__global__ void __launch_bounds__(256) cnn_inc_merge_kernel(const __grid_constant__ IncParams prm) {
+//
+// The pool `mkey_pool` keeps the RAW winner of every row (the 64-bit maximum over its block keys, before bias / relu).
+// With it the maximum over the clean blocks needs no reads: when the current row's winner sits in a clean block it IS that
+// maximum (the clean blocks' keys are the current row's keys, and the winner is the maximum over all of them), so
+//     winner(y) = max(winner(x), keys of the dirty blocks)                       - 1 + #dirty keys instead of NB,
+// and only a channel whose old winner sits in a dirty block (~15 % of them) rescans all NB keys.  max over u64 is
+// associative: the result is bit-identical to the full scan (tested against the full kernel).
+__global__ void __launch_bounds__(256, 4) cnn_inc_merge_kernel(const __grid_constant__ IncParams prm) {
     const int b = blockIdx.x;
     const int J2 = 2 * prm.m.C, NB = prm.NB, nets = prm.m.n_nets;
     const uint32_t all_blocks = (NB >= 32) ? 0xFFFFFFFFu : ((1u << NB) - 1u);
@@ -1177,6 +1206,7 @@ __global__ void __launch_bounds__(256) cnn_inc_merge_kernel(const __grid_constan
     const size_t row_keys = (size_t)nets * NB * J2;
     const int ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
     const int rx = prm.rows_x ? __ldg(prm.rows_x + b) : ry;
+    const bool have_old = prm.rows_x && prm.mkey_pool && !(prm.dbg & 8);   // raw winner of the current row available
     int slot[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -1189,23 +1219,24 @@ __global__ void __launch_bounds__(256) cnn_inc_merge_kernel(const __grid_constan
     for (int e = threadIdx.x; e < nets * J2; e += blockDim.x) {
         const int k = e / J2, j = e - k * J2;
         const size_t base = ((size_t)k * NB) * J2 + j;
+        unsigned long long best = 0ull;
+        uint32_t need = all_blocks;                         // blocks whose keys are read: all of them (old winner's block is dirty,
+                                                            // or a full evaluation), or only the dirty ones
+        if (have_old) {
+            const unsigned long long old = __ldcg(prm.mkey_pool + ((size_t)rx * nets + k) * J2 + j);
+            const uint32_t q_old = (0xFFFFFFFFu - (uint32_t)(old & 0xFFFFFFFFull)) >> 4;      // block of the old winner
+            if (!((mask >> q_old) & 1u)) { best = old; need = mask; }
+        }
         unsigned long long key[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-            key[q] = (q < NB) ? __ldcg(prm.bkey + (size_t)slot[q] * row_keys + base + (size_t)q * J2) : 0ull;
-        unsigned long long best = 0ull;
+            key[q] = (q < NB && ((need >> q) & 1u)) ? __ldcg(prm.bkey + (size_t)slot[q] * row_keys + base + (size_t)q * J2) : 0ull;
 #pragma unroll
         for (int q = 0; q < 16; ++q)
             if (q < NB) best = (key[q] > best) ? key[q] : best;
         const ppde_cnn_net_t& net = prm.m.net[k];
-        const float unscale = 1.f / (net.w1_scale * net.r1_scale);
-        const float u = f32_unordered((uint32_t)(best >> 32));
-        int pp = (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull));
-        float v = fmaf(u, unscale, __ldg(net.b1 + j));
-        if (!(v > 0.f)) { v = 0.f; pp = 0; }                // relu; all-nonpositive column -> (0, position 0)
-        const unsigned long long mk = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)pp);
-        prm.mkey[((size_t)b * nets + k) * J2 + j] = mk;
-        if (prm.mkey_pool) prm.mkey_pool[((size_t)ry * nets + k) * J2 + j] = mk;
+        prm.mkey[((size_t)b * nets + k) * J2 + j] = winner_from_raw(best, 1.f / (net.w1_scale * net.r1_scale), __ldg(net.b1 + j));
+        if (prm.mkey_pool) prm.mkey_pool[((size_t)ry * nets + k) * J2 + j] = best;
     }
     __syncthreads();                                        // every thread has read the current row's table (rx may equal ry never)
     if (threadIdx.x < NB) {
@@ -1353,7 +1384,7 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 // Entries (channel | side << 15; side 0 = y, 1 = x), counting-sorted by position and ordered by (side, channel) inside a
 // position: every winner sitting on a position of D0 (both sides), and both ends of every moved winner.  Same record layout
 // as cnn_winner_sort_kernel (start[P+1] | list[<= 2*J2]).
-__global__ void __launch_bounds__(128) cnn_winner_delta_kernel(int n_nets, int C, int P, int L, int aa_stride,
+__global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_constant__ ppde_cnn_t cm, int n_nets, int C, int P, int L, int aa_stride,
                                                                const uint8_t* __restrict__ aa_x, const uint8_t* __restrict__ aa_y,
                                                                const unsigned long long* __restrict__ mkey_y,
                                                                const unsigned long long* __restrict__ mkey_pool,
@@ -1382,8 +1413,10 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(int n_nets, int C
         const int pst = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
         return ((mj > 0.f) && pst >= 0 && pst < P) ? pst : -1;
     };
+    const float unscale = 1.f / (cm.net[k].w1_scale * cm.net[k].r1_scale);
     for (int j = threadIdx.x; j < J2; j += 128) {
-        const int py = decode(ky[j]), px = decode(kx[j]);
+        // the pool holds RAW winners (cnn_inc_merge_kernel): same bias / relu epilogue as for mkey
+        const int py = decode(ky[j]), px = decode(winner_from_raw(kx[j], unscale, __ldg(cm.net[k].b1 + j)));
         const bool moved = py != px;
         const int ey = (py >= 0 && (moved || sD0[py])) ? py : -1;
         const int ex = (px >= 0 && (moved || sD0[px])) ? px : -1;
@@ -2337,19 +2370,13 @@ static int choose_n_tile(int P, int* tiles) {
     return best_n;
 }
 
-static int g_forward_variant = -1;         // -1: read PPDE_TC_CTAS once (default 2); 1 or 2
-static long long* g_forward_prof = nullptr;  // device buffer [grid][16]; non-null selects the instrumented build of the kernel
-extern "C" int ppde_set_forward_profile(long long* buf) { g_forward_prof = buf; return 0; }
-extern "C" int ppde_set_forward_variant(int ctas) { g_forward_variant = (ctas == 1) ? 1 : 2; return 0; }
-
 extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
-                                   unsigned long long* mkey, uint8_t* r1mask, void* stream) {
+                                   unsigned long long* mkey, uint8_t* r1mask, const ppde_tune_t* tune, void* stream) {
     if (n <= 0) return 0;
+    if (!m || !aa || !mkey || aa_stride < m->L) return (int)cudaErrorInvalidValue;
     if (m->C > 256 || m->P < 1) return (int)cudaErrorInvalidValue;       // A must fit 256 TMEM columns
-    if (g_forward_variant < 0) {
-        const char* e = getenv("PPDE_TC_CTAS");
-        g_forward_variant = (e && e[0] == '1') ? 1 : 2;
-    }
+    const int forward_variant = (tune && tune->forward_ctas == 1) ? 1 : 2;
+    long long* const forward_prof = tune ? tune->prof : nullptr;
     tc::Params prm;
     prm.m = *m;
     prm.aa = aa;
@@ -2360,12 +2387,10 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     prm.prof = nullptr;
     prm.kpad = (m->C + 15) / 16 * 16;
     prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const int MT = (2 * m->C + 127) / 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_forward_variant == 2) {
+    if (forward_variant == 2) {
         prm.n_tile = tc::NT2;
         prm.tiles_per_chain = (m->P + tc::NT2 - 1) / tc::NT2;
         prm.MT = (MT + 1) / 2;                                             // channel-tile pairs
@@ -2382,15 +2407,11 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
             case 3: kern = tc::cnn_forward_tc2_kernel<3, false>; break;
             default: kern = tc::cnn_forward_tc2_kernel<4, false>; break;
         }
-        prm.prof = g_forward_prof;
-        if (g_forward_prof && prm.nch == 4) kern = tc::cnn_forward_tc2_kernel<4, true>;   // role-level cycle counters (tools/prof_fwd.py)
-        static size_t configured2[5] = {0, 0, 0, 0, 0};
-        const int cfg = (g_forward_prof && prm.nch == 4) ? 0 : prm.nch;
-        if (smem > configured2[cfg]) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            configured2[cfg] = smem;
-        }
+        prm.prof = forward_prof;
+        if (forward_prof && prm.nch == 4) kern = tc::cnn_forward_tc2_kernel<4, true>;   // role-level cycle counters (tools/prof_fwd.py)
+        static SmemCache configured2[5];
+        const int cfg = (forward_prof && prm.nch == 4) ? 0 : prm.nch;
+        if (cudaError_t e = ensure_dynamic_smem(kern, smem, configured2[cfg])) return (int)e;
         kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, st>>>(prm);
         return launch_done();
     }
@@ -2402,23 +2423,10 @@ extern "C" int ppde_cnn_forward_tc(const ppde_cnn_t* m, const uint8_t* aa, int32
     if (prm.ctas_per_combo > n) prm.ctas_per_combo = n;
     const size_t smem = (size_t)tc::NSLOT * tc::SLOT_BYTES + (size_t)100 * prm.nch * tc::KCH * sizeof(float) +
                         16 * sizeof(uint64_t) + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::cnn_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static SmemCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(tc::cnn_forward_tc_kernel, smem, configured)) return (int)e;
     tc::cnn_forward_tc_kernel<<<combos * prm.ctas_per_combo, tc::NTHREADS, smem, st>>>(prm);
     return launch_done();
-}
-
-// measurement aid (bench.py's per-kernel breakdown): which kernels the composite launchers run.
-// forward_inc: 1 = scan, 2 = tensor-core kernel, 4 = merge; backward_tc: 1 = winner sort, 2 = tensor-core kernel, 4 = combine.
-static int g_inc_parts = 7, g_bwd_parts = 7;
-extern "C" int ppde_set_profile_parts(int forward_inc_parts, int backward_parts) {
-    g_inc_parts = forward_inc_parts & 7;
-    g_bwd_parts = backward_parts & 7;
-    return 0;
 }
 
 extern "C" int ppde_cnn_dirty(const ppde_cnn_t* m, const uint8_t* aa_x, const uint8_t* aa_y, int32_t aa_stride, int32_t n,
@@ -2434,22 +2442,23 @@ extern "C" int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n) { return ((int64_t)n
 extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                                     unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask,
                                     unsigned long long* bkey, int32_t* btab, const int32_t* rows_x, const int32_t* rows_y,
-                                    int32_t row_base_y, unsigned long long* mkey_pool, void* ws, void* stream) {
+                                    int32_t row_base_y, unsigned long long* mkey_pool, void* ws, const ppde_tune_t* tune,
+                                    void* stream) {
     if (n <= 0) return 0;
+    if (!m || !aa || aa_stride < m->L) return (int)cudaErrorInvalidValue;
     const int NB = (m->P + 15) / 16;
     if (m->C > 256 || m->P < 1 || NB > 16 || !bkey || !btab || !mkey || !ws || (dmask && !rows_x)) return (int)cudaErrorInvalidValue;
+    const int inc_parts = (tune && (tune->parts & 7)) ? (tune->parts & 7) : 7;
     tc::IncParams prm;
     prm.m = *m; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey; prm.r1mask = r1mask; prm.dmask = dmask;
     prm.bkey = bkey; prm.btab = btab; prm.mkey_pool = mkey_pool;
     prm.rows_x = dmask ? rows_x : nullptr;   // full evaluation: nothing is read from a current row
     prm.rows_y = rows_y; prm.row_base_y = row_base_y; prm.NB = NB;
     prm.kpad = (m->C + 15) / 16 * 16;
-    { const char* e = getenv("PPDE_INC_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
-    prm.prof = g_forward_prof;
+    prm.dbg = tune ? tune->dbg : 0;
+    prm.prof = tune ? tune->prof : nullptr;
     const int nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const int MT = (2 * m->C + 127) / 128;
     prm.MT = (MT + 1) / 2;
     const int combos = m->n_nets * prm.MT;
@@ -2461,7 +2470,7 @@ extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int3
     int32_t* gtot = boff + n;
     uint32_t* blist = reinterpret_cast<uint32_t*>(gtot + 256);
     prm.boff = boff; prm.gtot = gtot; prm.blist = blist;
-    if (g_inc_parts & 1) {
+    if (inc_parts & 1) {
         tc::cnn_inc_scan_kernel<<<prm.ctas_per_combo, 1024, 0, (cudaStream_t)stream>>>(n, prm.ctas_per_combo, NB, dmask, boff, gtot, blist);
         int r0 = launch_done();
         if (r0) return r0;
@@ -2475,40 +2484,33 @@ extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int3
         case 3: kern = tc::cnn_forward_inc_kernel<3>; break;
         default: kern = tc::cnn_forward_inc_kernel<4>; break;
     }
-    static size_t configured[5] = {0, 0, 0, 0, 0};
-    if (smem > configured[nch]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured[nch] = smem;
-    }
-    if (g_inc_parts & 2) {
+    static SmemCache configured[5];
+    if (cudaError_t e = ensure_dynamic_smem(kern, smem, configured[nch])) return (int)e;
+    if (inc_parts & 2) {
         kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
         int r1 = launch_done();
         if (r1) return r1;
     }
-    if (g_inc_parts & 4) {
+    if (inc_parts & 4) {
         tc::cnn_inc_merge_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(prm);
         return launch_done();
     }
     return 0;
 }
 
-static long long* g_backward_prof = nullptr;
-extern "C" int ppde_set_backward_profile(long long* buf) { g_backward_prof = buf; return 0; }
-
 extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                                          int32_t n, const unsigned long long* mkey, float lamda,
                                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                                          float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
                                          const int32_t* mask_rows, int32_t mask_row_base, const int32_t* btab, float* scratch,
-                                         void* stream);
+                                         const ppde_tune_t* tune, void* stream);
 extern "C" int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
                                     int32_t n, const unsigned long long* mkey, float lamda,
                                     const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                                     float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
-                                    float* scratch, void* stream) {
+                                    float* scratch, const ppde_tune_t* tune, void* stream) {
     return ppde_cnn_backward_tc_rows(m, pm, aa, aa_stride, n, mkey, lamda, Gp, Gp_stride, gp_rows, G, G_stride, g_rows, r1mask,
-                                     nullptr, 0, nullptr, scratch, stream);
+                                     nullptr, 0, nullptr, scratch, tune, stream);
 }
 struct BwdDelta {                 // delta backward: gradient of the proposal = gradient of the current state + change
     const uint8_t* aa_x;          // current states [n, aa_stride]
@@ -2521,10 +2523,12 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
                            int32_t n, const unsigned long long* mkey, float lamda,
                            const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                            float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
-                           const int32_t* mask_rows, int32_t mask_row_base, const int32_t* btab, float* scratch, void* stream,
-                           const BwdDelta* dl) {
+                           const int32_t* mask_rows, int32_t mask_row_base, const int32_t* btab, float* scratch,
+                           const ppde_tune_t* tune, void* stream, const BwdDelta* dl) {
     if (n <= 0) return 0;
+    if (!m || !pm || !aa || !mkey || !G || aa_stride < m->L || (G_stride & 3) || (Gp && (Gp_stride & 3))) return (int)cudaErrorInvalidValue;
     if (m->C > 256 || m->P < 1 || !scratch || !r1mask) return (int)cudaErrorInvalidValue;
+    const int bwd_parts = (tune && (tune->parts & 7)) ? (tune->parts & 7) : 7;
     tc::BwdParams prm;
     prm.m = *m; prm.pm = *pm; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey;
     prm.Gc = scratch;
@@ -2533,21 +2537,17 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     prm.mask_row_base = mask_row_base;
     prm.mask_rows_x = dl ? dl->rows_x : nullptr;
     prm.btab = btab; prm.NB = (m->P + 15) / 16;
-    { const char* e = getenv("PPDE_BWD_DEBUG"); prm.dbg = e ? atoi(e) : 0; }
+    prm.dbg = tune ? tune->dbg : 0;
     prm.tiles_per_chain = (m->P + tc::BW_NT - 1) / tc::BW_NT;
     prm.kpad = (m->C + 15) / 16 * 16;
     prm.nch = (prm.kpad + tc::KCH - 1) / tc::KCH;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     prm.ctas_per_net = sms / m->n_nets;
     if (prm.ctas_per_net < 1) prm.ctas_per_net = 1;
     if (prm.ctas_per_net > n) prm.ctas_per_net = n;
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
-    // delta mode, compact records (default; PPDE_BWD_DELTA_COMPACT=0 keeps one column per position): npos | pos | start | list
-    static int compact_env = -1;
-    if (compact_env < 0) { const char* e = getenv("PPDE_BWD_DELTA_COMPACT"); compact_env = (e && e[0] == '0') ? 0 : 1; }
-    const bool compact = dl && compact_env;
+    // delta mode, compact records (default; tune->delta_layout = 1 keeps one column per position): npos | pos | start | list
+    const bool compact = dl && !(tune && tune->delta_layout == 1);
     const int rec = compact ? ((2 * P + 2 + 2 * J2 + 7) & ~7) : (((P + 1) + 2 * J2 + 7) & ~7);
     const size_t smem_fixed = 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
                               8 + 32 * sizeof(uint64_t);
@@ -2559,39 +2559,36 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     }
     prm.nrec = nrec;
     const size_t smem = smem_fixed + (size_t)nrec * rec * sizeof(uint16_t);
-    const bool prof = g_backward_prof != nullptr;
+    long long* const backward_prof = tune ? tune->prof : nullptr;
+    const bool prof = backward_prof != nullptr;
     void (*bkern)(tc::BwdParams) =
         compact ? (prof ? tc::cnn_backward_delta_kernel<true> : tc::cnn_backward_delta_kernel<false>)
                 : (dl ? (prof ? tc::cnn_backward_tc_kernel<true, true> : tc::cnn_backward_tc_kernel<false, true>)
                       : (prof ? tc::cnn_backward_tc_kernel<true, false> : tc::cnn_backward_tc_kernel<false, false>));
-    prm.prof = prof ? g_backward_prof : nullptr;
-    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+    prm.prof = backward_prof;
+    static SmemCache configured[6];
     const int cfg = (compact ? 4 : (dl ? 2 : 0)) + (prof ? 1 : 0);
-    if (smem > configured[cfg]) {
-        cudaError_t e = cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured[cfg] = smem;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(bkern, smem, configured[cfg])) return (int)e;
     cudaStream_t st = (cudaStream_t)stream;
     // winner records live behind the per-net gradient scratch: [n_nets*n*20L floats][n*n_nets*rec uint16]
     uint16_t* wl = reinterpret_cast<uint16_t*>(scratch + (size_t)m->n_nets * n * L * PPDE_Q);
     prm.wl = wl;
     prm.rec = rec;
-    if (g_bwd_parts & 1) {
+    if (bwd_parts & 1) {
         if (dl)
             tc::cnn_winner_delta_kernel<<<n * m->n_nets, 128, ((P + 1) + 2 * P + 4 * J2) * sizeof(int), st>>>(
-                m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, compact ? 1 : 0);
+                *m, m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, compact ? 1 : 0);
         else
             tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
         int r0 = launch_done();
         if (r0) return r0;
     }
-    if (g_bwd_parts & 2) {
+    if (bwd_parts & 2) {
         bkern<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
         int r = launch_done();
         if (r) return r;
     }
-    if (g_bwd_parts & 4) {
+    if (bwd_parts & 4) {
         if (dl)
             tc::cnn_grad_combine_delta_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
                                                                  Gp, Gp_stride, G, G_stride, dl->rows_x, dl->rows_y);
@@ -2608,18 +2605,19 @@ extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t
                                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                                          float* G, int64_t G_stride, const int32_t* g_rows, const uint8_t* r1mask,
                                          const int32_t* mask_rows, int32_t mask_row_base, const int32_t* btab, float* scratch,
-                                         void* stream) {
+                                         const ppde_tune_t* tune, void* stream) {
     return backward_launch(m, pm, aa, aa_stride, n, mkey, lamda, Gp, Gp_stride, gp_rows, G, G_stride, g_rows, r1mask, mask_rows,
-                           mask_row_base, btab, scratch, stream, nullptr);
+                           mask_row_base, btab, scratch, tune, stream, nullptr);
 }
 
 extern "C" int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa_x, const uint8_t* aa_y,
                                        int32_t aa_stride, int32_t n, const unsigned long long* mkey_y,
                                        const unsigned long long* mkey_pool, float lamda, const float* Gp, int64_t Gp_stride,
                                        float* G, int64_t G_stride, const int32_t* rows_x, const int32_t* rows_y,
-                                       const uint8_t* r1mask, const int32_t* btab, float* scratch, void* stream) {
+                                       const uint8_t* r1mask, const int32_t* btab, float* scratch, const ppde_tune_t* tune,
+                                       void* stream) {
     if (!aa_x || !mkey_pool || !rows_x || !rows_y || !G) return (int)cudaErrorInvalidValue;
     BwdDelta dl{aa_x, mkey_pool, rows_x, rows_y};
     return backward_launch(m, pm, aa_y, aa_stride, n, mkey_y, lamda, Gp, Gp_stride, rows_y, G, G_stride, rows_y, r1mask, rows_y, 0,
-                           btab, scratch, stream, &dl);
+                           btab, scratch, tune, stream, &dl);
 }

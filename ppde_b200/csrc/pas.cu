@@ -15,6 +15,10 @@ namespace ppde {
 
 __device__ __forceinline__ int y_row(int row_cur, int b, int n) { return row_cur == b ? n + b : b; }
 
+// mutation_mask (ppde/utils.py:17-28) in index form: at or above the edit-distance threshold the only legal target at position
+// i is "revert to the wild type", and only where the chain differs from it.  Returns the single allowed residue or -1.
+__device__ __forceinline__ int revert_only_target(uint8_t cur, uint8_t wt) { return (cur != wt) ? (int)wt : -1; }
+
 // softmax -> clamp -> renormalise statistics of one logit vector held in shared memory.
 // On return sP[j] = clamp(exp(l_j - m1) / s2) and the function returns s3 = sum_j sP[j].
 // (utils.py:106-111: logits - logsumexp, softmax, clamp_probs; Categorical.__init__: p / p.sum())
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
             if (i < lo || i > hi) {
                 l.x = l.y = l.z = l.w = -INFINITY;
             } else if (at_thr) {
-                const int w = (sAA[i] != sWT[i]) ? (int)sWT[i] : -1;   // the only legal target: revert to WT
+                const int w = revert_only_target(sAA[i], sWT[i]);      // the only legal target: revert to WT
                 if (a0 + 0 != w) l.x = -INFINITY;
                 if (a0 + 1 != w) l.y = -INFINITY;
                 if (a0 + 2 != w) l.z = -INFINITY;
@@ -267,6 +271,41 @@ __global__ void __launch_bounds__(NT) pas_reverse_accept_kernel(ppde_potts_t m, 
     }
 }
 
+// Known-answer entry point for the proposal arithmetic (tests only; not on the sampler's path): the SAME device functions the
+// two kernels above use, driven by caller-provided logits.  Per row b:
+//   dist[b]      = edit distance of aa[b] to wt                         (mut_distance, utils.py:5-14)
+//   mask[b, e]   = 1 where mutation_mask masks entry e = i*20 + a       (utils.py:17-28, before `mask[~flag] = False`)
+//   probs[b, :]  = clamp(softmax(logits[b] - LSE)) / sum               (safe_logits_to_probs + Categorical.__init__)
+//   logp[b]      = log(clamp(probs[b, idx[b]]))                         (Categorical.log_prob)
+template <int NT>
+__global__ void __launch_bounds__(NT) pas_kat_kernel(const uint8_t* __restrict__ aa, int aa_stride, const uint8_t* __restrict__ wt, int L,
+                                                     const float* __restrict__ logits, const int32_t* __restrict__ idx,
+                                                     int32_t* __restrict__ dist, uint8_t* __restrict__ mask,
+                                                     float* __restrict__ probs, float* __restrict__ logp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sP = reinterpret_cast<float*>(smem_raw);
+    __shared__ float red[33];
+    __shared__ int redi[33];
+    const int b = blockIdx.x, NE = L * PPDE_Q, n4 = NE / 4;
+    const uint8_t* a = aa + (int64_t)b * aa_stride;
+    int dpart = 0;
+    for (int i = threadIdx.x; i < L; i += NT) dpart += (a[i] != wt[i]);
+    const int d = block_sum_int<NT>(dpart, redi);
+    if (threadIdx.x == 0 && dist) dist[b] = d;
+    if (mask)
+        for (int e = threadIdx.x; e < NE; e += NT) {
+            const int i = e / PPDE_Q, r = e - i * PPDE_Q;
+            mask[(int64_t)b * NE + e] = (r != revert_only_target(a[i], wt[i])) ? 1 : 0;
+        }
+    if (!logits) return;
+    float lmax = -INFINITY;
+    for (int e = threadIdx.x; e < NE; e += NT) { const float l = logits[(int64_t)b * NE + e]; sP[e] = l; lmax = fmaxf(lmax, l); }
+    __syncthreads();
+    const float s3 = softmax_clamp_inplace<NT>(sP, n4, lmax, red);
+    for (int e = threadIdx.x; e < NE; e += NT) probs[(int64_t)b * NE + e] = sP[e] / s3;
+    if (threadIdx.x == 0 && logp && idx) logp[b] = logf(clamp_prob(sP[idx[b]] / s3));
+}
+
 }  // namespace ppde
 
 using namespace ppde;
@@ -278,12 +317,8 @@ extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, c
     if (c->n <= 0) return 0;
     if (p->S < 1 || p->S > PPDE_MAX_S) return (int)cudaErrorInvalidValue;
     size_t smem = pas_smem(c->L);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pas_propose_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static SmemCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(pas_propose_kernel<128>, smem, configured)) return (int)e;
     pas_propose_kernel<128><<<c->n, 128, smem, (cudaStream_t)stream>>>(*m, *c, *p);
     return launch_done();
 }
@@ -293,12 +328,19 @@ extern "C" int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_
     if (c->n <= 0) return 0;
     if (p->S < 1 || p->S > PPDE_MAX_S) return (int)cudaErrorInvalidValue;
     size_t smem = pas_smem(c->L);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pas_reverse_accept_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static SmemCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(pas_reverse_accept_kernel<128>, smem, configured)) return (int)e;
     pas_reverse_accept_kernel<128><<<c->n, 128, smem, (cudaStream_t)stream>>>(*m, *c, *p);
+    return launch_done();
+}
+
+extern "C" int ppde_pas_kat(const uint8_t* aa, int32_t aa_stride, const uint8_t* wt, int32_t n, int32_t L, const float* logits,
+                            const int32_t* idx, int32_t* dist, uint8_t* mask, float* probs, float* logp, void* stream) {
+    if (n <= 0) return 0;
+    if (!aa || !wt || L <= 0 || aa_stride < L || (logits && !probs)) return (int)cudaErrorInvalidValue;
+    const size_t smem = (size_t)L * PPDE_Q * sizeof(float);
+    static SmemCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(pas_kat_kernel<128>, smem, configured)) return (int)e;
+    pas_kat_kernel<128><<<n, 128, smem, (cudaStream_t)stream>>>(aa, aa_stride, wt, L, logits, idx, dist, mask, probs, logp);
     return launch_done();
 }

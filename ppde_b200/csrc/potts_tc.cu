@@ -332,18 +332,12 @@ extern "C" int ppde_potts_dense_full(const ppde_potts_t* m, const void* Jt, floa
     prm.NTc = (n + tc::PD_N - 1) / tc::PD_N;
     const int klast = m->D - (prm.KC - 1) * tc::KCH;
     prm.last_ksteps = (klast + 15) / 16;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const int tiles = prm.MT * prm.NTc;
     const int grid = tiles < sms ? tiles : sms;
     const size_t smem = 1024 + (size_t)tc::PD_STAGES * tc::PD_STAGE_BYTES + 32 * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::potts_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static SmemCache configured;
+    if (cudaError_t e = ensure_dynamic_smem(tc::potts_dense_tc_kernel, smem, configured)) return (int)e;
     cudaStream_t st = (cudaStream_t)stream;
     tc::potts_dense_tc_kernel<<<grid, tc::PD_NTHREADS, smem, st>>>(prm);
     int r = launch_done();

@@ -79,16 +79,106 @@ def owner_of(chain, n, world_size):
     raise ValueError("chain outside the population")
 
 
-def population_report(energy, fitness, oracle_fit, accepted, edit_dist, seq_hash=None):
-    """The reference's log_every report (ppde.py:158-168) from whole-population vectors (host numpy),
-    plus diversity (% unique sequences, scripts/make_figures.py:38-49) when hashes are given."""
-    rep = {
-        "energy_q": np.quantile(energy, [0.5, 0.9]),
-        "fitness_q": np.quantile(fitness, [0.5, 0.9]),
-        "oracle_q": np.quantile(oracle_fit, [0.5, 0.9]) if oracle_fit is not None else None,
-        "accepted": float(np.sum(accepted)),
-        "mean_dist": float(np.mean(edit_dist)),
-    }
-    if seq_hash is not None:
-        rep["diversity_pct"] = len(np.unique(seq_hash)) / len(seq_hash) * 100.0
-    return rep
+class PopulationReporter:
+    """The reference's log_every report (ppde.py:155-170) plus the population metrics of scripts/make_figures.py:29-49 and a
+    torch.topk of the energies, computed ON THE DEVICE: per-rank kernels, NCCL all-gathers / one all-reduce of the shards
+    (the only collectives of a run), exact selection / counting kernels on the gathered vectors, and ONE device->host copy
+    of the finished numbers.  Nothing here touches the host except that last copy.
+
+    Collectives per report: all-gather of [3, n/ws] floats (energy, predicted fitness, oracle fitness), all-gather of the
+    residue states u8 [n/ws, stride] (diversity), all-reduce of 4 int64 (accepted, sum dist, sum dist^2, n), all-gathers
+    of the k local top-k candidates (values, global chain ids, sequences).
+    """
+    Q = (0.5, 0.9)
+
+    def __init__(self, lib, device, n_global, L, aa_stride, wt_dev, top_k=16):
+        import ctypes as C
+        self.C = C
+        self.lib, self.dev = lib, device
+        self.n, self.L, self.stride, self.wt = int(n_global), int(L), int(aa_stride), wt_dev
+        _, ws = world()
+        sizes = shard_sizes(self.n, ws)
+        self.k = max(0, min(int(top_k), min(sizes), 1024))
+        self.q = torch.tensor(self.Q, dtype=torch.float64, device=device)
+        entries = int(lib.ppde_unique_count_table_entries(self.n))
+        self.table = torch.empty(entries, dtype=torch.int32, device=device)
+        self.out = torch.zeros(16, dtype=torch.float64, device=device)       # quantiles 0..5 | sums 6..9 | unique 10
+        self.sums = torch.zeros(4, dtype=torch.int64, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def _p(self, t):
+        return self.C.c_void_p(t.data_ptr()) if t is not None else self.C.c_void_p(0)
+
+    def _st(self):
+        return self.C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _check(self, code, what):
+        if code != 0:
+            raise RuntimeError(f"{what} failed with cudaError_t {code}")
+
+    def report(self, energy, fitness, oracle_fit, accept, aa, chain_lo, want_topk=True):
+        """energy / fitness / oracle_fit: float32 [n_local] (oracle_fit may be None); accept: uint8 [n_local] or None;
+        aa: uint8 [n_local, stride] current states; chain_lo: global id of local chain 0.  Returns a dict of host numbers
+        (and, with want_topk, 'topk_energy' / 'topk_chain' / 'topk_aa' as host arrays)."""
+        lib, dev, st = self.lib, self.dev, self._st()
+        nl = int(energy.shape[0])
+        # -- per-rank kernels ----------------------------------------------------------------------
+        dist_l = torch.empty(nl, dtype=torch.int32, device=dev)
+        self._check(lib.ppde_population_metrics(self._p(aa), self.stride, nl, self.L, self._p(self.wt), self._p(dist_l),
+                                                self._p(None), st), "population_metrics")
+        self._check(lib.ppde_population_sums(self._p(accept), self._p(dist_l), nl, self._p(self.sums), st), "population_sums")
+        packed = torch.stack([energy.float(), fitness.float(),
+                              oracle_fit.float() if oracle_fit is not None else torch.zeros_like(energy, dtype=torch.float32)])
+        # -- the collectives -----------------------------------------------------------------------
+        allv = all_gather_cat(packed, self.n, dim=1).contiguous()             # [3, n]
+        all_aa = all_gather_cat(aa, self.n)                                   # [n, stride]
+        all_reduce_sum(self.sums)
+        # -- exact order statistics / counts on the gathered vectors ---------------------------------
+        for j in range(3 if oracle_fit is not None else 2):
+            self._check(lib.ppde_quantiles(self._p(allv[j]), self.n, self._p(self.q), 2,
+                                           self.C.c_void_p(self.out.data_ptr() + 16 * j), st), "quantiles")
+        self._check(lib.ppde_unique_count(self._p(all_aa), self.stride, self.n, self.L, self._p(self.table),
+                                          self.table.numel(), self._p(self.count), st), "unique_count")
+        self.out[6:10] = self.sums.to(torch.float64)
+        self.out[10] = self.count.to(torch.float64)[0]
+        top = None
+        if want_topk and self.k > 0:
+            k = self.k
+            vals = torch.empty(k, dtype=torch.float32, device=dev)
+            ids = torch.empty(k, dtype=torch.int64, device=dev)
+            seqs = torch.empty(k, self.stride, dtype=torch.uint8, device=dev)
+            self._check(lib.ppde_topk(self._p(energy), nl, k, int(chain_lo), self._p(None), self._p(vals), self._p(ids), st), "topk")
+            self._check(lib.ppde_gather_rows(self._p(aa), self.stride, self._p(ids), k, int(chain_lo), self._p(seqs), st), "gather_rows")
+            _, ws = world()
+            if ws > 1:
+                cv, ci, cs = gather_equal(vals), gather_equal(ids), gather_equal(seqs)     # [ws*k] candidates, rank-major
+                pos = torch.empty(k, dtype=torch.int64, device=dev)
+                fv = torch.empty(k, dtype=torch.float32, device=dev)
+                self._check(lib.ppde_topk(self._p(cv), ws * k, k, 0, self._p(None), self._p(fv), self._p(pos), st), "topk(final)")
+                vals, ids, seqs = fv, ci[pos], cs[pos]
+            top = (vals, ids, seqs)
+        host = self.out.cpu().numpy()                                           # the one D2H of the report
+        n = float(host[9])
+        mean_d = host[7] / n
+        rep = {
+            "energy_q": host[0:2].copy(), "fitness_q": host[2:4].copy(),
+            "oracle_q": host[4:6].copy() if oracle_fit is not None else None,
+            "accepted": float(host[6]), "mean_dist": float(mean_d),
+            "std_dist": float(np.sqrt(max(host[8] / n - mean_d * mean_d, 0.0))),      # n_hops: population std (np.std)
+            "unique": int(host[10]), "diversity_pct": float(host[10]) / n * 100.0,
+        }
+        if top is not None:
+            rep["topk_energy"] = top[0].cpu().numpy()
+            rep["topk_chain"] = top[1].cpu().numpy()
+            rep["topk_aa"] = top[2][:, :self.L].cpu().numpy()
+        return rep
+
+
+def gather_equal(t):
+    """all-gather of equally sized shards, concatenated along dim 0 (rank-major)."""
+    _, ws = world()
+    if ws == 1:
+        return t
+    out = torch.empty((ws * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous())
+    return out

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ChainsT, CnnT, PasParamsT, PottsT
+from ._lib import ChainsT, CnnT, PasParamsT, PottsT, TuneT
 
 Q = 20
 INT32_MAX = int(np.iinfo(np.int32).max)
@@ -33,6 +33,50 @@ def _require_cuda(device):
 
 def aa_stride_for(L):
     return (L + 15) // 16 * 16
+
+
+class Workspace:
+    """Scratch buffers of the CNN kernels (winner keys, per-net gradient scratch + winner records, dirty-block lists, relu
+    masks).  One per OWNER: the model has one for stand-alone evaluations (`PoEModel.energy`), every ChainEngine has its
+    own, allocated once for the engine's n and kept alive with it - raw pointers into these buffers are baked into the
+    engine's captured CUDA graphs, so they must never be reallocated or shared with a differently sized user."""
+
+    def __init__(self, model):
+        self.m = model
+        self._buf = {}
+
+    def _get(self, name, need, dtype):
+        t = self._buf.get(name)
+        if t is None or t.numel() < need:
+            t = torch.empty(need, dtype=dtype, device=self.m.device)
+            self._buf[name] = t
+        return t
+
+    def grad_scratch(self, n):
+        m = self.m
+        rec = (2 * m.P + 2 + 4 * m.C + 7) // 8 * 8                    # winner records (uint16) behind the floats (compact delta layout is the larger)
+        return self._get("gscratch", m.n_nets * n * m.NE + (n * m.n_nets * rec + 1) // 2, torch.float32)
+
+    def inc_ws(self, n):
+        return self._get("inc_ws", int(self.m.lib.ppde_cnn_forward_inc_ws_bytes(n)), torch.uint8)
+
+    def r1mask(self, n):
+        m = self.m
+        return self._get("r1mask", n * m.n_nets * m.P * 32, torch.uint8)
+
+    def mkey(self, n):
+        m = self.m
+        return self._get("mkey", n * m.n_nets * 2 * m.C, torch.int64)
+
+
+def _tune(parts=0, base=None):
+    """ppde_tune_t for one call (None = production defaults)."""
+    if not parts and base is None:
+        return None
+    t = TuneT(parts=int(parts))
+    if base is not None:
+        t.forward_ctas, t.delta_layout, t.dbg, t.prof = base.forward_ctas, base.delta_layout, base.dbg, base.prof
+    return C.byref(t)
 
 
 class PoEModel:
@@ -134,7 +178,13 @@ class PoEModel:
                 adjmax = float((dvec.abs()[:, None] * W1.abs()).sum(0).max())      # bound on |sum_j d_j W1[j,c]|
                 cn.w0_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(float(W0.abs().max()), 1e-30)))))
                 cn.adj_scale = 2.0 ** (13 - int(np.ceil(np.log2(max(adjmax, 1e-30)))))
-        self._mkey = None
+        self.ws = Workspace(self)             # scratch of stand-alone evaluations (engines own theirs)
+        # A/B switches of the tensor-core kernels, per call (ppde_tune_t): PPDE_TC_CTAS=1 = 1-CTA forward kernel,
+        # PPDE_BWD_DELTA_COMPACT=0 = one column per position in the delta backward
+        self.tune = None
+        if os.environ.get("PPDE_TC_CTAS", "2") == "1" or os.environ.get("PPDE_BWD_DELTA_COMPACT", "1") == "0":
+            self.tune = TuneT(forward_ctas=1 if os.environ.get("PPDE_TC_CTAS", "2") == "1" else 0,
+                              delta_layout=1 if os.environ.get("PPDE_BWD_DELTA_COMPACT", "1") == "0" else 0)
         # CNN forward implementation: tcgen05 tensor-core kernel (needs the W1 tile in 256 TMEM columns,
         # i.e. C <= 256) or the fp32 SIMT kernel.  PPDE_CNN_FORWARD=simt forces the latter (A/B tests).
         want = os.environ.get("PPDE_CNN_FORWARD", "tc")
@@ -155,17 +205,19 @@ class PoEModel:
         self.potts_full_impl = os.environ.get("PPDE_POTTS_FULL", "dense")
         self.dense_min = int(os.environ.get("PPDE_POTTS_DENSE_MIN", "512"))
 
-    def cnn_forward(self, aa, n, mk, st):
+    def cnn_forward(self, aa, n, mk, st, ws=None):
+        ws = ws or self.ws
         if self.cnn_forward_impl == "tc":
-            rm = _ptr(self.r1mask(n)) if self.cnn_backward_impl == "tc" else C.c_void_p(0)
-            _lib.check(self.lib.ppde_cnn_forward_tc(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), rm, st),
-                       "cnn_forward_tc")
+            rm = _ptr(ws.r1mask(n)) if self.cnn_backward_impl == "tc" else C.c_void_p(0)
+            _lib.check(self.lib.ppde_cnn_forward_tc(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), rm,
+                                                    _tune(0, self.tune), st), "cnn_forward_tc")
         else:
             _lib.check(self.lib.ppde_cnn_forward(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), st),
                        "cnn_forward")
 
-    def cnn_backward_combine(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, st):
+    def cnn_backward_combine(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, st, ws=None):
         """fit / E from the winners, then (if g_ptr) the gradient rows G = Gp(window) + lamda/n_nets * sum_k dfit_k/dx."""
+        ws = ws or self.ws
         lib = self.lib
         null = C.c_void_p(0)
         if self.cnn_backward_impl == "tc" and self.cnn_forward_impl == "tc" and g_ptr:
@@ -174,23 +226,27 @@ class PoEModel:
                 null, self.D, null, ep_ptr, null, self.NE, null, _ptr(E), _ptr(fit), st), "cnn_fit")
             _lib.check(lib.ppde_cnn_backward_tc(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
-                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(self.r1mask(n)), _ptr(self.grad_scratch(n)), st),
-                "cnn_backward_tc")
+                gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(ws.r1mask(n)), _ptr(ws.grad_scratch(n)),
+                _tune(0, self.tune), st), "cnn_backward_tc")
         else:
             _lib.check(lib.ppde_cnn_backward_combine(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
                 gp_ptr, self.D, gp_rows, ep_ptr, g_ptr, self.NE, g_rows, _ptr(E), _ptr(fit), st), "cnn_backward_combine")
 
     # -- CNN with the block-key / relu-mask POOLS of a chain engine (incremental path) -----------------
-    def cnn_forward_pool(self, aa, n, mk, bkey, r1pool, dmask, rows_x, rows_y, row_base_y, st, mkpool=None, btab=None):
+    def cnn_forward_pool(self, aa, n, mk, bkey, r1pool, dmask, rows_x, rows_y, row_base_y, st, mkpool=None, btab=None,
+                         ws=None, parts=0):
         """Forward of n states into pool rows rows_y (None: row_base_y + b).  dmask None: every block is evaluated;
-        otherwise only the dirty blocks, the others come from rows_x (ppde_cnn_forward_inc)."""
+        otherwise only the dirty blocks, the others come from rows_x (ppde_cnn_forward_inc).  mkpool: the pool of RAW row
+        winners (lets the merge read 1 + #dirty keys per channel instead of all NB)."""
+        ws = ws or self.ws
         _lib.check(self.lib.ppde_cnn_forward_inc(C.byref(self.cnn), _ptr(aa), self.aa_stride, n, _ptr(mk), _ptr(r1pool),
                                                  _ptr(dmask), _ptr(bkey), _ptr(btab), _ptr(rows_x), _ptr(rows_y), int(row_base_y),
-                                                 _ptr(mkpool), _ptr(self.inc_ws(n)), st), "cnn_forward_inc")
+                                                 _ptr(mkpool), _ptr(ws.inc_ws(n)), _tune(parts, self.tune), st), "cnn_forward_inc")
 
     def cnn_backward_pool(self, aa, n, mk, gp_ptr, gp_rows, ep_ptr, g_ptr, g_rows, E, fit, r1pool, mask_rows, mask_row_base, st,
-                          do_fit=True, do_grad=True, btab=None):
+                          do_fit=True, do_grad=True, btab=None, ws=None, parts=0):
+        ws = ws or self.ws
         lib = self.lib
         null = C.c_void_p(0)
         if do_fit:
@@ -201,11 +257,12 @@ class PoEModel:
             _lib.check(lib.ppde_cnn_backward_tc_rows(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa), self.aa_stride, n, _ptr(mk), self.lamda,
                 gp_ptr, self.D, gp_rows, g_ptr, self.NE, g_rows, _ptr(r1pool), _ptr(mask_rows), int(mask_row_base), _ptr(btab),
-                _ptr(self.grad_scratch(n)), st), "cnn_backward_tc_rows")
+                _ptr(ws.grad_scratch(n)), _tune(parts, self.tune), st), "cnn_backward_tc_rows")
 
     def cnn_backward_delta(self, aa_x, aa_y, n, mk, mkpool, gp_ptr, ep_ptr, g_ptr, rows_x, rows_y, E, fit, r1pool, st,
-                           do_fit=True, do_grad=True, btab=None):
+                           do_fit=True, do_grad=True, btab=None, ws=None, parts=0):
         """fit / E of the proposals, and their gradient rows as  G[rows_y] = G[rows_x] + change  (ppde_cnn_backward_delta)."""
+        ws = ws or self.ws
         lib = self.lib
         null = C.c_void_p(0)
         if do_fit:
@@ -216,37 +273,11 @@ class PoEModel:
             _lib.check(lib.ppde_cnn_backward_delta(
                 C.byref(self.cnn), C.byref(self.potts), _ptr(aa_x), _ptr(aa_y), self.aa_stride, n, _ptr(mk), _ptr(mkpool),
                 self.lamda, gp_ptr, self.D, g_ptr, self.NE, _ptr(rows_x), _ptr(rows_y), _ptr(r1pool), _ptr(btab),
-                _ptr(self.grad_scratch(n)), st), "cnn_backward_delta")
-
-    # -- scratch ------------------------------------------------------------------------------
-    def grad_scratch(self, n):
-        rec = (2 * self.P + 2 + 4 * self.C + 7) // 8 * 8                    # winner records (uint16) behind the floats (compact delta layout is the larger)
-        need = self.n_nets * n * self.NE + (n * self.n_nets * rec + 1) // 2
-        if getattr(self, "_gscratch", None) is None or self._gscratch.numel() < need:
-            self._gscratch = torch.empty(need, dtype=torch.float32, device=self.device)
-        return self._gscratch
-
-    def inc_ws(self, n):
-        need = int(self.lib.ppde_cnn_forward_inc_ws_bytes(n))
-        if getattr(self, "_inc_ws", None) is None or self._inc_ws.numel() < need:
-            self._inc_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._inc_ws
-
-    def r1mask(self, n):
-        need = n * self.n_nets * self.P * 32
-        if getattr(self, "_r1mask", None) is None or self._r1mask.numel() < need:
-            self._r1mask = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._r1mask
-
-    def mkey(self, n):
-        need = n * self.n_nets * 2 * self.C
-        if self._mkey is None or self._mkey.numel() < need:
-            self._mkey = torch.empty(need, dtype=torch.int64, device=self.device)
-        return self._mkey
+                _ptr(ws.grad_scratch(n)), _tune(parts, self.tune), st), "cnn_backward_delta")
 
     # -- full evaluation ------------------------------------------------------------------------
     def evaluate_into(self, aa, n, G, g_row0, Gp, gp_row0, E, fit, Epotts, want_grad=True, bkey=None, r1pool=None, mkpool=None,
-                      btab=None):
+                      btab=None, ws=None):
         """Energy (+ gradient field) of n states `aa` [n, aa_stride] written into pool rows
         g_row0.. / gp_row0.. (contiguous). E, fit, Epotts: float tensors [n].
         bkey / r1pool: the engine's block-key and relu-mask pools (rows g_row0.. are filled too)."""
@@ -256,16 +287,17 @@ class PoEModel:
         if self.has_potts:
             gp_ptr, ep_ptr = C.c_void_p(Gp.data_ptr() + gp_row0 * self.D * 4), _ptr(Epotts)
             self.potts_full(aa, n, gp_ptr, ep_ptr, st)
-        mk = self.mkey(n)
+        ws = ws or self.ws
+        mk = ws.mkey(n)
         g_ptr = C.c_void_p(G.data_ptr() + g_row0 * self.NE * 4) if want_grad else C.c_void_p(0)
         if bkey is not None and want_grad:
-            self.cnn_forward_pool(aa, n, mk, bkey, r1pool, None, None, None, g_row0, st, mkpool=mkpool, btab=btab)
+            self.cnn_forward_pool(aa, n, mk, bkey, r1pool, None, None, None, g_row0, st, mkpool=mkpool, btab=btab, ws=ws)
             self.cnn_backward_pool(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr, C.c_void_p(0), E, fit,
-                                   r1pool, None, g_row0, st, btab=btab)
+                                   r1pool, None, g_row0, st, btab=btab, ws=ws)
             return
-        self.cnn_forward(aa, n, mk, st)
+        self.cnn_forward(aa, n, mk, st, ws=ws)
         self.cnn_backward_combine(aa, n, mk, gp_ptr, C.c_void_p(0), ep_ptr, g_ptr if want_grad else None,
-                                  C.c_void_p(0), E, fit, st)
+                                  C.c_void_p(0), E, fit, st, ws=ws)
 
     def potts_full(self, aa, n, gp_ptr, ep_ptr, st, impl=None):
         """Potts field rows (contiguous, stride D) + energies of n states: dense tensor-core GEMM for large batches,
@@ -330,6 +362,7 @@ class ChainEngine:
             model.win_lo + model.Lp - 1 if model.has_potts else model.L - 1)
         self._allocated = False
         self._graph = None
+        self.ws = Workspace(model)             # this engine's own kernel scratch (its pointers live in the captured graphs)
         # True: also evaluate the sub-steps s >= U[b] that the reference computes and then masks (complete idx / lqf / lqr
         # trace, as the golden comparisons read it); False: skip them (same states, energies and accept decisions)
         self.full_trace = False
@@ -419,14 +452,14 @@ class ChainEngine:
                 self.anchor_fixed = torch.arange(1, n + 1, dtype=torch.int32, device=m.device)
             ep = torch.empty(self.n_fixed, dtype=torch.float32, device=m.device)
             m.evaluate_into(self.aa_fixed, self.n_fixed, self.G, 2 * n, self.Gp, 2 * n, self.E_fixed, self.fit_fixed, ep,
-                            bkey=self.bkey, r1pool=self.r1pool, mkpool=self.mkpool, btab=self.btab)
+                            bkey=self.bkey, r1pool=self.r1pool, mkpool=self.mkpool, btab=self.btab, ws=self.ws)
             if all_wt:
                 self.row_cur.fill_(2 * n)
                 self.E.copy_(self.E_fixed[0].expand(n)); self.fit.copy_(self.fit_fixed[0].expand(n))
             else:
                 epn = torch.empty(n, dtype=torch.float32, device=m.device)
                 m.evaluate_into(self.aa, n, self.G, 0, self.Gp, 0, self.E, self.fit, epn, bkey=self.bkey, r1pool=self.r1pool,
-                                mkpool=self.mkpool, btab=self.btab)
+                                mkpool=self.mkpool, btab=self.btab, ws=self.ws)
                 self.row_cur.copy_(torch.arange(n, dtype=torch.int32, device=m.device))
             self.best_E.copy_(self.E); self.best_fit.copy_(self.fit); self.best_aa.copy_(self.aa)
             if self.E_hist is not None:
@@ -460,51 +493,52 @@ class ChainEngine:
         """CNN ensemble at the proposals aa_y: max-pool winners -> mkey (only the dirty blocks on the incremental path).
         dirty / parts select sub-kernels for per-kernel timing (bench.py); the defaults run everything."""
         m, n = self.m, self.n
-        mk = m.mkey(n)
+        mk = self.ws.mkey(n)
         if self.inc:
             if dirty:
                 _lib.check(self.lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(self.aa), _ptr(self.aa_y), m.aa_stride, n,
                                                    _ptr(self.dmask), st), "cnn_dirty")
             if parts:
-                self.lib.ppde_set_profile_parts(parts, 7)
-                try:
-                    m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st,
-                                       mkpool=self.mkpool, btab=self.btab)
-                finally:
-                    self.lib.ppde_set_profile_parts(7, 7)
+                m.cnn_forward_pool(self.aa_y, n, mk, self.bkey, self.r1pool, self.dmask, self.row_cur, self.rows_y, 0, st,
+                                   mkpool=self.mkpool, btab=self.btab, ws=self.ws, parts=0 if parts == 7 else parts)
         elif parts == 7:
-            m.cnn_forward(self.aa_y, n, mk, st)
+            m.cnn_forward(self.aa_y, n, mk, st, ws=self.ws)
 
     def cnn_backward_y(self, st, do_fit=True, parts=7, full=True):
         """fit_y / E_y and the gradient rows of the proposals from the winners in mkey.  full=False (incremental path
         only): the rows are updated from the current state's rows by the delta backward."""
         m, n = self.m, self.n
-        mk = m.mkey(n)
+        mk = self.ws.mkey(n)
         gp = _ptr(self.Gp) if m.has_potts else C.c_void_p(0)
         ep = _ptr(self.Epotts_y) if m.has_potts else C.c_void_p(0)
         if self.inc:
-            self.lib.ppde_set_profile_parts(7, parts if parts else 7)
-            try:
-                if self.delta and not full:
-                    m.cnn_backward_delta(self.aa, self.aa_y, n, mk, self.mkpool, gp, ep, _ptr(self.G), self.row_cur, self.rows_y,
-                                         self.E_y, self.fit_y, self.r1pool, st, do_fit=do_fit, do_grad=bool(parts), btab=self.btab)
-                else:
-                    m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
-                                        self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st, do_fit=do_fit, do_grad=bool(parts),
-                                        btab=self.btab)
-            finally:
-                self.lib.ppde_set_profile_parts(7, 7)
+            pp = 0 if parts in (0, 7) else parts
+            if self.delta and not full:
+                m.cnn_backward_delta(self.aa, self.aa_y, n, mk, self.mkpool, gp, ep, _ptr(self.G), self.row_cur, self.rows_y,
+                                     self.E_y, self.fit_y, self.r1pool, st, do_fit=do_fit, do_grad=bool(parts), btab=self.btab,
+                                     ws=self.ws, parts=pp)
+            else:
+                m.cnn_backward_pool(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
+                                    self.E_y, self.fit_y, self.r1pool, self.rows_y, 0, st, do_fit=do_fit, do_grad=bool(parts),
+                                    btab=self.btab, ws=self.ws, parts=pp)
         elif do_fit and parts == 7:
             m.cnn_backward_combine(self.aa_y, n, mk, gp, _ptr(self.rows_y), ep, _ptr(self.G), _ptr(self.rows_y),
-                                   self.E_y, self.fit_y, st)
+                                   self.E_y, self.fit_y, st, ws=self.ws)
 
     def full_backward_at(self, t):
         """Iteration t runs the exact backward (always without the delta path; every bwd_refresh-th iteration with it)."""
         return (not self.delta) or (t % self.m.bwd_refresh == self.m.bwd_refresh - 1)
 
+    def _check_room(self, k):
+        """The history rows E_hist / fit_hist / traj_aa [T+1, ...] are written at t+1 without a bound in the kernel."""
+        if self.T is not None and self.t + k > self.T:
+            raise ValueError(f"engine was allocated for num_steps={self.T}: cannot run iteration {self.t + k - 1} "
+                             "(its history rows would fall outside the buffers)")
+
     def step(self, uniforms=None):
         """One MCMC iteration (eager launches). `uniforms`: optional float32 device tensor
         [S, n, 20L] replacing the in-kernel Philox proposal stream (parity mode)."""
+        self._check_room(1)
         with torch.cuda.device(self.m.device):
             self._launch_step(self._params(self.t, uniforms), full=self.full_backward_at(self.t))
         self.t += 1
@@ -512,6 +546,7 @@ class ChainEngine:
     def run_steps(self, k, use_graph=True):
         """k iterations; the fixed-S launch sequence is captured once in a CUDA graph and replayed,
         with the iteration counter living on the device."""
+        self._check_room(k)
         if not use_graph:
             for _ in range(k):
                 self.step()
@@ -528,12 +563,12 @@ class ChainEngine:
 
     def _graph_setup(self):
         if self._graph is None:
-            self.m.mkey(self.n)
-            self.m.grad_scratch(self.n)
+            self.ws.mkey(self.n)
+            self.ws.grad_scratch(self.n)
             if not self.inc:
-                self.m.r1mask(self.n)
+                self.ws.r1mask(self.n)
             else:
-                self.m.inc_ws(self.n)
+                self.ws.inc_ws(self.n)
             self._graph_params = self._params(0, None, use_t_dev=True)
             self._graph = {}
 

@@ -29,7 +29,7 @@ class AugmentedLinearRegression:
         coef = np.asarray(coef, dtype=np.float32).astype(np.float64)          # reference casts to float32 first (nets.py:327)
         icpt = np.asarray(intercept, dtype=np.float32).astype(np.float64).reshape(-1)
         reg = np.asarray(reg, dtype=np.float64).reshape(-1)
-        if coef.ndim != 2 or coef.shape[1] != 1 + Q * model.L or coef.shape[0] != icpt.shape[0] != reg.shape[0]:
+        if coef.ndim != 2 or coef.shape[1] != 1 + Q * model.L or len({coef.shape[0], icpt.shape[0], reg.shape[0]}) != 1:
             raise ValueError(f"ridge heads must be [H, 1 + 20*{model.L}]; got {coef.shape}")
         if not model.has_potts:
             raise ValueError("the oracle model needs the Potts expert (nets.py:318)")

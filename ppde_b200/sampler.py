@@ -63,7 +63,13 @@ class PPDE_PAS:
         # True: `initial_population` is this rank's shard (equal sizes on every rank) and the returned
         # 6-tuple covers the local chains only; False (reference behaviour): global population in and out.
         self.local_population = bool(getattr(args, "ppde_local_population", False))
+        # opt-in: the population crosses the API as residue indices uint8 [n, L] (alphabet order
+        # ACDEFGHIKLMNPQRSTVWY, ppde/third_party/hsu/data_utils.py:48-72) instead of the float one-hot [n, L, 20], and best_x
+        # comes back in the same form - the lossless 1-byte form of the state, 80x fewer bytes than the one-hot
+        self.residue_io = bool(getattr(args, "ppde_residue_io", False))
         self.engine = None
+        self.top_k = int(getattr(args, "ppde_top_k", 16))
+        self.reports = []                                    # (iteration, report dict) of every log_every report
 
     def approximate_energy_change(self, score_change):       # ppde.py:20-21
         return score_change / self.ppde_temp
@@ -73,7 +79,9 @@ class PPDE_PAS:
             print(*a, **k)
 
     def run(self, initial_population, num_steps, energy_function, min_pos, max_pos, oracle, log_every=50):
-        """initial_population: float one-hot [n_chains, L, 20] (the GLOBAL population on every rank)."""
+        """initial_population: float one-hot [n_chains, L, 20] (the GLOBAL population on every rank), on the device or in
+        host memory (a host one-hot is reduced to residue indices by the host cores before the copy); with
+        `args.ppde_residue_io` uint8 residue indices [n_chains, L].  best_x comes back in the same form on the same device."""
         self._print(min_pos, max_pos)
         energy = as_b200_energy(energy_function)
         m = energy.model
@@ -93,7 +101,7 @@ class PPDE_PAS:
 
         ph = _Phases(m.device)
         with torch.cuda.device(m.device):
-            aa0 = m.onehot_to_aa(pop_local)
+            aa0 = self._residues_on_device(m, pop_local)
             ph.mark("onehot_to_aa")
             eng = ChainEngine(m, hi - lo, self.ppde_pas_length, thr, self.paper_results, seed=self.seed,
                               chain_offset=lo, num_steps=num_steps,
@@ -103,18 +111,18 @@ class PPDE_PAS:
             self.engine = eng
             ph.mark("engine_init")
 
-            def gather_host(t):
-                return D.all_gather_cat(t, n).cpu().numpy()
-
-            # iteration-0 report (ppde.py:48-57)
-            if oracle is not None:
-                gt = gather_host(self._oracle_scores(oracle, eng, m))
-            e0, f0 = gather_host(eng.E_hist[0]), gather_host(eng.fit_hist[0])
-            eq, fq = np.quantile(e0, [0.5, 0.9]), np.quantile(f0, [0.5, 0.9])
+            self.reporter = D.PopulationReporter(m.lib, m.device, n, m.L, m.aa_stride, m.wt,
+                                                 top_k=int(getattr(self, "top_k", 16)))
+            self._chain_lo = lo
+            # iteration-0 report (ppde.py:48-57), quantiles by the device-side selection kernels
+            gt = self._oracle_scores(oracle, eng, m) if oracle is not None else None
+            rep = self.reporter.report(eng.E_hist[0], eng.fit_hist[0], gt, None, eng.aa, lo, want_topk=False)
+            self.last_report = rep
+            eq, fq = rep["energy_q"], rep["fitness_q"]
             self._print(f'[Iteration 0] energy: 50% {eq[0]:.3f}, 90% {eq[1]:.3f}')
             self._print(f'[Iteration 0] pred fit 50% {fq[0]:.3f}, 90% {fq[1]:.3f}')
             if oracle is not None:
-                gq = np.quantile(gt, [0.5, 0.9])
+                gq = rep["oracle_q"]
                 self._print(f'[Iteration 0] oracle fit 50% {gq[0]:.3f}, 90% {gq[1]:.3f}')
             self._print('')
             ph.mark("report0")
@@ -128,7 +136,7 @@ class PPDE_PAS:
                 eng.run_steps(stop - t, use_graph=self.use_graph)
                 t = stop
                 if t == i + 1:
-                    self._log(eng, m, oracle, i, n, gather_host)
+                    self._log(eng, m, oracle, i)
 
             ph.mark("steps")
             # final 6-tuple (ppde.py:172-192)
@@ -136,7 +144,7 @@ class PPDE_PAS:
                 gat = lambda t, dim=0: t
             else:
                 gat = lambda t, dim=0: D.all_gather_cat(t, n, dim=dim)
-            best_x = m.aa_to_onehot(gat(eng.best_aa)).to(initial_population.device)
+            best_x = self._population_out(m, gat(eng.best_aa), initial_population.device)
             best_e, best_f = gat(eng.best_E).cpu().numpy(), gat(eng.best_fit).cpu().numpy()
             e_hist = gat(eng.E_hist, 1).cpu().numpy()
             f_hist = gat(eng.fit_hist, 1).cpu().numpy()
@@ -149,6 +157,61 @@ class PPDE_PAS:
             self.last_phases = dict(ph.rows)
         return best_x, best_e, best_f, e_hist, f_hist, random_traj
 
+    # -- the population across the API boundary ----------------------------------------------------------
+    @staticmethod
+    def _host_threads():
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
+        local_ws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        return max(1, min(32, cores // max(local_ws, 1)))
+
+    @staticmethod
+    def _pinned(m, key, shape, dtype):
+        """Pinned staging buffers are cached on the model (cudaHostAlloc costs milliseconds per call)."""
+        cache = m.__dict__.setdefault("_pinned_cache", {})
+        t = cache.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype).pin_memory()
+            cache[key] = t
+        return t
+
+    def _residues_on_device(self, m, pop):
+        """The caller's population as uint8 residues [n, aa_stride] on the model's device."""
+        n = int(pop.shape[0])
+        if self.residue_io:
+            if pop.dtype != torch.uint8 or pop.dim() != 2 or pop.shape[1] != m.L:
+                raise ValueError(f"ppde_residue_io: expected uint8 residues [n, {m.L}], got {pop.dtype} {tuple(pop.shape)}")
+            aa = torch.zeros(n, m.aa_stride, dtype=torch.uint8, device=m.device)
+            aa[:, :m.L].copy_(pop, non_blocking=True)
+            return aa
+        if pop.dim() != 3 or pop.shape[1] != m.L or pop.shape[2] != 20:
+            raise ValueError(f"expected one-hot [n, {m.L}, 20], got {tuple(pop.shape)}")
+        if pop.device.type == "cpu":
+            x = pop.detach().to(torch.float32).contiguous()
+            stage = self._pinned(m, "in", (n, m.aa_stride), torch.uint8)
+            rc = m.lib.ppde_host_onehot_to_aa(x.data_ptr(), n, m.L, stage.data_ptr(), m.aa_stride, self._host_threads())
+            if rc != 0:
+                raise RuntimeError(f"ppde_host_onehot_to_aa failed with {rc}")
+            return stage.to(m.device, non_blocking=True)
+        return m.onehot_to_aa(pop)
+
+    def _population_out(self, m, best_aa, device):
+        """best_x in the form and on the device the population came in (ppde.py:191: `.to(initial_population.device)`)."""
+        n = int(best_aa.shape[0])
+        if self.residue_io:
+            return best_aa[:, :m.L].to(device)
+        if torch.device(device).type == "cpu":
+            stage = self._pinned(m, "out", (n, m.aa_stride), torch.uint8)
+            stage.copy_(best_aa)                                      # D2H of 1 byte per residue (synchronous: pinned target)
+            x = torch.empty(n, m.L, 20, dtype=torch.float32)
+            rc = m.lib.ppde_host_aa_to_onehot(stage.data_ptr(), m.aa_stride, n, m.L, x.data_ptr(), self._host_threads())
+            if rc != 0:
+                raise RuntimeError(f"ppde_host_aa_to_onehot failed with {rc}")
+            return x
+        return m.aa_to_onehot(best_aa).to(device)
+
     @staticmethod
     def _oracle_scores(oracle, eng, m):
         """oracle(cur_x) (ppde.py:48,156): our own model scores the residue states straight from the sampler's
@@ -157,16 +220,12 @@ class PPDE_PAS:
             return oracle.score_engine(eng).reshape(-1)
         return oracle(m.aa_to_onehot(eng.aa)).detach().float().reshape(-1)
 
-    def _log(self, eng, m, oracle, i, n, gather_host):
-        e = gather_host(eng.E_hist[i + 1]); f = gather_host(eng.fit_hist[i + 1])
-        dist_d, hashes = eng.population_metrics()
-        rep_dist = gather_host(dist_d.float())
-        acc = gather_host(eng.accept.float())
-        gt = None
-        if oracle is not None:
-            gt = gather_host(self._oracle_scores(oracle, eng, m))
-        rep = D.population_report(e, f, gt, acc, rep_dist, gather_host(hashes))
+    def _log(self, eng, m, oracle, i):
+        """ppde.py:155-170: history row i+1 (pre-reset energies), post-reset states for the oracle and the distances."""
+        gt = self._oracle_scores(oracle, eng, m) if oracle is not None else None
+        rep = self.reporter.report(eng.E_hist[i + 1], eng.fit_hist[i + 1], gt, eng.accept, eng.aa, self._chain_lo)
         self.last_report = rep
+        self.reports.append((i, rep))
         self._print(f'[Iteration {i}] energy: 50% {rep["energy_q"][0]:.3f}, 90% {rep["energy_q"][1]:.3f}', flush=True)
         self._print(f'[Iteration {i}] pred 50% {rep["fitness_q"][0]:.3f}, 90% {rep["fitness_q"][1]:.3f}', flush=True)
         if gt is not None:

@@ -28,8 +28,10 @@ def _worker(rank, ws, port, n, T, out_dir):
           and float(acc) == n and torch.equal(traj, torch.full((T + 1, 4), float(owner))))
     # host-side draws differ between processes; the tracked-chain index must be made to agree (ppde.py:37)
     ok = ok and D.agree_int(100 + 17 * rank, 0) == 100 and D.agree_int(5 + rank, 1) == 6
-    rep = D.population_report(e.numpy(), e.numpy(), None, np.ones(n), np.arange(n), np.arange(n) % 3)
-    ok = ok and rep["diversity_pct"] == pytest.approx(300.0 / n) and rep["oracle_q"] is None
+    # equal-size gather used by the top-k candidates of the device-side report
+    cand = D.gather_equal(torch.full((3,), float(rank)))
+    ok = ok and torch.equal(cand, torch.tensor([0.0] * 3 + [1.0] * 3))
+    ok = ok and D.shard_sizes(n, ws) == [hi_ - lo_ for lo_, hi_ in (D.shard_range(n, r, ws) for r in range(ws))]
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("1" if ok else "0")
     dist.destroy_process_group()
 

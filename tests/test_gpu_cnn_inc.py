@@ -49,8 +49,11 @@ def _mutants(rng, x, L):
     return y
 
 
+@pytest.mark.parametrize("use_pool", [True, False])
 @pytest.mark.parametrize("L,n", [(40, 24), (104, 40), (237, 48), (238, 331)])
-def test_incremental_forward_is_bit_identical(L, n):
+def test_incremental_forward_is_bit_identical(L, n, use_pool):
+    """use_pool: the pool of raw row winners is kept, so the merge reads the current row's winner + the dirty blocks' keys
+    (the production path); without it the merge scans all NB block keys per channel.  Same bits either way."""
     from ppde_b200 import _lib
     from ppde_b200.engine import PoEModel, _ptr, _stream
     w = port.synthetic_weights(L, seed=L + 7, lamda=1.0)
@@ -74,17 +77,18 @@ def test_incremental_forward_is_bit_identical(L, n):
     bkey = torch.full((rows * nets * NB * J2,), -1, dtype=torch.int64, device=dev)
     r1pool = torch.full((rows * nets * P * 32,), 0xAB, dtype=torch.uint8, device=dev)
     btab = torch.full((rows * NB,), -1, dtype=torch.int32, device=dev)
+    mkpool = torch.full((rows * nets * J2,), -1, dtype=torch.int64, device=dev) if use_pool else None
     st = _stream()
     # current states: private row b for even chains, row n + b for odd ones (both halves of the pool get used)
     rows_x = torch.tensor([b if b % 2 == 0 else n + b for b in range(n)], dtype=torch.int32, device=dev)
     rows_y = torch.tensor([n + b if b % 2 == 0 else b for b in range(n)], dtype=torch.int32, device=dev)
     mk_x = torch.zeros(n * nets * J2, dtype=torch.int64, device=dev)
-    m.cnn_forward_pool(ax, n, mk_x, bkey, r1pool, None, None, rows_x, 0, st, btab=btab)         # full evaluation into rows_x
+    m.cnn_forward_pool(ax, n, mk_x, bkey, r1pool, None, None, rows_x, 0, st, btab=btab, mkpool=mkpool)         # full evaluation into rows_x
     # full tensor-core kernel on x and y (the reference for bit-exactness)
     mk_fx = torch.zeros_like(mk_x); mk_fy = torch.zeros_like(mk_x)
     rm_fx = torch.zeros(n * nets * P * 32, dtype=torch.uint8, device=dev); rm_fy = torch.zeros_like(rm_fx)
-    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ax), m.aa_stride, n, _ptr(mk_fx), _ptr(rm_fx), st), "tc x")
-    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ay), m.aa_stride, n, _ptr(mk_fy), _ptr(rm_fy), st), "tc y")
+    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ax), m.aa_stride, n, _ptr(mk_fx), _ptr(rm_fx), None, st), "tc x")
+    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ay), m.aa_stride, n, _ptr(mk_fy), _ptr(rm_fy), None, st), "tc y")
     torch.cuda.synchronize()
     assert torch.equal(mk_x, mk_fx), "full evaluation through the block-key kernel differs from the full kernel"
     tab = btab.view(rows, NB)
@@ -95,7 +99,7 @@ def test_incremental_forward_is_bit_identical(L, n):
     dmask = torch.zeros(n, dtype=torch.int32, device=dev)
     _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay), m.aa_stride, n, _ptr(dmask), st), "dirty")
     mk_y = torch.zeros_like(mk_x)
-    m.cnn_forward_pool(ay, n, mk_y, bkey, r1pool, dmask, rows_x, rows_y, 0, st, btab=btab)
+    m.cnn_forward_pool(ay, n, mk_y, bkey, r1pool, dmask, rows_x, rows_y, 0, st, btab=btab, mkpool=mkpool)
     torch.cuda.synchronize()
     # dirty masks against a host restatement
     dm = dmask.cpu().numpy().astype(np.uint32)
@@ -118,7 +122,7 @@ def test_incremental_forward_is_bit_identical(L, n):
     # the proposal rows now hold a complete cache: a second incremental step from y back to x reproduces x
     _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ay), _ptr(ax), m.aa_stride, n, _ptr(dmask), st), "dirty back")
     mk_b = torch.zeros_like(mk_x)
-    m.cnn_forward_pool(ax, n, mk_b, bkey, r1pool, dmask, rows_y, rows_x, 0, st, btab=btab)
+    m.cnn_forward_pool(ax, n, mk_b, bkey, r1pool, dmask, rows_y, rows_x, 0, st, btab=btab, mkpool=mkpool)
     torch.cuda.synchronize()
     assert torch.equal(mk_b, mk_fx), "second incremental step (y -> x) differs from the full kernel"
     assert torch.equal(_mask_rows(r1pool, btab, rows_x, nets, P, NB), rm_fx.view(n, nets, P, 32))
@@ -127,10 +131,10 @@ def test_incremental_forward_is_bit_identical(L, n):
     y2 = _mutants(np.random.default_rng(L + 99), x, L)
     ay2 = dev_aa(y2)
     mk_fy2 = torch.zeros_like(mk_x); rm_fy2 = torch.zeros_like(rm_fx)
-    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ay2), m.aa_stride, n, _ptr(mk_fy2), _ptr(rm_fy2), st), "tc y2")
+    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(ay2), m.aa_stride, n, _ptr(mk_fy2), _ptr(rm_fy2), None, st), "tc y2")
     _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay2), m.aa_stride, n, _ptr(dmask), st), "dirty 3")
     mk_y2 = torch.zeros_like(mk_x)
-    m.cnn_forward_pool(ay2, n, mk_y2, bkey, r1pool, dmask, rows_x, rows_y, 0, st, btab=btab)
+    m.cnn_forward_pool(ay2, n, mk_y2, bkey, r1pool, dmask, rows_x, rows_y, 0, st, btab=btab, mkpool=mkpool)
     torch.cuda.synchronize()
     assert torch.equal(mk_y2, mk_fy2), "third incremental step differs from the full kernel"
     assert torch.equal(_mask_rows(r1pool, btab, rows_y, nets, P, NB), rm_fy2.view(n, nets, P, 32))
@@ -177,7 +181,7 @@ def test_delta_backward_matches_full_backward(L, n):
     m.potts_full(ay, n, C.c_void_p(Gp.data_ptr() + n * m.D * 4), _ptr(Ep_y), st)
     dmask = torch.zeros(n, dtype=torch.int32, device=dev)
     _lib.check(lib.ppde_cnn_dirty(C.byref(m.cnn), _ptr(ax), _ptr(ay), m.aa_stride, n, _ptr(dmask), st), "dirty")
-    mk = m.mkey(n)
+    mk = m.ws.mkey(n)
     m.cnn_forward_pool(ay, n, mk, bkey, r1pool, dmask, rows_x, rows_y, 0, st, mkpool=mkpool, btab=btab)
     m.cnn_backward_delta(ax, ay, n, mk, mkpool, _ptr(Gp), _ptr(Ep_y), _ptr(G), rows_x, rows_y, E_y, fit_y, r1pool, st, btab=btab)
     torch.cuda.synchronize()

@@ -36,7 +36,7 @@ def test_tc_forward_matches_simt_and_oracle(L, n):
     mk2 = torch.full((n * nets * J2,), -1, dtype=torch.int64, device=m.device)
     lib = m.lib
     _lib.check(lib.ppde_cnn_forward(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk1), _stream()), "simt")
-    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk2), None, _stream()), "tc")
+    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk2), None, None, _stream()), "tc")
     torch.cuda.synchronize()
     v1, p1 = _decode(mk1, n, nets, J2)
     v2, p2 = _decode(mk2, n, nets, J2)

@@ -18,7 +18,7 @@ for L,n in [(40,7),(96,33),(104,20),(238,19)]:
     mk1 = torch.zeros(n*nets*J2, dtype=torch.int64, device=m.device)
     mk2 = torch.full((n*nets*J2,), -1, dtype=torch.int64, device=m.device)
     _lib.check(m.lib.ppde_cnn_forward(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk1), _stream()), "simt")
-    _lib.check(m.lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk2), None, _stream()), "tc")
+    _lib.check(m.lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk2), None, None, _stream()), "tc")
     torch.cuda.synchronize()
     v1,p1 = dec(mk1,n,nets,J2); v2,p2 = dec(mk2,n,nets,J2)
     # exact fp64 reference

@@ -1,24 +1,23 @@
 #!/bin/bash
 # Runs on the B200 box (under gpurun): GPU parity tests, smoke, full default bench, reference arm,
-# ncu launch list and `--set full` captures of the top kernels. Outputs under gpurun_out/.
-# usage: tools/gpu_check.sh <tag>
-TAG=${1:-r01}
+# ncu launch list and `--set full` captures of the step kernels. Outputs under gpurun_out/.
+# usage: tools/gpu_check.sh <tag> [quick]
+TAG=${1:-r02}
+MODE=${2:-full}
 K="timeout -s KILL"
 mkdir -p gpurun_out
-$K 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_pytest.log
+$K 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.log
 $K 120 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log
-$K 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json
-$K 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ref.json
+$K 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
+if [ "$MODE" = "full" ]; then
+$K 400 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ref.json
 $K 200 python bench.py --workload ube4b_potts_poe_4k --no-cpu-baseline > gpurun_out/${TAG}_bench_ube4b.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ube4b.json
 $K 300 python bench.py --workload gfp_paper_pas10 --no-cpu-baseline --steps 5 > gpurun_out/${TAG}_bench_pas10.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_pas10.json
-$K 200 python tools/bench_potts_full.py 64 128 238 512 1024 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
+$K 300 python bench.py --workload pabp_readme_128 --steps 100 --warmup 5 > gpurun_out/${TAG}_bench_pabp128.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_pabp128.json
+fi
 SMALL="python bench.py --chains 8192 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline"
 $K 200 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 && \
 $K 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
 $K 200 $SMALL > gpurun_out/${TAG}_plain2.log 2>&1 && \
-$K 400 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_dirty_kernel|cnn_backward_tc_kernel|cnn_backward_delta_kernel|cnn_winner_delta_kernel|cnn_grad_combine_delta_kernel|pas_propose_kernel|pas_reverse_accept_kernel|potts_incremental_kernel" -s 27 -c 9 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
+$K 500 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_backward_delta_kernel|cnn_winner_delta_kernel|cnn_grad_combine_delta_kernel|pas_propose_kernel|pas_reverse_accept_kernel|potts_incremental_kernel|cnn_fit_kernel" -s 27 -c 9 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_f.log
-PD="python tools/bench_potts_full.py 238"
-$K 200 $PD > gpurun_out/${TAG}_plain3.log 2>&1 && \
-$K 300 ncu --set full --clock-control none --import-source on -k regex:potts_dense_tc_kernel -s 6 -c 1 -o gpurun_out/${TAG}_potts_dense -f $PD > gpurun_out/${TAG}_ncu_p.log 2>&1
-tail -1 gpurun_out/${TAG}_ncu_p.log

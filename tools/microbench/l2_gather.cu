@@ -1,6 +1,6 @@
 // Microbenchmark: per-SM throughput of gathering 960-byte rows from an L2-resident table (the access pattern of the CNN
 // backward's adjoint rows), LSU path (LDG.128 into registers) vs bulk-copy path (cp.async.bulk into shared memory).
-// Build:  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o l2_gather l2_gather.cu ; run on a B200.
+// Build:  nvcc -O3 -std=c++17 -cudart shared -gencode arch=compute_100a,code=sm_100a -o /tmp/l2_gather l2_gather.cu (never leave the binary in the tree) ; run on a B200.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>

@@ -5,6 +5,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ppde_b200 import _lib
+from ppde_b200._lib import TuneT
 from ppde_b200.engine import PoEModel, _ptr, _stream
 from ppde_b200.synthetic import synthetic_problem
 
@@ -19,13 +20,13 @@ for b in range(n):
     pos = rng.integers(0, L, size=10); aa[b, pos] = rng.integers(0, 20, size=10)
 pad = np.zeros((n, m.aa_stride), dtype=np.uint8); pad[:, :L] = aa
 aad = torch.from_numpy(pad).to(m.device)
-mk = m.mkey(n); rm = m.r1mask(n)
+mk = m.ws.mkey(n); rm = m.ws.r1mask(n)
 G = torch.empty(n, m.NE, dtype=torch.float32, device=m.device)
 Gp = torch.zeros(n, m.D, dtype=torch.float32, device=m.device)
 E = torch.empty(n, dtype=torch.float32, device=m.device); fit = torch.empty_like(E); Ep = torch.zeros_like(E)
 st = _stream()
 def fwd():
-    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk), _ptr(rm), st), "fwd")
+    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk), _ptr(rm), None, st), "fwd")
 def bwd():
     m.cnn_backward_combine(aad, n, mk, _ptr(Gp), C.c_void_p(0), _ptr(Ep), _ptr(G), C.c_void_p(0), E, fit, st)
 fwd()
@@ -36,11 +37,11 @@ e0.record(); bwd(); e1.record(); torch.cuda.synchronize()
 print(f"plain backward (fit + sort + tc + combine): {e0.elapsed_time(e1):.3f} ms for {n} chains")
 grid = 148
 buf = torch.zeros(grid * 16, dtype=torch.int64, device=m.device)
-lib.ppde_set_backward_profile(_ptr(buf))
+m.tune = TuneT(prof=buf.data_ptr())
 bwd(); torch.cuda.synchronize()
 e0.record(); bwd(); e1.record(); torch.cuda.synchronize()
 print(f"instrumented: {e0.elapsed_time(e1):.3f} ms")
-lib.ppde_set_backward_profile(None)
+m.tune = None
 c = buf.cpu().numpy().reshape(grid, 16)[:147]
 P = L - 4; tpc = (P + 63) // 64
 tiles = n / 49 * tpc

@@ -5,6 +5,7 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ppde_b200 import _lib
+from ppde_b200._lib import TuneT
 from ppde_b200.engine import ChainEngine, PoEModel, _ptr, _stream
 from ppde_b200.synthetic import synthetic_problem
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
@@ -36,9 +37,9 @@ def step():
 ts = [step() for _ in range(4)]
 grid = 148
 buf = torch.zeros(grid * 16, dtype=torch.int64, device=m.device)
-lib.ppde_set_backward_profile(_ptr(buf))
+m.tune = TuneT(prof=buf.data_ptr())
 t_inst = step()
-lib.ppde_set_backward_profile(None)
+m.tune = None
 c = buf.cpu().numpy().reshape(grid, 16)[:147]
 P = L - 4; tpc = (P + 63) // 64
 tiles = n / 49 * tpc

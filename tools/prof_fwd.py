@@ -7,6 +7,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ppde_b200 import _lib
+from ppde_b200._lib import TuneT
 from ppde_b200.engine import PoEModel, _ptr, _stream
 from ppde_b200.synthetic import synthetic_problem
 
@@ -21,21 +22,22 @@ for b in range(n):
     pos = rng.integers(0, L, size=10); aa[b, pos] = rng.integers(0, 20, size=10)
 pad = np.zeros((n, m.aa_stride), dtype=np.uint8); pad[:, :L] = aa
 aad = torch.from_numpy(pad).to(m.device)
-mk = m.mkey(n); rm = m.r1mask(n)
+mk = m.ws.mkey(n); rm = m.ws.r1mask(n)
 grid = 148
 buf = torch.zeros(grid * 16, dtype=torch.int64, device=m.device)
+tune = TuneT()
 def run():
-    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk), _ptr(rm), _stream()), "fwd")
+    _lib.check(lib.ppde_cnn_forward_tc(C.byref(m.cnn), _ptr(aad), m.aa_stride, n, _ptr(mk), _ptr(rm), C.byref(tune), _stream()), "fwd")
 for _ in range(3): run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
 print(f"plain kernel: {e0.elapsed_time(e1):.3f} ms for {n} chains")
-lib.ppde_set_forward_profile(_ptr(buf))
+tune.prof = buf.data_ptr()
 run(); torch.cuda.synchronize()
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
 print(f"instrumented: {e0.elapsed_time(e1):.3f} ms")
-lib.ppde_set_forward_profile(None)
+tune.prof = None
 c = buf.cpu().numpy().reshape(grid, 16)[:144]
 P = L - 4; tpc = (P + 127) // 128
 tiles = n / 12 * tpc        # per cluster (12 clusters per combo at L=238)

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Incremental CNN forward inside a realistic PPDE step: time of the whole forward (dirty + scan + tensor-core + merge
 kernels) on fresh proposals, and role-level cycle counters of the tensor-core kernel (runtime-instrumented through
-ppde_set_forward_profile).   usage (GPU box): python tools/prof_inc.py [chains]   (PPDE_INC_DEBUG=1|2|4: experiments)"""
+ppde_tune_t.prof).   usage (GPU box): python tools/prof_inc.py [chains]   (PPDE_INC_DEBUG=1|2|4: experiments)"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from ppde_b200 import _lib
+from ppde_b200._lib import TuneT
 from ppde_b200.engine import ChainEngine, PoEModel, _ptr, _stream
 from ppde_b200.synthetic import synthetic_problem
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
@@ -35,16 +36,16 @@ def step(timed_forward):
     eng.t += 1
     return e0.elapsed_time(e1)
 
-if dbg: os.environ["PPDE_INC_DEBUG"] = dbg
+if dbg: m.tune = TuneT(dbg=int(dbg))
 ts = [step(lambda: eng.cnn_forward_y(st)) for _ in range(5)]
 nd = torch.tensor([bin(int(v) & 0xFFFF).count("1") for v in eng.dmask.cpu().numpy()[:4096]]).float()
 print(f"chains {n} dbg {dbg}: incremental forward {min(ts):.3f} ms (median {sorted(ts)[2]:.3f}); dirty blocks / chain mean {nd.mean():.2f} max {nd.max():.0f}")
 if dbg:
     sys.exit(0)
 buf = torch.zeros(148 * 16, dtype=torch.int64, device=m.device)
-lib.ppde_set_forward_profile(_ptr(buf))
+m.tune = TuneT(prof=buf.data_ptr())
 t_inst = step(lambda: eng.cnn_forward_y(st))
-lib.ppde_set_forward_profile(None)
+m.tune = None
 c = buf.cpu().numpy().reshape(148, 16)[:144]
 lead, peer = c[0::2], c[1::2]
 chains, tiles = lead[:, 10].mean(), lead[:, 9].mean()
