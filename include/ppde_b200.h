@@ -187,8 +187,11 @@ int ppde_cnn_backward_tc(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint
                          const float* Gp, int64_t Gp_stride, const int32_t* gp_rows,
                          float* G, int64_t G_stride, const int32_t* g_rows,
                          const uint8_t* r1mask /* from ppde_cnn_forward_tc */,
-                         float* scratch /* n_nets*n*20L floats + n*n_nets*roundup8(2P+2+4C) uint16 */,
+                         float* scratch /* ppde_cnn_backward_scratch_floats(m, n) floats */,
                          const ppde_tune_t* tune, void* stream);
+/* floats of `scratch` that ppde_cnn_backward_tc / _tc_rows / ppde_cnn_backward_delta need for n chains (per-net partial
+ * gradients or sparse row values, followed by the winner records) */
+int64_t ppde_cnn_backward_scratch_floats(const ppde_cnn_t* m, int32_t n);
 /* same as ppde_cnn_backward_tc with the relu-mask rows taken from a POOL: chain b's mask lives in row
  * mask_rows[b] (NULL: mask_row_base + b) of r1mask [rows, n_nets, P, 32]. */
 int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,
@@ -216,16 +219,16 @@ int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n);   /* workspace of ppde_cnn_for
 int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                          unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask, unsigned long long* bkey,
                          int32_t* btab, const int32_t* rows_x, const int32_t* rows_y, int32_t row_base_y,
-                         unsigned long long* mkey_pool /* optional [rows, n_nets, 2C]: RAW winner of every pool row (64-bit maximum
-                                                          over its block keys); with it the merge reads the current row's winner
-                                                          and the dirty blocks' keys instead of all NB keys per channel */,
+                         unsigned long long* mkey_pool /* optional [rows, n_nets, 2C][2]: the two largest raw block keys of every
+                                                          pool row (winner, runner-up or 0); with it the merge reads this list and
+                                                          the dirty blocks' keys instead of all NB keys per channel */,
                          void* ws /* ppde_cnn_forward_inc_ws_bytes(n) bytes */, const ppde_tune_t* tune, void* stream);
 /* DELTA backward: the CNN part of the gradient changes between the current state x and the proposal y only through the
  * conv rows whose relu mask changed and the channels whose max-pool winner moved (a few percent of the winners), so
  *     G[rows_y[b]] = G[rows_x[b]] + (Gp[rows_y[b]] - Gp[rows_x[b]])(window) + lamda/n_nets * sum_k d(dfit_k/dx)
  * with only those adjoint rows gathered (same tensor-core kernel, signed winner records).  Rounding differences accumulate
- * (~1e-7 of max|G| per update): callers refresh with ppde_cnn_backward_tc_rows periodically.  mkey_pool holds the winners
- * of every pool row (ppde_cnn_forward_inc), r1mask the relu-mask pool; same scratch as ppde_cnn_backward_tc. */
+ * (~1e-7 of max|G| per update): callers refresh with ppde_cnn_backward_tc_rows periodically.  mkey_pool [rows, n_nets, 2C][2]
+ * holds the raw winners of every pool row (ppde_cnn_forward_inc), r1mask the relu-mask pool; same scratch as ppde_cnn_backward_tc. */
 int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa_x, const uint8_t* aa_y,
                             int32_t aa_stride, int32_t n, const unsigned long long* mkey_y,
                             const unsigned long long* mkey_pool, float lamda, const float* Gp, int64_t Gp_stride,

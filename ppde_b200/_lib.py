@@ -70,6 +70,7 @@ SIGNATURES = {
                                             C.c_float, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp, vp]),
     "ppde_cnn_backward_tc": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
                                        vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.POINTER(TuneT), vp]),
+    "ppde_cnn_backward_scratch_floats": (C.c_int64, [C.POINTER(CnnT), C.c_int32]),
     "ppde_cnn_backward_tc_rows": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
                                             vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp,
                                             C.POINTER(TuneT), vp]),

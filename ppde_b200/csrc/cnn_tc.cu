@@ -767,8 +767,8 @@ struct IncParams {
     unsigned long long* mkey;           // [n, n_nets, 2C]
     uint8_t* r1mask;                    // pool [rows, n_nets, P, 32] or NULL
     const uint32_t* dmask;              // [n] dirty-block bits, NULL = every block is dirty (full evaluation into the pool)
-    unsigned long long* mkey_pool;      // optional pool [rows, n_nets, 2C]: RAW winner of every pool row (64-bit maximum over its block
-                                        // keys); read for the current row by the merge kernel, written for the proposal row
+    unsigned long long* mkey_pool;      // optional pool [rows, n_nets, 2C][2]: the two largest RAW block keys of every pool row (see
+                                        // cnn_inc_merge_kernel); read for the current row by the merge kernel, written for the proposal row
     unsigned long long* bkey;           // pool [rows, n_nets, NB, 2C]
     int32_t* btab;                      // pool [rows, NB]: the pool row whose slot holds block q of this row (keys AND relu-mask rows):
                                         // a proposal row only POINTS at the clean blocks of the current state instead of copying them
@@ -831,6 +831,26 @@ __device__ __forceinline__ void mbar_wait_cluster_relaxed(uint64_t* bar, uint32_
         "DONE_R:\n"
         "}\n" ::"r"(a), "r"(parity)
         : "memory");
+}
+
+// (value, first arg-max) of 16 raw accumulators held as bit patterns
+__device__ __forceinline__ void argmax16(const uint32_t (&r)[16], float& best, int& bidx) {
+    float v[8]; int ix[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float a = __uint_as_float(r[2 * i]), b = __uint_as_float(r[2 * i + 1]);
+        const bool gt = b > a;
+        v[i] = gt ? b : a; ix[i] = gt ? 2 * i + 1 : 2 * i;
+    }
+#pragma unroll
+    for (int w = 4; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const bool gt = v[2 * i + 1] > v[2 * i];
+            v[i] = gt ? v[2 * i + 1] : v[2 * i]; ix[i] = gt ? ix[2 * i + 1] : ix[2 * i];
+        }
+    }
+    best = v[0]; bidx = ix[0];
 }
 
 template <int NCH>
@@ -978,17 +998,12 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
                     tmem_ld16(lane_addr + buf * 128 + 16 * s, ra);
                     if (two) tmem_ld16(lane_addr + buf * 128 + 16 * (s + 1), rb);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float bu0 = __uint_as_float(ra[0]), bu1 = two ? __uint_as_float(rb[0]) : 0.f;
-                    int bi0 = 0, bi1 = 0;
-#pragma unroll
-                    for (int i = 1; i < 16; ++i) {
-                        const float u0 = __uint_as_float(ra[i]);
-                        if (u0 > bu0) { bu0 = u0; bi0 = i; }
-                        if (two) {
-                            const float u1 = __uint_as_float(rb[i]);
-                            if (u1 > bu1) { bu1 = u1; bi1 = i; }
-                        }
-                    }
+                    // first arg-max of 16 values as a 4-level tree (the right operand wins only if strictly greater, so the lowest
+                    // index survives ties): dependent depth 4 instead of the 15 of a running maximum
+                    float bu0, bu1 = 0.f;
+                    int bi0, bi1 = 0;
+                    argmax16(ra, bu0, bi0);
+                    if (two) argmax16(rb, bu1, bi1);
                     emit(s, bu0, bi0);
                     if (two) emit(s + 1, bu1, bi1);
                 }
@@ -1192,13 +1207,26 @@ __global__ void __launch_bounds__(128) cnn_dirty_kernel(int n, int L, int P, int
 // X's table points at it (X inherited that block from an earlier state that lived in Y) - then X's own slot, which neither
 // row references.  Only the two private rows of a chain and read-only fixed rows ever appear in its tables.
 //
-// The pool `mkey_pool` keeps the RAW winner of every row (the 64-bit maximum over its block keys, before bias / relu).
-// With it the maximum over the clean blocks needs no reads: when the current row's winner sits in a clean block it IS that
-// maximum (the clean blocks' keys are the current row's keys, and the winner is the maximum over all of them), so
-//     winner(y) = max(winner(x), keys of the dirty blocks)                       - 1 + #dirty keys instead of NB,
-// and only a channel whose old winner sits in a dirty block (~15 % of them) rescans all NB keys.  max over u64 is
-// associative: the result is bit-identical to the full scan (tested against the full kernel).
-__global__ void __launch_bounds__(256, 4) cnn_inc_merge_kernel(const __grid_constant__ IncParams prm) {
+// The pool `mkey_pool` keeps, per (row, net, channel), the two largest RAW block keys of the row (before bias / relu):
+//     K1 = maximum over all NB blocks (the row's winner),   K2 = maximum over the blocks other than K1's, or 0 = "not known".
+// Every block outside this list has a key <= min(list).  For a proposal y built from row x with dirty-block set Dm:
+//     R    = the list entries whose block is clean           (still the largest keys among the CLEAN blocks, in order)
+//     cand = the new keys of the dirty blocks that are >= min(old list)   (certain to outrank every unlisted clean block)
+//     new list = top-2 of R u cand                            - exact for the same reason; K2 = 0 when only one is certain
+// so the merge reads 16 bytes of list + the dirty blocks' keys (2.25 of NB = 15 at pas = 2) per channel instead of all NB keys,
+// fully coalesced.  Only when the new list is EMPTY (every listed block dirty and every new key below the old minimum: well
+// under 1 % of the channels) the clean blocks are rescanned.  max over u64 is associative and the list never holds a key that
+// is not a current block key of the row: the winner is bit-identical to the full scan (tested against the full kernel).
+__device__ __forceinline__ void top2_insert(unsigned long long k, unsigned long long& k1, unsigned long long& k2) {
+    if (k > k1) { k2 = k1; k1 = k; }
+    else if (k > k2) k2 = k;
+}
+// Memory-level parallelism: the dirty-block set is the same for every channel of a chain, so the CTA compacts it once
+// (s_dptr) and every thread works on MERGE_E channels at a time with the list loads and the first MERGE_DP dirty-key loads
+// of all of them issued before the first use (two dependent global loads per channel would otherwise bound the kernel).
+// Without a list (no pool, or a full evaluation) "every block is dirty" and the same loop scans all NB keys.
+constexpr int MERGE_NT = 256, MERGE_E = 3, MERGE_DP = 4;
+__global__ void __launch_bounds__(MERGE_NT, 4) cnn_inc_merge_kernel(const __grid_constant__ IncParams prm) {
     const int b = blockIdx.x;
     const int J2 = 2 * prm.m.C, NB = prm.NB, nets = prm.m.n_nets;
     const uint32_t all_blocks = (NB >= 32) ? 0xFFFFFFFFu : ((1u << NB) - 1u);
@@ -1206,44 +1234,87 @@ __global__ void __launch_bounds__(256, 4) cnn_inc_merge_kernel(const __grid_cons
     const size_t row_keys = (size_t)nets * NB * J2;
     const int ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
     const int rx = prm.rows_x ? __ldg(prm.rows_x + b) : ry;
-    const bool have_old = prm.rows_x && prm.mkey_pool && !(prm.dbg & 8);   // raw winner of the current row available
-    int slot[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        slot[q] = ry;
+    const bool have_old = prm.rows_x && prm.mkey_pool && !(prm.dbg & 8);   // top-2 list of the current row available
+    const uint32_t first = have_old ? mask : all_blocks;                   // blocks whose keys are read in the first round
+    __shared__ int s_slot[16];
+    __shared__ const unsigned long long* s_ptr[16];       // first key of every block (through the slot table)
+    __shared__ const unsigned long long* s_dptr[16];      // ... of the blocks of `first`, compacted
+    __shared__ int s_nd;
+    if (threadIdx.x < 16) {
+        const int q = threadIdx.x;
+        int sl = ry;
         if (q < NB && prm.rows_x) {
             const int tx = __ldg(prm.btab + (size_t)rx * NB + q);
-            slot[q] = ((mask >> q) & 1u) ? ((tx == ry) ? rx : ry) : tx;
+            sl = ((mask >> q) & 1u) ? ((tx == ry) ? rx : ry) : tx;
+        }
+        s_slot[q] = sl;
+        const unsigned long long* ptr = prm.bkey + (size_t)sl * row_keys + (size_t)(q < NB ? q : 0) * J2;
+        s_ptr[q] = ptr;
+        if (q < NB && ((first >> q) & 1u)) s_dptr[__popc(first & ((1u << q) - 1u))] = ptr;
+        if (q == 0) s_nd = __popc(first);
+    }
+    __syncthreads();
+    const int nd = s_nd, tot = nets * J2;
+    const ulonglong2* oldp = prm.mkey_pool ? reinterpret_cast<const ulonglong2*>(prm.mkey_pool) + (size_t)rx * tot : nullptr;
+    ulonglong2* newp = prm.mkey_pool ? reinterpret_cast<ulonglong2*>(prm.mkey_pool) + (size_t)ry * tot : nullptr;
+    unsigned long long* outp = prm.mkey + (size_t)b * tot;
+    for (int e0 = threadIdx.x; e0 < tot; e0 += MERGE_E * MERGE_NT) {
+        int off[MERGE_E], kk[MERGE_E], jj[MERGE_E];
+        ulonglong2 Lr[MERGE_E];
+        unsigned long long kr[MERGE_E][MERGE_DP];
+#pragma unroll
+        for (int u = 0; u < MERGE_E; ++u) {                 // issue: list of the current row
+            const int e = e0 + u * MERGE_NT;
+            const int k = min(e, tot - 1) / J2, j = min(e, tot - 1) - k * J2;
+            kk[u] = k; jj[u] = j;
+            off[u] = k * NB * J2 + j;                       // key (k, q, j) of a row sits at q * J2 + off
+            Lr[u] = (have_old && e < tot) ? __ldcg(oldp + e) : make_ulonglong2(0ull, 0ull);
+        }
+#pragma unroll
+        for (int d = 0; d < MERGE_DP; ++d)                  // issue: the first MERGE_DP keys of the first round
+#pragma unroll
+            for (int u = 0; u < MERGE_E; ++u)
+                kr[u][d] = (d < nd && e0 + u * MERGE_NT < tot) ? __ldcg(s_dptr[d] + off[u]) : 0ull;
+#pragma unroll
+        for (int u = 0; u < MERGE_E; ++u) {
+            const int e = e0 + u * MERGE_NT;
+            if (e < tot) {
+                unsigned long long k1 = 0ull, k2 = 0ull, omin = 0ull;
+                if (have_old) {
+                    const ulonglong2 L = Lr[u];
+                    const uint32_t q1 = (0xFFFFFFFFu - (uint32_t)(L.x & 0xFFFFFFFFull)) >> 4;    // blocks of the listed keys
+                    const uint32_t q2 = (0xFFFFFFFFu - (uint32_t)(L.y & 0xFFFFFFFFull)) >> 4;
+                    omin = L.y ? L.y : L.x;
+                    if (!((mask >> q1) & 1u)) k1 = L.x;                                            // R: listed keys of clean blocks
+                    if (L.y && !((mask >> q2) & 1u)) top2_insert(L.y, k1, k2);
+                }
+#pragma unroll
+                for (int d = 0; d < MERGE_DP; ++d)
+                    if (kr[u][d] >= omin) top2_insert(kr[u][d], k1, k2);          // (0 padding is never inserted: k1, k2 >= 0)
+                for (int d0 = MERGE_DP; d0 < nd; d0 += MERGE_DP) {                // more than MERGE_DP blocks: chunks of loads
+                    unsigned long long kx[MERGE_DP];
+#pragma unroll
+                    for (int d = 0; d < MERGE_DP; ++d) kx[d] = (d0 + d < nd) ? __ldcg(s_dptr[d0 + d] + off[u]) : 0ull;
+#pragma unroll
+                    for (int d = 0; d < MERGE_DP; ++d) if (kx[d] >= omin) top2_insert(kx[d], k1, k2);
+                }
+                if (have_old && k1 == 0ull) {               // nothing certain: exact top-2 of all NB blocks
+                    k2 = 0ull;
+                    for (int q0 = 0; q0 < NB; q0 += MERGE_DP) {
+                        unsigned long long kx[MERGE_DP];
+#pragma unroll
+                        for (int d = 0; d < MERGE_DP; ++d) kx[d] = (q0 + d < NB) ? __ldcg(s_ptr[q0 + d] + off[u]) : 0ull;
+#pragma unroll
+                        for (int d = 0; d < MERGE_DP; ++d) top2_insert(kx[d], k1, k2);
+                    }
+                }
+                const ppde_cnn_net_t& net = prm.m.net[kk[u]];
+                outp[e] = winner_from_raw(k1, 1.f / (net.w1_scale * net.r1_scale), __ldg(net.b1 + jj[u]));
+                if (newp) newp[e] = make_ulonglong2(k1, k2);
+            }
         }
     }
-    for (int e = threadIdx.x; e < nets * J2; e += blockDim.x) {
-        const int k = e / J2, j = e - k * J2;
-        const size_t base = ((size_t)k * NB) * J2 + j;
-        unsigned long long best = 0ull;
-        uint32_t need = all_blocks;                         // blocks whose keys are read: all of them (old winner's block is dirty,
-                                                            // or a full evaluation), or only the dirty ones
-        if (have_old) {
-            const unsigned long long old = __ldcg(prm.mkey_pool + ((size_t)rx * nets + k) * J2 + j);
-            const uint32_t q_old = (0xFFFFFFFFu - (uint32_t)(old & 0xFFFFFFFFull)) >> 4;      // block of the old winner
-            if (!((mask >> q_old) & 1u)) { best = old; need = mask; }
-        }
-        unsigned long long key[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-            key[q] = (q < NB && ((need >> q) & 1u)) ? __ldcg(prm.bkey + (size_t)slot[q] * row_keys + base + (size_t)q * J2) : 0ull;
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-            if (q < NB) best = (key[q] > best) ? key[q] : best;
-        const ppde_cnn_net_t& net = prm.m.net[k];
-        prm.mkey[((size_t)b * nets + k) * J2 + j] = winner_from_raw(best, 1.f / (net.w1_scale * net.r1_scale), __ldg(net.b1 + j));
-        if (prm.mkey_pool) prm.mkey_pool[((size_t)ry * nets + k) * J2 + j] = best;
-    }
-    __syncthreads();                                        // every thread has read the current row's table (rx may equal ry never)
-    if (threadIdx.x < NB) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-            if (q == (int)threadIdx.x) prm.btab[(size_t)ry * NB + q] = slot[q];
-    }
+    if (threadIdx.x < NB) prm.btab[(size_t)ry * NB + threadIdx.x] = s_slot[threadIdx.x];
 }
 
 // Dirty-block bookkeeping of the incremental forward: for chain range r = [n r / R, n (r+1) / R) (R = clusters per
@@ -1377,6 +1448,8 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+constexpr int BD_NT = 48;                // columns (touched positions) per tile of the compact delta backward
+constexpr int BD_RPW = BD_NT / 8;        // columns per producer warp (8 warps per producer set)
 // Winner records of the DELTA backward.  For chain b and net k the per-net gradient changes between the current state x
 // and the proposal y only through
 //   * the conv rows whose relu mask changed: p in D0 = U_{i: x_i != y_i} [i-4, i], and
@@ -1400,7 +1473,7 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     int* sList = sPx + J2;            // [2 J2]
     const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
     const unsigned long long* ky = mkey_y + (size_t)bk * J2;
-    const unsigned long long* kx = mkey_pool + ((size_t)rows_x[b] * n_nets + k) * J2;
+    const unsigned long long* kx = mkey_pool + 2 * ((size_t)rows_x[b] * n_nets + k) * J2;      // {K1, K2} per channel: K1 = raw winner
     for (int i = threadIdx.x; i <= P; i += 128) { sStart[i] = 0; if (i < P) { sFill[i] = 0; sD0[i] = 0; } }
     __syncthreads();
     for (int i = threadIdx.x; i < L; i += 128) {
@@ -1416,7 +1489,7 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     const float unscale = 1.f / (cm.net[k].w1_scale * cm.net[k].r1_scale);
     for (int j = threadIdx.x; j < J2; j += 128) {
         // the pool holds RAW winners (cnn_inc_merge_kernel): same bias / relu epilogue as for mkey
-        const int py = decode(ky[j]), px = decode(winner_from_raw(kx[j], unscale, __ldg(cm.net[k].b1 + j)));
+        const int py = decode(ky[j]), px = decode(winner_from_raw(kx[2 * j], unscale, __ldg(cm.net[k].b1 + j)));
         const bool moved = py != px;
         const int ey = (py >= 0 && (moved || sD0[py])) ? py : -1;
         const int ex = (px >= 0 && (moved || sD0[px])) ? px : -1;
@@ -1462,7 +1535,12 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
         for (int i = threadIdx.x; i <= P; i += 128) out[i] = (uint16_t)sStart[i];
         return;
     }
-    // compact record: npos | pos[npos] | start[npos+1] | list   (only the positions that received an entry)
+    // compact record (only the positions that received an entry):
+    //     npos | pos[npos] | start[npos+1] | list[nent] | ntile | tstart[ntile+1] | (orow, cfirst)[nr]
+    // The tensor-core kernel cuts the npos columns into tiles of BD_NT; column c of a tile (position p) contributes to the
+    // output rows p .. p+4 of the gradient.  Per tile: orow = the distinct output rows its columns touch (ascending),
+    // cfirst = the first column of the tile (tile-relative) with pos >= row - 4; tstart = prefix of the row counts.  A row
+    // touched by two tiles is listed in both (the combine adds the lists in order).
     __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
@@ -1485,12 +1563,110 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     }
     __syncthreads();
     const int npos = sFill[0];
+    int* sPosC = sPy;                                 // [npos] compact position list (sPy / sPx are free now: 2 J2 >= P ints)
     for (int pp = threadIdx.x; pp < P; pp += 128) {
         const int c = sD0[pp];
-        if (c >= 0) { out[1 + c] = (uint16_t)pp; out[1 + npos + c] = (uint16_t)sStart[pp]; }
+        if (c >= 0) { out[1 + c] = (uint16_t)pp; out[1 + npos + c] = (uint16_t)sStart[pp]; sPosC[c] = pp; }
     }
-    if (threadIdx.x == 0) { out[0] = (uint16_t)npos; out[1 + 2 * npos] = (uint16_t)sStart[P]; }
-    for (int u = threadIdx.x; u < sStart[P]; u += 128) out[2 + 2 * npos + u] = (uint16_t)sList[u];
+    const int nent = sStart[P];
+    if (threadIdx.x == 0) { out[0] = (uint16_t)npos; out[1 + 2 * npos] = (uint16_t)nent; }
+    for (int u = threadIdx.x; u < nent; u += 128) out[2 + 2 * npos + u] = (uint16_t)sList[u];
+    // ---- output-row lists of the tiles.  Columns ascend in position, so the rows [p, p+4] of column c that no earlier column of
+    // the tile covers are the last min(5, p - p_prev) of them, and for exactly those rows column c is the first contributor
+    // (p_prev < row - 4): cfirst = c.  One warp scans the counts of a tile's <= BD_NT columns.
+    const int ntile = (npos + BD_NT - 1) / BD_NT;
+    uint16_t* oo = out + 2 + 2 * npos + nent;         // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
+    uint16_t* pairs = oo + 2 + ntile;
+    if (threadIdx.x == 0) { oo[0] = (uint16_t)ntile; oo[1] = 0; }
+    __syncthreads();                                  // sPosC complete
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int nr_run = 0;
+        for (int t = 0; t < ntile; ++t) {
+            const int c0 = t * BD_NT, c1 = min(c0 + BD_NT, npos);
+            int cnt[2], incl = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {             // lane owns columns c0 + 2 lane, c0 + 2 lane + 1  (BD_NT <= 64)
+                const int c = c0 + 2 * lane + h;
+                cnt[h] = 0;
+                if (c < c1) cnt[h] = (c == c0) ? 5 : min(5, sPosC[c] - sPosC[c - 1]);
+                incl += cnt[h];
+            }
+            const int mine = incl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int base = nr_run + incl - mine;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + 2 * lane + h;
+                if (c < c1) {
+                    const int pp = sPosC[c];
+                    for (int j = 0; j < cnt[h]; ++j) {
+                        pairs[2 * (base + j)] = (uint16_t)(pp + 5 - cnt[h] + j);
+                        pairs[2 * (base + j) + 1] = (uint16_t)(c - c0);
+                    }
+                    base += cnt[h];
+                }
+            }
+            nr_run += __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) oo[2 + t] = (uint16_t)nr_run;
+        }
+    }
+}
+
+// Delta backward, second kernel: the proposal's gradient row from the current state's row, the change of the Potts field and the
+// SPARSE per-net changes the tensor-core kernel left in the scratch (rows listed in the records, values [row][20]):
+//     G_y = G_x + (Gp_y - Gp_x)(window);   then for k = 0 .. n_nets-1, tile by tile, row by row:  G_y[row] += lamda/n_nets * dGc_k[row]
+// One CTA per chain, the row is assembled in shared memory; fixed order (net, tile, row): deterministic.
+__global__ void __launch_bounds__(256) cnn_grad_combine_sparse_kernel(int n, int L, int n_nets, float scale, ppde_potts_t pm,
+                                                                      const float* __restrict__ vals, int vcap,
+                                                                      const uint16_t* __restrict__ wl, int rec,
+                                                                      const float* __restrict__ Gp, int64_t Gp_stride,
+                                                                      float* __restrict__ G, int64_t G_stride,
+                                                                      const int32_t* __restrict__ rows_x, const int32_t* __restrict__ rows_y) {
+    extern __shared__ __align__(16) float srow[];     // [20 L]
+    const int b = blockIdx.x, NE = L * PPDE_Q;
+    const int wlo = pm.win_lo * PPDE_Q, whi = (pm.win_lo + pm.Lp) * PPDE_Q;     // multiples of 4
+    const int rx = rows_x[b], ry = rows_y[b];
+    const float4* gx = reinterpret_cast<const float4*>(G + (int64_t)rx * G_stride);
+    const float* px = Gp ? Gp + (int64_t)rx * Gp_stride : nullptr;
+    const float* py = Gp ? Gp + (int64_t)ry * Gp_stride : nullptr;
+    float4* s4 = reinterpret_cast<float4*>(srow);
+    for (int q = threadIdx.x; q < NE / 4; q += blockDim.x) {
+        float4 base = __ldcs(gx + q);
+        const int e = q * 4;
+        if (Gp && e >= wlo && e < whi) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(py + (e - wlo)));
+            const float4 c = __ldcs(reinterpret_cast<const float4*>(px + (e - wlo)));
+            base.x += a.x - c.x; base.y += a.y - c.y; base.z += a.z - c.z; base.w += a.w - c.w;
+        }
+        s4[q] = base;
+    }
+    __syncthreads();
+    for (int k = 0; k < n_nets; ++k) {
+        const uint16_t* r = wl + ((size_t)b * n_nets + k) * rec;
+        const int npos = r[0];
+        const int nent = r[1 + 2 * npos];
+        const uint16_t* oo = r + 2 + 2 * npos + nent;
+        const int ntile = oo[0];
+        const uint16_t* tstart = oo + 1;
+        const uint16_t* pairs = oo + 2 + ntile;      // (orow, cfirst) per output row
+        const float* v = vals + ((size_t)k * n + b) * vcap;
+        for (int t = 0; t < ntile; ++t) {
+            const int r0 = tstart[t], r1 = tstart[t + 1];
+            for (int it = r0 * PPDE_Q + (int)threadIdx.x; it < r1 * PPDE_Q; it += blockDim.x) {
+                const int rr = it / PPDE_Q, a = it - rr * PPDE_Q;
+                const int e = (int)pairs[2 * rr] * PPDE_Q + a;
+                srow[e] = fmaf(scale, __ldcs(v + it), srow[e]);
+            }
+            __syncthreads();
+        }
+    }
+    float4* gy = reinterpret_cast<float4*>(G + (int64_t)ry * G_stride);
+    for (int q = threadIdx.x; q < NE / 4; q += blockDim.x) gy[q] = s4[q];
 }
 
 // G_y = G_x + (Gp_y - Gp_x)(window) + lamda / n_nets * (dGc_0 + dGc_1 + dGc_2)   (delta backward; fixed summation order)
@@ -1548,7 +1724,9 @@ struct BwdParams {
     int nrec;                           // compact delta kernel: record buffers in shared memory
     const int32_t* btab; int NB;        // optional block table of the pools [rows, NB]: the mask rows of block q of row r live in row btab[r][q]
     const uint16_t* wl; int rec;        // winner records from cnn_winner_sort_kernel
-    float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel)
+    float* Gc;                          // [n_nets][n][20L] per-net partial gradients (combined by cnn_grad_combine_kernel);
+                                        // compact delta kernel: [n_nets][n][vcap] sparse values [row][20] of the rows the record lists
+    int vcap;                           // floats per (net, chain) of the sparse scratch
     int ctas_per_net;
     int tiles_per_chain, nch, kpad;
     int dbg;                            // profiling experiments only (PPDE_BWD_DEBUG): 2 = skip gathers
@@ -1954,27 +2132,38 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
 
 // =====================================================================================================
 // COMPACT delta backward.  The change of the adjoint rows between the current state and the proposal is non-zero on a few
-// dozen positions only (cnn_winner_delta_kernel, compact record: npos | pos[npos] | start[npos+1] | list).  Instead of four
-// mostly-zero 64-position tiles per (chain, net) the kernel builds ceil(npos / 64) tiles - normally ONE - whose columns are
-// the touched positions, and scatters the product into the chain's gradient row:
-//     dGc[(pos[c] + t), a] += Y[(t,a), c]        (shared-memory float adds; columns in order: deterministic)
-// Roles and barriers as in cnn_backward_tc_kernel; differences: every role reads npos from the chain's record (three record
-// buffers; the epilogue releases them too, it needs pos[]), the global tile counter advances by the chain's own tile count.
+// dozen positions only (cnn_winner_delta_kernel, compact record).  Instead of four mostly-zero 64-position tiles per
+// (chain, net) the kernel builds ceil(npos / BD_NT) tiles - normally ONE - whose columns are the touched positions, and the
+// epilogue turns the product Y[(t,a), c] into the SPARSE change of the per-net gradient
+//     dGc[row, a] = sum over the columns c with pos[c] = row - t, t = 0..4, of Y[(t,a), c]      (ascending c: deterministic)
+// for the output rows the record lists for the tile: the accumulator goes TMEM -> registers -> shared memory [c][(a,t)]
+// (conflict-free, one store per column) and one thread per (row, a) gathers its <= 5 terms and writes the value straight
+// to the scratch (coalesced); cnn_grad_combine_sparse_kernel adds the three nets' lists to the row.  (The first version
+// scatter-added column by column into a dense shared-memory row, one warp barrier per column, and flushed / re-zeroed 19 KB per
+// chain and net: 6,100 of the ~9,500 cycles per tile, with the record buffers released only afterwards.)
+// Roles and barriers as in cnn_backward_tc_kernel; differences: every role reads npos from the chain's record (the epilogue
+// releases the record buffers too, it needs the lists), the global tile counter advances by the chain's own tile count,
+// tiles have BD_NT = 48 columns (6 per producer warp).
 constexpr int BD_NREC_MAX = 6;          // record buffers: as many as fit in shared memory (BwdParams.nrec, >= 3)
+constexpr int BD_MAT = BD_NT * KCH * 2; // one [48 x 64] fp16 operand matrix (6 KB)
+constexpr int BD_SLOT = 2 * BD_MAT;     // hi + lo
+constexpr int BD_NBUF = 3;             // operand tile buffers (3 x 48 KB).  4 buffers leave room for only 3 record buffers and
+                                       // measured slower (7.1 vs 5.9 ms / 64k chains): the records are what lets the roles run ahead
+constexpr int BD_TS = 100;              // floats per column of the transposed accumulator tile: index a * 5 + t
 template <bool PROF>
 __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int C = prm.m.C, P = prm.m.P, L = prm.m.L, J2 = 2 * C, NE = L * PPDE_Q;
+    const int C = prm.m.C, P = prm.m.P, J2 = 2 * C;
     const int nch = prm.nch;
     const int BD_NREC = prm.nrec;
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* sGc = reinterpret_cast<float*>(ring + BW_NBUF * BW_MAXCH * BW_SLOT);   // [NE] chain gradient row
-    float* sDj = sGc + ((NE + 3) & ~3);                                      // [J2] decoder weights
+    float* sT = reinterpret_cast<float*>(ring + BD_NBUF * BW_MAXCH * BD_SLOT);    // [BD_NT][BD_TS] transposed accumulator tile
+    float* sDj = sT + BD_NT * BD_TS;                                          // [J2] decoder weights
     uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sDj + J2) + 15) & ~(uintptr_t)15);   // [BD_NREC][rec]
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRec + BD_NREC * prm.rec) + 7) & ~(uintptr_t)7);
-    uint64_t* full = bars;                      // [BW_NBUF] tile buffers: producers -> MMA (8 warp arrivals: one producer set)
-    uint64_t* empty = full + BW_NBUF;           // [BW_NBUF] MMA -> producers
-    uint64_t* dfull = empty + BW_NBUF;          // [BW_NDBUF] MMA -> epilogue
+    uint64_t* full = bars;                      // [BD_NBUF] tile buffers: producers -> MMA (8 warp arrivals: one producer set)
+    uint64_t* empty = full + BD_NBUF;           // [BD_NBUF] MMA -> producers
+    uint64_t* dfull = empty + BD_NBUF;          // [BW_NDBUF] MMA -> epilogue
     uint64_t* dempty = dfull + BW_NDBUF;        // [BW_NDBUF] epilogue -> MMA (4 warp arrivals)
     uint64_t* recfull = dempty + BW_NDBUF;      // [BD_NREC] record landed (bulk copy, tx bytes)
     uint64_t* recempty = recfull + BD_NREC_MAX; // [BD_NREC] producers and epilogue done with the record (20 warp arrivals)
@@ -1992,7 +2181,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
     const uint32_t rec_a = smem_u32(sRec);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BW_NBUF; ++s) { mbar_init(&full[s], BW_NT_PROD / 64); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < BD_NBUF; ++s) { mbar_init(&full[s], BW_NT_PROD / 64); mbar_init(&empty[s], 1); }
         for (int s = 0; s < BD_NREC; ++s) { mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BW_NT_PROD / 32 + NT_EPI / 32); }
         for (int d = 0; d < BW_NDBUF; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI / 32); }
         fence_barrier_init();
@@ -2034,72 +2223,86 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
     tc_fence_after();
 
     if (warp < 4) {
-        // ===== EPILOGUE: lane = (a, t); column c of a tile is position pos[c]: scatter-add into the chain's row =====
+        // ===== EPILOGUE: TMEM lane = (a, t) -> sT[c][a * 5 + t]; then one thread per (output row, a) gathers its <= 5 terms =====
         const int grp = lane / 5, d = lane - 5 * grp, a = 6 * warp + grp;
         const bool rowok = lane < 30 && a < PPDE_Q;
         const int tid = threadIdx.x;
         const float unscale = 1.f / (net.w0_scale * net.adj_scale);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
-        const uint32_t gc_a = smem_u32(sGc);
+        const uint32_t st_a = smem_u32(sT) + 4u * (uint32_t)(d * PPDE_Q + a);   // my element of column 0: sT[c][t * 20 + a]
+        const uint32_t t_a = smem_u32(sT);
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
         int it = 0;
-        {   // the row accumulates changes: zero once, every flush leaves it zeroed again
-            float4* z = reinterpret_cast<float4*>(sGc);
-            for (int e = tid; e < NE / 4; e += NT_EPI) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        named_bar(2, NT_EPI);
-        const uint32_t my_a = gc_a + 4u * (uint32_t)(d * PPDE_Q + a);     // (p + d) * 20 + a  =  p * 20 + (d * 20 + a)
         for (int ci = 0; ci < nchains; ++ci) {
             const int rb = ci % BD_NREC;
             mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
-            const int tiles = (npos + BW_NT - 1) / BW_NT;
+            const int tiles = (npos + BD_NT - 1) / BD_NT;
+            const int nent = lds_u16(rs + 2u * (uint32_t)(1 + 2 * npos));
+            const uint32_t oo = rs + 2u * (uint32_t)(2 + 2 * npos + nent);          // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
+            const uint32_t pairs_a = oo + 2u * (uint32_t)(2 + tiles);
+            float* vout = prm.Gc + ((size_t)k * prm.n + (b_lo + ci)) * prm.vcap;
             if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
             for (int t = 0; t < tiles; ++t, ++it) {
                 const int buf = it & (BW_NDBUF - 1);
                 mbar_wait(&dfull[buf], (uint32_t)((it / BW_NDBUF) & 1));
                 if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                 tc_fence_after();
-                uint32_t y[64];
-                tmem_ld32(lane_addr + buf * BW_NT, y);
-                tmem_ld32(lane_addr + buf * BW_NT + 32, y + 32);
+                uint32_t y[BD_NT];
+                tmem_ld32(lane_addr + buf * 64, y);
+                tmem_ld16(lane_addr + buf * 64 + 32, y + 32);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&dempty[buf]);
                 if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-                const int ncol = min(BW_NT, npos - t * BW_NT);
-                const uint32_t pa = rs + 2u * (uint32_t)(1 + t * BW_NT);
-                // column c = position pos[c]: lane (a, tap d) adds to G[(pos + d), a].  Within a column the 30 lanes hit 30
-                // different words; across columns (ascending positions, taps overlap when positions are < 5 apart) the
-                // read-modify-writes are ordered by the warp barrier: plain shared-memory adds, deterministic order.
-                int pn = lds_u16(pa);                                      // position of the next column, one ahead
+                const int ncol = min(BD_NT, npos - t * BD_NT);
+                named_bar(2, NT_EPI);                                      // the previous tile's gather has read sT
+                if (rowok) {
 #pragma unroll
-                for (int c = 0; c < BW_NT; ++c) {
-                    if (c < ncol) {                                        // warp-uniform
-                        const uint32_t addr = my_a + 80u * (uint32_t)pn;
-                        if (c + 1 < BW_NT) pn = lds_u16(pa + 2u * (uint32_t)min(c + 1, BW_NT - 1));
-                        if (rowok) sts_f32(addr, lds_f32(addr) + __uint_as_float(y[c]) * unscale);
-                        __syncwarp();
+                    for (int c = 0; c < BD_NT; ++c)
+                        if (c < ncol) sts_f32(st_a + (uint32_t)(c * BD_TS * 4), __uint_as_float(y[c]) * unscale);
+                }
+                named_bar(2, NT_EPI);
+                // output rows of this tile: r in [tstart[t], tstart[t+1]); row i = orow[r] gets the columns c = cfirst[r] .. while
+                // pos[c] <= i (at most 5, tap t = i - pos[c]); one thread per row: 5 x 16-byte loads per term, 80 bytes out
+                const int r0 = lds_u16(oo + 2u * (uint32_t)(1 + t)), r1 = lds_u16(oo + 2u * (uint32_t)(2 + t));
+                const uint32_t pa = rs + 2u * (uint32_t)(1 + t * BD_NT);                  // pos[] of the tile's columns
+                for (int r = r0 + tid; r < r1; r += NT_EPI) {
+                    const int i = lds_u16(pairs_a + 4u * (uint32_t)r);
+                    const int cf = lds_u16(pairs_a + 4u * (uint32_t)r + 2u);
+                    int pp[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) pp[u] = lds_u16(pa + 2u * (uint32_t)min(cf + u, ncol - 1));
+                    float4 acc[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) {                                       // ascending columns: the order of the sums is fixed
+                        const bool on = (cf + u < ncol) && (pp[u] <= i);                  // (pos >= i - 4 for every column >= cfirst)
+                        const uint32_t src = t_a + 4u * (uint32_t)(min(cf + u, ncol - 1) * BD_TS + (on ? (i - pp[u]) : 0) * PPDE_Q);
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            float4 v;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + 16u * q));
+                            if (on) { acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w; }
+                        }
                     }
+                    float4* dst = reinterpret_cast<float4*>(vout + (size_t)r * PPDE_Q);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) __stcs(dst + q, acc[q]);
                 }
                 if (PROF) { const long long t1 = clock64(); pc[2] += t1 - tp; tp = t1; }
             }
-            // flush the chain's change of the per-net gradient (streaming 16-byte stores) and leave the row zeroed
-            named_bar(2, NT_EPI);
-            float4* dst = reinterpret_cast<float4*>(prm.Gc + ((size_t)k * prm.n + (b_lo + ci)) * NE);
-            float4* src = reinterpret_cast<float4*>(sGc);
-            for (int e = tid; e < NE / 4; e += NT_EPI) { __stcs(dst + e, src[e]); src[e] = make_float4(0.f, 0.f, 0.f, 0.f); }
-            named_bar(2, NT_EPI);
+            __syncwarp();
             if (lane == 0) mbar_arrive(&recempty[rb]);
-            if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
         }
         if (PROF && prm.prof && threadIdx.x == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3]; }
     } else if (warp == BW_WARP_MMA) {
         // ===== MMA ISSUER: warp-uniform loop, one elected lane issues; also stages the records (bulk copies) =====
-        const uint32_t idesc = make_idesc(128, BW_NT);
+        const uint32_t idesc = make_idesc(128, BD_NT);
         const uint32_t ring_addr = smem_u32(ring);
         const int last_ksteps = (prm.kpad - (nch - 1) * KCH) / 16;
         const uint32_t a_lo_off = (uint32_t)(prm.kpad / 2);
@@ -2136,23 +2339,23 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
             const int npos = lds_u16(rec_a + (uint32_t)rb * rec_bytes);
             nread = ci + 1;
-            const int tiles = (npos + BW_NT - 1) / BW_NT;
+            const int tiles = (npos + BD_NT - 1) / BD_NT;
             for (int t = 0; t < tiles; ++t, ++it) {
-                const int tb = it % BW_NBUF;
+                const int tb = it % BD_NBUF;
                 const int buf = it & (BW_NDBUF - 1);
                 if (it >= BW_NDBUF) mbar_wait(&dempty[buf], (uint32_t)(((it / BW_NDBUF) + 1) & 1));
                 if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                 // keep the records flowing while the tile is being built: bounded SUSPENDING waits, not a spin (this is the
                 // top-priority warp of its scheduler: spinning here starves four producer warps, measured as a 10x slower kernel)
-                while (!mbar_try_wait_for(&full[tb], (uint32_t)((it / BW_NBUF) & 1), 2000u)) stage_records(0);
+                while (!mbar_try_wait_for(&full[tb], (uint32_t)((it / BD_NBUF) & 1), 2000u)) stage_records(0);
                 if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + D_COL0 + buf * BW_NT;
+                const uint32_t d_tmem = tmem_base + D_COL0 + buf * 64;
                 if (elect_one()) {
                     for (int kc = 0; kc < nch; ++kc) {
                         const int slot = tb * BW_MAXCH + kc;
-                        const uint64_t dhi = make_b_desc(ring_addr + slot * BW_SLOT);
-                        const uint64_t dlo = make_b_desc(ring_addr + slot * BW_SLOT + BW_MAT);
+                        const uint64_t dhi = make_b_desc(ring_addr + slot * BD_SLOT);
+                        const uint64_t dlo = make_b_desc(ring_addr + slot * BD_SLOT + BD_MAT);
                         const int ksteps = (kc == nch - 1) ? last_ksteps : KCH / 16;
                         const uint32_t a_hi0 = tmem_base + kc * (KCH / 2);
 #pragma unroll
@@ -2175,15 +2378,15 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         }
         if (PROF && prm.prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[4] = pc[0]; o[5] = pc[1]; o[6] = pc[2]; o[7] = it; }
     } else {
-        // ===== PRODUCERS: two sets of 8 warps alternate over the tiles.  A tile has ncol <= 64 live columns (touched positions, in
-        // order) and 64 - ncol zero columns: the live ones are split evenly over the set's 8 warps (rpw = ceil(ncol / 8) adjacent
-        // columns each, so a warp's entries are one run of the list), the dead ones likewise =====
+        // ===== PRODUCERS: two sets of 8 warps alternate over the tiles.  A tile has ncol <= BD_NT live columns (touched positions,
+        // in order) and BD_NT - ncol zero columns: the live ones are split evenly over the set's 8 warps (rpw = ceil(ncol / 8)
+        // adjacent columns each, so a warp's entries are one run of the list), the dead ones likewise =====
         const int pw = warp - 4;
         const int pset = pw >> 3, w8 = pw & 7;
         const bool lact = 8 * lane < prm.kpad;
         const float adj_scale = net.adj_scale;
         const float* wbase = net.W1p + 8 * lane;
-        const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BW_SLOT);
+        const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BD_SLOT);
         const uint32_t unit = (uint32_t)(lane & 7);
         const uint32_t dj_a = smem_u32(sDj);
         const int NB = prm.NB;
@@ -2199,24 +2402,24 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
-            const int tiles = (npos + BW_NT - 1) / BW_NT;
+            const int tiles = (npos + BD_NT - 1) / BD_NT;
             const uint32_t ps = rs + 2u;                                   // pos[c]
             const uint32_t ss = rs + 2u * (uint32_t)(1 + npos);            // start[c]
             const uint32_t ls = rs + 2u * (uint32_t)(2 + 2 * npos);        // list
             for (int t = 0; t < tiles; ++t, ++it) {
                 if ((it & 1) != pset) continue;
-                const int tb = it % BW_NBUF;
-                const int ncol = min(BW_NT, npos - t * BW_NT);
-                const int rpw = (ncol + 7) >> 3;                           // live columns per warp
+                const int tb = it % BD_NBUF;
+                const int ncol = min(BD_NT, npos - t * BD_NT);
+                const int rpw = (ncol + 7) >> 3;                           // live columns per warp (<= BD_RPW)
                 const int rl0 = w8 * rpw;                                  // my first live row of the tile
-                const int rd0 = 8 * rpw + w8 * (8 - rpw) - rpw;            // my dead rows: rd0 + cur for cur = rpw .. 7
-                const int c0 = t * BW_NT + rl0;                            // my first column (compact position index)
+                const int rd0 = 8 * rpw + w8 * (BD_RPW - rpw) - rpw;       // my dead rows: rd0 + cur for cur = rpw .. BD_RPW-1
+                const int c0 = t * BD_NT + rl0;                            // my first column (compact position index)
                 // relu-mask bytes of my live columns, both sides (byte rr of the 64-bit words): two dependent global loads per byte
                 // (block table -> mask row), requested right AFTER the first group of W1 rows so that the two latencies overlap
                 unsigned long long m8 = 0ull, m8x = 0ull;
                 auto load_masks = [&]() {
 #pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
+                    for (int rr = 0; rr < BD_RPW; ++rr) {
                         if (rr < rpw && c0 + rr < npos && lact) {
                             const int p = lds_u16(ps + 2u * (uint32_t)(c0 + rr));
                             int ry = mry, rx = mrx;
@@ -2227,7 +2430,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                     }
                 };
                 bool need_masks = true;
-                const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BW_SLOT);
+                const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BD_SLOT);
                 int e = lds_u16(ss + 2u * (uint32_t)min(c0, npos));
                 const int eB = lds_u16(ss + 2u * (uint32_t)min(c0 + rpw, npos));
                 int cur = 0;
@@ -2239,14 +2442,14 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 auto store_row = [&]() {   // column r0 + cur <- scale * acc (masks were applied per entry), fp16 hi + lo
                     if (!have_buf) {
                         if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-                        mbar_wait(&empty[tb], (uint32_t)(((it / BW_NBUF) + 1) & 1));
+                        mbar_wait(&empty[tb], (uint32_t)(((it / BD_NBUF) + 1) & 1));
                         have_buf = true;
                         if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                     }
                     const int r = (cur < rpw) ? rl0 + cur : rd0 + cur;
                     const uint32_t addr = tile_addr + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((unit ^ (uint32_t)(r & 7)) << 4);
                     if (!dirty_row) {
-                        if (lact) { sts128(addr, 0u, 0u, 0u, 0u); sts128(addr + BW_MAT, 0u, 0u, 0u, 0u); }
+                        if (lact) { sts128(addr, 0u, 0u, 0u, 0u); sts128(addr + BD_MAT, 0u, 0u, 0u, 0u); }
                     } else {
                         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -2259,7 +2462,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                         }
                         if (lact) {
                             sts128(addr, hi[0], hi[1], hi[2], hi[3]);
-                            sts128(addr + BW_MAT, lo[0], lo[1], lo[2], lo[3]);
+                            sts128(addr + BD_MAT, lo[0], lo[1], lo[2], lo[3]);
                         }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) acc[q] = 0.f;
@@ -2310,7 +2513,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                         }
                     }
                 }
-                while (cur < 8) store_row();
+                while (cur < BD_RPW) store_row();
                 if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                 fence_proxy_async();
                 __syncwarp();
@@ -2492,7 +2695,7 @@ extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int3
         if (r1) return r1;
     }
     if (inc_parts & 4) {
-        tc::cnn_inc_merge_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(prm);
+        tc::cnn_inc_merge_kernel<<<n, tc::MERGE_NT, 0, (cudaStream_t)stream>>>(prm);
         return launch_done();
     }
     return 0;
@@ -2548,9 +2751,14 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
     // delta mode, compact records (default; tune->delta_layout = 1 keeps one column per position): npos | pos | start | list
     const bool compact = dl && !(tune && tune->delta_layout == 1);
-    const int rec = compact ? ((2 * P + 2 + 2 * J2 + 7) & ~7) : (((P + 1) + 2 * J2 + 7) & ~7);
-    const size_t smem_fixed = 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 +
-                              8 + 32 * sizeof(uint64_t);
+    // compact record: npos | pos[P] | start[P+1] | list[2 J2] | ntile | tstart[TMAX+1] | orow[RMAX] | cfirst[RMAX]  (uint16)
+    const int tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
+    const int rec = compact ? ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) : (((P + 1) + 2 * J2 + 7) & ~7);
+    const int vcap = compact ? rmax * PPDE_Q : L * PPDE_Q;                       // floats of scratch per (net, chain)
+    prm.vcap = vcap;
+    const size_t smem_fixed = compact
+        ? 1024 + (size_t)tc::BD_NBUF * tc::BW_MAXCH * tc::BD_SLOT + ((size_t)tc::BD_NT * tc::BD_TS + J2) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t)
+        : 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t);
     int nrec = 2;
     if (compact) {                                   // as many record buffers as fit under the 227 KB limit (3 .. BD_NREC_MAX)
         nrec = (int)((232448 - smem_fixed) / ((size_t)rec * sizeof(uint16_t)));
@@ -2570,8 +2778,8 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     const int cfg = (compact ? 4 : (dl ? 2 : 0)) + (prof ? 1 : 0);
     if (cudaError_t e = ensure_dynamic_smem(bkern, smem, configured[cfg])) return (int)e;
     cudaStream_t st = (cudaStream_t)stream;
-    // winner records live behind the per-net gradient scratch: [n_nets*n*20L floats][n*n_nets*rec uint16]
-    uint16_t* wl = reinterpret_cast<uint16_t*>(scratch + (size_t)m->n_nets * n * L * PPDE_Q);
+    // winner records live behind the per-net gradient scratch: [n_nets*n*vcap floats][n*n_nets*rec uint16]
+    uint16_t* wl = reinterpret_cast<uint16_t*>(scratch + (size_t)m->n_nets * n * vcap);
     prm.wl = wl;
     prm.rec = rec;
     if (bwd_parts & 1) {
@@ -2589,7 +2797,13 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
         if (r) return r;
     }
     if (bwd_parts & 4) {
-        if (dl)
+        if (compact) {
+            const size_t csm = (size_t)L * PPDE_Q * sizeof(float);
+            static SmemCache cconf;
+            if (cudaError_t e = ensure_dynamic_smem(tc::cnn_grad_combine_sparse_kernel, csm, cconf)) return (int)e;
+            tc::cnn_grad_combine_sparse_kernel<<<n, 256, csm, st>>>(n, L, m->n_nets, lamda / (float)m->n_nets, *pm, scratch, vcap, wl, rec,
+                                                                    Gp, Gp_stride, G, G_stride, dl->rows_x, dl->rows_y);
+        } else if (dl)
             tc::cnn_grad_combine_delta_kernel<<<n, 256, 0, st>>>(n, L * PPDE_Q, m->n_nets, lamda / (float)m->n_nets, *pm, scratch,
                                                                  Gp, Gp_stride, G, G_stride, dl->rows_x, dl->rows_y);
         else
@@ -2598,6 +2812,17 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
         return launch_done();
     }
     return 0;
+}
+
+// floats of `scratch` the tensor-core backward entry points need for n chains (the largest of the three layouts)
+extern "C" int64_t ppde_cnn_backward_scratch_floats(const ppde_cnn_t* m, int32_t n) {
+    if (!m || n <= 0) return 0;
+    const int64_t P = m->P, L = m->L, J2 = 2 * (int64_t)m->C;
+    const int64_t tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
+    const int64_t rec_c = (2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~(int64_t)7, rec_d = ((P + 1) + 2 * J2 + 7) & ~(int64_t)7;
+    const int64_t a = (int64_t)m->n_nets * n * rmax * PPDE_Q + ((int64_t)n * m->n_nets * rec_c + 1) / 2;     // compact delta
+    const int64_t b = (int64_t)m->n_nets * n * L * PPDE_Q + ((int64_t)n * m->n_nets * rec_d + 1) / 2;        // exact / per-position delta
+    return (a > b ? a : b) + 16;
 }
 
 extern "C" int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const uint8_t* aa, int32_t aa_stride,

@@ -54,8 +54,7 @@ class Workspace:
 
     def grad_scratch(self, n):
         m = self.m
-        rec = (2 * m.P + 2 + 4 * m.C + 7) // 8 * 8                    # winner records (uint16) behind the floats (compact delta layout is the larger)
-        return self._get("gscratch", m.n_nets * n * m.NE + (n * m.n_nets * rec + 1) // 2, torch.float32)
+        return self._get("gscratch", int(m.lib.ppde_cnn_backward_scratch_floats(C.byref(m.cnn), n)), torch.float32)
 
     def inc_ws(self, n):
         return self._get("inc_ws", int(self.m.lib.ppde_cnn_forward_inc_ws_bytes(n)), torch.uint8)
@@ -182,9 +181,10 @@ class PoEModel:
         # A/B switches of the tensor-core kernels, per call (ppde_tune_t): PPDE_TC_CTAS=1 = 1-CTA forward kernel,
         # PPDE_BWD_DELTA_COMPACT=0 = one column per position in the delta backward
         self.tune = None
-        if os.environ.get("PPDE_TC_CTAS", "2") == "1" or os.environ.get("PPDE_BWD_DELTA_COMPACT", "1") == "0":
+        dbg = int(os.environ.get("PPDE_TUNE_DBG", "0"))       # 8: the merge scans all NB keys (A/B of the top-2 list)
+        if os.environ.get("PPDE_TC_CTAS", "2") == "1" or os.environ.get("PPDE_BWD_DELTA_COMPACT", "1") == "0" or dbg:
             self.tune = TuneT(forward_ctas=1 if os.environ.get("PPDE_TC_CTAS", "2") == "1" else 0,
-                              delta_layout=1 if os.environ.get("PPDE_BWD_DELTA_COMPACT", "1") == "0" else 0)
+                              delta_layout=1 if os.environ.get("PPDE_BWD_DELTA_COMPACT", "1") == "0" else 0, dbg=dbg)
         # CNN forward implementation: tcgen05 tensor-core kernel (needs the W1 tile in 256 TMEM columns,
         # i.e. C <= 256) or the fp32 SIMT kernel.  PPDE_CNN_FORWARD=simt forces the latter (A/B tests).
         want = os.environ.get("PPDE_CNN_FORWARD", "tc")
@@ -410,7 +410,8 @@ class ChainEngine:
         self.bkey = self.r1pool = self.dmask = self.mkpool = self.btab = None
         self.delta = bool(m.cnn_bwd_delta)
         if self.inc:
-            self.mkpool = torch.empty(rows * m.n_nets * 2 * m.C, dtype=torch.int64, device=dev)
+            # per (row, net, channel): the two largest raw block keys (winner, runner-up) - ppde_cnn_forward_inc
+            self.mkpool = torch.empty(rows * m.n_nets * 2 * m.C * 2, dtype=torch.int64, device=dev)
             # block table: btab[r][q] = the pool row whose slot holds block q (keys and relu-mask rows) of row r
             self.btab = torch.arange(rows, dtype=i32, device=dev).repeat_interleave(m.NB).contiguous()
             self.bkey = torch.empty(rows * m.n_nets * m.NB * 2 * m.C, dtype=torch.int64, device=dev)

@@ -77,7 +77,7 @@ def test_incremental_forward_is_bit_identical(L, n, use_pool):
     bkey = torch.full((rows * nets * NB * J2,), -1, dtype=torch.int64, device=dev)
     r1pool = torch.full((rows * nets * P * 32,), 0xAB, dtype=torch.uint8, device=dev)
     btab = torch.full((rows * NB,), -1, dtype=torch.int32, device=dev)
-    mkpool = torch.full((rows * nets * J2,), -1, dtype=torch.int64, device=dev) if use_pool else None
+    mkpool = torch.full((rows * nets * J2 * 2,), -1, dtype=torch.int64, device=dev) if use_pool else None
     st = _stream()
     # current states: private row b for even chains, row n + b for odd ones (both halves of the pool get used)
     rows_x = torch.tensor([b if b % 2 == 0 else n + b for b in range(n)], dtype=torch.int32, device=dev)
@@ -170,7 +170,7 @@ def test_delta_backward_matches_full_backward(L, n):
     Gp = torch.zeros(rows, m.D, dtype=f32, device=dev)
     bkey = torch.zeros(rows * nets * NB * J2, dtype=torch.int64, device=dev)
     r1pool = torch.zeros(rows * nets * P * 32, dtype=torch.uint8, device=dev)
-    mkpool = torch.zeros(rows * nets * J2, dtype=torch.int64, device=dev)
+    mkpool = torch.zeros(rows * nets * J2 * 2, dtype=torch.int64, device=dev)
     btab = torch.full((rows * NB,), -1, dtype=torch.int32, device=dev)
     E = torch.zeros(n, dtype=f32, device=dev); fit = torch.zeros_like(E); Ep = torch.zeros_like(E)
     st = _stream()
