@@ -173,19 +173,25 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gfp_potts_poe_64k", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: the workload's)")
-    ap.add_argument("--cpu-chains", type=int, default=1024, help="bounded CPU sample size (>= 1024 saturates the host cores)")
+    ap.add_argument("--cpu-chains", type=int, default=None,
+                    help="bounded CPU sample size (default: min(1024, the workload's chains); >= 1024 saturates the host cores)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's chains are the GLOBAL population, "
                                                           "sharded over the ranks (default: that many chains PER GPU, weak)")
+    ap.add_argument("--global-population", action="store_true",
+                    help="e2e leg: every rank passes the GLOBAL population and gets the global 6-tuple back (the reference's "
+                         "calling convention; default: each rank passes its shard, ppde_local_population)")
     ap.add_argument("--log-every", type=int, default=0, help="e2e leg: run the log_every population report (device kernels + "
                                                              "NCCL all-gathers) every this many iterations (0 = never)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.chains:
         wl["chains"] = args.chains
+    if args.cpu_chains is None:
+        args.cpu_chains = min(1024, wl["chains"])
     pr = build_problem(wl)
     if args.impl == "reference":
         run_reference(args, wl, pr)
@@ -317,32 +323,37 @@ def main():
             NE = 20 * L
             tflop = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12
             gbs = lambda by, ms_: by / (ms_ * 1e-3) / 1e9
+            # `traffic` = dram__bytes_read + dram__bytes_write of one launch from the committed `ncu --set full` captures of
+            # round 2 (profiles/r02_*_ncu_full_summary.txt, 16,384 chains in steady state, scaled to this launch)
+            nd_ = (dirty_blocks / n) if dirty_blocks is not None else 2.25
             cand = {
                 "cnn_backward_tc": dict(kernel=("cnn_backward_delta_kernel" if eng.delta else "cnn_backward_tc_kernel"), bound="tensor", unit="TFLOP/s",
                                         work=3 * (4 * Cc * Cc + 200 * P * Cc) * n, peak=pk["bf16_sustained"],
-                                        # dram read+write bytes from the committed ncu captures at 8192 chains (profiles/r01_v16_ncu_full_summary.txt:
-                                        # compact delta 109.6 + 413.2 MB; profiles/r01_v10_ncu_full_summary.txt: exact 244.6 + 415.9 MB)
-                                        traffic=((522.8e6 if eng.delta else 660.6e6) / 8192) * n if L == 238 else None,
+                                        traffic=((0.763e9 / 16384) if eng.delta else (660.6e6 / 8192)) * n if L == 238 else None,
                                         note="gradient of the CNN ensemble for every proposal: 3*(4C^2+200PC) algorithmic flops per chain; "
                                              "fp16 hi/lo split = 3 tensor-core passes per flop; " +
-                                             ("delta mode: one tile of the touched positions per chain and net, only the adjoint rows that differ are gathered" if eng.delta else
+                                             ("delta mode: one tile of the touched positions per chain and net, only the adjoint rows that differ are gathered "
+                                              "(~70 W1 rows of 960 B per chain and net from L2); bound by the producers' instruction issue, not by the tensor pipe" if eng.delta else
                                               "limited by the L2->SM gather of the winners' W1 rows (422 KB per chain and net)")),
                 "cnn_forward_inc_tc": dict(kernel="cnn_forward_inc_kernel", bound="tensor", unit="TFLOP/s",
-                                           work=3 * 2 * P * Cc * 2 * Cc * n, peak=pk["bf16_sustained"], traffic=(190.6e6 / 8192) * n if L == 238 else None,
-                                           note="max-pool winners of every proposal: 3*2*P*C*2C algorithmic flops per chain, of which only the dirty "
-                                                "16-position blocks are executed (3 fp16 passes per flop)"),
-                "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s", work=None, peak=pk["hbm_gbs"],
-                                      traffic=(833.2e6 / 8192) * n if L == 238 else None, note="chain-level winner = max over the NB block keys read through the block table"),
+                                           # EXECUTED algorithmic flops: only the dirty 16-position blocks are evaluated (the full-evaluation
+                                           # equivalent, 3*2*P*C*2C per chain, is reported under roofline.forward_incremental)
+                                           work=nd_ * n * 3 * 2 * 16 * Cc * 2 * Cc, peak=pk["bf16_sustained"],
+                                           traffic=(0.431e9 / 16384) * n if L == 238 else None,
+                                           note="max-pool winners of every proposal: 3 nets * 2*16*C*2C flops per dirty 16-position block "
+                                                "(3 fp16 passes per flop); bound by the shared-memory pipe of the r1 producers (5 table reads per element)"),
+                "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s",
+                                      # per channel: 16 B top-2 list read + 8 B per dirty block key + 16 B list + 8 B winner written
+                                      work=int(n * 3 * 2 * Cc * (16 + 8 * nd_ + 24)), peak=pk["hbm_gbs"],
+                                      traffic=(1.909e9 / 16384) * n if L == 238 else None,
+                                      note="chain-level winner from the row's top-2 list and the dirty blocks' keys (exact, csrc/cnn_tc.cu)"),
                 "pas_propose": dict(kernel="pas_propose_kernel", bound="hbm", unit="GB/s", work=(4 * NE + L) * n, peak=pk["hbm_gbs"],
-                                    traffic=(163.3e6 / 8192) * n if L == 238 else None,
-                                    note="reads one gradient row per chain; bound by the per-entry Philox + softmax arithmetic "
-                                         "(one uniform per entry of [n, 20L] per sub-step), not by bytes"),
+                                    traffic=(166.9e6 / 8192) * n if L == 238 else None,
+                                    note="reads one gradient row per chain; bound by instruction issue (Philox4x32-10 + race test for each of the "
+                                         "20L entries of every live sub-step: torch.multinomial needs one uniform per entry), not by bytes"),
             }
             dom = max(cand, key=lambda k_: breakdown[k_])
             cd = cand[dom]
-            if dom == "cnn_inc_merge":
-                nb_ = (P + 15) // 16
-                cd["work"] = int(n * 3 * 2 * Cc * 8 * (nb_ + 2))
             ach = tflop(cd["work"], breakdown[dom]) if cd["unit"] == "TFLOP/s" else gbs(cd["work"], breakdown[dom])
             roof = {"kernel": cd["kernel"], "bound": cd["bound"], "achieved": ach, "peak": cd["peak"], "unit": cd["unit"],
                     "frac": ach / cd["peak"], "traffic": cd["traffic"],
@@ -367,8 +378,8 @@ def main():
                     "executed_algorithmic_tflops": f_inc / t_inc / 1e12, "avg_launch_ms": breakdown["cnn_forward_inc_tc"],
                     "full_evaluation_equivalent_tflops": 3 * 2 * P * Cc * 2 * Cc * n / ((breakdown["cnn_dirty"] + breakdown["cnn_inc_scan"]
                                                          + breakdown["cnn_forward_inc_tc"] + breakdown["cnn_inc_merge"]) * 1e-3) / 1e12}
-                nb_ = (P + 15) // 16                # per channel: NB block keys read through the block table; mkey and its pool copy written
-                mbytes = int(n * 3 * 2 * Cc * 8 * (nb_ + 2))
+                # per channel: 16 B top-2 list + the dirty blocks' keys read; 16 B list + 8 B winner written
+                mbytes = int(n * 3 * 2 * Cc * (16 + 8 * (dirty_blocks / n) + 24))
                 roof["merge_kernel"] = {"kernel": "cnn_inc_merge_kernel", "bound": "hbm", "algorithmic_bytes": mbytes,
                                         "achieved_gbs": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
                                         "frac": mbytes / (breakdown["cnn_inc_merge"] * 1e-3) / 1e9 / pk["hbm_gbs"]}
@@ -405,14 +416,16 @@ def main():
 
         def e2e_call(residue_io):
             """One PPDE_PAS.run from HOST buffers to HOST results; returns (seconds, bytes in, bytes out, phases, reports)."""
+            local = not args.global_population
             sargs = ap_.Namespace(ppde_pas_length=wl["pas"], nmut_threshold=wl["nmut"], paper_results=wl["paper"], seed=0,
-                                  ppde_verbose=False, ppde_local_population=True, ppde_residue_io=residue_io)
+                                  ppde_verbose=False, ppde_local_population=local, ppde_residue_io=residue_io)
             smp = PPDE_PAS(sargs)
+            n_in = n if local else n * world
             if residue_io:   # opt-in boundary format (INTEGRATION.md): uint8 residue indices [n, L], 1 byte per residue
-                pop_host = torch.from_numpy(np.tile(pr["wt"], (n, 1))).pin_memory()
+                pop_host = torch.from_numpy(np.tile(pr["wt"], (n_in, 1))).pin_memory()
             else:            # the reference's format: float one-hot [n, L, 20] in host memory
                 pop_host = torch.nn.functional.one_hot(torch.from_numpy(pr["wt"].astype(np.int64)), 20).float()[None] \
-                    .repeat(n, 1, 1).pin_memory()
+                    .repeat(n_in, 1, 1).pin_memory()
             gc.collect()
             gc.disable()     # no generational collection in the middle of the timed call
             barrier()
@@ -428,30 +441,38 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 dt = float(tt.item())
             # bytes that actually crossed PCIe: residues in, residues + histories + best energies out
-            h2d = n * m.aa_stride * world
-            d2h = (n * m.aa_stride + out[3].nbytes + out[4].nbytes + out[1].nbytes + out[2].nbytes) * world
-            return dt, h2d, d2h, dict(getattr(smp, "last_phases", {})), len(smp.reports)
+            h2d = n_in * L * world
+            d2h = (n_in * m.aa_stride + out[3].nbytes + out[4].nbytes + out[1].nbytes + out[2].nbytes) * world
+            rep_ms = [round(r_["device_ms"], 3) for _, r_ in smp.reports]
+            return dt, h2d, d2h, dict(getattr(smp, "last_phases", {})), rep_ms
 
         # FIRST call of each variant is the reported one (no best-of); a second call is recorded beside it
         calls = {}
-        for variant, rio in (("residue_io", True), ("onehot_host", False)):
+        variants = [("residue_io", True)]
+        if not (args.global_population and world > 1):     # a global float one-hot is 80 bytes per residue on EVERY rank's host
+            variants.append(("onehot_host", False))
+        for variant, rio in variants:
             r1 = e2e_call(rio)
             r2 = e2e_call(rio)
             calls[variant] = (r1, r2)
-        dt, h2d, d2h, phases, nrep = calls["residue_io"][0]
-        dt_oh = calls["onehot_host"][0][0]
+        dt, h2d, d2h, phases, rep_ms = calls["residue_io"][0]
+        dt_oh = calls["onehot_host"][0][0] if "onehot_host" in calls else None
         e2e = {"value": n * world * K / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                "what": "PPDE_PAS.run(host population -> 6-tuple on the host), K iterations incl. engine set-up and the t=0 "
                        "evaluation; wall clock of the FIRST call; population crosses the API as uint8 residue indices "
                        "(args.ppde_residue_io, INTEGRATION.md)",
                "calls_ms": [round(1e3 * c_[0], 1) for c_ in calls["residue_io"]],
-               "log_reports_in_call": nrep,
-               "host_phases_ms": {k_: round(v_, 2) for k_, v_ in phases.items()},
-               # the reference's own boundary format: float one-hot [n, L, 20] in HOST memory in and out; the host cores reduce it to
-               # residues before the copy and expand best_x after it (ppde_host_onehot_to_aa / ppde_host_aa_to_onehot)
-               "onehot_host_api": {"value": n * world * K / dt_oh, "calls_ms": [round(1e3 * c_[0], 1) for c_ in calls["onehot_host"]],
-                                   "host_onehot_bytes_per_call": 2 * n * L * 20 * 4 * world,
-                                   "host_phases_ms": {k_: round(v_, 2) for k_, v_ in calls["onehot_host"][0][3].items()}}}
+               "population": "global on every rank (reference convention)" if args.global_population else "one shard per rank",
+               # log_every population reports inside the call: device time of each (per-rank kernels + NCCL all-gathers /
+               # all-reduce over NVLink + selection / unique-count kernels on the gathered vectors)
+               "log_reports_in_call": len(rep_ms), "log_report_device_ms": rep_ms,
+               "host_phases_ms": {k_: round(v_, 2) for k_, v_ in phases.items()}}
+        if dt_oh is not None:
+            # the reference's own boundary format: float one-hot [n, L, 20] in HOST memory in and out; the host cores reduce it to
+            # residues before the copy and expand best_x after it (ppde_host_onehot_to_aa / ppde_host_aa_to_onehot)
+            e2e["onehot_host_api"] = {"value": n * world * K / dt_oh, "calls_ms": [round(1e3 * c_[0], 1) for c_ in calls["onehot_host"]],
+                                      "host_onehot_bytes_per_call": 2 * n * L * 20 * 4 * world,
+                                      "host_phases_ms": {k_: round(v_, 2) for k_, v_ in calls["onehot_host"][0][3].items()}}
 
     # ---- CPU baseline (the unmodified reference on host cores when staged, else the port), rank 0, N=1 only -----------
     cpu = None

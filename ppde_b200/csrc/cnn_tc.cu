@@ -1450,6 +1450,7 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 
 constexpr int BD_NT = 48;                // columns (touched positions) per tile of the compact delta backward
 constexpr int BD_RPW = BD_NT / 8;        // columns per producer warp (8 warps per producer set)
+constexpr int BD_MC = 64;                // touched positions whose relu-mask bytes travel inside the record (64 bytes each)
 // Winner records of the DELTA backward.  For chain b and net k the per-net gradient changes between the current state x
 // and the proposal y only through
 //   * the conv rows whose relu mask changed: p in D0 = U_{i: x_i != y_i} [i-4, i], and
@@ -1462,7 +1463,9 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
                                                                const unsigned long long* __restrict__ mkey_y,
                                                                const unsigned long long* __restrict__ mkey_pool,
                                                                const int32_t* __restrict__ rows_x,
-                                                               uint16_t* __restrict__ wl, int rec, int compact) {
+                                                               uint16_t* __restrict__ wl, int rec, int compact,
+                                                               const uint8_t* __restrict__ r1mask, const int32_t* __restrict__ btab,
+                                                               int NB, const int32_t* __restrict__ rows_y) {
     extern __shared__ int sw[];
     const int J2 = 2 * C;
     int* sStart = sw;                 // [P+1]
@@ -1472,6 +1475,11 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     int* sPx = sPy + J2;              // [J2]
     int* sList = sPx + J2;            // [2 J2]
     const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
+    __shared__ int sBt[2][16];                        // block-table rows of the proposal / current state (mask fetch at the end)
+    if (r1mask && btab && threadIdx.x < 32) {
+        const int side = threadIdx.x >> 4, q = threadIdx.x & 15;
+        if (q < NB) sBt[side][q] = __ldg(btab + (size_t)(side ? rows_x[b] : rows_y[b]) * NB + q);
+    }
     const unsigned long long* ky = mkey_y + (size_t)bk * J2;
     const unsigned long long* kx = mkey_pool + 2 * ((size_t)rows_x[b] * n_nets + k) * J2;      // {K1, K2} per channel: K1 = raw winner
     for (int i = threadIdx.x; i <= P; i += 128) { sStart[i] = 0; if (i < P) { sFill[i] = 0; sD0[i] = 0; } }
@@ -1571,6 +1579,21 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     const int nent = sStart[P];
     if (threadIdx.x == 0) { out[0] = (uint16_t)npos; out[1 + 2 * npos] = (uint16_t)nent; }
     for (int u = threadIdx.x; u < nent; u += 128) out[2 + 2 * npos + u] = (uint16_t)sList[u];
+    __syncthreads();                                  // sPosC complete
+    // ---- relu-mask bytes of the first BD_MC touched positions, both sides, in the LAST BD_MC * 64 bytes of the record:
+    // [c][side 0 = proposal y, 1 = current x][32 bytes].  The tensor-core kernel's producers need them before their first
+    // FMA; from here they are one shared-memory read away instead of two dependent global loads (block table -> mask row).
+    if (r1mask) {
+        const int my = rows_y[b], mx = rows_x[b];
+        uint4* mout = reinterpret_cast<uint4*>(out + rec - BD_MC * 32);
+        for (int it = threadIdx.x; it < min(npos, BD_MC) * 4; it += 128) {          // 4 x 16 bytes per position: y lo, y hi, x lo, x hi
+            const int c = it >> 2, part = it & 3, side = part >> 1;
+            const int pp = sPosC[c];
+            int row = side ? mx : my;
+            if (btab) row = sBt[side][pp >> 4];
+            mout[it] = __ldg(reinterpret_cast<const uint4*>(r1mask + (((size_t)row * n_nets + k) * P + pp) * 32) + (part & 1));
+        }
+    }
     // ---- output-row lists of the tiles.  Columns ascend in position, so the rows [p, p+4] of column c that no earlier column of
     // the tile covers are the last min(5, p - p_prev) of them, and for exactly those rows column c is the first contributor
     // (p_prev < row - 4): cfirst = c.  One warp scans the counts of a tile's <= BD_NT columns.
@@ -2149,7 +2172,8 @@ constexpr int BD_MAT = BD_NT * KCH * 2; // one [48 x 64] fp16 operand matrix (6 
 constexpr int BD_SLOT = 2 * BD_MAT;     // hi + lo
 constexpr int BD_NBUF = 3;             // operand tile buffers (3 x 48 KB).  4 buffers leave room for only 3 record buffers and
                                        // measured slower (7.1 vs 5.9 ms / 64k chains): the records are what lets the roles run ahead
-constexpr int BD_TS = 100;              // floats per column of the transposed accumulator tile: index a * 5 + t
+constexpr int BD_TS = 100;              // floats per column of the transposed accumulator tile: index t * 20 + a
+constexpr int BD_FLAT = 64;             // entries of a producer warp's flattened list (more are processed in chunks)
 template <bool PROF>
 __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -2159,7 +2183,8 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* sT = reinterpret_cast<float*>(ring + BD_NBUF * BW_MAXCH * BD_SLOT);    // [BD_NT][BD_TS] transposed accumulator tile
     float* sDj = sT + BD_NT * BD_TS;                                          // [J2] decoder weights
-    uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sDj + J2) + 15) & ~(uintptr_t)15);   // [BD_NREC][rec]
+    uint32_t* sFlat = reinterpret_cast<uint32_t*>(sDj + J2);                  // [16 producer warps][BD_FLAT] flattened entries
+    uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sFlat + 16 * BD_FLAT) + 15) & ~(uintptr_t)15);   // [BD_NREC][rec]
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRec + BD_NREC * prm.rec) + 7) & ~(uintptr_t)7);
     uint64_t* full = bars;                      // [BD_NBUF] tile buffers: producers -> MMA (8 warp arrivals: one producer set)
     uint64_t* empty = full + BD_NBUF;           // [BD_NBUF] MMA -> producers
@@ -2234,9 +2259,12 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
         int it = 0;
+        int rb = -1;
+        uint32_t rph = 1u;                                                  // record ring: buffer index and phase parity of chain ci
         for (int ci = 0; ci < nchains; ++ci) {
-            const int rb = ci % BD_NREC;
-            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            if (++rb == BD_NREC) rb = 0;
+            if (rb == 0) rph ^= 1u;
+            mbar_wait(&recfull[rb], rph);
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
             const int tiles = (npos + BD_NT - 1) / BD_NT;
@@ -2260,10 +2288,12 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                 const int ncol = min(BD_NT, npos - t * BD_NT);
                 named_bar(2, NT_EPI);                                      // the previous tile's gather has read sT
-                if (rowok) {
+                if (rowok) {       // accumulator column j = operand row j holds column c = (j % BD_RPW) * 8 + j / BD_RPW (producers' permutation)
 #pragma unroll
-                    for (int c = 0; c < BD_NT; ++c)
-                        if (c < ncol) sts_f32(st_a + (uint32_t)(c * BD_TS * 4), __uint_as_float(y[c]) * unscale);
+                    for (int j = 0; j < BD_NT; ++j) {
+                        const int c = (j % BD_RPW) * 8 + j / BD_RPW;
+                        if (c < ncol) sts_f32(st_a + (uint32_t)(c * BD_TS * 4), __uint_as_float(y[j]) * unscale);
+                    }
                 }
                 named_bar(2, NT_EPI);
                 // output rows of this tile: r in [tstart[t], tstart[t+1]); row i = orow[r] gets the columns c = cfirst[r] .. while
@@ -2311,32 +2341,36 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         // Records are staged up to BD_NREC chains ahead, OPPORTUNISTICALLY: buffer c % BD_NREC is free once the producers and
         // the epilogue have released chain c - BD_NREC; blocking on that here would serialise the MMAs of a chain behind the
         // epilogue of an earlier one, so the release is only polled (and waited for when the record is needed right now).
-        int staged = 0;
+        int staged = 0, srb = 0;               // next chain to stage and its ring buffer
+        uint32_t sph = 1u;                     // parity of the release that frees buffer srb for chain `staged` (>= BD_NREC)
         int nread = 0;                         // chains whose npos THIS warp has read: their buffers may be reused, not before
                                                // (a chain without tiles is released by the other roles without waiting for the MMAs)
         auto stage_records = [&](int need) {   // stage what is free; block until chains < need are staged
             while (staged < nchains) {
-                const int c = staged, rb = c % BD_NREC;
+                const int c = staged;
                 if (c >= BD_NREC) {
                     if (c - BD_NREC >= nread) break;
-                    const uint32_t par = (uint32_t)(((c / BD_NREC) + 1) & 1);
-                    if (c < need) mbar_wait(&recempty[rb], par);
-                    else if (!mbar_test(&recempty[rb], par)) break;
+                    if (c < need) mbar_wait(&recempty[srb], sph ^ 1u);
+                    else if (!mbar_test(&recempty[srb], sph ^ 1u)) break;
                 }
                 if (elect_one()) {
-                    mbar_expect_tx(&recfull[rb], rec_bytes);
-                    bulk_g2s(sRec + (size_t)rb * prm.rec, prm.wl + ((size_t)(b_lo + c) * prm.m.n_nets + k) * prm.rec, rec_bytes,
-                             &recfull[rb]);
+                    mbar_expect_tx(&recfull[srb], rec_bytes);
+                    bulk_g2s(sRec + (size_t)srb * prm.rec, prm.wl + ((size_t)(b_lo + c) * prm.m.n_nets + k) * prm.rec, rec_bytes,
+                             &recfull[srb]);
                 }
                 __syncwarp();
                 ++staged;
+                if (++srb == BD_NREC) { srb = 0; sph ^= 1u; }
             }
         };
         int it = 0;
+        int rb = -1;
+        uint32_t rph = 1u;
         for (int ci = 0; ci < nchains; ++ci) {
             stage_records(ci + 1);
-            const int rb = ci % BD_NREC;
-            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            if (++rb == BD_NREC) rb = 0;
+            if (rb == 0) rph ^= 1u;
+            mbar_wait(&recfull[rb], rph);
             const int npos = lds_u16(rec_a + (uint32_t)rb * rec_bytes);
             nread = ci + 1;
             const int tiles = (npos + BD_NT - 1) / BD_NT;
@@ -2378,27 +2412,35 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         }
         if (PROF && prm.prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[4] = pc[0]; o[5] = pc[1]; o[6] = pc[2]; o[7] = it; }
     } else {
-        // ===== PRODUCERS: two sets of 8 warps alternate over the tiles.  A tile has ncol <= BD_NT live columns (touched positions,
-        // in order) and BD_NT - ncol zero columns: the live ones are split evenly over the set's 8 warps (rpw = ceil(ncol / 8)
-        // adjacent columns each, so a warp's entries are one run of the list), the dead ones likewise =====
+        // ===== PRODUCERS: two sets of 8 warps alternate over the tiles.  Warp w of a set owns the columns c = w, w + 8, w + 16, ..
+        // (STRIDED: the touched positions come in runs - the 5 conv rows of a mutated residue carry every winner sitting on them,
+        // both sides, ~4 entries per column, while a moved winner's column carries one - and with contiguous ownership one warp
+        // of the 8 got a whole run, ~2.5x the mean, and the tile waited for it).  The operand row of column c is
+        // r = (c % 8) * BD_RPW + c / 8, so a warp's rows are contiguous; the epilogue undoes the permutation when it writes sT.
+        // A warp first FLATTENS the entries of its <= BD_RPW columns into a private list (slot << 16 | entry) so that the gather
+        // keeps 4 W1 rows in flight across column boundaries. =====
         const int pw = warp - 4;
         const int pset = pw >> 3, w8 = pw & 7;
         const bool lact = 8 * lane < prm.kpad;
         const float adj_scale = net.adj_scale;
         const float* wbase = net.W1p + 8 * lane;
+        const uint32_t row_bytes = (uint32_t)prm.kpad * 4u;                 // one padded W1 row
         const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BD_SLOT);
         const uint32_t unit = (uint32_t)(lane & 7);
         const uint32_t dj_a = smem_u32(sDj);
+        const uint32_t flat_a = smem_u32(sFlat) + (uint32_t)(pw * BD_FLAT * 4);
         const int NB = prm.NB;
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
         int it = 0;
+        int rb = -1;
+        uint32_t rph = 1u;
         for (int ci = 0; ci < nchains; ++ci) {
-            const int rb = ci % BD_NREC;
+            if (++rb == BD_NREC) rb = 0;
+            if (rb == 0) rph ^= 1u;
             const int bb = b_lo + ci;
-            const int mry = __ldg(prm.mask_rows + bb), mrx = __ldg(prm.mask_rows_x + bb);     // pool rows of the proposal / current state
             if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            mbar_wait(&recfull[rb], rph);
             if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
@@ -2410,43 +2452,58 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 if ((it & 1) != pset) continue;
                 const int tb = it % BD_NBUF;
                 const int ncol = min(BD_NT, npos - t * BD_NT);
-                const int rpw = (ncol + 7) >> 3;                           // live columns per warp (<= BD_RPW)
-                const int rl0 = w8 * rpw;                                  // my first live row of the tile
-                const int rd0 = 8 * rpw + w8 * (BD_RPW - rpw) - rpw;       // my dead rows: rd0 + cur for cur = rpw .. BD_RPW-1
-                const int c0 = t * BD_NT + rl0;                            // my first column (compact position index)
-                // relu-mask bytes of my live columns, both sides (byte rr of the 64-bit words): two dependent global loads per byte
-                // (block table -> mask row), requested right AFTER the first group of W1 rows so that the two latencies overlap
-                unsigned long long m8 = 0ull, m8x = 0ull;
-                auto load_masks = [&]() {
+                const int cbase = t * BD_NT + w8;                          // my columns: cbase + 8 i, i < BD_RPW, while < t * BD_NT + ncol
+                // ---- flatten: lane i < BD_RPW looks at column i; exclusive prefix of the entry counts; lanes copy the entries
+                int s_i = 0, n_i = 0;
+                if (lane < BD_RPW && w8 + 8 * lane < ncol) {
+                    s_i = lds_u16(ss + 2u * (uint32_t)(cbase + 8 * lane));
+                    n_i = lds_u16(ss + 2u * (uint32_t)(cbase + 8 * lane + 1)) - s_i;
+                }
+                int off_i = n_i;
 #pragma unroll
-                    for (int rr = 0; rr < BD_RPW; ++rr) {
-                        if (rr < rpw && c0 + rr < npos && lact) {
-                            const int p = lds_u16(ps + 2u * (uint32_t)(c0 + rr));
+                for (int o = 1; o < 8; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, off_i, o);
+                    if (lane >= o) off_i += v;
+                }
+                const int ntot = __shfl_sync(0xffffffffu, off_i, BD_RPW - 1);
+                off_i -= n_i;
+                // relu-mask bytes of my columns, both sides (byte i of the 64-bit words = column slot i)
+                unsigned long long m8 = 0ull, m8x = 0ull;
+#pragma unroll
+                for (int i = 0; i < BD_RPW; ++i) {
+                    const int c = cbase + 8 * i;
+                    if (w8 + 8 * i < ncol && lact) {
+                        if (c < BD_MC) {                    // from the record (shared memory)
+                            const uint32_t ma = rs + rec_bytes - (uint32_t)(BD_MC * 64) + (uint32_t)(c * 64) + (uint32_t)lane;
+                            uint32_t by, bx;
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(by) : "r"(ma));
+                            asm volatile("ld.shared.u8 %0, [%1+32];" : "=r"(bx) : "r"(ma));
+                            m8 |= (unsigned long long)by << (8 * i);
+                            m8x |= (unsigned long long)bx << (8 * i);
+                        } else {                            // beyond the record's capacity: block table -> mask row in global memory
+                            const int mry = __ldg(prm.mask_rows + bb), mrx = __ldg(prm.mask_rows_x + bb);
+                            const int p = lds_u16(ps + 2u * (uint32_t)c);
                             int ry = mry, rx = mrx;
                             if (prm.btab) { ry = __ldg(prm.btab + (size_t)mry * NB + (p >> 4)); rx = __ldg(prm.btab + (size_t)mrx * NB + (p >> 4)); }
-                            m8 |= (unsigned long long)__ldg(prm.r1mask + (((size_t)ry * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * rr);
-                            m8x |= (unsigned long long)__ldg(prm.r1mask + (((size_t)rx * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * rr);
+                            m8 |= (unsigned long long)__ldg(prm.r1mask + (((size_t)ry * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * i);
+                            m8x |= (unsigned long long)__ldg(prm.r1mask + (((size_t)rx * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * i);
                         }
                     }
-                };
-                bool need_masks = true;
+                }
                 const uint32_t tile_addr = ring_lane + (uint32_t)(tb * BW_MAXCH * BD_SLOT);
-                int e = lds_u16(ss + 2u * (uint32_t)min(c0, npos));
-                const int eB = lds_u16(ss + 2u * (uint32_t)min(c0 + rpw, npos));
-                int cur = 0;
-                int rend = lds_u16(ss + 2u * (uint32_t)min(c0 + 1, npos));
+                int cur = 0;                                // column slot being accumulated (rows before it are stored)
                 bool have_buf = false, dirty_row = false;
                 float acc[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-                auto store_row = [&]() {   // column r0 + cur <- scale * acc (masks were applied per entry), fp16 hi + lo
+                auto store_row = [&]() {   // operand row of slot `cur` <- scale * acc (masks were applied per entry), fp16 hi + lo
                     if (!have_buf) {
                         if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
                         mbar_wait(&empty[tb], (uint32_t)(((it / BD_NBUF) + 1) & 1));
                         have_buf = true;
                         if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                     }
-                    const int r = (cur < rpw) ? rl0 + cur : rd0 + cur;
+                    const int r = w8 * BD_RPW + cur;
                     const uint32_t addr = tile_addr + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128) + ((unit ^ (uint32_t)(r & 7)) << 4);
                     if (!dirty_row) {
                         if (lact) { sts128(addr, 0u, 0u, 0u, 0u); sts128(addr + BD_MAT, 0u, 0u, 0u, 0u); }
@@ -2469,47 +2526,71 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                         dirty_row = false;
                     }
                     ++cur;
-                    rend = lds_u16(ss + 2u * (uint32_t)min(c0 + min(cur + 1, rpw), npos));
                 };
-                for (; e < eB; e += 4) {
-                    float4 w[4][2];
-                    float dj[4];
-                    bool sd[4];
-                    int jn[4];
+                // entries in chunks of BD_FLAT (one chunk unless a warp's columns carry more than BD_FLAT entries); lane f copies
+                // flattened entry f: its slot is the number of columns whose entries end at or before f
+                for (int f0 = 0; f0 < ntot; f0 += BD_FLAT) {
+                    __syncwarp();                           // the previous chunk has been consumed
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) jn[v] = (e + v < eB) ? lds_u16(ls + 2u * (uint32_t)(e + v)) : 0;
+                    for (int h = 0; h < BD_FLAT / 32; ++h) {
+                        const int f = f0 + h * 32 + lane;
+                        int slot = 0, base = __shfl_sync(0xffffffffu, off_i, 0), st0 = __shfl_sync(0xffffffffu, s_i, 0);
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        sd[v] = (jn[v] >> 15) != 0;
-                        jn[v] &= 0x7FFF;
-                        w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (e + v < eB && lact) {
-                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn[v] * prm.kpad);
-                            w[v][0] = __ldg(src);
-                            w[v][1] = __ldg(src + 1);
+                        for (int i = 1; i < BD_RPW; ++i) {
+                            const int oi = __shfl_sync(0xffffffffu, off_i, i), si = __shfl_sync(0xffffffffu, s_i, i);
+                            if (f >= oi) { slot = i; base = oi; st0 = si; }
+                        }
+                        if (f < ntot) {
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(flat_a + 4u * (uint32_t)(h * 32 + lane)),
+                                         "r"((uint32_t)lds_u16(ls + 2u * (uint32_t)(st0 + f - base)) | ((uint32_t)slot << 16)) : "memory");
                         }
                     }
+                    __syncwarp();
+                    const int nf = min(BD_FLAT, ntot - f0);
+                    for (int e = 0; e < nf; e += 4) {
+                        float4 w[4][2];
+                        float dj[4];
+                        bool sd[4];
+                        int jn[4], sl[4];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn[v]);
-                        dj[v] = sd[v] ? -d0 : d0;
-                    }
-                    if (need_masks) { load_masks(); need_masks = false; }
+                        for (int v = 0; v < 4; ++v) {
+                            uint32_t fe = 0u;
+                            if (e + v < nf) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(fe) : "r"(flat_a + 4u * (uint32_t)(e + v)));
+                            sl[v] = (int)(fe >> 16);
+                            sd[v] = ((fe >> 15) & 1u) != 0u;
+                            jn[v] = (int)(fe & 0x7FFFu);
+                        }
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        if (e + v < eB) {
-                            while (e + v >= rend) store_row();
-                            dirty_row = true;
-                            const float dd = dj[v];
-                            const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
-                            w[v][0].x = (mb & 1u) ? w[v][0].x : 0.f;   w[v][0].y = (mb & 2u) ? w[v][0].y : 0.f;
-                            w[v][0].z = (mb & 4u) ? w[v][0].z : 0.f;   w[v][0].w = (mb & 8u) ? w[v][0].w : 0.f;
-                            w[v][1].x = (mb & 16u) ? w[v][1].x : 0.f;  w[v][1].y = (mb & 32u) ? w[v][1].y : 0.f;
-                            w[v][1].z = (mb & 64u) ? w[v][1].z : 0.f;  w[v][1].w = (mb & 128u) ? w[v][1].w : 0.f;
-                            acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
-                            acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
-                            acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
-                            acc[6] = fmaf(dd, w[v][1].z, acc[6]); acc[7] = fmaf(dd, w[v][1].w, acc[7]);
+                        for (int v = 0; v < 4; ++v) {
+                            w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (e + v < nf && lact) {
+                                const float4* src = reinterpret_cast<const float4*>(
+                                    reinterpret_cast<const char*>(wbase) + (uint32_t)jn[v] * row_bytes);
+                                w[v][0] = __ldg(src);
+                                w[v][1] = __ldg(src + 1);
+                            }
+                        }
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn[v]);
+                            dj[v] = sd[v] ? -d0 : d0;
+                        }
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            if (e + v < nf) {
+                                while (cur < sl[v]) store_row();
+                                dirty_row = true;
+                                const float dd = dj[v];
+                                const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
+                                w[v][0].x = (mb & 1u) ? w[v][0].x : 0.f;   w[v][0].y = (mb & 2u) ? w[v][0].y : 0.f;
+                                w[v][0].z = (mb & 4u) ? w[v][0].z : 0.f;   w[v][0].w = (mb & 8u) ? w[v][0].w : 0.f;
+                                w[v][1].x = (mb & 16u) ? w[v][1].x : 0.f;  w[v][1].y = (mb & 32u) ? w[v][1].y : 0.f;
+                                w[v][1].z = (mb & 64u) ? w[v][1].z : 0.f;  w[v][1].w = (mb & 128u) ? w[v][1].w : 0.f;
+                                acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
+                                acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
+                                acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
+                                acc[6] = fmaf(dd, w[v][1].z, acc[6]); acc[7] = fmaf(dd, w[v][1].w, acc[7]);
+                            }
                         }
                     }
                 }
@@ -2751,13 +2832,13 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
     // delta mode, compact records (default; tune->delta_layout = 1 keeps one column per position): npos | pos | start | list
     const bool compact = dl && !(tune && tune->delta_layout == 1);
-    // compact record: npos | pos[P] | start[P+1] | list[2 J2] | ntile | tstart[TMAX+1] | orow[RMAX] | cfirst[RMAX]  (uint16)
+    // compact record: npos | pos[P] | start[P+1] | list[2 J2] | ntile | tstart[TMAX+1] | (orow, cfirst)[RMAX] | ... | masks[BD_MC][2][32 B]  (uint16)
     const int tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
-    const int rec = compact ? ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) : (((P + 1) + 2 * J2 + 7) & ~7);
+    const int rec = compact ? (((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) + tc::BD_MC * 32) : (((P + 1) + 2 * J2 + 7) & ~7);
     const int vcap = compact ? rmax * PPDE_Q : L * PPDE_Q;                       // floats of scratch per (net, chain)
     prm.vcap = vcap;
     const size_t smem_fixed = compact
-        ? 1024 + (size_t)tc::BD_NBUF * tc::BW_MAXCH * tc::BD_SLOT + ((size_t)tc::BD_NT * tc::BD_TS + J2) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t)
+        ? 1024 + (size_t)tc::BD_NBUF * tc::BW_MAXCH * tc::BD_SLOT + ((size_t)tc::BD_NT * tc::BD_TS + J2 + 16 * tc::BD_FLAT) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t)
         : 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t);
     int nrec = 2;
     if (compact) {                                   // as many record buffers as fit under the 227 KB limit (3 .. BD_NREC_MAX)
@@ -2785,7 +2866,8 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     if (bwd_parts & 1) {
         if (dl)
             tc::cnn_winner_delta_kernel<<<n * m->n_nets, 128, ((P + 1) + 2 * P + 4 * J2) * sizeof(int), st>>>(
-                *m, m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, compact ? 1 : 0);
+                *m, m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, compact ? 1 : 0,
+                compact ? r1mask : nullptr, btab, prm.NB, dl->rows_y);
         else
             tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
         int r0 = launch_done();
@@ -2819,7 +2901,7 @@ extern "C" int64_t ppde_cnn_backward_scratch_floats(const ppde_cnn_t* m, int32_t
     if (!m || n <= 0) return 0;
     const int64_t P = m->P, L = m->L, J2 = 2 * (int64_t)m->C;
     const int64_t tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
-    const int64_t rec_c = (2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~(int64_t)7, rec_d = ((P + 1) + 2 * J2 + 7) & ~(int64_t)7;
+    const int64_t rec_c = ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~(int64_t)7) + tc::BD_MC * 32, rec_d = ((P + 1) + 2 * J2 + 7) & ~(int64_t)7;
     const int64_t a = (int64_t)m->n_nets * n * rmax * PPDE_Q + ((int64_t)n * m->n_nets * rec_c + 1) / 2;     // compact delta
     const int64_t b = (int64_t)m->n_nets * n * L * PPDE_Q + ((int64_t)n * m->n_nets * rec_d + 1) / 2;        // exact / per-position delta
     return (a > b ? a : b) + 16;

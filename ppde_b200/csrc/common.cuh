@@ -31,7 +31,13 @@ struct Philox {
 };
 enum { KIND_PROPOSAL = 0, KIND_PATHLEN = 1, KIND_ACCEPT = 2 };
 
-__device__ __forceinline__ float u32_to_unit(uint32_t x) {      // strictly inside (0,1), exact
+// 24 random bits -> (k + 0.5) 2^-24.  For k < 2^23 the value is exact and strictly inside (0, 1); for k >= 2^23 the "+ 0.5" is
+// a round-to-even tie in fp32, so the grid is the even multiples of 2^-24 there and k = 2^24 - 1 gives exactly 1.0f (probability
+// 2^-24 per draw: -log(u) = 0 makes that entry's race quotient infinite-negative, i.e. it cannot win; an accept uniform of 1.0
+// accepts only log_acc >= 0).  ppde_b200/philox.py has the same formula and the reference consumed these streams when the golden
+// vectors were made, so the definition is part of the pinned stream; a 23-bit variant would be exact everywhere but needs the
+// goldens regenerated (deliberate differences 1).
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {
     return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
 }
 

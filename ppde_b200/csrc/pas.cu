@@ -130,22 +130,33 @@ __global__ void __launch_bounds__(NT) pas_propose_kernel(ppde_potts_t m, ppde_ch
         float best = -1.f; int bidx = 0x7fffffff;
         const float* um = p.uniforms ? p.uniforms + ((int64_t)s * c.n + b) * NE : nullptr;
         for (int q = threadIdx.x; q < n4; q += NT) {
-            float4 u;
-            if (um) {
-                u = reinterpret_cast<const float4*>(um)[q];
-            } else {
-                uint4 w = rng((uint32_t)q, gid, (uint32_t)t, (uint32_t)(s | (KIND_PROPOSAL << 16)));
-                u = make_float4(u32_to_unit(w.x), u32_to_unit(w.y), u32_to_unit(w.z), u32_to_unit(w.w));
-            }
+            // the cheap test first, on the raw Philox words: entry j can still win only if p_j (1 + 1e-5) > thr (1 - u_j), and
+            // 1 - u_j = ((~x_j >> 8) + 0.5) 2^-24 needs no uniform; one branch per float4, taken for a handful of entries per vector
             const float4 pr = p4[q];
-            const float thr = fmaxf(best, __int_as_float(*(volatile int*)&s_best)) * s3;
-            const float pv[4] = {pr.x, pr.y, pr.z, pr.w};
-            const float uv[4] = {u.x, u.y, u.z, u.w};
+            const float thr = fmaxf(best, __int_as_float(*(volatile int*)&s_best)) * s3 * (1.0f / 1.00001f);
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            float4 u1;                                                       // 1 - u
+            if (um) {
+                const float4 u = reinterpret_cast<const float4*>(um)[q];
+                u1 = make_float4(1.0f - u.x, 1.0f - u.y, 1.0f - u.z, 1.0f - u.w);
+            } else {
+                w = rng((uint32_t)q, gid, (uint32_t)t, (uint32_t)(s | (KIND_PROPOSAL << 16)));
+                u1 = make_float4(u32_to_unit(~w.x), u32_to_unit(~w.y), u32_to_unit(~w.z), u32_to_unit(~w.w));
+            }
+            const bool c0 = pr.x > thr * u1.x, c1 = pr.y > thr * u1.y, c2 = pr.z > thr * u1.z, c3 = pr.w > thr * u1.w;
+            if (c0 | c1 | c2 | c3) {                                         // may still win: exact evaluation, in entry order
+                float4 u;
+                if (um) u = reinterpret_cast<const float4*>(um)[q];
+                else u = make_float4(u32_to_unit(w.x), u32_to_unit(w.y), u32_to_unit(w.z), u32_to_unit(w.w));
+                const float pv[4] = {pr.x, pr.y, pr.z, pr.w};
+                const float uv[4] = {u.x, u.y, u.z, u.w};
+                const bool cv[4] = {c0, c1, c2, c3};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (pv[k] * 1.00001f > thr * (1.0f - uv[k])) {           // may still win: exact evaluation
-                    const float r = (pv[k] / s3) / (-logf(uv[k]));
-                    if (r > best) { best = r; bidx = q * 4 + k; atomicMax(&s_best, __float_as_int(r)); }
+                for (int k = 0; k < 4; ++k) {
+                    if (cv[k]) {
+                        const float r = (pv[k] / s3) / (-logf(uv[k]));
+                        if (r > best) { best = r; bidx = q * 4 + k; atomicMax(&s_best, __float_as_int(r)); }
+                    }
                 }
             }
         }

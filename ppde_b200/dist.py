@@ -122,6 +122,8 @@ class PopulationReporter:
         (and, with want_topk, 'topk_energy' / 'topk_chain' / 'topk_aa' as host arrays)."""
         lib, dev, st = self.lib, self.dev, self._st()
         nl = int(energy.shape[0])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         # -- per-rank kernels ----------------------------------------------------------------------
         dist_l = torch.empty(nl, dtype=torch.int32, device=dev)
         self._check(lib.ppde_population_metrics(self._p(aa), self.stride, nl, self.L, self._p(self.wt), self._p(dist_l),
@@ -157,6 +159,7 @@ class PopulationReporter:
                 self._check(lib.ppde_topk(self._p(cv), ws * k, k, 0, self._p(None), self._p(fv), self._p(pos), st), "topk(final)")
                 vals, ids, seqs = fv, ci[pos], cs[pos]
             top = (vals, ids, seqs)
+        ev1.record()
         host = self.out.cpu().numpy()                                           # the one D2H of the report
         n = float(host[9])
         mean_d = host[7] / n
@@ -166,6 +169,7 @@ class PopulationReporter:
             "accepted": float(host[6]), "mean_dist": float(mean_d),
             "std_dist": float(np.sqrt(max(host[8] / n - mean_d * mean_d, 0.0))),      # n_hops: population std (np.std)
             "unique": int(host[10]), "diversity_pct": float(host[10]) / n * 100.0,
+            "device_ms": float(ev0.elapsed_time(ev1)),        # kernels + collectives of this report, on the device
         }
         if top is not None:
             rep["topk_energy"] = top[0].cpu().numpy()

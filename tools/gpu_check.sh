@@ -15,9 +15,17 @@ $K 200 python bench.py --workload ube4b_potts_poe_4k --no-cpu-baseline > gpurun_
 $K 300 python bench.py --workload gfp_paper_pas10 --no-cpu-baseline --steps 5 > gpurun_out/${TAG}_bench_pas10.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_pas10.json
 $K 300 python bench.py --workload pabp_readme_128 --steps 100 --warmup 5 > gpurun_out/${TAG}_bench_pabp128.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_pabp128.json
 fi
-SMALL="python bench.py --chains 8192 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline"
+SMALL="python bench.py --chains 16384 --steps 3 --warmup 44 --no-e2e --no-cpu-baseline --no-breakdown"
 $K 200 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 && \
-$K 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
+$K 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 560 -c 120 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
+# steady state (44 warm-up iterations): 9 matching kernels per iteration -> skip 44 * 9 launches, capture one iteration
 $K 200 $SMALL > gpurun_out/${TAG}_plain2.log 2>&1 && \
-$K 500 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_backward_delta_kernel|cnn_winner_delta_kernel|cnn_grad_combine_delta_kernel|pas_propose_kernel|pas_reverse_accept_kernel|potts_incremental_kernel|cnn_fit_kernel" -s 27 -c 9 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
+$K 600 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_backward_delta_kernel|cnn_winner_delta_kernel|cnn_grad_combine_sparse_kernel|pas_propose|pas_reverse_accept|potts_incremental_kernel|cnn_fit_kernel" -s 396 -c 9 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_f.log
+if [ "$MODE" = "full" ]; then
+$K 200 python tools/bench_potts_full.py 64 128 238 512 1024 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
+PD="python tools/bench_potts_full.py 238"
+$K 200 $PD > gpurun_out/${TAG}_plain3.log 2>&1 && \
+$K 300 ncu --set full --clock-control none --import-source on -k regex:potts_dense_tc_kernel -s 6 -c 1 -o gpurun_out/${TAG}_potts_dense -f $PD > gpurun_out/${TAG}_ncu_p.log 2>&1
+tail -1 gpurun_out/${TAG}_ncu_p.log
+fi
