@@ -2259,12 +2259,9 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
         int it = 0;
-        int rb = -1;
-        uint32_t rph = 1u;                                                  // record ring: buffer index and phase parity of chain ci
         for (int ci = 0; ci < nchains; ++ci) {
-            if (++rb == BD_NREC) rb = 0;
-            if (rb == 0) rph ^= 1u;
-            mbar_wait(&recfull[rb], rph);
+            const int rb = ci % BD_NREC;
+            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
             const int tiles = (npos + BD_NT - 1) / BD_NT;
@@ -2342,7 +2339,8 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         // the epilogue have released chain c - BD_NREC; blocking on that here would serialise the MMAs of a chain behind the
         // epilogue of an earlier one, so the release is only polled (and waited for when the record is needed right now).
         int staged = 0, srb = 0;               // next chain to stage and its ring buffer
-        uint32_t sph = 1u;                     // parity of the release that frees buffer srb for chain `staged` (>= BD_NREC)
+        uint32_t sph = 1u;                     // parity of the release that frees buffer srb for chain `staged` >= BD_NREC (toggles at
+                                               // every wrap of srb: 0 for the first reuse)
         int nread = 0;                         // chains whose npos THIS warp has read: their buffers may be reused, not before
                                                // (a chain without tiles is released by the other roles without waiting for the MMAs)
         auto stage_records = [&](int need) {   // stage what is free; block until chains < need are staged
@@ -2350,8 +2348,8 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 const int c = staged;
                 if (c >= BD_NREC) {
                     if (c - BD_NREC >= nread) break;
-                    if (c < need) mbar_wait(&recempty[srb], sph ^ 1u);
-                    else if (!mbar_test(&recempty[srb], sph ^ 1u)) break;
+                    if (c < need) mbar_wait(&recempty[srb], sph);
+                    else if (!mbar_test(&recempty[srb], sph)) break;
                 }
                 if (elect_one()) {
                     mbar_expect_tx(&recfull[srb], rec_bytes);
@@ -2364,13 +2362,10 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             }
         };
         int it = 0;
-        int rb = -1;
-        uint32_t rph = 1u;
         for (int ci = 0; ci < nchains; ++ci) {
             stage_records(ci + 1);
-            if (++rb == BD_NREC) rb = 0;
-            if (rb == 0) rph ^= 1u;
-            mbar_wait(&recfull[rb], rph);
+            const int rb = ci % BD_NREC;
+            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
             const int npos = lds_u16(rec_a + (uint32_t)rb * rec_bytes);
             nread = ci + 1;
             const int tiles = (npos + BD_NT - 1) / BD_NT;
@@ -2424,7 +2419,6 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         const bool lact = 8 * lane < prm.kpad;
         const float adj_scale = net.adj_scale;
         const float* wbase = net.W1p + 8 * lane;
-        const uint32_t row_bytes = (uint32_t)prm.kpad * 4u;                 // one padded W1 row
         const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BD_SLOT);
         const uint32_t unit = (uint32_t)(lane & 7);
         const uint32_t dj_a = smem_u32(sDj);
@@ -2433,14 +2427,11 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
         int it = 0;
-        int rb = -1;
-        uint32_t rph = 1u;
         for (int ci = 0; ci < nchains; ++ci) {
-            if (++rb == BD_NREC) rb = 0;
-            if (rb == 0) rph ^= 1u;
+            const int rb = ci % BD_NREC;
             const int bb = b_lo + ci;
             if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-            mbar_wait(&recfull[rb], rph);
+            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
             if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
@@ -2564,8 +2555,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                         for (int v = 0; v < 4; ++v) {
                             w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (e + v < nf && lact) {
-                                const float4* src = reinterpret_cast<const float4*>(
-                                    reinterpret_cast<const char*>(wbase) + (uint32_t)jn[v] * row_bytes);
+                                const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn[v] * prm.kpad);
                                 w[v][0] = __ldg(src);
                                 w[v][1] = __ldg(src + 1);
                             }
@@ -2582,14 +2572,15 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                                 dirty_row = true;
                                 const float dd = dj[v];
                                 const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
-                                w[v][0].x = (mb & 1u) ? w[v][0].x : 0.f;   w[v][0].y = (mb & 2u) ? w[v][0].y : 0.f;
-                                w[v][0].z = (mb & 4u) ? w[v][0].z : 0.f;   w[v][0].w = (mb & 8u) ? w[v][0].w : 0.f;
-                                w[v][1].x = (mb & 16u) ? w[v][1].x : 0.f;  w[v][1].y = (mb & 32u) ? w[v][1].y : 0.f;
-                                w[v][1].z = (mb & 64u) ? w[v][1].z : 0.f;  w[v][1].w = (mb & 128u) ? w[v][1].w : 0.f;
-                                acc[0] = fmaf(dd, w[v][0].x, acc[0]); acc[1] = fmaf(dd, w[v][0].y, acc[1]);
-                                acc[2] = fmaf(dd, w[v][0].z, acc[2]); acc[3] = fmaf(dd, w[v][0].w, acc[3]);
-                                acc[4] = fmaf(dd, w[v][1].x, acc[4]); acc[5] = fmaf(dd, w[v][1].y, acc[5]);
-                                acc[6] = fmaf(dd, w[v][1].z, acc[6]); acc[7] = fmaf(dd, w[v][1].w, acc[7]);
+                                // (a masked-off channel contributes exactly 0: skipping the FMA leaves acc unchanged, same value)
+                                if (mb & 1u) acc[0] = fmaf(dd, w[v][0].x, acc[0]);
+                                if (mb & 2u) acc[1] = fmaf(dd, w[v][0].y, acc[1]);
+                                if (mb & 4u) acc[2] = fmaf(dd, w[v][0].z, acc[2]);
+                                if (mb & 8u) acc[3] = fmaf(dd, w[v][0].w, acc[3]);
+                                if (mb & 16u) acc[4] = fmaf(dd, w[v][1].x, acc[4]);
+                                if (mb & 32u) acc[5] = fmaf(dd, w[v][1].y, acc[5]);
+                                if (mb & 64u) acc[6] = fmaf(dd, w[v][1].z, acc[6]);
+                                if (mb & 128u) acc[7] = fmaf(dd, w[v][1].w, acc[7]);
                             }
                         }
                     }
