@@ -1640,6 +1640,164 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     }
 }
 
+// Record builder of the compact delta backward, second version (same record, bit for bit; cnn_winner_delta_kernel stays for
+// the per-position layout).  The first version bucketed the entries with a counting sort over all P positions (zeroing, atomics
+// and serial scans over P-sized arrays, ten block barriers: 1.42 ms per 64k chains, 5.1 k warp-instructions per (chain, net))
+// although a (chain, net) has only ~70 entries.  Here: the D0 rows are a 256-bit set; every channel emits its 0..2 entries as
+// keys  position << 16 | side << 15 | channel  into an unordered list (warp ballots + one shared counter); the list is
+// rank-sorted (each entry counts the smaller keys: n^2 / 128 broadcast reads per thread, one barrier); positions, starts and
+// the entry list fall out of one scan over the sorted keys.
+__global__ void __launch_bounds__(128) cnn_delta_record_kernel(const __grid_constant__ ppde_cnn_t cm, int n_nets, int C, int P, int L, int aa_stride,
+                                                               const uint8_t* __restrict__ aa_x, const uint8_t* __restrict__ aa_y,
+                                                               const unsigned long long* __restrict__ mkey_y,
+                                                               const unsigned long long* __restrict__ mkey_pool,
+                                                               const int32_t* __restrict__ rows_x,
+                                                               uint16_t* __restrict__ wl, int rec,
+                                                               const uint8_t* __restrict__ r1mask, const int32_t* __restrict__ btab,
+                                                               int NB, const int32_t* __restrict__ rows_y) {
+    extern __shared__ int sw[];
+    const int J2 = 2 * C;
+    uint32_t* sKey = reinterpret_cast<uint32_t*>(sw);       // [2 J2] unordered keys
+    uint32_t* sSorted = sKey + 2 * J2;                       // [2 J2]
+    int* sPosC = reinterpret_cast<int*>(sSorted + 2 * J2);   // [P] compact position list
+    __shared__ uint32_t sD0[8];                              // bit p: the relu mask of conv row p changed (P <= 252)
+    __shared__ int sCount, sBase[5];
+    __shared__ int sBt[2][16];                               // block-table rows of the proposal / current state (mask fetch)
+    const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 8) sD0[threadIdx.x] = 0u;
+    if (threadIdx.x == 8) sCount = 0;
+    if (r1mask && btab && threadIdx.x >= 32 && threadIdx.x < 64) {
+        const int side = (threadIdx.x - 32) >> 4, q = threadIdx.x & 15;
+        if (q < NB) sBt[side][q] = __ldg(btab + (size_t)(side ? rows_x[b] : rows_y[b]) * NB + q);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += 128) {
+        if (aa_x[(size_t)b * aa_stride + i] != aa_y[(size_t)b * aa_stride + i])
+            for (int pp = max(i - 4, 0); pp <= min(i, P - 1); ++pp) atomicOr(&sD0[pp >> 5], 1u << (pp & 31));
+    }
+    __syncthreads();
+    const unsigned long long* ky = mkey_y + (size_t)bk * J2;
+    const unsigned long long* kx = mkey_pool + 2 * ((size_t)rows_x[b] * n_nets + k) * J2;      // {K1, K2} per channel: K1 = raw winner
+    const float unscale = 1.f / (cm.net[k].w1_scale * cm.net[k].r1_scale);
+    auto decode = [&](unsigned long long key) -> int {
+        const float mj = __uint_as_float((unsigned)(key >> 32));
+        const int pst = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
+        return ((mj > 0.f) && pst >= 0 && pst < P) ? pst : -1;
+    };
+    for (int j0 = 0; j0 < J2; j0 += 128) {
+        const int j = j0 + threadIdx.x;
+        int ey = -1, ex = -1;
+        if (j < J2) {
+            const int py = decode(ky[j]), px = decode(winner_from_raw(kx[2 * j], unscale, __ldg(cm.net[k].b1 + j)));
+            const bool moved = py != px;
+            if (py >= 0 && (moved || ((sD0[py >> 5] >> (py & 31)) & 1u))) ey = py;
+            if (px >= 0 && (moved || ((sD0[px >> 5] >> (px & 31)) & 1u))) ex = px;
+        }
+        const uint32_t by = __ballot_sync(0xffffffffu, ey >= 0), bx = __ballot_sync(0xffffffffu, ex >= 0);
+        int base = 0;
+        if (lane == 0 && (by | bx)) base = atomicAdd(&sCount, __popc(by) + __popc(bx));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        if (ey >= 0) sKey[base + __popc(by & below)] = ((uint32_t)ey << 16) | (uint32_t)j;
+        if (ex >= 0) sKey[base + __popc(by) + __popc(bx & below)] = ((uint32_t)ex << 16) | 0x8000u | (uint32_t)j;
+    }
+    __syncthreads();
+    const int nent = sCount;
+    for (int i = threadIdx.x; i < nent; i += 128) {          // rank sort (keys are distinct)
+        const uint32_t ki = sKey[i];
+        int rank = 0;
+        for (int q = 0; q < nent; ++q) rank += (sKey[q] < ki);
+        sSorted[rank] = ki;
+    }
+    __syncthreads();
+    // one scan over the sorted keys: a key starts a new column when its position differs from its predecessor's
+    uint16_t* out = wl + (size_t)bk * rec;
+    int run = 0;                                             // columns before this chunk
+    for (int i0 = 0; i0 < nent; i0 += 128) {
+        const int i = i0 + threadIdx.x;
+        uint32_t ki = 0u;
+        bool head = false;
+        if (i < nent) {
+            ki = sSorted[i];
+            head = (i == 0) || ((sSorted[i - 1] >> 16) != (ki >> 16));
+        }
+        const uint32_t bh = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) sBase[warp] = __popc(bh);
+        __syncthreads();
+        int off = run;
+        for (int w = 0; w < warp; ++w) off += sBase[w];
+        const int c = off + __popc(bh & ((1u << lane) - 1u));     // column of a head entry
+        const int chunk_total = sBase[0] + sBase[1] + sBase[2] + sBase[3];
+        __syncthreads();
+        if (head) sPosC[c] = (int)(ki >> 16);
+        if (i < nent) sKey[i] = head ? (uint32_t)c : 0xFFFFFFFFu;   // (sKey is free: remember the head entries' columns)
+        run += chunk_total;
+    }
+    __syncthreads();
+    const int npos = run;
+    // record: npos | pos[npos] | start[npos+1] | list[nent] | ...
+    for (int i = threadIdx.x; i < nent; i += 128) {
+        const uint32_t ki = sSorted[i];
+        out[2 + 2 * npos + i] = (uint16_t)(ki & 0xFFFFu);
+        const uint32_t c = sKey[i];
+        if (c != 0xFFFFFFFFu) { out[1 + c] = (uint16_t)(ki >> 16); out[1 + npos + c] = (uint16_t)i; }
+    }
+    if (threadIdx.x == 0) { out[0] = (uint16_t)npos; out[1 + 2 * npos] = (uint16_t)nent; }
+    // ---- relu-mask bytes of the first BD_MC touched positions, both sides, in the LAST BD_MC * 64 bytes of the record
+    if (r1mask) {
+        const int my = rows_y[b], mx = rows_x[b];
+        uint4* mout = reinterpret_cast<uint4*>(out + rec - BD_MC * 32);
+        for (int it = threadIdx.x; it < min(npos, BD_MC) * 4; it += 128) {          // 4 x 16 bytes per position: y lo, y hi, x lo, x hi
+            const int c = it >> 2, part = it & 3, side = part >> 1;
+            const int pp = sPosC[c];
+            int row = side ? mx : my;
+            if (btab) row = sBt[side][pp >> 4];
+            mout[it] = __ldg(reinterpret_cast<const uint4*>(r1mask + (((size_t)row * n_nets + k) * P + pp) * 32) + (part & 1));
+        }
+    }
+    // ---- output-row lists of the tiles (see cnn_winner_delta_kernel)
+    const int ntile = (npos + BD_NT - 1) / BD_NT;
+    uint16_t* oo = out + 2 + 2 * npos + nent;         // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
+    uint16_t* pairs = oo + 2 + ntile;
+    if (threadIdx.x == 0) { oo[0] = (uint16_t)ntile; oo[1] = 0; }
+    if (threadIdx.x < 32) {
+        int nr_run = 0;
+        for (int t = 0; t < ntile; ++t) {
+            const int c0 = t * BD_NT, c1 = min(c0 + BD_NT, npos);
+            int cnt[2], incl = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {             // lane owns columns c0 + 2 lane, c0 + 2 lane + 1  (BD_NT <= 64)
+                const int c = c0 + 2 * lane + h;
+                cnt[h] = 0;
+                if (c < c1) cnt[h] = (c == c0) ? 5 : min(5, sPosC[c] - sPosC[c - 1]);
+                incl += cnt[h];
+            }
+            const int mine = incl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int base = nr_run + incl - mine;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + 2 * lane + h;
+                if (c < c1) {
+                    const int pp = sPosC[c];
+                    for (int j = 0; j < cnt[h]; ++j) {
+                        pairs[2 * (base + j)] = (uint16_t)(pp + 5 - cnt[h] + j);
+                        pairs[2 * (base + j) + 1] = (uint16_t)(c - c0);
+                    }
+                    base += cnt[h];
+                }
+            }
+            nr_run += __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) oo[2 + t] = (uint16_t)nr_run;
+        }
+    }
+}
+
 // Delta backward, second kernel: the proposal's gradient row from the current state's row, the change of the Potts field and the
 // SPARSE per-net changes the tensor-core kernel left in the scratch (rows listed in the records, values [row][20]):
 //     G_y = G_x + (Gp_y - Gp_x)(window);   then for k = 0 .. n_nets-1, tile by tile, row by row:  G_y[row] += lamda/n_nets * dGc_k[row]
@@ -2855,10 +3013,13 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     prm.wl = wl;
     prm.rec = rec;
     if (bwd_parts & 1) {
-        if (dl)
+        if (compact)
+            tc::cnn_delta_record_kernel<<<n * m->n_nets, 128, (4 * J2 + P) * sizeof(int), st>>>(
+                *m, m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, r1mask, btab, prm.NB, dl->rows_y);
+        else if (dl)
             tc::cnn_winner_delta_kernel<<<n * m->n_nets, 128, ((P + 1) + 2 * P + 4 * J2) * sizeof(int), st>>>(
-                *m, m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, compact ? 1 : 0,
-                compact ? r1mask : nullptr, btab, prm.NB, dl->rows_y);
+                *m, m->n_nets, C, P, L, aa_stride, dl->aa_x, aa, mkey, dl->mkey_pool, dl->rows_x, wl, rec, 0,
+                nullptr, btab, prm.NB, dl->rows_y);
         else
             tc::cnn_winner_sort_kernel<<<n * m->n_nets, 128, ((P + 1) + P + 2 * J2) * sizeof(int), st>>>(m->n_nets, C, P, mkey, wl, rec);
         int r0 = launch_done();
