@@ -307,8 +307,8 @@ def main():
             for i, (k, _) in enumerate(seq):
                 tot[k] += evs[i].elapsed_time(evs[i + 1])
             if eng.inc and rep == reps - 1:
-                dm = eng.dmask.to(torch.int64) & 0xFFFF
-                dirty_blocks = float(sum(((dm >> q) & 1).sum() for q in range(16)).item())
+                dm = eng.dmask.to(torch.int64) & 0xFFFFFFFF
+                dirty_blocks = float(sum(((dm >> q) & 1).sum() for q in range(32)).item())
         breakdown = {k: v / reps for k, v in tot.items()}
         if eng.inc and eng.delta:
             # the exact backward that replaces the delta backward every bwd_refresh-th iteration (same inputs, same outputs)
@@ -338,9 +338,9 @@ def main():
                 "cnn_forward_inc_tc": dict(kernel="cnn_forward_inc_kernel", bound="tensor", unit="TFLOP/s",
                                            # EXECUTED algorithmic flops: only the dirty 16-position blocks are evaluated (the full-evaluation
                                            # equivalent, 3*2*P*C*2C per chain, is reported under roofline.forward_incremental)
-                                           work=nd_ * n * 3 * 2 * 16 * Cc * 2 * Cc, peak=pk["bf16_sustained"],
+                                           work=nd_ * n * 3 * 2 * m.PB * Cc * 2 * Cc, peak=pk["bf16_sustained"],
                                            traffic=(0.431e9 / 16384) * n if L == 238 else None,
-                                           note="max-pool winners of every proposal: 3 nets * 2*16*C*2C flops per dirty 16-position block "
+                                           note="max-pool winners of every proposal: 3 nets * 2*PB*C*2C flops per dirty PB-position block (PB = 8) "
                                                 "(3 fp16 passes per flop); bound by the shared-memory pipe of the r1 producers (5 table reads per element)"),
                 "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s",
                                       # per channel: 16 B top-2 list read + 8 B per dirty block key + 16 B list + 8 B winner written
@@ -371,10 +371,10 @@ def main():
                                     "value_at_long_run_refresh_share": n * world / ((ms / K - over) * 1e-3)}
             # the incremental forward computes only the dirty 16-position blocks: 3 nets * 2*16*C*2C flops per block
             if dirty_blocks is not None:
-                f_inc = dirty_blocks * 3 * 2 * 16 * Cc * 2 * Cc
+                f_inc = dirty_blocks * 3 * 2 * m.PB * Cc * 2 * Cc
                 t_inc = breakdown["cnn_forward_inc_tc"] * 1e-3
                 roof["forward_incremental"] = {
-                    "kernel": "cnn_forward_inc_kernel", "dirty_blocks_per_chain": dirty_blocks / n, "blocks_per_chain": (P + 15) // 16,
+                    "kernel": "cnn_forward_inc_kernel", "dirty_blocks_per_chain": dirty_blocks / n, "blocks_per_chain": m.NB, "positions_per_block": m.PB,
                     "executed_algorithmic_tflops": f_inc / t_inc / 1e12, "avg_launch_ms": breakdown["cnn_forward_inc_tc"],
                     "full_evaluation_equivalent_tflops": 3 * 2 * P * Cc * 2 * Cc * n / ((breakdown["cnn_dirty"] + breakdown["cnn_inc_scan"]
                                                          + breakdown["cnn_forward_inc_tc"] + breakdown["cnn_inc_merge"]) * 1e-3) / 1e12}

@@ -203,8 +203,8 @@ int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const
                               float* scratch, const ppde_tune_t* tune, void* stream);
 /* Incremental CNN forward (same quantity as ppde_cnn_forward_tc, bit for bit; OnehotCNN.forward, ppde/nets.py:363-376).
  * A proposal differs from the chain's current state in a few residues, and a residue only moves the 5 conv rows that
- * read it, so the max-pool over positions is kept per BLOCK of 16 positions in a pool
- *     bkey [rows, n_nets, NB = ceil(P/16), 2C] uint64   (rows indexed like the G / Gp pools)
+ * read it, so the max-pool over positions is kept per BLOCK of PB positions in a pool
+ *     bkey [rows, n_nets, NB = ceil(P/PB), 2C] uint64   (rows indexed like the G / Gp pools; PB = ppde_cnn_block_positions() = 8)
  * and only the dirty blocks of every chain are recomputed on the tensor cores.
  * A proposal row does not copy the clean blocks of the current state, it POINTS at them:
  *     btab [rows, NB] int32   btab[r][q] = the pool row whose slot holds block q of row r (its keys in bkey and its 16
@@ -216,6 +216,7 @@ int ppde_cnn_backward_tc_rows(const ppde_cnn_t* m, const ppde_potts_t* pm, const
 int ppde_cnn_dirty(const ppde_cnn_t* m, const uint8_t* aa_x, const uint8_t* aa_y, int32_t aa_stride, int32_t n,
                    uint32_t* dmask /* [n] */, void* stream);
 int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n);   /* workspace of ppde_cnn_forward_inc (block prefix sums and lists) */
+int32_t ppde_cnn_block_positions(void);              /* PB: conv-output positions per block of the max-pool cache (8) */
 int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                          unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask, unsigned long long* bkey,
                          int32_t* btab, const int32_t* rows_x, const int32_t* rows_y, int32_t row_base_y,

@@ -76,6 +76,7 @@ SIGNATURES = {
                                             C.POINTER(TuneT), vp]),
     "ppde_cnn_dirty": (C.c_int, [C.POINTER(CnnT), vp, vp, C.c_int32, C.c_int32, vp, vp]),
     "ppde_cnn_forward_inc_ws_bytes": (C.c_int64, [C.c_int32]),
+    "ppde_cnn_block_positions": (C.c_int32, []),
     "ppde_cnn_forward_inc": (C.c_int, [C.POINTER(CnnT), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp, vp,
                                        C.POINTER(TuneT), vp]),
     "ppde_cnn_backward_delta": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, vp, C.c_int32, C.c_int32, vp, vp, C.c_float,

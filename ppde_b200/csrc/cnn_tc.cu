@@ -759,6 +759,13 @@ cnn_forward_tc2_kernel(const __grid_constant__ Params prm) {
 // copies the clean blocks' keys from the current row to the proposal row and writes the same `mkey` the full kernel
 // writes, bit for bit: every accumulator element depends only on its own r1 row and W1 row, in the same K order.  The relu-mask rows of the dirty positions go to the proposal
 // row of the r1mask pool (the clean rows were copied there by cnn_dirty_kernel).
+// Block of the max-pool cache: PB conv-output positions (a tile of the incremental kernel = 128 positions = PB_TILE blocks).
+// Round 1 used 16-position blocks; a changed residue dirties the rows [i-4, i], i.e. 1 + 4/PB blocks on average: 20 positions
+// to recompute per mutation at PB = 16, 12 at PB = 8 (and twice as many, half as large, keys per pool row).
+constexpr int PB_SHIFT = 3;
+constexpr int PB = 1 << PB_SHIFT;
+constexpr int PB_TILE = 128 / PB;              // blocks per MMA tile
+constexpr int PB_MAXNB = 32;                   // blocks per row <= 32 (dirty-block masks are 32-bit words)
 struct IncParams {
     ppde_cnn_t m;
     const uint8_t* aa;                  // proposal states [n, aa_stride]
@@ -777,8 +784,8 @@ struct IncParams {
     int row_base_y;
     const int32_t* boff;                // [n] dirty blocks of the CTA's chains before chain b (cnn_inc_scan_kernel)
     const int32_t* gtot;                // [ctas_per_combo] dirty blocks per chain range
-    const uint32_t* blist;              // [n * 16] compact (chain << 4 | block) list, range r starts at 16 * b_lo(r)
-    int NB;                             // blocks of 16 positions per chain = ceil(P / 16) <= 16
+    const uint32_t* blist;              // [n * PB_MAXNB] compact (chain << 5 | block) list, range r starts at PB_MAXNB * b_lo(r)
+    int NB;                             // blocks of PB positions per chain = ceil(P / PB) <= PB_MAXNB
     int ctas_per_combo;
     int MT;                             // channel-tile pairs
     int kpad;
@@ -833,17 +840,17 @@ __device__ __forceinline__ void mbar_wait_cluster_relaxed(uint64_t* bar, uint32_
         : "memory");
 }
 
-// (value, first arg-max) of 16 raw accumulators held as bit patterns
-__device__ __forceinline__ void argmax16(const uint32_t (&r)[16], float& best, int& bidx) {
-    float v[8]; int ix[8];
+// (value, first arg-max) of the 8 raw accumulators r[o .. o+8) held as bit patterns
+__device__ __forceinline__ void argmax8(const uint32_t (&r)[16], int o, float& best, int& bidx) {
+    float v[4]; int ix[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float a = __uint_as_float(r[2 * i]), b = __uint_as_float(r[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) {
+        const float a = __uint_as_float(r[o + 2 * i]), b = __uint_as_float(r[o + 2 * i + 1]);
         const bool gt = b > a;
         v[i] = gt ? b : a; ix[i] = gt ? 2 * i + 1 : 2 * i;
     }
 #pragma unroll
-    for (int w = 4; w >= 1; w >>= 1) {
+    for (int w = 2; w >= 1; w >>= 1) {
 #pragma unroll
         for (int i = 0; i < w; ++i) {
             const bool gt = v[2 * i + 1] > v[2 * i];
@@ -886,8 +893,8 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
         return (b < b_hi) ? (prm.dmask ? (__ldg(prm.dmask + b) & all_blocks) : all_blocks) : 0u;
     };
     const int G = idle ? 0 : __ldg(prm.gtot + within);       // dirty blocks of my chains
-    const int ntiles = (G + 7) >> 3;                         // tiles of 8 blocks (the last one may be shorter)
-    const uint32_t* bl = prm.blist + (size_t)b_lo * 16;
+    const int ntiles = (G + PB_TILE - 1) / PB_TILE;          // tiles of PB_TILE blocks (the last one may be shorter)
+    const uint32_t* bl = prm.blist + (size_t)b_lo * PB_MAXNB;
 
     for (int e = threadIdx.x; e < 100 * KS; e += NTHREADS) {
         const int row = e / KS, c = e - row * KS;
@@ -939,24 +946,24 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
     tc_fence_after();
 
     if (warp < 4) {
-        // ===== EPILOGUE (both CTAs): thread = channel j; per TILE: the 8 blocks' keys go straight to their final place in
-        // the proposal rows of the pool (no per-chain work here: cnn_inc_merge_kernel copies the clean keys and forms mkey) =====
+        // ===== EPILOGUE (both CTAs): thread = channel j; per TILE: the PB_TILE blocks' keys go straight to their final place in
+        // the proposal rows of the pool (no per-chain work here: cnn_inc_merge_kernel forms mkey) =====
         const int j = mt * 128 + warp * 32 + lane;
         const bool jok = j < J2;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
         const size_t row_keys = (size_t)prm.m.n_nets * NB * J2;            // keys per pool row
         const size_t koff = ((size_t)k * NB) * J2 + j;
-        // lane l (mod 8) holds block l of the tile: entry (chain << 4 | block) two tiles ahead, its pool row one tile ahead
+        // lane l (mod PB_TILE) holds block l of the tile: entry (chain << 5 | block) two tiles ahead, its pool row one tile ahead
         auto ld_ent = [&](int T) -> uint32_t {
-            const int g = 8 * T + (lane & 7);
+            const int g = PB_TILE * T + (lane & (PB_TILE - 1));
             return (g < G) ? __ldg(bl + g) : 0u;
         };
         // slot that receives block (b, q): the proposal row's own, unless the current row still points at it (then the current
         // row's own slot is free: it is referenced by neither row) - see cnn_inc_merge_kernel for the table update
         auto ld_row = [&](int T, uint32_t ent) -> int {
-            const int g = 8 * T + (lane & 7);
+            const int g = PB_TILE * T + (lane & (PB_TILE - 1));
             if (g >= G) return 0;
-            const int b = (int)(ent >> 4), q = (int)(ent & 15u);
+            const int b = (int)(ent >> 5), q = (int)(ent & 31u);
             const int ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
             if (!prm.rows_x) return ry;
             const int rx = __ldg(prm.rows_x + b);
@@ -969,7 +976,7 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
         long long pc[4] = {0, 0, 0, 0};
         long long tp = prof ? clock64() : 0;
         for (int T = 0; T < ntiles; ++T) {
-            const int cnt = min(8, G - 8 * T);
+            const int cnt = min(PB_TILE, G - PB_TILE * T);
             const int buf = T & 1;
             const uint32_t ent = ent_a;
             const int row = row_a;
@@ -980,32 +987,33 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
             mbar_wait(&dfull[buf], (uint32_t)((T >> 1) & 1));
             tc_fence_after();
             if (prof) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-            // two blocks per tcgen05.wait::ld: the two 16-deep compare chains are independent (ILP) and the TMEM load latency is
-            // paid 4 times per tile instead of 8 (the serial per-block epilogue was at the tile period)
+            // four blocks (32 accumulator columns) per tcgen05.wait::ld; the first arg-max of a block's PB = 8 values is a
+            // 3-level compare tree (the right operand wins only if strictly greater: the lowest index survives ties)
             auto emit = [&](int s, float bu, int bi) {
                 const uint32_t e_s = __shfl_sync(0xffffffffu, ent, s);
                 const int r_s = __shfl_sync(0xffffffffu, row, s);
-                const int q = (int)(e_s & 15u);
+                const int q = (int)(e_s & 31u);
                 const unsigned long long key = ((unsigned long long)f32_ordered(bu) << 32) |
-                                               (unsigned long long)(0xFFFFFFFFu - (unsigned)(16 * q + bi));
+                                               (unsigned long long)(0xFFFFFFFFu - (unsigned)(PB * q + bi));
                 if (jok && !(prm.dbg & 1)) __stcg(prm.bkey + (size_t)r_s * row_keys + koff + (size_t)q * J2, key);
             };
 #pragma unroll
-            for (int s = 0; s < 8; s += 2) {
+            for (int s = 0; s < PB_TILE; s += 4) {
                 if (s < cnt) {                                              // warp-uniform
                     uint32_t ra[16], rb[16];
-                    const bool two = s + 1 < cnt;
-                    tmem_ld16(lane_addr + buf * 128 + 16 * s, ra);
-                    if (two) tmem_ld16(lane_addr + buf * 128 + 16 * (s + 1), rb);
+                    const bool second = s + 2 < cnt;
+                    tmem_ld16(lane_addr + buf * 128 + PB * s, ra);          // blocks s, s + 1
+                    if (second) tmem_ld16(lane_addr + buf * 128 + PB * (s + 2), rb);   // blocks s + 2, s + 3
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // first arg-max of 16 values as a 4-level tree (the right operand wins only if strictly greater, so the lowest
-                    // index survives ties): dependent depth 4 instead of the 15 of a running maximum
-                    float bu0, bu1 = 0.f;
-                    int bi0, bi1 = 0;
-                    argmax16(ra, bu0, bi0);
-                    if (two) argmax16(rb, bu1, bi1);
-                    emit(s, bu0, bi0);
-                    if (two) emit(s + 1, bu1, bi1);
+                    float bu[4] = {0.f, 0.f, 0.f, 0.f};
+                    int bi[4] = {0, 0, 0, 0};
+                    argmax8(ra, 0, bu[0], bi[0]);
+                    argmax8(ra, 8, bu[1], bi[1]);
+                    if (second) { argmax8(rb, 0, bu[2], bi[2]); argmax8(rb, 8, bu[3], bi[3]); }
+                    emit(s, bu[0], bi[0]);
+                    if (s + 1 < cnt) emit(s + 1, bu[1], bi[1]);
+                    if (s + 2 < cnt) emit(s + 2, bu[2], bi[2]);
+                    if (s + 3 < cnt) emit(s + 3, bu[3], bi[3]);
                 }
             }
             tc_fence_before();
@@ -1029,8 +1037,8 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
             long long tp = prof ? clock64() : 0;
             const long long tstart = tp;
             for (int it = 0; it < ntiles; ++it) {
-                const int cnt = min(8, G - 8 * it);
-                const uint32_t idesc = make_idesc(256, 16 * cnt);
+                const int cnt = min(PB_TILE, G - PB_TILE * it);
+                const uint32_t idesc = make_idesc(256, (PB * cnt + 15) & ~15);
                 const int buf = it & 1;
                 if (it >= 2) mbar_wait_cluster_relaxed(&dempty[buf], (uint32_t)(((it >> 1) + 1) & 1));
                 if (prof) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
@@ -1077,7 +1085,8 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
             }
         }
     } else {
-        // ===== PRODUCERS (both CTAs): one row per thread; a tile = 8 consecutive dirty blocks of the CTA.s sequence, this CTA.s half =====
+        // ===== PRODUCERS (both CTAs): one row per thread; a tile = PB_TILE consecutive dirty blocks of the CTA's sequence (N rounded
+        // up to a multiple of 16 rows: an odd block count leaves one pad block, produced by nobody and read by nobody), this CTA's half =====
         const int pw = warp - 4;
         const int g = lane & 7, q = lane >> 3;
         const int r = 16 * (pw >> 2) + (pw & 3) + 4 * q;      // local row 0..63
@@ -1086,17 +1095,19 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
         const uint32_t st0 = smem_u32(ring) + o0, st1 = smem_u32(ring) + (o0 ^ 64u);
         int slot = 0;
         uint32_t phase = 0;
-        // my row of tile T: block entry (chain << 4 | block) from the compact list two tiles ahead, residues one tile ahead
+        // my row of tile T: block entry (chain << 5 | block) from the compact list two tiles ahead, residues one tile ahead
         auto my_row = [&](int T, bool& act, int& gr) {
-            const int half = 8 * min(8, G - 8 * T);
-            act = r < half;
-            gr = (int)rank * half + (act ? r : 0);
+            const int cntT = min(PB_TILE, G - PB_TILE * T);
+            const int half = ((PB * cntT + 15) & ~15) >> 1;          // rows of this CTA (the MMA's N is a multiple of 16)
+            gr = (int)rank * half + r;
+            act = r < half && (gr >> PB_SHIFT) < cntT;
+            if (!act) gr = 0;
         };
         auto ld_entry = [&](int T) -> uint32_t {
             if (T >= ntiles) return 0u;
             bool act; int gr;
             my_row(T, act, gr);
-            return __ldg(bl + 8 * T + (gr >> 4));
+            return __ldg(bl + PB_TILE * T + (gr >> PB_SHIFT));
         };
         uint32_t an[5] = {0u, 0u, 0u, 0u, 0u};
         bool nact = false;
@@ -1106,8 +1117,8 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
             if (T >= ntiles) return;
             int gr;
             my_row(T, nact, gr);
-            nb = (int)(ent >> 4);
-            npos = 16 * (int)(ent & 15u) + (gr & 15);
+            nb = (int)(ent >> 5);
+            npos = PB * (int)(ent & 31u) + (gr & (PB - 1));
             const uint8_t* ap = prm.aa + (size_t)nb * prm.aa_stride + min(npos, P - 1);   // rows past the end replicate P-1
             if (!(prm.dbg & 4)) {
 #pragma unroll
@@ -1161,7 +1172,7 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
                     int mrow = prm.rows_y ? __ldg(prm.rows_y + bcur) : prm.row_base_y + bcur;
                     if (prm.rows_x) {                          // same slot rule as the block keys
                         const int rx = __ldg(prm.rows_x + bcur);
-                        if (__ldg(prm.btab + (size_t)rx * NB + (pos >> 4)) == mrow) mrow = rx;
+                        if (__ldg(prm.btab + (size_t)rx * NB + (pos >> PB_SHIFT)) == mrow) mrow = rx;
                     }
                     reinterpret_cast<uint32_t*>(prm.r1mask + (((size_t)mrow * prm.m.n_nets + k) * P + pos) * 32)[g] = word;
                 }
@@ -1191,7 +1202,7 @@ __global__ void __launch_bounds__(128) cnn_dirty_kernel(int n, int L, int P, int
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         if (aa_x[(size_t)b * aa_stride + i] != aa_y[(size_t)b * aa_stride + i]) {
             const int p_lo = max(i - 4, 0), p_hi = min(i, P - 1);
-            if (p_lo <= p_hi) m |= (1u << (p_lo >> 4)) | (1u << (p_hi >> 4));
+            if (p_lo <= p_hi) m |= (1u << (p_lo >> PB_SHIFT)) | (1u << (p_hi >> PB_SHIFT));
         }
     }
     m = __reduce_or_sync(0xffffffffu, m);
@@ -1213,9 +1224,11 @@ __global__ void __launch_bounds__(128) cnn_dirty_kernel(int n, int L, int P, int
 //     R    = the list entries whose block is clean           (still the largest keys among the CLEAN blocks, in order)
 //     cand = the new keys of the dirty blocks that are >= min(old list)   (certain to outrank every unlisted clean block)
 //     new list = top-2 of R u cand                            - exact for the same reason; K2 = 0 when only one is certain
-// so the merge reads 16 bytes of list + the dirty blocks' keys (2.25 of NB = 15 at pas = 2) per channel instead of all NB keys,
-// fully coalesced.  Only when the new list is EMPTY (every listed block dirty and every new key below the old minimum: well
-// under 1 % of the channels) the clean blocks are rescanned.  max over u64 is associative and the list never holds a key that
+// so the merge reads 16 bytes of list + the dirty blocks' keys (2.8 of NB = 30 at pas = 2) per channel instead of all NB keys,
+// fully coalesced.  Only when the new list is EMPTY (every listed block dirty and every new key below the old minimum) the clean
+// blocks are rescanned: 5 % of the channels in steady state (tools/merge_stats.py) - far more than independence would give
+// (0.6 %), because the proposal favours the residues the winners read.  A separate exact bound of the unlisted blocks (24-byte
+// entries) did not lower that rate and measured slower (4.1 vs 3.1 ms).  max over u64 is associative and the list never holds a key that
 // is not a current block key of the row: the winner is bit-identical to the full scan (tested against the full kernel).
 __device__ __forceinline__ void top2_insert(unsigned long long k, unsigned long long& k1, unsigned long long& k2) {
     if (k > k1) { k2 = k1; k1 = k; }
@@ -1225,7 +1238,7 @@ __device__ __forceinline__ void top2_insert(unsigned long long k, unsigned long 
 // (s_dptr) and every thread works on MERGE_E channels at a time with the list loads and the first MERGE_DP dirty-key loads
 // of all of them issued before the first use (two dependent global loads per channel would otherwise bound the kernel).
 // Without a list (no pool, or a full evaluation) "every block is dirty" and the same loop scans all NB keys.
-constexpr int MERGE_NT = 256, MERGE_E = 3, MERGE_DP = 4;
+constexpr int MERGE_NT = 256, MERGE_E = 3, MERGE_DP = 6;
 __global__ void __launch_bounds__(MERGE_NT, 4) cnn_inc_merge_kernel(const __grid_constant__ IncParams prm) {
     const int b = blockIdx.x;
     const int J2 = 2 * prm.m.C, NB = prm.NB, nets = prm.m.n_nets;
@@ -1236,11 +1249,11 @@ __global__ void __launch_bounds__(MERGE_NT, 4) cnn_inc_merge_kernel(const __grid
     const int rx = prm.rows_x ? __ldg(prm.rows_x + b) : ry;
     const bool have_old = prm.rows_x && prm.mkey_pool && !(prm.dbg & 8);   // top-2 list of the current row available
     const uint32_t first = have_old ? mask : all_blocks;                   // blocks whose keys are read in the first round
-    __shared__ int s_slot[16];
-    __shared__ const unsigned long long* s_ptr[16];       // first key of every block (through the slot table)
-    __shared__ const unsigned long long* s_dptr[16];      // ... of the blocks of `first`, compacted
+    __shared__ int s_slot[PB_MAXNB];
+    __shared__ const unsigned long long* s_ptr[PB_MAXNB];       // first key of every block (through the slot table)
+    __shared__ const unsigned long long* s_dptr[PB_MAXNB];      // ... of the blocks of `first`, compacted
     __shared__ int s_nd;
-    if (threadIdx.x < 16) {
+    if (threadIdx.x < PB_MAXNB) {
         const int q = threadIdx.x;
         int sl = ry;
         if (q < NB && prm.rows_x) {
@@ -1282,8 +1295,8 @@ __global__ void __launch_bounds__(MERGE_NT, 4) cnn_inc_merge_kernel(const __grid
                 unsigned long long k1 = 0ull, k2 = 0ull, omin = 0ull;
                 if (have_old) {
                     const ulonglong2 L = Lr[u];
-                    const uint32_t q1 = (0xFFFFFFFFu - (uint32_t)(L.x & 0xFFFFFFFFull)) >> 4;    // blocks of the listed keys
-                    const uint32_t q2 = (0xFFFFFFFFu - (uint32_t)(L.y & 0xFFFFFFFFull)) >> 4;
+                    const uint32_t q1 = (0xFFFFFFFFu - (uint32_t)(L.x & 0xFFFFFFFFull)) >> PB_SHIFT;    // blocks of the listed keys
+                    const uint32_t q2 = (0xFFFFFFFFu - (uint32_t)(L.y & 0xFFFFFFFFull)) >> PB_SHIFT;
                     omin = L.y ? L.y : L.x;
                     if (!((mask >> q1) & 1u)) k1 = L.x;                                            // R: listed keys of clean blocks
                     if (L.y && !((mask >> q2) & 1u)) top2_insert(L.y, k1, k2);
@@ -1331,7 +1344,7 @@ __global__ void __launch_bounds__(1024) cnn_inc_scan_kernel(int n, int R, int NB
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();
-    uint32_t* out = blist + (size_t)b_lo * 16;
+    uint32_t* out = blist + (size_t)b_lo * PB_MAXNB;
     for (int base = b_lo; base < b_hi; base += 1024) {
         const int b = base + (int)threadIdx.x;
         uint32_t mask = 0u;
@@ -1362,7 +1375,7 @@ __global__ void __launch_bounds__(1024) cnn_inc_scan_kernel(int n, int R, int NB
             while (mask) {
                 const int q = __ffs((int)mask) - 1;
                 mask &= mask - 1u;
-                out[off++] = ((uint32_t)b << 4) | (uint32_t)q;
+                out[off++] = ((uint32_t)b << 5) | (uint32_t)q;
             }
         }
         __syncthreads();
@@ -1475,9 +1488,9 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     int* sPx = sPy + J2;              // [J2]
     int* sList = sPx + J2;            // [2 J2]
     const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
-    __shared__ int sBt[2][16];                        // block-table rows of the proposal / current state (mask fetch at the end)
-    if (r1mask && btab && threadIdx.x < 32) {
-        const int side = threadIdx.x >> 4, q = threadIdx.x & 15;
+    __shared__ int sBt[2][PB_MAXNB];                  // block-table rows of the proposal / current state (mask fetch at the end)
+    if (r1mask && btab && threadIdx.x < 64) {
+        const int side = threadIdx.x >> 5, q = threadIdx.x & 31;
         if (q < NB) sBt[side][q] = __ldg(btab + (size_t)(side ? rows_x[b] : rows_y[b]) * NB + q);
     }
     const unsigned long long* ky = mkey_y + (size_t)bk * J2;
@@ -1590,7 +1603,7 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
             const int c = it >> 2, part = it & 3, side = part >> 1;
             const int pp = sPosC[c];
             int row = side ? mx : my;
-            if (btab) row = sBt[side][pp >> 4];
+            if (btab) row = sBt[side][pp >> PB_SHIFT];
             mout[it] = __ldg(reinterpret_cast<const uint4*>(r1mask + (((size_t)row * n_nets + k) * P + pp) * 32) + (part & 1));
         }
     }
@@ -1662,13 +1675,13 @@ __global__ void __launch_bounds__(128) cnn_delta_record_kernel(const __grid_cons
     int* sPosC = reinterpret_cast<int*>(sSorted + 2 * J2);   // [P] compact position list
     __shared__ uint32_t sD0[8];                              // bit p: the relu mask of conv row p changed (P <= 252)
     __shared__ int sCount, sBase[5];
-    __shared__ int sBt[2][16];                               // block-table rows of the proposal / current state (mask fetch)
+    __shared__ int sBt[2][PB_MAXNB];                         // block-table rows of the proposal / current state (mask fetch)
     const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 8) sD0[threadIdx.x] = 0u;
     if (threadIdx.x == 8) sCount = 0;
-    if (r1mask && btab && threadIdx.x >= 32 && threadIdx.x < 64) {
-        const int side = (threadIdx.x - 32) >> 4, q = threadIdx.x & 15;
+    if (r1mask && btab && threadIdx.x >= 64) {
+        const int side = (threadIdx.x - 64) >> 5, q = threadIdx.x & 31;
         if (q < NB) sBt[side][q] = __ldg(btab + (size_t)(side ? rows_x[b] : rows_y[b]) * NB + q);
     }
     __syncthreads();
@@ -1752,7 +1765,7 @@ __global__ void __launch_bounds__(128) cnn_delta_record_kernel(const __grid_cons
             const int c = it >> 2, part = it & 3, side = part >> 1;
             const int pp = sPosC[c];
             int row = side ? mx : my;
-            if (btab) row = sBt[side][pp >> 4];
+            if (btab) row = sBt[side][pp >> PB_SHIFT];
             mout[it] = __ldg(reinterpret_cast<const uint4*>(r1mask + (((size_t)row * n_nets + k) * P + pp) * 32) + (part & 1));
         }
     }
@@ -2174,7 +2187,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
         auto load_masks = [&](int bb, int pp0, unsigned long long& my, unsigned long long& mx) {
             my = 0ull; mx = 0ull;
             int mr = prm.mask_rows ? __ldg(prm.mask_rows + bb) : prm.mask_row_base + bb;
-            const int blk = min((pp0 + r0) >> 4, prm.NB - 1);            // my 8 rows lie in one 16-position block
+            const int blk = min((pp0 + r0) >> PB_SHIFT, prm.NB - 1);     // my 8 rows (aligned to 8) lie in one block of PB positions
             if (prm.btab) mr = __ldg(prm.btab + (size_t)mr * prm.NB + blk);
             const uint8_t* mrow = prm.r1mask + (((size_t)mr * prm.m.n_nets + k) * P + pp0 + r0) * 32 + lane;
 #pragma unroll
@@ -2633,7 +2646,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                             const int mry = __ldg(prm.mask_rows + bb), mrx = __ldg(prm.mask_rows_x + bb);
                             const int p = lds_u16(ps + 2u * (uint32_t)c);
                             int ry = mry, rx = mrx;
-                            if (prm.btab) { ry = __ldg(prm.btab + (size_t)mry * NB + (p >> 4)); rx = __ldg(prm.btab + (size_t)mrx * NB + (p >> 4)); }
+                            if (prm.btab) { ry = __ldg(prm.btab + (size_t)mry * NB + (p >> PB_SHIFT)); rx = __ldg(prm.btab + (size_t)mrx * NB + (p >> PB_SHIFT)); }
                             m8 |= (unsigned long long)__ldg(prm.r1mask + (((size_t)ry * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * i);
                             m8x |= (unsigned long long)__ldg(prm.r1mask + (((size_t)rx * prm.m.n_nets + k) * P + p) * 32 + lane) << (8 * i);
                         }
@@ -2870,7 +2883,8 @@ extern "C" int ppde_cnn_dirty(const ppde_cnn_t* m, const uint8_t* aa_x, const ui
     return launch_done();
 }
 
-extern "C" int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n) { return ((int64_t)n + 256 + (int64_t)n * 16) * 4; }
+extern "C" int64_t ppde_cnn_forward_inc_ws_bytes(int32_t n) { return ((int64_t)n + 256 + (int64_t)n * tc::PB_MAXNB) * 4; }
+extern "C" int32_t ppde_cnn_block_positions(void) { return tc::PB; }
 
 extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n,
                                     unsigned long long* mkey, uint8_t* r1mask, const uint32_t* dmask,
@@ -2879,8 +2893,8 @@ extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int3
                                     void* stream) {
     if (n <= 0) return 0;
     if (!m || !aa || aa_stride < m->L) return (int)cudaErrorInvalidValue;
-    const int NB = (m->P + 15) / 16;
-    if (m->C > 256 || m->P < 1 || NB > 16 || !bkey || !btab || !mkey || !ws || (dmask && !rows_x)) return (int)cudaErrorInvalidValue;
+    const int NB = (m->P + tc::PB - 1) / tc::PB;
+    if (m->C > 256 || m->P < 1 || NB > tc::PB_MAXNB || !bkey || !btab || !mkey || !ws || (dmask && !rows_x)) return (int)cudaErrorInvalidValue;
     const int inc_parts = (tune && (tune->parts & 7)) ? (tune->parts & 7) : 7;
     tc::IncParams prm;
     prm.m = *m; prm.aa = aa; prm.aa_stride = aa_stride; prm.n = n; prm.mkey = mkey; prm.r1mask = r1mask; prm.dmask = dmask;
@@ -2969,7 +2983,7 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     prm.mask_rows = dl ? dl->rows_y : mask_rows;
     prm.mask_row_base = mask_row_base;
     prm.mask_rows_x = dl ? dl->rows_x : nullptr;
-    prm.btab = btab; prm.NB = (m->P + 15) / 16;
+    prm.btab = btab; prm.NB = (m->P + tc::PB - 1) / tc::PB;
     prm.dbg = tune ? tune->dbg : 0;
     prm.tiles_per_chain = (m->P + tc::BW_NT - 1) / tc::BW_NT;
     prm.kpad = (m->C + 15) / 16 * 16;

@@ -193,9 +193,10 @@ class PoEModel:
         self.cnn_backward_impl = "tc" if (wantb == "tc" and self.C <= 256) else "simt"
         # incremental CNN forward (block-wise max-pool cache in the chain engine's row pools); needs both tensor-core
         # kernels and <= 16 blocks of 16 positions.  PPDE_CNN_INC=0 re-evaluates every position of every proposal.
-        self.NB = (self.P + 15) // 16
+        self.PB = int(self.lib.ppde_cnn_block_positions())              # positions per block of the max-pool cache
+        self.NB = (self.P + self.PB - 1) // self.PB
         self.cnn_inc = (os.environ.get("PPDE_CNN_INC", "1") != "0" and self.cnn_forward_impl == "tc"
-                        and self.cnn_backward_impl == "tc" and self.NB <= 16)
+                        and self.cnn_backward_impl == "tc" and self.NB <= 32)
         # delta backward on top of the incremental forward: gradient rows updated by the change of the few adjoint rows that
         # differ between the current state and the proposal; an exact (full) backward every `bwd_refresh` iterations bounds the
         # accumulated rounding.  PPDE_CNN_BWD_DELTA=0 always runs the full backward.

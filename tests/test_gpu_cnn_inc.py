@@ -12,12 +12,13 @@ from oracle import ppde_port as port
 pytestmark = pytest.mark.gpu
 
 
-def _mask_rows(r1pool, btab, rows, nets, P, NB):
+def _mask_rows(r1pool, btab, rows, nets, P, NB, PB=None):
     """Relu-mask rows [n, nets, P, 32] of the pool rows `rows`, read through the block table."""
+    PB = PB or (P + NB - 1) // NB                    # positions per block (8: NB = ceil(P / PB))
     n_rows = btab.numel() // NB
     pool = r1pool.view(n_rows, nets, P, 32)
     tab = btab.view(n_rows, NB).long()[rows.long()]                    # [n, NB]
-    src = tab[:, (torch.arange(P, device=tab.device) >> 4)]            # [n, P] source row of every position
+    src = tab[:, (torch.arange(P, device=tab.device) // PB)]           # [n, P] source row of every position
     pidx = torch.arange(P, device=tab.device)[None, :].expand_as(src)
     return pool[src, :, pidx, :].permute(0, 2, 1, 3).contiguous()      # [n, P, nets, 32] -> [n, nets, P, 32]
 
@@ -107,7 +108,7 @@ def test_incremental_forward_is_bit_identical(L, n, use_pool):
         want = 0
         for i in np.nonzero(x[b] != y[b])[0]:
             for p in range(max(i - 4, 0), min(i, P - 1) + 1):
-                want |= 1 << (p >> 4)
+                want |= 1 << (p // m.PB)
         assert dm[b] == want, f"chain {b}: dirty mask {dm[b]:#x} != {want:#x}"
     assert (dm[::8] == 0).all() and (dm[6::8] == (1 << NB) - 1).all()
     assert torch.equal(mk_y, mk_fy), "incremental winners differ from the full kernel"

@@ -38,7 +38,7 @@ def step(timed_forward):
 
 if dbg: m.tune = TuneT(dbg=int(dbg))
 ts = [step(lambda: eng.cnn_forward_y(st)) for _ in range(5)]
-nd = torch.tensor([bin(int(v) & 0xFFFF).count("1") for v in eng.dmask.cpu().numpy()[:4096]]).float()
+nd = torch.tensor([bin(int(v) & 0xFFFFFFFF).count("1") for v in eng.dmask.cpu().numpy()[:4096]]).float()
 print(f"chains {n} dbg {dbg}: incremental forward {min(ts):.3f} ms (median {sorted(ts)[2]:.3f}); dirty blocks / chain mean {nd.mean():.2f} max {nd.max():.0f}")
 if dbg:
     sys.exit(0)
