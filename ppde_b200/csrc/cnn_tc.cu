@@ -953,36 +953,44 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
         const size_t row_keys = (size_t)prm.m.n_nets * NB * J2;            // keys per pool row
         const size_t koff = ((size_t)k * NB) * J2 + j;
-        // lane l (mod PB_TILE) holds block l of the tile: entry (chain << 5 | block) two tiles ahead, its pool row one tile ahead
+        // lane l (mod PB_TILE) holds block l of the tile.  Three-stage prefetch, each stage one tile apart so that no load is waited
+        // for in the iteration that issues it: entry (chain << 5 | block) three tiles ahead, the chain's pool rows two tiles ahead,
+        // the block-table lookup that picks the slot one tile ahead (the table entry depends on the rows: a two-level chain that
+        // cost ~700 cycles per tile when both levels were issued in the same iteration).
         auto ld_ent = [&](int T) -> uint32_t {
             const int g = PB_TILE * T + (lane & (PB_TILE - 1));
-            return (g < G) ? __ldg(bl + g) : 0u;
+            return (g < G) ? __ldg(bl + g) : 0xFFFFFFFFu;                   // all ones: no block
+        };
+        auto ld_rows = [&](uint32_t ent, int& ry, int& rx) {
+            ry = 0; rx = -1;
+            if (ent == 0xFFFFFFFFu) return;
+            const int b = (int)(ent >> 5);
+            ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
+            if (prm.rows_x) rx = __ldg(prm.rows_x + b);
         };
         // slot that receives block (b, q): the proposal row's own, unless the current row still points at it (then the current
         // row's own slot is free: it is referenced by neither row) - see cnn_inc_merge_kernel for the table update
-        auto ld_row = [&](int T, uint32_t ent) -> int {
-            const int g = PB_TILE * T + (lane & (PB_TILE - 1));
-            if (g >= G) return 0;
-            const int b = (int)(ent >> 5), q = (int)(ent & 31u);
-            const int ry = prm.rows_y ? __ldg(prm.rows_y + b) : prm.row_base_y + b;
-            if (!prm.rows_x) return ry;
-            const int rx = __ldg(prm.rows_x + b);
-            return (__ldg(prm.btab + (size_t)rx * NB + q) == ry) ? rx : ry;
+        auto ld_slot = [&](uint32_t ent, int ry, int rx) -> int {
+            if (ent == 0xFFFFFFFFu || rx < 0) return ry;
+            return (__ldg(prm.btab + (size_t)rx * NB + (int)(ent & 31u)) == ry) ? rx : ry;
         };
-        uint32_t ent_a = ld_ent(0);
-        int row_a = ld_row(0, ent_a);
-        uint32_t ent_b = ld_ent(1);
+        uint32_t ent0 = ld_ent(0), ent1 = ld_ent(1), ent2 = ld_ent(2);      // entries of tiles T, T+1, T+2
+        int ry1, rx1, ry0, rx0;
+        ld_rows(ent0, ry0, rx0);
+        ld_rows(ent1, ry1, rx1);                                            // rows of tile T+1
+        int row0 = ld_slot(ent0, ry0, rx0);                                 // slot of tile T
         const bool prof = prm.prof != nullptr;
         long long pc[4] = {0, 0, 0, 0};
         long long tp = prof ? clock64() : 0;
         for (int T = 0; T < ntiles; ++T) {
             const int cnt = min(PB_TILE, G - PB_TILE * T);
             const int buf = T & 1;
-            const uint32_t ent = ent_a;
-            const int row = row_a;
-            ent_a = ent_b;
-            row_a = ld_row(T + 1, ent_a);
-            ent_b = ld_ent(T + 2);
+            const uint32_t ent = ent0;
+            const int row = row0;
+            row0 = ld_slot(ent1, ry1, rx1);                                 // tile T+1: rows were requested one iteration ago
+            ent0 = ent1; ent1 = ent2;
+            ld_rows(ent1, ry1, rx1);                                        // tile T+2
+            ent2 = ld_ent(T + 3);
             if (prof) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
             mbar_wait(&dfull[buf], (uint32_t)((T >> 1) & 1));
             tc_fence_after();
