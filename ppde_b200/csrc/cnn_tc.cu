@@ -1260,7 +1260,9 @@ __global__ void __launch_bounds__(MERGE_NT, 4) cnn_inc_merge_kernel(const __grid
     __shared__ int s_slot[PB_MAXNB];
     __shared__ const unsigned long long* s_ptr[PB_MAXNB];       // first key of every block (through the slot table)
     __shared__ const unsigned long long* s_dptr[PB_MAXNB];      // ... of the blocks of `first`, compacted
-    __shared__ int s_nd;
+    __shared__ int s_nd, s_nres;
+    __shared__ uint16_t s_res[PPDE_MAX_NETS * 2 * 256];                   // channels (net * J2 + j) whose clean blocks have to be rescanned
+    if (threadIdx.x == 0) s_nres = 0;
     if (threadIdx.x < PB_MAXNB) {
         const int q = threadIdx.x;
         int sl = ry;
@@ -1319,18 +1321,46 @@ __global__ void __launch_bounds__(MERGE_NT, 4) cnn_inc_merge_kernel(const __grid
 #pragma unroll
                     for (int d = 0; d < MERGE_DP; ++d) if (kx[d] >= omin) top2_insert(kx[d], k1, k2);
                 }
-                if (have_old && k1 == 0ull) {               // nothing certain: exact top-2 of all NB blocks
-                    k2 = 0ull;
-                    for (int q0 = 0; q0 < NB; q0 += MERGE_DP) {
-                        unsigned long long kx[MERGE_DP];
-#pragma unroll
-                        for (int d = 0; d < MERGE_DP; ++d) kx[d] = (q0 + d < NB) ? __ldcg(s_ptr[q0 + d] + off[u]) : 0ull;
-#pragma unroll
-                        for (int d = 0; d < MERGE_DP; ++d) top2_insert(kx[d], k1, k2);
-                    }
+                if (have_old && k1 == 0ull) {               // nothing certain: the clean blocks have to be rescanned - deferred
+                    s_res[atomicAdd(&s_nres, 1)] = (uint16_t)e;
+                    continue;
                 }
                 const ppde_cnn_net_t& net = prm.m.net[kk[u]];
                 outp[e] = winner_from_raw(k1, 1.f / (net.w1_scale * net.r1_scale), __ldg(net.b1 + jj[u]));
+                if (newp) newp[e] = make_ulonglong2(k1, k2);
+            }
+        }
+    }
+    // Rescans, cooperatively: 5 % of the channels need the exact top-2 of all NB block keys.  Inside the loop above that was a
+    // divergent branch with ceil(NB / MERGE_DP) dependent rounds of loads which nearly every warp entered (96 channels per warp
+    // and iteration: 1 - 0.95^32 = 80 % per unrolled entry), i.e. ~24 dependent global-load rounds per warp - the kernel's whole
+    // critical path (2.9 ms).  Now the channels are queued and 8 lanes share one: 4 independent loads per lane, three shuffle
+    // levels of top-2 merges.  Order of the queue does not matter (one result per channel); max over u64 keys is exact.
+    if (have_old) {
+        __syncthreads();
+        const int nres = s_nres;
+        const int g8 = threadIdx.x & 7;
+        for (int r0 = (threadIdx.x >> 5) * 4; r0 < nres; r0 += MERGE_NT / 8) {        // warp-uniform trip count (shuffles below)
+            const int r = r0 + ((threadIdx.x & 31) >> 3);
+            const bool live = r < nres;
+            const int e = live ? s_res[r] : 0;
+            const int k = e / J2, j = e - k * J2;
+            const int off = k * NB * J2 + j;
+            unsigned long long kx[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) kx[d] = (live && g8 + 8 * d < NB) ? __ldcg(s_ptr[g8 + 8 * d] + off) : 0ull;
+            unsigned long long k1 = 0ull, k2 = 0ull;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) top2_insert(kx[d], k1, k2);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {               // merge the top-2 lists of lane pairs (block keys are distinct)
+                const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+                top2_insert(o1, k1, k2);
+                top2_insert(o2, k1, k2);
+            }
+            if (g8 == 0 && live) {
+                const ppde_cnn_net_t& net = prm.m.net[k];
+                outp[e] = winner_from_raw(k1, 1.f / (net.w1_scale * net.r1_scale), __ldg(net.b1 + j));
                 if (newp) newp[e] = make_ulonglong2(k1, k2);
             }
         }
