@@ -294,7 +294,7 @@ def main():
         reps = min(K, 5)
         launches_per_step, dirty_blocks = 0, None
         for rep in range(reps):
-            p_holder["p"] = eng._params(eng.t)
+            p_holder["p"] = eng._params(eng.t, full=not eng.delta)
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(seq) + 1)]
             c_before = lib.ppde_last_launch_count()
             evs[0].record()

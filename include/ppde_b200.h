@@ -137,6 +137,19 @@ typedef struct ppde_pas_params {
     int32_t full_trace;    /* 1: evaluate all S sub-steps of every chain (the reference computes, then masks, the sub-steps
                             * s >= U[b], ppde.py:83,111-115,132); 0: skip those dead sub-steps - nothing they produce reaches
                             * the state, the log-ratio or the accept decision - and record idx = -1, lqf = lqr = 0 for them */
+    /* Fused gradient combine (ppde_pas_reverse_accept only; comb_nets = 0: off).  The reverse kernel stages the proposal's
+     * gradient row in shared memory anyway (ppde.py:126-127 reads it for every reverse softmax); with comb_nets > 0 it first
+     * ASSEMBLES that row - G[y] = G[x] + (Gp[y] - Gp[x])(window) + comb_scale * the sparse per-net changes
+     * ppde_cnn_backward_delta left in its scratch when called with tune->parts = 3 (records + tensor-core kernel, no combine
+     * kernel; layout from ppde_cnn_backward_delta_layout) - writes it to the pool once and goes on from shared memory:
+     * ppde/energy.py:104-108 (one gradient, one sum) without a separate pass over four 19 KB rows per chain.
+     * Needs L <= ppde_pas_reverse_fuse_max_len(), comb_nets <= 3, and c->Gp when the Potts expert is present. */
+    int32_t comb_nets;
+    const float* comb_vals;     /* [comb_nets][n][comb_vcap] values [row][20] of the output rows the records list */
+    const uint16_t* comb_wl;    /* [n][comb_nets][comb_rec] records of cnn_delta_record_kernel */
+    int32_t comb_vcap;
+    int32_t comb_rec;
+    float comb_scale;           /* lamda / n_nets */
     int32_t _pad;
 } ppde_pas_params_t;
 
@@ -236,6 +249,11 @@ int ppde_cnn_backward_delta(const ppde_cnn_t* m, const ppde_potts_t* pm, const u
                             float* G, int64_t G_stride, const int32_t* rows_x, const int32_t* rows_y,
                             const uint8_t* r1mask, const int32_t* btab, float* scratch, const ppde_tune_t* tune,
                             void* stream);
+/* Where ppde_cnn_backward_delta (compact records) keeps its outputs inside `scratch` for n chains: the sparse per-net
+ * changes at scratch[0 .. n_nets * n * vcap) floats, the records (uint16, `rec` each) behind them at float offset wl_offset.
+ * For ppde_pas_params_t.comb_* (fused combine in ppde_pas_reverse_accept). */
+int ppde_cnn_backward_delta_layout(const ppde_cnn_t* m, int32_t n, int32_t* vcap, int32_t* rec, int64_t* wl_offset);
+int32_t ppde_pas_reverse_fuse_max_len(void);   /* largest L for which ppde_pas_reverse_accept accepts comb_nets > 0 */
 /* dH_potts of n states from field rows already in the pool: Epotts[b] = 1/2 sum_i (Gp[rows[b]][(i,aa_i)] + h) - H(wt);
  * rows == NULL means row b. */
 int ppde_potts_energy_rows(const ppde_potts_t* m, const uint8_t* aa, int32_t aa_stride, int32_t n, const float* Gp,

@@ -51,7 +51,8 @@ class TuneT(C.Structure):
 class PasParamsT(C.Structure):
     _fields_ = [("S", C.c_int32), ("nmut_threshold", C.c_int32), ("paper_results", C.c_int32), ("t", C.c_int32),
                 ("min_pos", C.c_int32), ("max_pos", C.c_int32), ("seed", C.c_uint64), ("uniforms", vp), ("t_dev", vp),
-                ("full_trace", C.c_int32), ("_pad", C.c_int32)]
+                ("full_trace", C.c_int32), ("comb_nets", C.c_int32), ("comb_vals", vp), ("comb_wl", vp),
+                ("comb_vcap", C.c_int32), ("comb_rec", C.c_int32), ("comb_scale", C.c_float), ("_pad", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/ppde_b200.h
@@ -71,6 +72,9 @@ SIGNATURES = {
     "ppde_cnn_backward_tc": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
                                        vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.POINTER(TuneT), vp]),
     "ppde_cnn_backward_scratch_floats": (C.c_int64, [C.POINTER(CnnT), C.c_int32]),
+    "ppde_cnn_backward_delta_layout": (C.c_int, [C.POINTER(CnnT), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                                 C.POINTER(C.c_int64)]),
+    "ppde_pas_reverse_fuse_max_len": (C.c_int32, []),
     "ppde_cnn_backward_tc_rows": (C.c_int, [C.POINTER(CnnT), C.POINTER(PottsT), vp, C.c_int32, C.c_int32, vp, C.c_float,
                                             vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp,
                                             C.POINTER(TuneT), vp]),

@@ -1502,6 +1502,10 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 constexpr int BD_NT = 48;                // columns (touched positions) per tile of the compact delta backward
 constexpr int BD_RPW = BD_NT / 8;        // columns per producer warp (8 warps per producer set)
 constexpr int BD_MC = 64;                // touched positions whose relu-mask bytes travel inside the record (64 bytes each)
+constexpr int BD_TRAIL = 16;             // uint16 words at a FIXED place (just before the mask bytes) of a compact record:
+                                         // ntile | index of the (orow, cfirst) pairs | tstart[1 .. 14] - what the fused combine
+                                         // (pas_reverse_accept) needs in ONE load level instead of three dependent ones (P <= 252:
+                                         // <= 6 tiles); 32 bytes, so that records stay sector-aligned
 // Winner records of the DELTA backward.  For chain b and net k the per-net gradient changes between the current state x
 // and the proposal y only through
 //   * the conv rows whose relu mask changed: p in D0 = U_{i: x_i != y_i} [i-4, i], and
@@ -1812,7 +1816,10 @@ __global__ void __launch_bounds__(128) cnn_delta_record_kernel(const __grid_cons
     uint16_t* oo = out + 2 + 2 * npos + nent;         // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
     uint16_t* pairs = oo + 2 + ntile;
     if (threadIdx.x == 0) { oo[0] = (uint16_t)ntile; oo[1] = 0; }
+    __shared__ __align__(16) uint16_t sTr[BD_TRAIL];
     if (threadIdx.x < 32) {
+        if (lane < BD_TRAIL) sTr[lane] = 0;
+        __syncwarp();
         int nr_run = 0;
         for (int t = 0; t < ntile; ++t) {
             const int c0 = t * BD_NT, c1 = min(c0 + BD_NT, npos);
@@ -1844,8 +1851,15 @@ __global__ void __launch_bounds__(128) cnn_delta_record_kernel(const __grid_cons
                 }
             }
             nr_run += __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 0) oo[2 + t] = (uint16_t)nr_run;
+            if (lane == 0) {
+                oo[2 + t] = (uint16_t)nr_run;
+                if (t < BD_TRAIL - 2) sTr[2 + t] = (uint16_t)nr_run;
+            }
         }
+        if (lane == 0) { sTr[0] = (uint16_t)ntile; sTr[1] = (uint16_t)(2 + 2 * npos + nent + 2 + ntile); }
+        __syncwarp();
+        // the fixed trailer, one full 32-byte sector (two 16-byte stores)
+        if (lane < 2) reinterpret_cast<uint4*>(out + rec - BD_MC * 32 - BD_TRAIL)[lane] = reinterpret_cast<const uint4*>(sTr)[lane];
     }
 }
 
@@ -3035,7 +3049,7 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     const bool compact = dl && !(tune && tune->delta_layout == 1);
     // compact record: npos | pos[P] | start[P+1] | list[2 J2] | ntile | tstart[TMAX+1] | (orow, cfirst)[RMAX] | ... | masks[BD_MC][2][32 B]  (uint16)
     const int tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
-    const int rec = compact ? (((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) + tc::BD_MC * 32) : (((P + 1) + 2 * J2 + 7) & ~7);
+    const int rec = compact ? (((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) + tc::BD_TRAIL + tc::BD_MC * 32) : (((P + 1) + 2 * J2 + 7) & ~7);
     const int vcap = compact ? rmax * PPDE_Q : L * PPDE_Q;                       // floats of scratch per (net, chain)
     prm.vcap = vcap;
     const size_t smem_fixed = compact
@@ -3100,12 +3114,22 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     return 0;
 }
 
+extern "C" int ppde_cnn_backward_delta_layout(const ppde_cnn_t* m, int32_t n, int32_t* vcap, int32_t* rec, int64_t* wl_offset) {
+    if (!m || n <= 0 || !vcap || !rec || !wl_offset) return (int)cudaErrorInvalidValue;
+    const int P = m->P, L = m->L, J2 = 2 * m->C;                 // same formulas as backward_launch (compact records)
+    const int tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
+    *rec = ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) + tc::BD_TRAIL + tc::BD_MC * 32;
+    *vcap = rmax * PPDE_Q;
+    *wl_offset = (int64_t)m->n_nets * n * (*vcap);
+    return 0;
+}
+
 // floats of `scratch` the tensor-core backward entry points need for n chains (the largest of the three layouts)
 extern "C" int64_t ppde_cnn_backward_scratch_floats(const ppde_cnn_t* m, int32_t n) {
     if (!m || n <= 0) return 0;
     const int64_t P = m->P, L = m->L, J2 = 2 * (int64_t)m->C;
     const int64_t tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
-    const int64_t rec_c = ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~(int64_t)7) + tc::BD_MC * 32, rec_d = ((P + 1) + 2 * J2 + 7) & ~(int64_t)7;
+    const int64_t rec_c = ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~(int64_t)7) + tc::BD_TRAIL + tc::BD_MC * 32, rec_d = ((P + 1) + 2 * J2 + 7) & ~(int64_t)7;
     const int64_t a = (int64_t)m->n_nets * n * rmax * PPDE_Q + ((int64_t)n * m->n_nets * rec_c + 1) / 2;     // compact delta
     const int64_t b = (int64_t)m->n_nets * n * L * PPDE_Q + ((int64_t)n * m->n_nets * rec_d + 1) / 2;        // exact / per-position delta
     return (a > b ? a : b) + 16;

@@ -641,6 +641,374 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_reg_kernel(ppde_
     }
 }
 
+// ======================================================================================================================
+// Position-per-thread variants (L <= 256; default).  Thread i of a 256-thread CTA owns position i: its 20 gradient entries,
+// logits and probabilities live in REGISTERS for the whole kernel and are indexed by compile-time constants only.
+//   * no shared-memory copy of the row, no `q < n4` predicates, no q / 5 index arithmetic, G[i, cur_i] and the state of the
+//     position are thread-local (a move updates ONE thread's registers: no barrier for it);
+//   * the logits are fma(g, 0.5, -0.5 gc) - bit-identical to (g - gc) * 0.5: scaling by 0.5 is exact;
+//   * Philox counters are the same float4 indices q = 5 i + k as in the kernels above: same streams, entry for entry;
+//   * 3 barriers per reverse sub-step, 5 per forward sub-step; block sums are fixed-order (deterministic).
+// ncu (r02, fused strided kernel): 20 k warp-instructions per chain and 47 % of the warp time waiting for global loads;
+// this layout executes about a third of that.
+constexpr int PAS_CN = 3;                  // nets the fused gradient combine handles
+constexpr int PAS_TRAIL = 16, PAS_MC32 = 64 * 32;     // tc::BD_TRAIL, tc::BD_MC * 32 (csrc/cnn_tc.cu): record trailer position
+
+__device__ __forceinline__ float pick20(const float (&v)[PPDE_Q], int a) {
+    float r = v[0];
+#pragma unroll
+    for (int k = 1; k < PPDE_Q; ++k) r = (a == k) ? v[k] : r;
+    return r;
+}
+__device__ __forceinline__ void load_row20(float (&g)[PPDE_Q], const float* src) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float4 v = __ldcs(s4 + k);
+        g[4 * k] = v.x; g[4 * k + 1] = v.y; g[4 * k + 2] = v.z; g[4 * k + 3] = v.w;
+    }
+}
+// softmax -> clamp -> renormalise of the logits l (thread-local, -inf for masked / inactive entries): on return
+// e[k] = clamp(exp(l - m1) / s2) for an active thread; returns s3 = sum over the block.  Same formulas as softmax_clamp_regs.
+template <int NW>
+__device__ __forceinline__ float softmax_clamp_pos(float (&e)[PPDE_Q], bool active, float* red) {
+    float lmax = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < PPDE_Q; ++k) lmax = fmaxf(lmax, e[k]);
+    const float m1 = red_max1<NW>(lmax, red);
+    const float off = (m1 == -INFINITY) ? 0.f : m1;
+    float sum = 0.f;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < PPDE_Q; k += 4) {
+            e[k] = __expf(e[k] - off); e[k + 1] = __expf(e[k + 1] - off); e[k + 2] = __expf(e[k + 2] - off); e[k + 3] = __expf(e[k + 3] - off);
+            sum += (e[k] + e[k + 1]) + (e[k + 2] + e[k + 3]);
+        }
+    }
+    const float s2 = red_sum1<NW>(sum, red + NW);
+    const float r2 = 1.0f / s2;
+    float sum3 = 0.f;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < PPDE_Q; k += 4) {
+            e[k] = clamp_prob(e[k] * r2); e[k + 1] = clamp_prob(e[k + 1] * r2);
+            e[k + 2] = clamp_prob(e[k + 2] * r2); e[k + 3] = clamp_prob(e[k + 3] * r2);
+            sum3 += (e[k] + e[k + 1]) + (e[k + 2] + e[k + 3]);
+        }
+    }
+    return red_sum1<NW>(sum3, red + 2 * NW);
+}
+
+// The same statistics for UNMASKED Taylor logits l_k = fma(g_k, 0.5, hgc) of a thread's position (hgc = -0.5 G[i, cur_i], or -inf
+// for a position outside the window / an inactive thread), straight from the gradient entries:
+//   * the thread's largest logit is fma(gmax, 0.5, hgc) with gmax = max_k g_k, constant along the path (fma is monotone in g);
+//   * exp(l_k - m1) = ex2(fma(g_k, 0.5 log2e, (hgc - m1) log2e)): one FFMA + one MUFU per entry, the logits are never stored
+//     (the argument is rounded once instead of three times; ex2.approx itself is 2^-22 relative).
+template <int NW>
+__device__ __forceinline__ float softmax_clamp_pos_fast(float (&e)[PPDE_Q], const float (&g)[PPDE_Q], float hgc, float gmax,
+                                                        bool active, float* red) {
+    const float m1 = red_max1<NW>(fmaf(gmax, 0.5f, hgc), red);
+    const float off = (m1 == -INFINITY) ? 0.f : m1;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float c2 = (hgc - off) * LOG2E;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < PPDE_Q; k += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k + j]) : "f"(fmaf(g[k + j], 0.5f * LOG2E, c2)));
+        sum += (e[k] + e[k + 1]) + (e[k + 2] + e[k + 3]);
+    }
+    const float s2 = red_sum1<NW>(sum, red + NW);
+    const float r2 = 1.0f / s2;
+    float sum3 = 0.f;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < PPDE_Q; k += 4) {
+            e[k] = clamp_prob(e[k] * r2); e[k + 1] = clamp_prob(e[k + 1] * r2);
+            e[k + 2] = clamp_prob(e[k + 2] * r2); e[k + 3] = clamp_prob(e[k + 3] * r2);
+            sum3 += (e[k] + e[k + 1]) + (e[k + 2] + e[k + 3]);
+        }
+    }
+    return red_sum1<NW>(sum3, red + 2 * NW);
+}
+
+__global__ void __launch_bounds__(PAS_NT, 4) pas_propose_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p) {
+    constexpr int NW = PAS_NT / 32;
+    __shared__ float red[4 * NW];
+    __shared__ int redi[2 * NW];
+    __shared__ int s_best;                                   // bits of the best race quotient so far (positive floats order as ints)
+    __shared__ int s_dist;
+    const int L = c.L, NE = L * PPDE_Q;
+    const int b = blockIdx.x, tid = threadIdx.x, i = tid;
+    const bool active = i < L;
+    const uint32_t gid = (uint32_t)(c.chain_offset + b);
+    const int t = p.t_dev ? *p.t_dev : p.t;
+    const Philox rng(p.seed);
+    float g[PPDE_Q];
+#pragma unroll
+    for (int k = 0; k < PPDE_Q; ++k) g[k] = 0.f;
+    int ai = 0, wi = 0;                                      // residue of my position: evolving state, wild type
+    if (active) {
+        load_row20(g, c.G + (int64_t)c.row_cur[b] * NE + i * PPDE_Q);
+        ai = c.aa[(int64_t)b * c.aa_stride + i];
+        wi = m.wt[i];
+    }
+    const int span = p.S;                                      // 2*pas-1 values: U in {1..S}  (ppde.py:67)
+    const int U = 1 + (int)(rng(0u, gid, (uint32_t)t, (uint32_t)(KIND_PATHLEN << 16)).x % (uint32_t)span);
+    if (tid == 0) c.U[b] = U;
+    const int S_eff = p.full_trace ? p.S : U;                  // dead sub-steps (s >= U) only on request
+    for (int s = S_eff + tid; s < p.S; s += PAS_NT) {
+        const int64_t o = (int64_t)s * c.n + b;
+        c.idx[o] = -1; c.old_aa[o] = 0; c.lqf[o] = 0.f;
+    }
+    {   // edit distance to WT (utils.py:5-14), once; updated per move below
+        const int d0 = red_sum1i<NW>((active && ai != wi) ? 1 : 0, redi);
+        if (tid == 0) s_dist = d0;
+    }
+    float hgc = -0.5f * pick20(g, ai);                         // -0.5 G[i, cur_i]
+    const bool inwin = active && i >= p.min_pos && i <= p.max_pos;
+    float gmax = g[0];
+#pragma unroll
+    for (int k = 1; k < PPDE_Q; ++k) gmax = fmaxf(gmax, g[k]);
+    __syncthreads();
+
+    for (int s = 0; s < S_eff; ++s) {
+        const bool at_thr = s_dist >= p.nmut_threshold;       // ppde.py:86-91
+        if (tid == 0) s_best = 0;
+        // Taylor logits with the revert-only mask and the window mask (ppde.py:95-104, utils.py:17-28)
+        float e[PPDE_Q];
+        float s3;                                              // (the barriers of the softmax also publish s_best = 0)
+        if (!at_thr) {                                         // only the window mask: a whole position is in or out
+            s3 = softmax_clamp_pos_fast<NW>(e, g, inwin ? hgc : -INFINITY, gmax, active, red);
+        } else {
+            const int w = revert_only_target((uint8_t)ai, (uint8_t)wi);      // the only legal target: revert to WT
+#pragma unroll
+            for (int k = 0; k < PPDE_Q; ++k) e[k] = (inwin && w == k) ? fmaf(g[k], 0.5f, hgc) : -INFINITY;
+            s3 = softmax_clamp_pos<NW>(e, active, red);
+        }
+        // exponential race: argmax_j p_j / E_j, E_j = -log(u_j)  (= torch.multinomial(p, 1, True)); an entry whose upper bound
+        // p_j / (s3 (1 - u_j)) is below the best quotient seen so far by any thread (s_best, monotone), with a 1e-5 margin, cannot
+        // win and is not evaluated; the quotient itself is evaluated exactly as in pas_propose_kernel.
+        float best = -1.f; int bidx = 0x7fffffff;
+        if (active) {
+            const float* um = p.uniforms ? p.uniforms + ((int64_t)s * c.n + b) * NE + i * PPDE_Q : nullptr;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float thr = fmaxf(best, __int_as_float(*(volatile int*)&s_best)) * s3 * (1.0f / 1.00001f);
+                uint4 wd = make_uint4(0u, 0u, 0u, 0u);
+                float4 u1;                                                       // a lower bound of 1 - u (the test must never skip a winner)
+                if (um) {
+                    const float4 u = reinterpret_cast<const float4*>(um)[k];
+                    u1 = make_float4(1.0f - u.x, 1.0f - u.y, 1.0f - u.z, 1.0f - u.w);
+                } else {
+                    wd = rng((uint32_t)(5 * i + k), gid, (uint32_t)t, (uint32_t)(s | (KIND_PROPOSAL << 16)));
+                    // 1 - u = ((~x >> 8) + 0.5) 2^-24 >= (~x >> 9) 2^-23 = [1.mantissa] - 1: shift, one LOP3, one exact subtraction
+                    u1 = make_float4(__uint_as_float(((~wd.x) >> 9) | 0x3F800000u) - 1.0f, __uint_as_float(((~wd.y) >> 9) | 0x3F800000u) - 1.0f,
+                                     __uint_as_float(((~wd.z) >> 9) | 0x3F800000u) - 1.0f, __uint_as_float(((~wd.w) >> 9) | 0x3F800000u) - 1.0f);
+                }
+                const bool c0 = e[4 * k] > thr * u1.x, c1 = e[4 * k + 1] > thr * u1.y, c2 = e[4 * k + 2] > thr * u1.z, c3 = e[4 * k + 3] > thr * u1.w;
+                if (c0 | c1 | c2 | c3) {                                         // may still win: exact evaluation, in entry order
+                    float4 u;
+                    if (um) u = reinterpret_cast<const float4*>(um)[k];
+                    else u = make_float4(u32_to_unit(wd.x), u32_to_unit(wd.y), u32_to_unit(wd.z), u32_to_unit(wd.w));
+                    const float pq[4] = {e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]};
+                    const float uq[4] = {u.x, u.y, u.z, u.w};
+                    const bool cq[4] = {c0, c1, c2, c3};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (cq[j]) {
+                            const float r = (pq[j] / s3) / (-logf(uq[j]));
+                            if (r > best) { best = r; bidx = i * PPDE_Q + 4 * k + j; atomicMax(&s_best, __float_as_int(r)); }
+                        }
+                    }
+                }
+            }
+        }
+        red_argmax1<NW>(best, bidx, red + 3 * NW, redi + NW);
+        const int pos = bidx / PPDE_Q, a = bidx - pos * PPDE_Q;
+        if (i == pos) {                                        // the thread that owns the position records the move
+            const int64_t o = (int64_t)s * c.n + b;
+            c.idx[o] = bidx;
+            c.old_aa[o] = (uint8_t)ai;
+            c.lqf[o] = logf(clamp_prob(pick20(e, a) / s3));                  // Categorical.log_prob
+            if (s < U) {                                                     // ppde.py:111-115 (masked by u_mask)
+                s_dist += (int)(a != wi) - (int)(ai != wi);
+                ai = a;
+                hgc = -0.5f * pick20(g, a);
+            }
+        }
+        __syncthreads();                                       // s_dist, s_best of the next sub-step
+    }
+    if (active) c.aa_y[(int64_t)b * c.aa_stride + i] = (uint8_t)ai;
+}
+
+__global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p) {
+    constexpr int NT = PAS_NT, NW = PAS_NT / 32;
+    __shared__ float red[3 * NW];
+    __shared__ int redi[NW];
+    __shared__ int s_flag;
+    __shared__ float s_ratio;
+    __shared__ uint32_t s_map[2][PAS_NT];                    // output row -> entry of the net's row list, tagged with the epoch
+
+    const int L = c.L, NE = L * PPDE_Q;
+    const int b = blockIdx.x, n = c.n, tid = threadIdx.x, i = tid;
+    const bool active = i < L;
+    const uint32_t gid = (uint32_t)(c.chain_offset + b);
+    const int t = p.t_dev ? *p.t_dev : p.t;
+    const int rx = c.row_cur[b];
+    const int ry = y_row(rx, b, n);
+    uint8_t* ax = c.aa + (int64_t)b * c.aa_stride;
+    const uint8_t* ay = c.aa_y + (int64_t)b * c.aa_stride;
+    const int U = c.U[b];
+    const int S_eff = p.full_trace ? p.S : U;                      // dead sub-steps (s >= U) only on request
+    int cpre[4];                                                   // proposal indices of the first sub-steps (loaded early)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) cpre[s] = (s < S_eff) ? c.idx[(int64_t)s * n + b] : 0;
+    float g[PPDE_Q];
+#pragma unroll
+    for (int k = 0; k < PPDE_Q; ++k) g[k] = 0.f;
+    int zi = active ? (int)ax[i] : 0;                              // trajectory state of my position
+    if (tid == 0) s_ratio = 0.f;
+    if (p.comb_nets > 0) {
+        // Fused gradient combine (delta backward): G_y = G_x + (Gp_y - Gp_x)(window), then for k = 0 .. nets-1, tile by tile:
+        // G_y[row] += scale * dGc_k[row] for the output rows the record lists - the sparse changes cnn_backward_delta_kernel left
+        // in the scratch.  Fixed order (net, tile): the same sums as cnn_grad_combine_sparse_kernel, bit for bit.  An output row IS
+        // a thread here: thread r of the list publishes "row orow[r] is entry r" in shared memory (tagged with the epoch, two
+        // maps alternate: one barrier per (net, tile), nothing to clear) and the owner adds the 20 values to its registers.
+        // Load levels: (1) the records' fixed trailers + the three base rows, (2) the row lists, (3) the values.
+        const int nets = p.comb_nets;
+        uint4 tr[PAS_CN][2];
+#pragma unroll
+        for (int k = 0; k < PAS_CN; ++k) {
+            const uint4* tp = reinterpret_cast<const uint4*>(p.comb_wl + ((size_t)b * nets + (k < nets ? k : 0)) * p.comb_rec + p.comb_rec - PAS_MC32 - PAS_TRAIL);
+            tr[k][0] = (k < nets) ? __ldg(tp) : make_uint4(0u, 0u, 0u, 0u);
+            tr[k][1] = (k < nets) ? __ldg(tp + 1) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (active) {
+            load_row20(g, c.G + (int64_t)rx * NE + i * PPDE_Q);
+            const int ip = i - m.win_lo;
+            if (c.Gp && ip >= 0 && ip < m.Lp) {
+                float a[PPDE_Q], d[PPDE_Q];
+                load_row20(a, c.Gp + (int64_t)ry * m.D + ip * PPDE_Q);
+                load_row20(d, c.Gp + (int64_t)rx * m.D + ip * PPDE_Q);
+#pragma unroll
+                for (int k = 0; k < PPDE_Q; ++k) g[k] += a[k] - d[k];
+            }
+        }
+        s_map[0][tid] = 0u; s_map[1][tid] = 0u;                // tag 0 = no entry (epochs start at 1)
+        __syncthreads();
+        uint32_t epoch = 0;
+#pragma unroll
+        for (int k = 0; k < PAS_CN; ++k) {
+            if (k < nets) {
+                const uint32_t tw[8] = {tr[k][0].x, tr[k][0].y, tr[k][0].z, tr[k][0].w, tr[k][1].x, tr[k][1].y, tr[k][1].z, tr[k][1].w};
+                const int ntile = (int)(tw[0] & 0xFFFFu), poff = (int)(tw[0] >> 16);
+                const uint16_t* pairs = p.comb_wl + ((size_t)b * nets + k) * p.comb_rec + poff;
+                const float* v = p.comb_vals + ((size_t)k * n + b) * p.comb_vcap;
+                int r0 = 0;
+                for (int tl = 0; tl < ntile; ++tl) {
+                    const int wsel = (tl + 2) >> 1;                               // tstart[tl + 1] = 16-bit word tl + 2 of the trailer
+                    uint32_t wv = tw[1];
+#pragma unroll
+                    for (int q = 2; q < 8; ++q) wv = (wsel == q) ? tw[q] : wv;
+                    const int r1 = (tl + 2 < 2 * 8) ? (int)((wv >> (16 * (tl & 1))) & 0xFFFFu) : r0;
+                    ++epoch;
+                    uint32_t* map = s_map[epoch & 1u];
+                    for (int r = r0 + tid; r < r1; r += NT) map[__ldg(pairs + 2 * r)] = (epoch << 16) | (uint32_t)(r - r0);
+                    __syncthreads();
+                    const uint32_t me = active ? map[i] : 0u;
+                    if ((me >> 16) == epoch) {
+                        float d[PPDE_Q];
+                        load_row20(d, v + (size_t)(r0 + (int)(me & 0xFFFFu)) * PPDE_Q);
+#pragma unroll
+                        for (int q = 0; q < PPDE_Q; ++q) g[q] = fmaf(p.comb_scale, d[q], g[q]);
+                    }
+                    r0 = r1;
+                }
+            }
+        }
+        if (active) {
+            float4* gy = reinterpret_cast<float4*>(c.G + (int64_t)ry * NE + i * PPDE_Q);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) gy[k] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
+        }
+    } else if (active) {
+        load_row20(g, c.G + (int64_t)ry * NE + i * PPDE_Q);
+    }
+    float hgc = active ? -0.5f * pick20(g, zi) : -INFINITY;        // -0.5 G_y[i, z_i]; one position changes per sub-step
+    float gmax = g[0];
+#pragma unroll
+    for (int k = 1; k < PPDE_Q; ++k) gmax = fmaxf(gmax, g[k]);
+
+    for (int s = S_eff + tid; s < p.S; s += NT) c.lqr[(int64_t)s * n + b] = 0.f;
+    for (int s = 0; s < S_eff; ++s) {
+        const int64_t o = (int64_t)s * n + b;
+        int cidx = cpre[0];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) cidx = (s == q) ? cpre[q] : cidx;
+        if (s >= 4) cidx = c.idx[o];
+        const int pos = cidx / PPDE_Q, a = cidx - pos * PPDE_Q;
+        if (s < U && i == pos) { zi = a; hgc = -0.5f * pick20(g, a); }        // state AFTER move s (ppde.py:124-125)
+        float e[PPDE_Q];
+        const float s3 = softmax_clamp_pos_fast<NW>(e, g, hgc, gmax, active, red);     // NO masks on the reverse path (ppde.py:126-127)
+        if (i == pos) {
+            const float lqr = logf(clamp_prob(pick20(e, a) / s3));
+            c.lqr[o] = lqr;
+            if (s < U) s_ratio += lqr - c.lqf[o];                  // u_mask * (rev - fwd), ppde.py:132 (one thread per sub-step, in order)
+        }
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        const float log_ratio = s_ratio;
+        const float e_x = c.E[b], f_x = c.fit[b];
+        const float e_y = c.E_y[b], f_y = c.fit_y[b];
+        const float log_acc = (e_y - e_x) + log_ratio;             // ppde.py:135-136
+        const float u = u32_to_unit(Philox(p.seed)(0u, gid, (uint32_t)t, (uint32_t)(KIND_ACCEPT << 16)).x);
+        const bool acc = expf(log_acc) >= u;                       // '>=' (ppde.py:138); NaN rejects
+        c.log_acc[b] = log_acc;
+        c.accept[b] = acc ? 1 : 0;
+        const float e_rec = acc ? e_y : e_x, f_rec = acc ? f_y : f_x;   // ppde.py:141-143
+        if (c.E_hist) c.E_hist[(int64_t)(t + 1) * n + b] = e_rec;
+        if (c.fit_hist) c.fit_hist[(int64_t)(t + 1) * n + b] = f_rec;
+        // 0: keep current state; 1: take y; 2: fall back to the paper-mode anchor
+        s_flag = acc ? 1 : (p.paper_results ? 2 : 0);
+        if (acc) { c.E[b] = e_y; c.fit[b] = f_y; c.row_cur[b] = ry; }
+        else if (p.paper_results) {                                // x is never refreshed: reject = back to x0 (ppde.py:76-77,139)
+            const int f = c.anchor_fixed ? c.anchor_fixed[b] : (c.row_wt - 2 * n);
+            c.E[b] = c.E_fixed[f]; c.fit[b] = c.fit_fixed[f]; c.row_cur[b] = 2 * n + f;
+        }
+        const bool better = e_rec > c.best_E[b];                   // strict: first occurrence of the max (ppde.py:173)
+        if (better) { c.best_E[b] = e_rec; c.best_fit[b] = f_rec; }
+        s_flag |= better ? 4 : 0;
+    }
+    __syncthreads();
+    const int flag = s_flag & 3;
+    const bool better = (s_flag & 4) != 0;
+    const uint8_t* src = ax;
+    if (flag == 1) src = ay;
+    else if (flag == 2) {
+        const int f = c.anchor_fixed ? c.anchor_fixed[b] : (c.row_wt - 2 * n);
+        src = c.aa_fixed + (int64_t)f * c.aa_stride;
+    }
+    // recorded state (post-accept, pre-reset): best-of-history and the random trajectory (ppde.py:142,146,172-183)
+    int dpart = 0;
+    uint8_t v = 0, wv = 0;
+    if (active) {
+        v = src[i]; wv = m.wt[i];
+        dpart = (v != wv);
+        if (better) c.best_aa[(int64_t)b * c.aa_stride + i] = v;
+        if (c.traj_aa && b == c.traj_chain) c.traj_aa[(int64_t)(t + 1) * c.aa_stride + i] = v;
+    }
+    const int dist = red_sum1i<NW>(dpart, redi);
+    const bool reset = !p.paper_results && dist >= p.nmut_threshold;   // hard reset to WT (ppde.py:148-153)
+    if (active) ax[i] = reset ? wv : v;
+    if (reset && tid == 0) {
+        const int f = c.row_wt - 2 * n;
+        c.E[b] = c.E_fixed[f]; c.fit[b] = c.fit_fixed[f]; c.row_cur[b] = c.row_wt;
+    }
+}
+
 // Known-answer entry point for the proposal arithmetic (tests only; not on the sampler's path): the SAME device functions the
 // two kernels above use, driven by caller-provided logits.  Per row b:
 //   dist[b]      = edit distance of aa[b] to wt                         (mut_distance, utils.py:5-14)
@@ -684,6 +1052,11 @@ static size_t pas_smem(int L) { return (size_t)(2 * L * PPDE_Q + L) * sizeof(flo
 static size_t pas_reg_smem(int L) { return (size_t)(L * PPDE_Q + L) * sizeof(float) + 2 * ((L + 15) & ~15); }
 // register-resident kernels: the 5 L float4 of a row fit PAS_MAXQ per thread of a PAS_NT-thread CTA (L <= 256)
 static bool pas_use_reg(int L) { return 5 * L <= PAS_NT * PAS_MAXQ; }
+// position-per-thread kernels (default for L <= PAS_NT); PPDE_PAS_POS=0 falls back to the strided kernels (A/B)
+static bool pas_use_pos(int L) {
+    static const bool on = [] { const char* e = getenv("PPDE_PAS_POS"); return !(e && e[0] == '0'); }();
+    return on && L <= PAS_NT;
+}
 static int pas_check(const ppde_potts_t* m, const ppde_chains_t* c, const ppde_pas_params_t* p) {
     if (!m || !c || !p) return (int)cudaErrorInvalidValue;
     if (p->S < 1 || p->S > PPDE_MAX_S || c->L < 1 || c->aa_stride < c->L) return (int)cudaErrorInvalidValue;
@@ -707,6 +1080,10 @@ extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, c
         pas_propose_reg_kernel<<<c->n, PAS_NT, smem, (cudaStream_t)stream>>>(*m, *c, *p);
         return launch_done();
     }
+    if (pas_use_pos(c->L)) {
+        pas_propose_pos_kernel<<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p);
+        return launch_done();
+    }
     size_t smem = pas_smem(c->L);
     static SmemCache configured;
     if (cudaError_t e = ensure_dynamic_smem(pas_propose_kernel<128>, smem, configured)) return (int)e;
@@ -720,6 +1097,14 @@ extern "C" int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_
     if (c->n <= 0) return 0;
     if (!c->E || !c->fit || !c->E_y || !c->fit_y || !c->log_acc || !c->accept || !c->best_E || !c->best_fit || !c->best_aa)
         return (int)cudaErrorInvalidValue;
+    if (p->comb_nets > 0) {              // fused gradient combine: position-per-thread kernel only, every pointer it reads present
+        if (!pas_use_pos(c->L) || p->comb_nets > PAS_CN || !p->comb_vals || !p->comb_wl || p->comb_vcap < 1 || p->comb_rec < 1)
+            return (int)cudaErrorInvalidValue;
+    }
+    if (pas_use_pos(c->L)) {
+        pas_reverse_accept_pos_kernel<<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p);
+        return launch_done();
+    }
     if (pas_use_reg(c->L)) {
         const size_t smem = pas_reg_smem(c->L);
         static SmemCache configured_reg;
@@ -733,6 +1118,8 @@ extern "C" int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_
     pas_reverse_accept_kernel<128><<<c->n, 128, smem, (cudaStream_t)stream>>>(*m, *c, *p);
     return launch_done();
 }
+
+extern "C" int32_t ppde_pas_reverse_fuse_max_len(void) { return pas_use_pos(1) ? PAS_NT : 0; }
 
 extern "C" int ppde_pas_kat(const uint8_t* aa, int32_t aa_stride, const uint8_t* wt, int32_t n, int32_t L, const float* logits,
                             const int32_t* idx, int32_t* dist, uint8_t* mask, float* probs, float* logp, void* stream) {

@@ -410,6 +410,11 @@ class ChainEngine:
         self.inc = bool(m.cnn_inc)
         self.bkey = self.r1pool = self.dmask = self.mkpool = self.btab = None
         self.delta = bool(m.cnn_bwd_delta)
+        # fused gradient combine: pas_reverse_accept assembles the proposal's row from the delta backward's sparse output
+        # (no cnn_grad_combine_sparse_kernel launch).  PPDE_FUSE_COMBINE=0 keeps the separate kernel (A/B).
+        compact = m.tune is None or m.tune.delta_layout == 0
+        self.fuse_combine = (self.delta and compact and os.environ.get("PPDE_FUSE_COMBINE", "1") != "0"
+                             and m.L <= int(m.lib.ppde_pas_reverse_fuse_max_len()) and m.n_nets <= 3)
         if self.inc:
             # per (row, net, channel): the two largest raw block keys (winner, runner-up) - ppde_cnn_forward_inc
             self.mkpool = torch.empty(rows * m.n_nets * 2 * m.C * 2, dtype=torch.int64, device=dev)
@@ -474,11 +479,21 @@ class ChainEngine:
             self._graph = None
 
     # -- one iteration ------------------------------------------------------------------------------
-    def _params(self, t, uniforms=None, use_t_dev=False):
-        return PasParamsT(S=self.S, nmut_threshold=self.thr, paper_results=int(self.paper), t=int(t),
-                          min_pos=self.min_pos, max_pos=self.max_pos, seed=self.seed,
-                          uniforms=uniforms.data_ptr() if uniforms is not None else None,
-                          t_dev=self.t_dev.data_ptr() if use_t_dev else None, full_trace=int(self.full_trace))
+    def _params(self, t, uniforms=None, use_t_dev=False, full=True):
+        """full=False (an iteration with the delta backward) + fuse_combine: the reverse kernel also assembles the gradient row."""
+        p = PasParamsT(S=self.S, nmut_threshold=self.thr, paper_results=int(self.paper), t=int(t),
+                       min_pos=self.min_pos, max_pos=self.max_pos, seed=self.seed,
+                       uniforms=uniforms.data_ptr() if uniforms is not None else None,
+                       t_dev=self.t_dev.data_ptr() if use_t_dev else None, full_trace=int(self.full_trace))
+        if self.fuse_combine and not full:
+            m = self.m
+            vcap, rec, off = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+            _lib.check(self.lib.ppde_cnn_backward_delta_layout(C.byref(m.cnn), self.n, C.byref(vcap), C.byref(rec), C.byref(off)),
+                       "cnn_backward_delta_layout")
+            base = self.ws.grad_scratch(self.n).data_ptr()
+            p.comb_nets, p.comb_vals, p.comb_wl = m.n_nets, base, base + 4 * off.value
+            p.comb_vcap, p.comb_rec, p.comb_scale = vcap.value, rec.value, float(m.lamda) / m.n_nets
+        return p
 
     def _launch_step(self, p, full=True):
         m, lib, c, n = self.m, self.lib, self.chains, self.n
@@ -516,6 +531,10 @@ class ChainEngine:
         if self.inc:
             pp = 0 if parts in (0, 7) else parts
             if self.delta and not full:
+                if self.fuse_combine and parts in (4, 7):      # the combine runs inside pas_reverse_accept (_params(full=False))
+                    pp = 3 if parts == 7 else 0
+                    if parts == 4:
+                        parts = 0
                 m.cnn_backward_delta(self.aa, self.aa_y, n, mk, self.mkpool, gp, ep, _ptr(self.G), self.row_cur, self.rows_y,
                                      self.E_y, self.fit_y, self.r1pool, st, do_fit=do_fit, do_grad=bool(parts), btab=self.btab,
                                      ws=self.ws, parts=pp)
@@ -542,7 +561,8 @@ class ChainEngine:
         [S, n, 20L] replacing the in-kernel Philox proposal stream (parity mode)."""
         self._check_room(1)
         with torch.cuda.device(self.m.device):
-            self._launch_step(self._params(self.t, uniforms), full=self.full_backward_at(self.t))
+            full = self.full_backward_at(self.t)
+            self._launch_step(self._params(self.t, uniforms, full=full), full=full)
         self.t += 1
 
     def run_steps(self, k, use_graph=True):
@@ -571,7 +591,7 @@ class ChainEngine:
                 self.ws.r1mask(self.n)
             else:
                 self.ws.inc_ws(self.n)
-            self._graph_params = self._params(0, None, use_t_dev=True)
+            self._graph_params = {full: self._params(0, None, use_t_dev=True, full=full) for full in (True, False)}
             self._graph = {}
 
     def _capture(self, full):
@@ -586,7 +606,7 @@ class ChainEngine:
         with torch.cuda.stream(side):
             g.capture_begin()
             try:
-                self._launch_step(self._graph_params, full=full)
+                self._launch_step(self._graph_params[full], full=full)
                 _lib.check(self.lib.ppde_counter_add(_ptr(self.t_dev), 1, _stream()), "counter_add")
             finally:
                 g.capture_end()

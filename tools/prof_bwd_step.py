@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 st = _stream()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 def step():
-    p = eng._params(eng.t)
+    p = eng._params(eng.t, full=full)
     _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "propose")
     _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(eng.chains), C.byref(p), st), "inc")
     _lib.check(lib.ppde_step_rows(C.byref(eng.chains), _ptr(eng.rows_y), st), "rows")
