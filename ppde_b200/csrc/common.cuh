@@ -29,6 +29,27 @@ struct Philox {
         return make_uint4(c0, c1, c2, c3);
     }
 };
+// The same generator with the ten round keys precomputed on the host and passed as a kernel argument: the keys sit in the
+// constant bank and feed the LOP3 of every round directly (the in-kernel key schedule was 18 integer adds per call - a quarter
+// of the call - because the seed arrives in a vector register).
+struct PhiloxKeys {
+    uint32_t a[10], b[10];
+    __host__ __device__ explicit PhiloxKeys(uint64_t seed) {
+        uint32_t x = (uint32_t)seed, y = (uint32_t)(seed >> 32);
+        for (int r = 0; r < 10; ++r) { a[r] = x; b[r] = y; x += 0x9E3779B9u; y += 0xBB67AE85u; }
+    }
+};
+__device__ __forceinline__ uint4 philox_keyed(const PhiloxKeys& K, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ K.a[r];
+        const uint32_t n2 = hi0 ^ c3 ^ K.b[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 enum { KIND_PROPOSAL = 0, KIND_PATHLEN = 1, KIND_ACCEPT = 2 };
 
 // 24 random bits -> (k + 0.5) 2^-24.  For k < 2^23 the value is exact and strictly inside (0, 1); for k >= 2^23 the "+ 0.5" is

@@ -732,7 +732,8 @@ __device__ __forceinline__ float softmax_clamp_pos_fast(float (&e)[PPDE_Q], cons
     return red_sum1<NW>(sum3, red + 2 * NW);
 }
 
-__global__ void __launch_bounds__(PAS_NT, 4) pas_propose_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p) {
+__global__ void __launch_bounds__(PAS_NT, 4) pas_propose_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p,
+                                                                    const __grid_constant__ PhiloxKeys keys) {
     constexpr int NW = PAS_NT / 32;
     __shared__ float red[4 * NW];
     __shared__ int redi[2 * NW];
@@ -790,24 +791,49 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_propose_pos_kernel(ppde_potts_t
         // p_j / (s3 (1 - u_j)) is below the best quotient seen so far by any thread (s_best, monotone), with a 1e-5 margin, cannot
         // win and is not evaluated; the quotient itself is evaluated exactly as in pas_propose_kernel.
         float best = -1.f; int bidx = 0x7fffffff;
+        const uint32_t amask = __ballot_sync(0xffffffffu, active);
         if (active) {
             const float* um = p.uniforms ? p.uniforms + ((int64_t)s * c.n + b) * NE + i * PPDE_Q : nullptr;
+            const uint32_t ctr3 = (uint32_t)(s | (KIND_PROPOSAL << 16));
+            const float rs3 = 1.0f / s3;
+            // Seed of the threshold: -log u <= (1 - u) / u, so r_j >= (p_j / s3) u_j / (1 - u_j); the largest such LOWER bound over
+            // the first four entries of every thread (cheap: no logarithm, approximate reciprocal, 1e-5 margin) is published
+            // before anything is evaluated exactly - otherwise every thread evaluates its first four entries (a fifth of the
+            // vector) with two divisions and a logarithm each.  u >= k 2^-23 = f - 1 and 1 - u <= 2 - f, f = [1.k], k = x >> 9.
+            uint4 wd0 = make_uint4(0u, 0u, 0u, 0u);
+            if (!um) {
+                wd0 = philox_keyed(keys, (uint32_t)(5 * i), gid, (uint32_t)t, ctr3);
+                const uint32_t ww[4] = {wd0.x, wd0.y, wd0.z, wd0.w};
+                float lb = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float f = __uint_as_float((ww[j] >> 9) | 0x3F800000u);
+                    float rc;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(2.0f - f));
+                    lb = fmaxf(lb, e[j] * (f - 1.0f) * rc);
+                }
+                lb *= rs3 * 0.99999f;
+                const int lbw = __reduce_max_sync(amask, __float_as_int(lb));        // (non-negative floats order as ints)
+                if ((tid & 31) == 0) atomicMax(&s_best, lbw);
+            }
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const float thr = fmaxf(best, __int_as_float(*(volatile int*)&s_best)) * s3 * (1.0f / 1.00001f);
-                uint4 wd = make_uint4(0u, 0u, 0u, 0u);
+                uint4 wd = wd0;
                 float4 u1;                                                       // a lower bound of 1 - u (the test must never skip a winner)
                 if (um) {
                     const float4 u = reinterpret_cast<const float4*>(um)[k];
                     u1 = make_float4(1.0f - u.x, 1.0f - u.y, 1.0f - u.z, 1.0f - u.w);
                 } else {
-                    wd = rng((uint32_t)(5 * i + k), gid, (uint32_t)t, (uint32_t)(s | (KIND_PROPOSAL << 16)));
-                    // 1 - u = ((~x >> 8) + 0.5) 2^-24 >= (~x >> 9) 2^-23 = [1.mantissa] - 1: shift, one LOP3, one exact subtraction
-                    u1 = make_float4(__uint_as_float(((~wd.x) >> 9) | 0x3F800000u) - 1.0f, __uint_as_float(((~wd.y) >> 9) | 0x3F800000u) - 1.0f,
-                                     __uint_as_float(((~wd.z) >> 9) | 0x3F800000u) - 1.0f, __uint_as_float(((~wd.w) >> 9) | 0x3F800000u) - 1.0f);
+                    if (k) wd = philox_keyed(keys, (uint32_t)(5 * i + k), gid, (uint32_t)t, ctr3);
+                    // 1 - u = 1 - ((x >> 8) + 0.5) 2^-24 > 1 - (k + 1) 2^-23 = (2 - 2^-23) - [1.k], k = x >> 9: exact subtraction
+                    constexpr float C2 = 1.99999988079071044921875f;
+                    u1 = make_float4(C2 - __uint_as_float((wd.x >> 9) | 0x3F800000u), C2 - __uint_as_float((wd.y >> 9) | 0x3F800000u),
+                                     C2 - __uint_as_float((wd.z >> 9) | 0x3F800000u), C2 - __uint_as_float((wd.w >> 9) | 0x3F800000u));
                 }
                 const bool c0 = e[4 * k] > thr * u1.x, c1 = e[4 * k + 1] > thr * u1.y, c2 = e[4 * k + 2] > thr * u1.z, c3 = e[4 * k + 3] > thr * u1.w;
                 if (c0 | c1 | c2 | c3) {                                         // may still win: exact evaluation, in entry order
+                    asm volatile("" : "+r"(wd.x), "+r"(wd.y), "+r"(wd.z), "+r"(wd.w));   // (keeps the conversions below inside the branch)
                     float4 u;
                     if (um) u = reinterpret_cast<const float4*>(um)[k];
                     else u = make_float4(u32_to_unit(wd.x), u32_to_unit(wd.y), u32_to_unit(wd.z), u32_to_unit(wd.w));
@@ -1081,7 +1107,7 @@ extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, c
         return launch_done();
     }
     if (pas_use_pos(c->L)) {
-        pas_propose_pos_kernel<<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p);
+        pas_propose_pos_kernel<<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
         return launch_done();
     }
     size_t smem = pas_smem(c->L);
