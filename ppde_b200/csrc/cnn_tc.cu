@@ -1702,7 +1702,7 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
 // keys  position << 16 | side << 15 | channel  into an unordered list (warp ballots + one shared counter); the list is
 // rank-sorted (each entry counts the smaller keys: n^2 / 128 broadcast reads per thread, one barrier); positions, starts and
 // the entry list fall out of one scan over the sorted keys.
-__global__ void __launch_bounds__(128) cnn_delta_record_kernel(const __grid_constant__ ppde_cnn_t cm, int n_nets, int C, int P, int L, int aa_stride,
+__global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_constant__ ppde_cnn_t cm, int n_nets, int C, int P, int L, int aa_stride,
                                                                const uint8_t* __restrict__ aa_x, const uint8_t* __restrict__ aa_y,
                                                                const unsigned long long* __restrict__ mkey_y,
                                                                const unsigned long long* __restrict__ mkey_pool,

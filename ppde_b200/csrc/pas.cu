@@ -732,7 +732,8 @@ __device__ __forceinline__ float softmax_clamp_pos_fast(float (&e)[PPDE_Q], cons
     return red_sum1<NW>(sum3, red + 2 * NW);
 }
 
-__global__ void __launch_bounds__(PAS_NT, 4) pas_propose_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p,
+template <int MINB>
+__global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p,
                                                                     const __grid_constant__ PhiloxKeys keys) {
     constexpr int NW = PAS_NT / 32;
     __shared__ float red[4 * NW];
@@ -1107,7 +1108,9 @@ extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, c
         return launch_done();
     }
     if (pas_use_pos(c->L)) {
-        pas_propose_pos_kernel<<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
+        static const bool minb3 = [] { const char* e = getenv("PPDE_PAS_MINB"); return e && e[0] == '3'; }();
+        if (minb3) pas_propose_pos_kernel<3><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
+        else pas_propose_pos_kernel<4><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
         return launch_done();
     }
     size_t smem = pas_smem(c->L);
