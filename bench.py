@@ -276,7 +276,9 @@ def main():
         st = _stream()
         p_holder = {}
         seq = [("pas_propose", lambda: _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(eng.chains), C.byref(p_holder["p"]), st), "propose")),
-               ("potts_incremental", lambda: (_lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(eng.chains), C.byref(p_holder["p"]), st), "inc"),
+               # (with the fused Potts update the propose kernel has done this work already: only the row indices remain)
+               ("potts_incremental", lambda: ((None if p_holder["p"].fuse_potts else
+                                               _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(eng.chains), C.byref(p_holder["p"]), st), "inc")),
                                               _lib.check(lib.ppde_step_rows(C.byref(eng.chains), _ptr(eng.rows_y), st), "rows")))]
         if eng.inc:
             seq += [("cnn_dirty", lambda: eng.cnn_forward_y(st, dirty=True, parts=0)),

@@ -150,7 +150,10 @@ typedef struct ppde_pas_params {
     int32_t comb_vcap;
     int32_t comb_rec;
     float comb_scale;           /* lamda / n_nets */
-    int32_t _pad;
+    int32_t fuse_potts;         /* 1: ppde_pas_propose also does the work of ppde_potts_incremental for its chain (Gp of the
+                                 * proposal = Gp of the current state + net coupling-row differences, Epotts_y from the new
+                                 * field; nets.py:259-299): the CTA knows the moves, and the memory-bound row update of one
+                                 * chain overlaps the Philox arithmetic of the others.  Same L limit as the fused combine. */
 } ppde_pas_params_t;
 
 /* Per-call tuning / measurement switches of the tensor-core CNN entry points (NULL = defaults = production behaviour).

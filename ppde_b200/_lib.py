@@ -52,7 +52,7 @@ class PasParamsT(C.Structure):
     _fields_ = [("S", C.c_int32), ("nmut_threshold", C.c_int32), ("paper_results", C.c_int32), ("t", C.c_int32),
                 ("min_pos", C.c_int32), ("max_pos", C.c_int32), ("seed", C.c_uint64), ("uniforms", vp), ("t_dev", vp),
                 ("full_trace", C.c_int32), ("comb_nets", C.c_int32), ("comb_vals", vp), ("comb_wl", vp),
-                ("comb_vcap", C.c_int32), ("comb_rec", C.c_int32), ("comb_scale", C.c_float), ("_pad", C.c_int32)]
+                ("comb_vcap", C.c_int32), ("comb_rec", C.c_int32), ("comb_scale", C.c_float), ("fuse_potts", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/ppde_b200.h

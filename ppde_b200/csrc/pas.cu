@@ -750,11 +750,14 @@ __global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_pott
 #pragma unroll
     for (int k = 0; k < PPDE_Q; ++k) g[k] = 0.f;
     int ai = 0, wi = 0;                                      // residue of my position: evolving state, wild type
+    const int rx = c.row_cur[b];
     if (active) {
-        load_row20(g, c.G + (int64_t)c.row_cur[b] * NE + i * PPDE_Q);
+        load_row20(g, c.G + (int64_t)rx * NE + i * PPDE_Q);
         ai = c.aa[(int64_t)b * c.aa_stride + i];
         wi = m.wt[i];
     }
+    const int ai0 = ai;
+    __shared__ int s_mpos[PPDE_MAX_S];                       // positions of the applied moves, in sub-step order (fused Potts update)
     const int span = p.S;                                      // 2*pas-1 values: U in {1..S}  (ppde.py:67)
     const int U = 1 + (int)(rng(0u, gid, (uint32_t)t, (uint32_t)(KIND_PATHLEN << 16)).x % (uint32_t)span);
     if (tid == 0) c.U[b] = U;
@@ -862,11 +865,62 @@ __global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_pott
                 s_dist += (int)(a != wi) - (int)(ai != wi);
                 ai = a;
                 hgc = -0.5f * pick20(g, a);
+                s_mpos[s] = pos;
             }
         }
         __syncthreads();                                       // s_dist, s_best of the next sub-step
     }
     if (active) c.aa_y[(int64_t)b * c.aa_stride + i] = (uint8_t)ai;
+    if (p.fuse_potts) {
+        // Potts field of the proposal (potts_incremental_kernel, same sums in the same order): Gp_y = Gp_x + sum over the net
+        // changes of (Jsym[new] - Jsym[old]); thread = position, 5 x 16-byte loads per coupling row; Epotts_y from the new field.
+        __shared__ int s_new[PPDE_MAX_S], s_old[PPDE_MAX_S];
+        __shared__ int s_cnt;
+        __shared__ uint8_t s_ax[PAS_NT], s_ay[PAS_NT];
+        s_ax[tid] = (uint8_t)ai0; s_ay[tid] = (uint8_t)ai;
+        __syncthreads();
+        if (tid == 0) {
+            int cnt = 0;
+            for (int s = 0; s < p.S && s < U; ++s) {
+                const int pos = s_mpos[s];
+                if (pos < m.win_lo || pos >= m.win_lo + m.Lp) continue;       // outside the Potts window: no coupling
+                if (s_ax[pos] == s_ay[pos]) continue;                         // no net change at this position
+                const int rn = (pos - m.win_lo) * PPDE_Q + s_ay[pos];
+                bool dup = false;
+                for (int q = 0; q < cnt; ++q) dup |= (s_new[q] == rn);
+                if (dup) continue;
+                s_new[cnt] = rn;
+                s_old[cnt] = (pos - m.win_lo) * PPDE_Q + s_ax[pos];
+                ++cnt;
+            }
+            s_cnt = cnt;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        const int ry = y_row(rx, b, c.n);
+        const int D4 = m.D / 4;
+        const float4* J4 = reinterpret_cast<const float4*>(m.Jsym);
+        const float4* gx = reinterpret_cast<const float4*>(c.Gp + (int64_t)rx * m.D);
+        float4* gy = reinterpret_cast<float4*>(c.Gp + (int64_t)ry * m.D);
+        for (int q = tid; q < D4; q += PAS_NT) {               // coalesced: consecutive threads, consecutive 16-byte words
+            float4 a4 = __ldcs(gx + q);
+            for (int k = 0; k < cnt; ++k) {
+                const float4 vn = __ldg(J4 + (int64_t)s_new[k] * D4 + q);
+                const float4 vo = __ldg(J4 + (int64_t)s_old[k] * D4 + q);
+                a4.x += vn.x - vo.x; a4.y += vn.y - vo.y; a4.z += vn.z - vo.z; a4.w += vn.w - vo.w;
+            }
+            gy[q] = a4;
+        }
+        __syncthreads();
+        const int ip = i - m.win_lo;
+        float part = 0.f;
+        if (active && ip >= 0 && ip < m.Lp) {
+            const int r = ip * PPDE_Q + ai;
+            part = c.Gp[(int64_t)ry * m.D + r] + m.h[r];
+        }
+        const float tot = red_sum1<NW>(part, red);
+        if (tid == 0) c.Epotts_y[b] = 0.5f * tot - m.wt_H;
+    }
 }
 
 __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p) {
@@ -1107,6 +1161,7 @@ extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, c
         pas_propose_reg_kernel<<<c->n, PAS_NT, smem, (cudaStream_t)stream>>>(*m, *c, *p);
         return launch_done();
     }
+    if (p->fuse_potts && (!pas_use_pos(c->L) || !c->Gp || !c->Epotts_y || !m->Jsym || !m->h)) return (int)cudaErrorInvalidValue;
     if (pas_use_pos(c->L)) {
         static const bool minb3 = [] { const char* e = getenv("PPDE_PAS_MINB"); return e && e[0] == '3'; }();
         if (minb3) pas_propose_pos_kernel<3><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));

@@ -412,6 +412,9 @@ class ChainEngine:
         self.delta = bool(m.cnn_bwd_delta)
         # fused gradient combine: pas_reverse_accept assembles the proposal's row from the delta backward's sparse output
         # (no cnn_grad_combine_sparse_kernel launch).  PPDE_FUSE_COMBINE=0 keeps the separate kernel (A/B).
+        # fused Potts field update: pas_propose does the work of ppde_potts_incremental (PPDE_FUSE_POTTS=0: separate kernel)
+        self.fuse_potts = (m.has_potts and os.environ.get("PPDE_FUSE_POTTS", "1") != "0"
+                           and m.L <= int(m.lib.ppde_pas_reverse_fuse_max_len()))
         compact = m.tune is None or m.tune.delta_layout == 0
         self.fuse_combine = (self.delta and compact and os.environ.get("PPDE_FUSE_COMBINE", "1") != "0"
                              and m.L <= int(m.lib.ppde_pas_reverse_fuse_max_len()) and m.n_nets <= 3)
@@ -485,6 +488,7 @@ class ChainEngine:
                        min_pos=self.min_pos, max_pos=self.max_pos, seed=self.seed,
                        uniforms=uniforms.data_ptr() if uniforms is not None else None,
                        t_dev=self.t_dev.data_ptr() if use_t_dev else None, full_trace=int(self.full_trace))
+        p.fuse_potts = int(self.fuse_potts)
         if self.fuse_combine and not full:
             m = self.m
             vcap, rec, off = C.c_int32(0), C.c_int32(0), C.c_int64(0)
@@ -499,7 +503,7 @@ class ChainEngine:
         m, lib, c, n = self.m, self.lib, self.chains, self.n
         st = _stream()
         _lib.check(lib.ppde_pas_propose(C.byref(m.potts), C.byref(c), C.byref(p), st), "pas_propose")
-        if m.has_potts:
+        if m.has_potts and not p.fuse_potts:
             _lib.check(lib.ppde_potts_incremental(C.byref(m.potts), C.byref(c), C.byref(p), st), "potts_incremental")
         _lib.check(lib.ppde_step_rows(C.byref(c), _ptr(self.rows_y), st), "step_rows")
         self.cnn_forward_y(st)
