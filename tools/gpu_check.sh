@@ -17,10 +17,10 @@ $K 300 python bench.py --workload pabp_readme_128 --steps 100 --warmup 5 > gpuru
 fi
 SMALL="python bench.py --chains 16384 --steps 3 --warmup 44 --no-e2e --no-cpu-baseline --no-breakdown"
 $K 200 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 && \
-$K 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 560 -c 120 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
-# steady state (44 warm-up iterations): 9 matching kernels per iteration -> skip 44 * 9 launches, capture one iteration
+$K 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 380 -c 110 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu_l.log 2>&1
+# steady state (44 warm-up iterations, 7 matching kernels per delta iteration): skip ~41 iterations, capture two
 $K 200 $SMALL > gpurun_out/${TAG}_plain2.log 2>&1 && \
-$K 600 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_backward_delta_kernel|cnn_winner_delta_kernel|cnn_grad_combine_sparse_kernel|pas_propose|pas_reverse_accept|potts_incremental_kernel|cnn_fit_kernel" -s 396 -c 9 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
+$K 600 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_backward_delta_kernel|cnn_delta_record_kernel|pas_propose|pas_reverse_accept|cnn_fit_kernel" -s 290 -c 14 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_f.log
 if [ "$MODE" = "full" ]; then
 $K 200 python tools/bench_potts_full.py 64 128 238 512 1024 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
