@@ -326,12 +326,12 @@ def main():
             tflop = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12
             gbs = lambda by, ms_: by / (ms_ * 1e-3) / 1e9
             # `traffic` = dram__bytes_read + dram__bytes_write of one launch from the committed `ncu --set full` captures of
-            # round 2 (profiles/r02_*_ncu_full_summary.txt, 16,384 chains in steady state, scaled to this launch)
+            # round 2 (profiles/r02_ncu_full_summary_v33.txt, 16,384 chains in steady state, scaled to this launch)
             nd_ = (dirty_blocks / n) if dirty_blocks is not None else 2.25
             cand = {
                 "cnn_backward_tc": dict(kernel=("cnn_backward_delta_kernel" if eng.delta else "cnn_backward_tc_kernel"), bound="tensor", unit="TFLOP/s",
                                         work=3 * (4 * Cc * Cc + 200 * P * Cc) * n, peak=pk["bf16_sustained"],
-                                        traffic=((0.763e9 / 16384) if eng.delta else (660.6e6 / 8192)) * n if L == 238 else None,
+                                        traffic=((0.765e9 / 16384) if eng.delta else (660.6e6 / 8192)) * n if L == 238 else None,
                                         note="gradient of the CNN ensemble for every proposal: 3*(4C^2+200PC) algorithmic flops per chain; "
                                              "fp16 hi/lo split = 3 tensor-core passes per flop; " +
                                              ("delta mode: one tile of the touched positions per chain and net, only the adjoint rows that differ are gathered "
@@ -341,18 +341,20 @@ def main():
                                            # EXECUTED algorithmic flops: only the dirty 16-position blocks are evaluated (the full-evaluation
                                            # equivalent, 3*2*P*C*2C per chain, is reported under roofline.forward_incremental)
                                            work=nd_ * n * 3 * 2 * m.PB * Cc * 2 * Cc, peak=pk["bf16_sustained"],
-                                           traffic=(0.431e9 / 16384) * n if L == 238 else None,
+                                           traffic=(0.502e9 / 16384) * n if L == 238 else None,
                                            note="max-pool winners of every proposal: 3 nets * 2*PB*C*2C flops per dirty PB-position block (PB = 8) "
                                                 "(3 fp16 passes per flop); bound by the shared-memory pipe of the r1 producers (5 table reads per element)"),
                 "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s",
                                       # per channel: 16 B top-2 list read + 8 B per dirty block key + 16 B list + 8 B winner written
                                       work=int(n * 3 * 2 * Cc * (16 + 8 * nd_ + 24)), peak=pk["hbm_gbs"],
-                                      traffic=(1.909e9 / 16384) * n if L == 238 else None,
+                                      traffic=(2.643e9 / 16384) * n if L == 238 else None,
                                       note="chain-level winner from the row's top-2 list and the dirty blocks' keys (exact, csrc/cnn_tc.cu)"),
-                "pas_propose": dict(kernel="pas_propose_kernel", bound="hbm", unit="GB/s", work=(4 * NE + L) * n, peak=pk["hbm_gbs"],
-                                    traffic=(166.9e6 / 8192) * n if L == 238 else None,
-                                    note="reads one gradient row per chain; bound by instruction issue (Philox4x32-10 + race test for each of the "
-                                         "20L entries of every live sub-step: torch.multinomial needs one uniform per entry), not by bytes"),
+                "pas_propose": dict(kernel="pas_propose_pos_kernel", bound="hbm", unit="GB/s",
+                                    work=((4 * NE + L) + ((8 * m.D) if p_holder["p"].fuse_potts else 0)) * n, peak=pk["hbm_gbs"],
+                                    traffic=(1.285e9 / 16384) * n if L == 238 else None,
+                                    note="reads one gradient row per chain (and, fused, reads / writes the chain's Potts field rows); bound by instruction "
+                                         "issue (Philox4x32-10 + race test for each of the 20L entries of every live sub-step: torch.multinomial needs one "
+                                         "uniform per entry), not by bytes"),
             }
             dom = max(cand, key=lambda k_: breakdown[k_])
             cd = cand[dom]
@@ -398,10 +400,21 @@ def main():
                     "algorithmic_flops_per_launch": flops_fwd, "avg_launch_ms": breakdown["cnn_forward"]}
         hbm_bytes = (8 * m.D + 2 * L + 16) * n                        # SURVEY.md §8d B_alg per chain-step
         t_hbm = (breakdown["pas_propose"] + breakdown["potts_incremental"] + breakdown["pas_reverse_accept"]) * 1e-3
+        pp_ = p_holder["p"]
+        fused = bool(pp_.comb_nets > 0)
+        # what these kernels move by design: the gradient row read by the proposal and by the reverse proposal (4 NE each), the
+        # Potts field rows (8 D) and - with the gradient combine fused into the reverse kernel - the current state's gradient
+        # row, both field rows again and the proposal's row written once (8 NE + 8 D; the sparse per-net changes not counted)
+        design_bytes = (8 * m.D + 2 * L + 16 + 8 * 20 * L + ((8 * 20 * L + 8 * m.D - 4 * 20 * L) if fused else 0)) * n
         roof["hbm_kernels"] = {"achieved_gbs": hbm_bytes / t_hbm / 1e9, "peak_gbs": pk["hbm_gbs"],
                                "frac": hbm_bytes / t_hbm / 1e9 / pk["hbm_gbs"],
-                               "kernels": "pas_propose + potts_incremental + pas_reverse_accept",
-                               "algorithmic_bytes_per_step": hbm_bytes}
+                               "kernels": "pas_propose (+ Potts field update) + pas_reverse_accept" + (" (+ gradient combine)" if fused else "")
+                                          if pp_.fuse_potts else "pas_propose + potts_incremental + pas_reverse_accept",
+                               "algorithmic_bytes_per_step": hbm_bytes,
+                               "bytes_moved_by_design_per_step": design_bytes,
+                               "frac_of_design_bytes": design_bytes / t_hbm / 1e9 / pk["hbm_gbs"],
+                               "note": "algorithmic bytes = SURVEY.md 8d (Potts field update + state); the same kernels also read the gradient rows"
+                                       " and (fused) assemble / write the proposal's gradient row: bytes_moved_by_design counts those too"}
     if launches_per_step is None:
         launches_per_step = 12 if m.cnn_inc else 9
 
