@@ -766,6 +766,12 @@ constexpr int PB_SHIFT = 3;
 constexpr int PB = 1 << PB_SHIFT;
 constexpr int PB_TILE = 128 / PB;              // blocks per MMA tile
 constexpr int PB_MAXNB = 32;                   // blocks per row <= 32 (dirty-block masks are 32-bit words)
+// Two epilogue groups (role counters, r02: the epilogue - 16 block arg-maxima and key stores per channel and tile, one warp per
+// scheduler - was the critical path at 5.5 k cycles per tile with the MMA issuer waiting 3.8 k for a free accumulator):
+// warps 0-3 take the even tiles (accumulator buffer 0), warps 24-27 the odd ones (buffer 1); both sets sit on the TMEM lane
+// quarters 0-3 (warp id mod 4).  Warps 21-23 are idle padding.
+constexpr int INC_NTHREADS = 28 * 32;
+constexpr int INC_EPI2_WARP0 = 24;
 struct IncParams {
     ppde_cnn_t m;
     const uint8_t* aa;                  // proposal states [n, aa_stride]
@@ -861,7 +867,7 @@ __device__ __forceinline__ void argmax8(const uint32_t (&r)[16], int o, float& b
 }
 
 template <int NCH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(INC_NTHREADS, 1)
 cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int C = prm.m.C, P = prm.m.P, J2 = 2 * C, NB = prm.NB;
@@ -896,7 +902,7 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
     const int ntiles = (G + PB_TILE - 1) / PB_TILE;          // tiles of PB_TILE blocks (the last one may be shorter)
     const uint32_t* bl = prm.blist + (size_t)b_lo * PB_MAXNB;
 
-    for (int e = threadIdx.x; e < 100 * KS; e += NTHREADS) {
+    for (int e = threadIdx.x; e < 100 * KS; e += INC_NTHREADS) {
         const int row = e / KS, c = e - row * KS;
         float v = 0.f;
         if (c < C) {
@@ -945,12 +951,14 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
     cluster_sync_all();
     tc_fence_after();
 
-    if (warp < 4) {
-        // ===== EPILOGUE (both CTAs): thread = channel j; per TILE: the PB_TILE blocks' keys go straight to their final place in
-        // the proposal rows of the pool (no per-chain work here: cnn_inc_merge_kernel forms mkey) =====
-        const int j = mt * 128 + warp * 32 + lane;
+    if (warp < 4 || warp >= INC_EPI2_WARP0) {
+        // ===== EPILOGUE (both CTAs, two groups of 4 warps: group g takes the tiles T = g, g + 2, ..): thread = channel j; per
+        // TILE: the PB_TILE blocks' keys go straight to their final place in the proposal rows of the pool (no per-chain work
+        // here: cnn_inc_merge_kernel forms mkey) =====
+        const int eg = warp >= INC_EPI2_WARP0 ? 1 : 0, ew = warp & 3;
+        const int j = mt * 128 + ew * 32 + lane;
         const bool jok = j < J2;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + D_COL0;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + D_COL0;
         const size_t row_keys = (size_t)prm.m.n_nets * NB * J2;            // keys per pool row
         const size_t koff = ((size_t)k * NB) * J2 + j;
         // lane l (mod PB_TILE) holds block l of the tile.  Three-stage prefetch, each stage one tile apart so that no load is waited
@@ -974,23 +982,23 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
             if (ent == 0xFFFFFFFFu || rx < 0) return ry;
             return (__ldg(prm.btab + (size_t)rx * NB + (int)(ent & 31u)) == ry) ? rx : ry;
         };
-        uint32_t ent0 = ld_ent(0), ent1 = ld_ent(1), ent2 = ld_ent(2);      // entries of tiles T, T+1, T+2
+        uint32_t ent0 = ld_ent(eg), ent1 = ld_ent(eg + 2), ent2 = ld_ent(eg + 4);   // entries of my tiles T, T+2, T+4
         int ry1, rx1, ry0, rx0;
         ld_rows(ent0, ry0, rx0);
-        ld_rows(ent1, ry1, rx1);                                            // rows of tile T+1
+        ld_rows(ent1, ry1, rx1);                                            // rows of my next tile
         int row0 = ld_slot(ent0, ry0, rx0);                                 // slot of tile T
         const bool prof = prm.prof != nullptr;
         long long pc[4] = {0, 0, 0, 0};
         long long tp = prof ? clock64() : 0;
-        for (int T = 0; T < ntiles; ++T) {
+        for (int T = eg; T < ntiles; T += 2) {
             const int cnt = min(PB_TILE, G - PB_TILE * T);
             const int buf = T & 1;
             const uint32_t ent = ent0;
             const int row = row0;
-            row0 = ld_slot(ent1, ry1, rx1);                                 // tile T+1: rows were requested one iteration ago
+            row0 = ld_slot(ent1, ry1, rx1);                                 // my next tile: rows were requested one iteration ago
             ent0 = ent1; ent1 = ent2;
-            ld_rows(ent1, ry1, rx1);                                        // tile T+2
-            ent2 = ld_ent(T + 3);
+            ld_rows(ent1, ry1, rx1);                                        // the one after
+            ent2 = ld_ent(T + 6);
             if (prof) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
             mbar_wait(&dfull[buf], (uint32_t)((T >> 1) & 1));
             tc_fence_after();
@@ -1092,7 +1100,7 @@ cnn_forward_inc_kernel(const __grid_constant__ IncParams prm) {
                 if (++slot == NSLOT2) { slot = 0; sphase ^= 1; }
             }
         }
-    } else {
+    } else if (warp < WARP_MMA2) {
         // ===== PRODUCERS (both CTAs): one row per thread; a tile = PB_TILE consecutive dirty blocks of the CTA's sequence (N rounded
         // up to a multiple of 16 rows: an odd block count leaves one pad block, produced by nobody and read by nobody), this CTA's half =====
         const int pw = warp - 4;
@@ -2986,7 +2994,7 @@ extern "C" int ppde_cnn_forward_inc(const ppde_cnn_t* m, const uint8_t* aa, int3
     static SmemCache configured[5];
     if (cudaError_t e = ensure_dynamic_smem(kern, smem, configured[nch])) return (int)e;
     if (inc_parts & 2) {
-        kern<<<2 * combos * prm.ctas_per_combo, tc::NTHREADS, smem, (cudaStream_t)stream>>>(prm);
+        kern<<<2 * combos * prm.ctas_per_combo, tc::INC_NTHREADS, smem, (cudaStream_t)stream>>>(prm);
         int r1 = launch_done();
         if (r1) return r1;
     }
