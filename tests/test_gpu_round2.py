@@ -313,3 +313,52 @@ def test_host_population_forms_give_the_same_run():
     assert torch.equal(d[0].cpu(), h[0]) and np.array_equal(h[0].argmax(-1).numpy(), r[0].numpy())
     for k in (1, 2, 3, 4):
         assert np.array_equal(d[k], h[k]) and np.array_equal(d[k], r[k])
+
+
+# ------------------------------------------------------------------------------------------- fused step kernels
+def test_fused_step_equals_separate_kernels(monkeypatch):
+    """Default step (Potts field update inside pas_propose, gradient combine inside pas_reverse_accept) against the same engine
+    with the separate ppde_potts_incremental / cnn_grad_combine_sparse launches (PPDE_FUSE_POTTS=0, PPDE_FUSE_COMBINE=0): the
+    fused kernels perform the same sums in the same order, so every row and every decision must agree BIT FOR BIT, across an
+    exact-refresh iteration too."""
+    from ppde_b200.engine import ChainEngine
+    L, n, T, seed = 238, 96, 36, 11
+    w = port.synthetic_weights(L, seed=2, lamda=15.0)
+    m = _model(w)
+    a = ChainEngine(m, n, 2, 0, False, seed=seed, num_steps=T)
+    a.init_population(_wt_pop(m, w, n))
+    monkeypatch.setenv("PPDE_FUSE_POTTS", "0")
+    monkeypatch.setenv("PPDE_FUSE_COMBINE", "0")
+    b = ChainEngine(m, n, 2, 0, False, seed=seed, num_steps=T)
+    b.init_population(_wt_pop(m, w, n))
+    assert a.fuse_potts and a.fuse_combine and not b.fuse_potts and not b.fuse_combine
+    for t in range(T):
+        a.run_steps(1, use_graph=True)
+        b.run_steps(1, use_graph=(t % 2 == 0))          # graph replay and eager launches alternate on the reference side
+        torch.cuda.synchronize()
+        assert torch.equal(a.idx, b.idx) and torch.equal(a.accept, b.accept) and torch.equal(a.aa, b.aa), f"t={t}"
+        assert torch.equal(a.row_cur, b.row_cur)
+        rc, ry = a.row_cur.long(), a.rows_y.long()
+        assert torch.equal(a.G[ry], b.G[ry]) and torch.equal(a.Gp[ry], b.Gp[ry]), f"t={t}: proposal rows differ"
+        assert torch.equal(a.G[rc], b.G[rc]) and torch.equal(a.Gp[rc], b.Gp[rc])
+        assert torch.equal(a.E_y, b.E_y) and torch.equal(a.lqr, b.lqr) and torch.equal(a.lqf, b.lqf)
+    assert torch.equal(a.E_hist, b.E_hist) and torch.equal(a.best_aa, b.best_aa)
+
+
+def test_long_sequence_kernels_vs_port():
+    """L = 272 > 256: the position-per-thread PAS kernels, the fused Potts update / gradient combine and the tensor-core CNN do
+    not apply; the strided shared-memory PAS kernels, ppde_potts_incremental and the fp32 SIMT CNN run instead.  A short run
+    against the oracle port keeps that path covered."""
+    from ppde_b200.engine import ChainEngine
+    L, n, T, seed = 272, 6, 5, 3
+    w = port.synthetic_weights(L, seed=4, lamda=3.0)
+    m = _model(w)
+    eng = ChainEngine(m, n, 2, 0, False, seed=seed, num_steps=T)
+    eng.init_population(_wt_pop(m, w, n))
+    assert not eng.fuse_potts and not eng.fuse_combine
+    eng.run_steps(T, use_graph=True)
+    torch.cuda.synchronize()
+    en = port.PortEnergy(w)
+    ref = port.PortSampler(2, 0, False, seed=seed).run(en.wt_onehot.repeat(n, 1, 1), T, en)
+    assert _rel(eng.E_hist.cpu().numpy(), ref[3], abs(m.wt_H)) < 1e-4
+    assert np.array_equal(eng.best_aa.cpu().numpy()[:, :L], ref[0].argmax(-1).numpy())
