@@ -1511,9 +1511,11 @@ constexpr int BD_NT = 48;                // columns (touched positions) per tile
 constexpr int BD_RPW = BD_NT / 8;        // columns per producer warp (8 warps per producer set)
 constexpr int BD_MC = 64;                // touched positions whose relu-mask bytes travel inside the record (64 bytes each)
 constexpr int BD_TRAIL = 16;             // uint16 words at a FIXED place (just before the mask bytes) of a compact record:
-                                         // ntile | index of the (orow, cfirst) pairs | tstart[1 .. 14] - what the fused combine
-                                         // (pas_reverse_accept) needs in ONE load level instead of three dependent ones (P <= 252:
-                                         // <= 6 tiles); 32 bytes, so that records stay sector-aligned
+                                         // ntile | (index of the pair list) | tstart[1 .. 14]; the (orow, cfirst) pair list
+                                         // itself sits at a fixed place too, the 2 rmax words before the trailer (rmax = L + 4 tmax
+                                         // rows at most) - what the fused combine (pas_reverse_accept) needs is addressable from
+                                         // the chain index alone: ONE load level instead of four dependent ones.  32 bytes, so that
+                                         // records stay sector-aligned
 // Winner records of the DELTA backward.  For chain b and net k the per-net gradient changes between the current state x
 // and the proposal y only through
 //   * the conv rows whose relu mask changed: p in D0 = U_{i: x_i != y_i} [i-4, i], and
@@ -1662,7 +1664,7 @@ __global__ void __launch_bounds__(128) cnn_winner_delta_kernel(const __grid_cons
     // (p_prev < row - 4): cfirst = c.  One warp scans the counts of a tile's <= BD_NT columns.
     const int ntile = (npos + BD_NT - 1) / BD_NT;
     uint16_t* oo = out + 2 + 2 * npos + nent;         // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
-    uint16_t* pairs = oo + 2 + ntile;
+    uint16_t* pairs = out + rec - BD_MC * 32 - BD_TRAIL - 2 * (L + 4 * ((P + BD_NT - 1) / BD_NT));   // fixed place (see BD_TRAIL)
     if (threadIdx.x == 0) { oo[0] = (uint16_t)ntile; oo[1] = 0; }
     __syncthreads();                                  // sPosC complete
     if (threadIdx.x < 32) {
@@ -1822,7 +1824,7 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
     // ---- output-row lists of the tiles (see cnn_winner_delta_kernel)
     const int ntile = (npos + BD_NT - 1) / BD_NT;
     uint16_t* oo = out + 2 + 2 * npos + nent;         // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
-    uint16_t* pairs = oo + 2 + ntile;
+    uint16_t* pairs = out + rec - BD_MC * 32 - BD_TRAIL - 2 * (L + 4 * ((P + BD_NT - 1) / BD_NT));   // fixed place (see BD_TRAIL)
     if (threadIdx.x == 0) { oo[0] = (uint16_t)ntile; oo[1] = 0; }
     __shared__ __align__(16) uint16_t sTr[BD_TRAIL];
     if (threadIdx.x < 32) {
@@ -1907,7 +1909,7 @@ __global__ void __launch_bounds__(256) cnn_grad_combine_sparse_kernel(int n, int
         const uint16_t* oo = r + 2 + 2 * npos + nent;
         const int ntile = oo[0];
         const uint16_t* tstart = oo + 1;
-        const uint16_t* pairs = oo + 2 + ntile;      // (orow, cfirst) per output row
+        const uint16_t* pairs = r + rec - BD_MC * 32 - BD_TRAIL - 2 * (vcap / PPDE_Q);      // (orow, cfirst) per output row, fixed place
         const float* v = vals + ((size_t)k * n + b) * vcap;
         for (int t = 0; t < ntile; ++t) {
             const int r0 = tstart[t], r1 = tstart[t + 1];
@@ -2498,7 +2500,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             const int tiles = (npos + BD_NT - 1) / BD_NT;
             const int nent = lds_u16(rs + 2u * (uint32_t)(1 + 2 * npos));
             const uint32_t oo = rs + 2u * (uint32_t)(2 + 2 * npos + nent);          // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
-            const uint32_t pairs_a = oo + 2u * (uint32_t)(2 + tiles);
+            const uint32_t pairs_a = rs + 2u * (uint32_t)(prm.rec - BD_MC * 32 - BD_TRAIL - 2 * (prm.vcap / PPDE_Q));   // fixed place
             float* vout = prm.Gc + ((size_t)k * prm.n + (b_lo + ci)) * prm.vcap;
             if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
             for (int t = 0; t < tiles; ++t, ++it) {

@@ -930,6 +930,7 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_
     __shared__ int s_flag;
     __shared__ float s_ratio;
     __shared__ uint32_t s_map[2][PAS_NT];                    // output row -> entry of the net's row list, tagged with the epoch
+    __shared__ uint32_t s_map0[PAS_CN][PAS_NT];              // the same for the first tile of every net (entry + 1), built at once
 
     const int L = c.L, NE = L * PPDE_Q;
     const int b = blockIdx.x, n = c.n, tid = threadIdx.x, i = tid;
@@ -956,14 +957,20 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_
         // in the scratch.  Fixed order (net, tile): the same sums as cnn_grad_combine_sparse_kernel, bit for bit.  An output row IS
         // a thread here: thread r of the list publishes "row orow[r] is entry r" in shared memory (tagged with the epoch, two
         // maps alternate: one barrier per (net, tile), nothing to clear) and the owner adds the 20 values to its registers.
-        // Load levels: (1) the records' fixed trailers + the three base rows, (2) the row lists, (3) the values.
+        // Load levels: (1) the records' fixed trailers, the first-tile row lists of all nets (both at fixed places of the record)
+        // and the three base rows, (2) the values - the maps of all nets' first tiles are published behind ONE barrier.
         const int nets = p.comb_nets;
+        const int rmax = p.comb_vcap / PPDE_Q;                                   // rows a net's list can hold (<= PAS_NT + 24)
+        const int poff = p.comb_rec - PAS_MC32 - PAS_TRAIL - 2 * rmax;            // the (orow, cfirst) pairs sit at a fixed place
         uint4 tr[PAS_CN][2];
+        int orow[PAS_CN];                                                        // my entry of every net's first-tile row list
 #pragma unroll
         for (int k = 0; k < PAS_CN; ++k) {
-            const uint4* tp = reinterpret_cast<const uint4*>(p.comb_wl + ((size_t)b * nets + (k < nets ? k : 0)) * p.comb_rec + p.comb_rec - PAS_MC32 - PAS_TRAIL);
+            const uint16_t* rk = p.comb_wl + ((size_t)b * nets + (k < nets ? k : 0)) * p.comb_rec;
+            const uint4* tp = reinterpret_cast<const uint4*>(rk + p.comb_rec - PAS_MC32 - PAS_TRAIL);
             tr[k][0] = (k < nets) ? __ldg(tp) : make_uint4(0u, 0u, 0u, 0u);
             tr[k][1] = (k < nets) ? __ldg(tp + 1) : make_uint4(0u, 0u, 0u, 0u);
+            orow[k] = (k < nets && tid < rmax) ? (int)__ldg(rk + poff + 2 * tid) : 0;      // (garbage beyond the list: filtered below)
         }
         if (active) {
             load_row20(g, c.G + (int64_t)rx * NE + i * PPDE_Q);
@@ -976,18 +983,38 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_
                 for (int k = 0; k < PPDE_Q; ++k) g[k] += a[k] - d[k];
             }
         }
-        s_map[0][tid] = 0u; s_map[1][tid] = 0u;                // tag 0 = no entry (epochs start at 1)
+        // first tiles of all nets: one map per net, ONE barrier; entry = list index + 1 (0 = not an output row of this net)
+#pragma unroll
+        for (int k = 0; k < PAS_CN; ++k) s_map0[k][tid] = 0u;
+        s_map[0][tid] = 0u; s_map[1][tid] = 0u;                // later tiles: tag 0 = no entry (epochs start at 1)
+        __syncthreads();
+        int r1k[PAS_CN], ntk[PAS_CN];
+#pragma unroll
+        for (int k = 0; k < PAS_CN; ++k) {
+            ntk[k] = (int)(tr[k][0].x & 0xFFFFu);
+            r1k[k] = ntk[k] ? (int)(tr[k][0].y & 0xFFFFu) : 0;                   // tstart[1]: rows of the first tile
+            if (tid < r1k[k] && orow[k] < PAS_NT) s_map0[k][orow[k]] = (uint32_t)tid + 1u;
+        }
         __syncthreads();
         uint32_t epoch = 0;
 #pragma unroll
         for (int k = 0; k < PAS_CN; ++k) {
             if (k < nets) {
                 const uint32_t tw[8] = {tr[k][0].x, tr[k][0].y, tr[k][0].z, tr[k][0].w, tr[k][1].x, tr[k][1].y, tr[k][1].z, tr[k][1].w};
-                const int ntile = (int)(tw[0] & 0xFFFFu), poff = (int)(tw[0] >> 16);
                 const uint16_t* pairs = p.comb_wl + ((size_t)b * nets + k) * p.comb_rec + poff;
                 const float* v = p.comb_vals + ((size_t)k * n + b) * p.comb_vcap;
-                int r0 = 0;
-                for (int tl = 0; tl < ntile; ++tl) {
+                {
+                    const uint32_t me = active ? s_map0[k][i] : 0u;
+                    if (me) {
+                        float d[PPDE_Q];
+                        load_row20(d, v + (size_t)(me - 1u) * PPDE_Q);
+#pragma unroll
+                        for (int q = 0; q < PPDE_Q; ++q) g[q] = fmaf(p.comb_scale, d[q], g[q]);
+                    }
+                    // (a first tile with more than PAS_NT rows cannot occur: <= 5 * 48 = 240 rows per tile)
+                }
+                int r0 = r1k[k];
+                for (int tl = 1; tl < ntk[k]; ++tl) {                             // more than one tile of touched positions (12 % of the units)
                     const int wsel = (tl + 2) >> 1;                               // tstart[tl + 1] = 16-bit word tl + 2 of the trailer
                     uint32_t wv = tw[1];
 #pragma unroll
