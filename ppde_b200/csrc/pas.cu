@@ -951,6 +951,12 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_
     for (int k = 0; k < PPDE_Q; ++k) g[k] = 0.f;
     int zi = active ? (int)ax[i] : 0;                              // trajectory state of my position
     if (tid == 0) s_ratio = 0.f;
+    // what the accept / commit tail needs, requested now (three more dependent DRAM round trips at the end of the kernel otherwise)
+    const int xi0 = zi;
+    const int yi0 = active ? (int)ay[i] : 0;
+    const int wti = active ? (int)m.wt[i] : 0;
+    float pe_x = 0.f, pf_x = 0.f, pe_y = 0.f, pf_y = 0.f, pbest = 0.f;
+    if (tid == 0) { pe_x = c.E[b]; pf_x = c.fit[b]; pe_y = c.E_y[b]; pf_y = c.fit_y[b]; pbest = c.best_E[b]; }
     if (p.comb_nets > 0) {
         // Fused gradient combine (delta backward): G_y = G_x + (Gp_y - Gp_x)(window), then for k = 0 .. nets-1, tile by tile:
         // G_y[row] += scale * dGc_k[row] for the output rows the record lists - the sparse changes cnn_backward_delta_kernel left
@@ -1069,8 +1075,8 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_
 
     if (tid == 0) {
         const float log_ratio = s_ratio;
-        const float e_x = c.E[b], f_x = c.fit[b];
-        const float e_y = c.E_y[b], f_y = c.fit_y[b];
+        const float e_x = pe_x, f_x = pf_x;
+        const float e_y = pe_y, f_y = pf_y;
         const float log_acc = (e_y - e_x) + log_ratio;             // ppde.py:135-136
         const float u = u32_to_unit(Philox(p.seed)(0u, gid, (uint32_t)t, (uint32_t)(KIND_ACCEPT << 16)).x);
         const bool acc = expf(log_acc) >= u;                       // '>=' (ppde.py:138); NaN rejects
@@ -1086,7 +1092,7 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_
             const int f = c.anchor_fixed ? c.anchor_fixed[b] : (c.row_wt - 2 * n);
             c.E[b] = c.E_fixed[f]; c.fit[b] = c.fit_fixed[f]; c.row_cur[b] = 2 * n + f;
         }
-        const bool better = e_rec > c.best_E[b];                   // strict: first occurrence of the max (ppde.py:173)
+        const bool better = e_rec > pbest;                         // strict: first occurrence of the max (ppde.py:173)
         if (better) { c.best_E[b] = e_rec; c.best_fit[b] = f_rec; }
         s_flag |= better ? 4 : 0;
     }
@@ -1103,7 +1109,7 @@ __global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_pos_kernel(ppde_
     int dpart = 0;
     uint8_t v = 0, wv = 0;
     if (active) {
-        v = src[i]; wv = m.wt[i];
+        v = (uint8_t)(flag == 1 ? yi0 : (flag == 2 ? (int)src[i] : xi0)); wv = (uint8_t)wti;
         dpart = (v != wv);
         if (better) c.best_aa[(int64_t)b * c.aa_stride + i] = v;
         if (c.traj_aa && b == c.traj_chain) c.traj_aa[(int64_t)(t + 1) * c.aa_stride + i] = v;
