@@ -1726,11 +1726,13 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
     uint32_t* sSorted = sKey + 2 * J2;                       // [2 J2]
     int* sPosC = reinterpret_cast<int*>(sSorted + 2 * J2);   // [P] compact position list
     __shared__ uint32_t sD0[8];                              // bit p: the relu mask of conv row p changed (P <= 252)
-    __shared__ int sCount, sBase[5];
+    __shared__ uint32_t sTouched[8];                         // bit p: position p carries an entry (a column of the record)
+    __shared__ int sPre[9];                                  // columns before word w of sTouched; sPre[8] = npos
+    __shared__ int sCount;
     __shared__ int sBt[2][PB_MAXNB];                         // block-table rows of the proposal / current state (mask fetch)
     const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 8) sD0[threadIdx.x] = 0u;
+    if (threadIdx.x < 8) { sD0[threadIdx.x] = 0u; sTouched[threadIdx.x] = 0u; }
     if (threadIdx.x == 8) sCount = 0;
     if (r1mask && btab && threadIdx.x >= 64) {
         const int side = (threadIdx.x - 64) >> 5, q = threadIdx.x & 31;
@@ -1764,51 +1766,53 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
         if (lane == 0 && (by | bx)) base = atomicAdd(&sCount, __popc(by) + __popc(bx));
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t below = (1u << lane) - 1u;
-        if (ey >= 0) sKey[base + __popc(by & below)] = ((uint32_t)ey << 16) | (uint32_t)j;
-        if (ex >= 0) sKey[base + __popc(by) + __popc(bx & below)] = ((uint32_t)ex << 16) | 0x8000u | (uint32_t)j;
+        if (ey >= 0) { sKey[base + __popc(by & below)] = ((uint32_t)ey << 16) | (uint32_t)j; atomicOr(&sTouched[ey >> 5], 1u << (ey & 31)); }
+        if (ex >= 0) { sKey[base + __popc(by) + __popc(bx & below)] = ((uint32_t)ex << 16) | 0x8000u | (uint32_t)j; atomicOr(&sTouched[ex >> 5], 1u << (ex & 31)); }
     }
     __syncthreads();
     const int nent = sCount;
-    for (int i = threadIdx.x; i < nent; i += 128) {          // rank sort (keys are distinct)
+    // columns = touched positions in ascending order: column of position p = number of touched positions below p
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < 8; ++w) { sPre[w] = run; run += __popc(sTouched[w]); }
+        sPre[8] = run;
+    }
+    __syncthreads();
+    const int npos = sPre[8];
+    const int ntile = (npos + BD_NT - 1) / BD_NT;
+    const int nw = 8 * ntile + 1;
+    auto col_of = [&](int pp) -> int { return sPre[pp >> 5] + __popc(sTouched[pp >> 5] & ((1u << (pp & 31)) - 1u)); };
+    // re-key every entry with its place in the producers' work order: tile t = c / BD_NT, producer warp w = (c % BD_NT) % 8,
+    // slot sl = (c % BD_NT) / 8 of that warp, then (side, channel) as before:   key = (48 t + 6 w + sl) << 16 | side << 15 | sl << 12 | channel
+    // The rank sort then yields the list each producer warp of cnn_backward_delta_kernel walks front to back (it used to
+    // flatten the entries of its 6 strided columns itself: shuffles, prefix sums and a staging list per tile and warp - 12 % of
+    // that kernel's instructions, on the producers' critical path).  Within a column the order (side, channel) is unchanged.
+    for (int i = threadIdx.x; i < nent; i += 128) {
+        const uint32_t ki = sKey[i];
+        const int c = col_of((int)(ki >> 16));
+        const int t = c / BD_NT, r = c - t * BD_NT, w = r & 7, sl = r >> 3;
+        sKey[i] = ((uint32_t)(t * BD_NT + w * BD_RPW + sl) << 16) | (ki & 0x81FFu) | ((uint32_t)sl << 12);
+    }
+    __syncthreads();
+    // record: npos | pos[npos] | woff[8 ntile + 1] | list[nent] | (fixed places) pairs | trailer | masks
+    uint16_t* out = wl + (size_t)bk * rec;
+    for (int i = threadIdx.x; i < nent; i += 128) {          // rank sort (keys are distinct): entry = low half of the key
         const uint32_t ki = sKey[i];
         int rank = 0;
         for (int q = 0; q < nent; ++q) rank += (sKey[q] < ki);
-        sSorted[rank] = ki;
+        out[1 + npos + nw + rank] = (uint16_t)(ki & 0xFFFFu);
     }
+    for (int x = threadIdx.x; x < nw; x += 128) {            // woff[8 t + w] = entries before the group of (tile t, warp w)
+        const uint32_t bound = (uint32_t)((x >> 3) * BD_NT + (x & 7) * BD_RPW) << 16;
+        int cnt = 0;
+        for (int q = 0; q < nent; ++q) cnt += (sKey[q] < bound);
+        out[1 + npos + x] = (uint16_t)cnt;
+    }
+    for (int pp = threadIdx.x; pp < P; pp += 128) {
+        if ((sTouched[pp >> 5] >> (pp & 31)) & 1u) { const int c = col_of(pp); sPosC[c] = pp; out[1 + c] = (uint16_t)pp; }
+    }
+    if (threadIdx.x == 0) out[0] = (uint16_t)npos;
     __syncthreads();
-    // one scan over the sorted keys: a key starts a new column when its position differs from its predecessor's
-    uint16_t* out = wl + (size_t)bk * rec;
-    int run = 0;                                             // columns before this chunk
-    for (int i0 = 0; i0 < nent; i0 += 128) {
-        const int i = i0 + threadIdx.x;
-        uint32_t ki = 0u;
-        bool head = false;
-        if (i < nent) {
-            ki = sSorted[i];
-            head = (i == 0) || ((sSorted[i - 1] >> 16) != (ki >> 16));
-        }
-        const uint32_t bh = __ballot_sync(0xffffffffu, head);
-        if (lane == 0) sBase[warp] = __popc(bh);
-        __syncthreads();
-        int off = run;
-        for (int w = 0; w < warp; ++w) off += sBase[w];
-        const int c = off + __popc(bh & ((1u << lane) - 1u));     // column of a head entry
-        const int chunk_total = sBase[0] + sBase[1] + sBase[2] + sBase[3];
-        __syncthreads();
-        if (head) sPosC[c] = (int)(ki >> 16);
-        if (i < nent) sKey[i] = head ? (uint32_t)c : 0xFFFFFFFFu;   // (sKey is free: remember the head entries' columns)
-        run += chunk_total;
-    }
-    __syncthreads();
-    const int npos = run;
-    // record: npos | pos[npos] | start[npos+1] | list[nent] | ...
-    for (int i = threadIdx.x; i < nent; i += 128) {
-        const uint32_t ki = sSorted[i];
-        out[2 + 2 * npos + i] = (uint16_t)(ki & 0xFFFFu);
-        const uint32_t c = sKey[i];
-        if (c != 0xFFFFFFFFu) { out[1 + c] = (uint16_t)(ki >> 16); out[1 + npos + c] = (uint16_t)i; }
-    }
-    if (threadIdx.x == 0) { out[0] = (uint16_t)npos; out[1 + 2 * npos] = (uint16_t)nent; }
     // ---- relu-mask bytes of the first BD_MC touched positions, both sides, in the LAST BD_MC * 64 bytes of the record
     if (r1mask) {
         const int my = rows_y[b], mx = rows_x[b];
@@ -1822,10 +1826,7 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
         }
     }
     // ---- output-row lists of the tiles (see cnn_winner_delta_kernel)
-    const int ntile = (npos + BD_NT - 1) / BD_NT;
-    uint16_t* oo = out + 2 + 2 * npos + nent;         // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
     uint16_t* pairs = out + rec - BD_MC * 32 - BD_TRAIL - 2 * (L + 4 * ((P + BD_NT - 1) / BD_NT));   // fixed place (see BD_TRAIL)
-    if (threadIdx.x == 0) { oo[0] = (uint16_t)ntile; oo[1] = 0; }
     __shared__ __align__(16) uint16_t sTr[BD_TRAIL];
     if (threadIdx.x < 32) {
         if (lane < BD_TRAIL) sTr[lane] = 0;
@@ -1861,12 +1862,9 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
                 }
             }
             nr_run += __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 0) {
-                oo[2 + t] = (uint16_t)nr_run;
-                if (t < BD_TRAIL - 2) sTr[2 + t] = (uint16_t)nr_run;
-            }
+            if (lane == 0 && t < BD_TRAIL - 2) sTr[2 + t] = (uint16_t)nr_run;        // tstart[t + 1]
         }
-        if (lane == 0) { sTr[0] = (uint16_t)ntile; sTr[1] = (uint16_t)(2 + 2 * npos + nent + 2 + ntile); }
+        if (lane == 0) { sTr[0] = (uint16_t)ntile; sTr[1] = (uint16_t)nent; }
         __syncwarp();
         // the fixed trailer, one full 32-byte sector (two 16-byte stores)
         if (lane < 2) reinterpret_cast<uint4*>(out + rec - BD_MC * 32 - BD_TRAIL)[lane] = reinterpret_cast<const uint4*>(sTr)[lane];
@@ -1904,15 +1902,12 @@ __global__ void __launch_bounds__(256) cnn_grad_combine_sparse_kernel(int n, int
     __syncthreads();
     for (int k = 0; k < n_nets; ++k) {
         const uint16_t* r = wl + ((size_t)b * n_nets + k) * rec;
-        const int npos = r[0];
-        const int nent = r[1 + 2 * npos];
-        const uint16_t* oo = r + 2 + 2 * npos + nent;
-        const int ntile = oo[0];
-        const uint16_t* tstart = oo + 1;
+        const uint16_t* tr = r + rec - BD_MC * 32 - BD_TRAIL;                              // trailer: ntile | nent | tstart[1 ..]
+        const int ntile = tr[0];
         const uint16_t* pairs = r + rec - BD_MC * 32 - BD_TRAIL - 2 * (vcap / PPDE_Q);      // (orow, cfirst) per output row, fixed place
         const float* v = vals + ((size_t)k * n + b) * vcap;
         for (int t = 0; t < ntile; ++t) {
-            const int r0 = tstart[t], r1 = tstart[t + 1];
+            const int r0 = t ? tr[1 + t] : 0, r1 = tr[2 + t];
             for (int it = r0 * PPDE_Q + (int)threadIdx.x; it < r1 * PPDE_Q; it += blockDim.x) {
                 const int rr = it / PPDE_Q, a = it - rr * PPDE_Q;
                 const int e = (int)pairs[2 * rr] * PPDE_Q + a;
@@ -2498,8 +2493,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
             const int tiles = (npos + BD_NT - 1) / BD_NT;
-            const int nent = lds_u16(rs + 2u * (uint32_t)(1 + 2 * npos));
-            const uint32_t oo = rs + 2u * (uint32_t)(2 + 2 * npos + nent);          // ntile | tstart[ntile+1] | (orow, cfirst)[nr]
+            const uint32_t oo = rs + 2u * (uint32_t)(prm.rec - BD_MC * 32 - BD_TRAIL);   // trailer: ntile | nent | tstart[1 ..]
             const uint32_t pairs_a = rs + 2u * (uint32_t)(prm.rec - BD_MC * 32 - BD_TRAIL - 2 * (prm.vcap / PPDE_Q));   // fixed place
             float* vout = prm.Gc + ((size_t)k * prm.n + (b_lo + ci)) * prm.vcap;
             if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
@@ -2528,7 +2522,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 named_bar(2, NT_EPI);
                 // output rows of this tile: r in [tstart[t], tstart[t+1]); row i = orow[r] gets the columns c = cfirst[r] .. while
                 // pos[c] <= i (at most 5, tap t = i - pos[c]); one thread per row: 5 x 16-byte loads per term, 80 bytes out
-                const int r0 = lds_u16(oo + 2u * (uint32_t)(1 + t)), r1 = lds_u16(oo + 2u * (uint32_t)(2 + t));
+                const int r0 = t ? lds_u16(oo + 2u * (uint32_t)(1 + t)) : 0, r1 = lds_u16(oo + 2u * (uint32_t)(2 + t));   // tstart[t], tstart[t + 1]
                 const uint32_t pa = rs + 2u * (uint32_t)(1 + t * BD_NT);                  // pos[] of the tile's columns
                 for (int r = r0 + tid; r < r1; r += NT_EPI) {
                     const int i = lds_u16(pairs_a + 4u * (uint32_t)r);
@@ -2670,27 +2664,15 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             const int npos = lds_u16(rs);
             const int tiles = (npos + BD_NT - 1) / BD_NT;
             const uint32_t ps = rs + 2u;                                   // pos[c]
-            const uint32_t ss = rs + 2u * (uint32_t)(1 + npos);            // start[c]
-            const uint32_t ls = rs + 2u * (uint32_t)(2 + 2 * npos);        // list
+            const uint32_t ws = rs + 2u * (uint32_t)(1 + npos);            // woff[8 t + w]: my entries of tile t are list[woff .. woff')
+            const uint32_t ls = ws + 2u * (uint32_t)(8 * tiles + 1);       // list, in the producers' work order (cnn_delta_record_kernel)
             for (int t = 0; t < tiles; ++t, ++it) {
                 if ((it & 1) != pset) continue;
                 const int tb = it % BD_NBUF;
                 const int ncol = min(BD_NT, npos - t * BD_NT);
                 const int cbase = t * BD_NT + w8;                          // my columns: cbase + 8 i, i < BD_RPW, while < t * BD_NT + ncol
-                // ---- flatten: lane i < BD_RPW looks at column i; exclusive prefix of the entry counts; lanes copy the entries
-                int s_i = 0, n_i = 0;
-                if (lane < BD_RPW && w8 + 8 * lane < ncol) {
-                    s_i = lds_u16(ss + 2u * (uint32_t)(cbase + 8 * lane));
-                    n_i = lds_u16(ss + 2u * (uint32_t)(cbase + 8 * lane + 1)) - s_i;
-                }
-                int off_i = n_i;
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, off_i, o);
-                    if (lane >= o) off_i += v;
-                }
-                const int ntot = __shfl_sync(0xffffffffu, off_i, BD_RPW - 1);
-                off_i -= n_i;
+                const int f_lo = lds_u16(ws + 2u * (uint32_t)(8 * t + w8));
+                const int ntot = lds_u16(ws + 2u * (uint32_t)(8 * t + w8 + 1)) - f_lo;
                 // relu-mask bytes of my columns, both sides (byte i of the 64-bit words = column slot i)
                 unsigned long long m8 = 0ull, m8x = 0ull;
 #pragma unroll
@@ -2751,70 +2733,50 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                     }
                     ++cur;
                 };
-                // entries in chunks of BD_FLAT (one chunk unless a warp's columns carry more than BD_FLAT entries); lane f copies
-                // flattened entry f: its slot is the number of columns whose entries end at or before f
-                for (int f0 = 0; f0 < ntot; f0 += BD_FLAT) {
-                    __syncwarp();                           // the previous chunk has been consumed
+                // my entries, front to back: entry = channel | slot << 12 | side << 15, four W1 rows in flight across column boundaries
+                const uint32_t fl = ls + 2u * (uint32_t)f_lo;
+                for (int e = 0; e < ntot; e += 4) {
+                    float4 w[4][2];
+                    float dj[4];
+                    bool sd[4];
+                    int jn[4], sl[4];
 #pragma unroll
-                    for (int h = 0; h < BD_FLAT / 32; ++h) {
-                        const int f = f0 + h * 32 + lane;
-                        int slot = 0, base = __shfl_sync(0xffffffffu, off_i, 0), st0 = __shfl_sync(0xffffffffu, s_i, 0);
+                    for (int v = 0; v < 4; ++v) {
+                        const uint32_t fe = (e + v < ntot) ? (uint32_t)lds_u16(fl + 2u * (uint32_t)(e + v)) : 0u;
+                        sl[v] = (int)((fe >> 12) & 7u);
+                        sd[v] = (fe >> 15) != 0u;
+                        jn[v] = (int)(fe & 0x1FFu);
+                    }
 #pragma unroll
-                        for (int i = 1; i < BD_RPW; ++i) {
-                            const int oi = __shfl_sync(0xffffffffu, off_i, i), si = __shfl_sync(0xffffffffu, s_i, i);
-                            if (f >= oi) { slot = i; base = oi; st0 = si; }
-                        }
-                        if (f < ntot) {
-                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(flat_a + 4u * (uint32_t)(h * 32 + lane)),
-                                         "r"((uint32_t)lds_u16(ls + 2u * (uint32_t)(st0 + f - base)) | ((uint32_t)slot << 16)) : "memory");
+                    for (int v = 0; v < 4; ++v) {
+                        w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e + v < ntot && lact) {
+                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn[v] * prm.kpad);
+                            w[v][0] = __ldg(src);
+                            w[v][1] = __ldg(src + 1);
                         }
                     }
-                    __syncwarp();
-                    const int nf = min(BD_FLAT, ntot - f0);
-                    for (int e = 0; e < nf; e += 4) {
-                        float4 w[4][2];
-                        float dj[4];
-                        bool sd[4];
-                        int jn[4], sl[4];
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            uint32_t fe = 0u;
-                            if (e + v < nf) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(fe) : "r"(flat_a + 4u * (uint32_t)(e + v)));
-                            sl[v] = (int)(fe >> 16);
-                            sd[v] = ((fe >> 15) & 1u) != 0u;
-                            jn[v] = (int)(fe & 0x7FFFu);
-                        }
+                    for (int v = 0; v < 4; ++v) {
+                        const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn[v]);
+                        dj[v] = sd[v] ? -d0 : d0;
+                    }
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (e + v < nf && lact) {
-                                const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn[v] * prm.kpad);
-                                w[v][0] = __ldg(src);
-                                w[v][1] = __ldg(src + 1);
-                            }
-                        }
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn[v]);
-                            dj[v] = sd[v] ? -d0 : d0;
-                        }
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            if (e + v < nf) {
-                                while (cur < sl[v]) store_row();
-                                dirty_row = true;
-                                const float dd = dj[v];
-                                const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
-                                // (a masked-off channel contributes exactly 0: skipping the FMA leaves acc unchanged, same value)
-                                if (mb & 1u) acc[0] = fmaf(dd, w[v][0].x, acc[0]);
-                                if (mb & 2u) acc[1] = fmaf(dd, w[v][0].y, acc[1]);
-                                if (mb & 4u) acc[2] = fmaf(dd, w[v][0].z, acc[2]);
-                                if (mb & 8u) acc[3] = fmaf(dd, w[v][0].w, acc[3]);
-                                if (mb & 16u) acc[4] = fmaf(dd, w[v][1].x, acc[4]);
-                                if (mb & 32u) acc[5] = fmaf(dd, w[v][1].y, acc[5]);
-                                if (mb & 64u) acc[6] = fmaf(dd, w[v][1].z, acc[6]);
-                                if (mb & 128u) acc[7] = fmaf(dd, w[v][1].w, acc[7]);
-                            }
+                    for (int v = 0; v < 4; ++v) {
+                        if (e + v < ntot) {
+                            while (cur < sl[v]) store_row();
+                            dirty_row = true;
+                            const float dd = dj[v];
+                            const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
+                            // (a masked-off channel contributes exactly 0: skipping the FMA leaves acc unchanged, same value)
+                            if (mb & 1u) acc[0] = fmaf(dd, w[v][0].x, acc[0]);
+                            if (mb & 2u) acc[1] = fmaf(dd, w[v][0].y, acc[1]);
+                            if (mb & 4u) acc[2] = fmaf(dd, w[v][0].z, acc[2]);
+                            if (mb & 8u) acc[3] = fmaf(dd, w[v][0].w, acc[3]);
+                            if (mb & 16u) acc[4] = fmaf(dd, w[v][1].x, acc[4]);
+                            if (mb & 32u) acc[5] = fmaf(dd, w[v][1].y, acc[5]);
+                            if (mb & 64u) acc[6] = fmaf(dd, w[v][1].z, acc[6]);
+                            if (mb & 128u) acc[7] = fmaf(dd, w[v][1].w, acc[7]);
                         }
                     }
                 }
@@ -3057,9 +3019,9 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     const int C = m->C, P = m->P, L = m->L, J2 = 2 * C;
     // delta mode, compact records (default; tune->delta_layout = 1 keeps one column per position): npos | pos | start | list
     const bool compact = dl && !(tune && tune->delta_layout == 1);
-    // compact record: npos | pos[P] | start[P+1] | list[2 J2] | ntile | tstart[TMAX+1] | (orow, cfirst)[RMAX] | ... | masks[BD_MC][2][32 B]  (uint16)
+    // compact record: npos | pos[P] | woff[8 TMAX + 1] | list[2 J2] | ... | (orow, cfirst)[RMAX] | trailer[BD_TRAIL] | masks[BD_MC][2][32 B]  (uint16)
     const int tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
-    const int rec = compact ? (((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) + tc::BD_TRAIL + tc::BD_MC * 32) : (((P + 1) + 2 * J2 + 7) & ~7);
+    const int rec = compact ? (((1 + P + 8 * tmax + 1 + 2 * J2 + 2 * rmax + 7) & ~7) + tc::BD_TRAIL + tc::BD_MC * 32) : (((P + 1) + 2 * J2 + 7) & ~7);
     const int vcap = compact ? rmax * PPDE_Q : L * PPDE_Q;                       // floats of scratch per (net, chain)
     prm.vcap = vcap;
     const size_t smem_fixed = compact
@@ -3128,7 +3090,7 @@ extern "C" int ppde_cnn_backward_delta_layout(const ppde_cnn_t* m, int32_t n, in
     if (!m || n <= 0 || !vcap || !rec || !wl_offset) return (int)cudaErrorInvalidValue;
     const int P = m->P, L = m->L, J2 = 2 * m->C;                 // same formulas as backward_launch (compact records)
     const int tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
-    *rec = ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~7) + tc::BD_TRAIL + tc::BD_MC * 32;
+    *rec = ((1 + P + 8 * tmax + 1 + 2 * J2 + 2 * rmax + 7) & ~7) + tc::BD_TRAIL + tc::BD_MC * 32;
     *vcap = rmax * PPDE_Q;
     *wl_offset = (int64_t)m->n_nets * n * (*vcap);
     return 0;
@@ -3139,7 +3101,7 @@ extern "C" int64_t ppde_cnn_backward_scratch_floats(const ppde_cnn_t* m, int32_t
     if (!m || n <= 0) return 0;
     const int64_t P = m->P, L = m->L, J2 = 2 * (int64_t)m->C;
     const int64_t tmax = (P + tc::BD_NT - 1) / tc::BD_NT, rmax = L + 4 * tmax;
-    const int64_t rec_c = ((2 * P + 2 + 2 * J2 + 2 + tmax + 2 * rmax + 7) & ~(int64_t)7) + tc::BD_TRAIL + tc::BD_MC * 32, rec_d = ((P + 1) + 2 * J2 + 7) & ~(int64_t)7;
+    const int64_t rec_c = ((1 + P + 8 * tmax + 1 + 2 * J2 + 2 * rmax + 7) & ~(int64_t)7) + tc::BD_TRAIL + tc::BD_MC * 32, rec_d = ((P + 1) + 2 * J2 + 7) & ~(int64_t)7;
     const int64_t a = (int64_t)m->n_nets * n * rmax * PPDE_Q + ((int64_t)n * m->n_nets * rec_c + 1) / 2;     // compact delta
     const int64_t b = (int64_t)m->n_nets * n * L * PPDE_Q + ((int64_t)n * m->n_nets * rec_d + 1) / 2;        // exact / per-position delta
     return (a > b ? a : b) + 16;
