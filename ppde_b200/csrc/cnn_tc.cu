@@ -2444,7 +2444,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                      "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int j = threadIdx.x; j < J2; j += BW_NTHREADS) sDj[j] = net.d[j];
+    for (int j = threadIdx.x; j < J2; j += BW_NTHREADS) sDj[j] = net.d[j] * net.adj_scale;   // (power of two: the operand rows come out scaled, exactly)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -2487,9 +2487,12 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
         int it = 0;
+        int rb = -1;                                   // record buffer of the chain and the parity of its landing (BD_NREC is a
+        uint32_t rph = 1u;                             // run-time value: `ci % BD_NREC` / `ci / BD_NREC` were real divisions, per chain and warp)
         for (int ci = 0; ci < nchains; ++ci) {
-            const int rb = ci % BD_NREC;
-            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            if (++rb == BD_NREC) rb = 0;
+            if (rb == 0) rph ^= 1u;
+            mbar_wait(&recfull[rb], rph);
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
             const int tiles = (npos + BD_NT - 1) / BD_NT;
@@ -2589,10 +2592,13 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             }
         };
         int it = 0;
+        int rb = -1;
+        uint32_t rph = 1u;
         for (int ci = 0; ci < nchains; ++ci) {
             stage_records(ci + 1);
-            const int rb = ci % BD_NREC;
-            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            if (++rb == BD_NREC) rb = 0;
+            if (rb == 0) rph ^= 1u;
+            mbar_wait(&recfull[rb], rph);
             const int npos = lds_u16(rec_a + (uint32_t)rb * rec_bytes);
             nread = ci + 1;
             const int tiles = (npos + BD_NT - 1) / BD_NT;
@@ -2644,7 +2650,6 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         const int pw = warp - 4;
         const int pset = pw >> 3, w8 = pw & 7;
         const bool lact = 8 * lane < prm.kpad;
-        const float adj_scale = net.adj_scale;
         const float* wbase = net.W1p + 8 * lane;
         const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BD_SLOT);
         const uint32_t unit = (uint32_t)(lane & 7);
@@ -2654,11 +2659,14 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
         int it = 0;
+        int rbp = (BD_NREC - 1) | 16;                  // record buffer (low 4 bits) and landing parity (bit 4) of the chain, one register
         for (int ci = 0; ci < nchains; ++ci) {
-            const int rb = ci % BD_NREC;
+            rbp = ((rbp & 15) + 1 == BD_NREC) ? ((rbp & 16) ^ 16) : rbp + 1;
+            const int rb = rbp & 15;
+            const uint32_t rph = (uint32_t)(rbp >> 4);
             const int bb = b_lo + ci;
             if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-            mbar_wait(&recfull[rb], (uint32_t)((ci / BD_NREC) & 1));
+            mbar_wait(&recfull[rb], rph);
             if (PROF) { const long long t1 = clock64(); pc[3] += t1 - tp; tp = t1; }
             const uint32_t rs = rec_a + (uint32_t)rb * rec_bytes;
             const int npos = lds_u16(rs);
@@ -2669,6 +2677,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             for (int t = 0; t < tiles; ++t, ++it) {
                 if ((it & 1) != pset) continue;
                 const int tb = it % BD_NBUF;
+                const uint32_t tparity = (uint32_t)(((it / BD_NBUF) + 1) & 1);
                 const int ncol = min(BD_NT, npos - t * BD_NT);
                 const int cbase = t * BD_NT + w8;                          // my columns: cbase + 8 i, i < BD_RPW, while < t * BD_NT + ncol
                 const int f_lo = lds_u16(ws + 2u * (uint32_t)(8 * t + w8));
@@ -2705,7 +2714,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 auto store_row = [&]() {   // operand row of slot `cur` <- scale * acc (masks were applied per entry), fp16 hi + lo
                     if (!have_buf) {
                         if (PROF) { const long long t1 = clock64(); pc[1] += t1 - tp; tp = t1; }
-                        mbar_wait(&empty[tb], (uint32_t)(((it / BD_NBUF) + 1) & 1));
+                        mbar_wait(&empty[tb], tparity);
                         have_buf = true;
                         if (PROF) { const long long t1 = clock64(); pc[0] += t1 - tp; tp = t1; }
                     }
@@ -2717,7 +2726,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float2 x = make_float2(acc[2 * q] * adj_scale, acc[2 * q + 1] * adj_scale);
+                            const float2 x = make_float2(acc[2 * q], acc[2 * q + 1]);
                             const float2 h = make_float2(h_trunc(x.x), h_trunc(x.y));
                             const float2 l = sub2(x, h);
                             hi[q] = pack_h2(h.x, h.y);
