@@ -2747,36 +2747,31 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 for (int e = 0; e < ntot; e += 4) {
                     float4 w[4][2];
                     float dj[4];
-                    bool sd[4];
-                    int jn[4], sl[4];
+                    uint32_t fe[4];                         // the entries stay packed: slot / side / channel are decoded where they are used
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const uint32_t fe = (e + v < ntot) ? (uint32_t)lds_u16(fl + 2u * (uint32_t)(e + v)) : 0u;
-                        sl[v] = (int)((fe >> 12) & 7u);
-                        sd[v] = (fe >> 15) != 0u;
-                        jn[v] = (int)(fe & 0x1FFu);
-                    }
+                    for (int v = 0; v < 4; ++v) fe[v] = (e + v < ntot) ? (uint32_t)lds_u16(fl + 2u * (uint32_t)(e + v)) : 0u;
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         w[v][0] = w[v][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (e + v < ntot && lact) {
-                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)jn[v] * prm.kpad);
+                            const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)(fe[v] & 0x1FFu) * prm.kpad);
                             w[v][0] = __ldg(src);
                             w[v][1] = __ldg(src + 1);
                         }
                     }
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        const float d0 = lds_f32(dj_a + 4u * (uint32_t)jn[v]);
-                        dj[v] = sd[v] ? -d0 : d0;
+                        const float d0 = lds_f32(dj_a + 4u * (fe[v] & 0x1FFu));
+                        dj[v] = (fe[v] >> 15) ? -d0 : d0;
                     }
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         if (e + v < ntot) {
-                            while (cur < sl[v]) store_row();
+                            const int slv = (int)((fe[v] >> 12) & 7u);
+                            while (cur < slv) store_row();
                             dirty_row = true;
                             const float dd = dj[v];
-                            const uint32_t mb = (uint32_t)(((sd[v] ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
+                            const uint32_t mb = (uint32_t)((((fe[v] >> 15) ? m8x : m8) >> (8 * cur)) & 0xffull);   // relu mask of the entry's side
                             // (a masked-off channel contributes exactly 0: skipping the FMA leaves acc unchanged, same value)
                             if (mb & 1u) acc[0] = fmaf(dd, w[v][0].x, acc[0]);
                             if (mb & 2u) acc[1] = fmaf(dd, w[v][0].y, acc[1]);
