@@ -1728,11 +1728,13 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
     __shared__ uint32_t sD0[8];                              // bit p: the relu mask of conv row p changed (P <= 252)
     __shared__ uint32_t sTouched[8];                         // bit p: position p carries an entry (a column of the record)
     __shared__ int sPre[9];                                  // columns before word w of sTouched; sPre[8] = npos
+    __shared__ int sWoff[64];                                // first rank of every (tile, producer warp) group
     __shared__ int sCount;
     __shared__ int sBt[2][PB_MAXNB];                         // block-table rows of the proposal / current state (mask fetch)
     const int bk = blockIdx.x, b = bk / n_nets, k = bk - b * n_nets;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 8) { sD0[threadIdx.x] = 0u; sTouched[threadIdx.x] = 0u; }
+    if (threadIdx.x < 64) sWoff[threadIdx.x] = 0x7fffffff;
     if (threadIdx.x == 8) sCount = 0;
     if (r1mask && btab && threadIdx.x >= 64) {
         const int side = (threadIdx.x - 64) >> 5, q = threadIdx.x & 31;
@@ -1801,12 +1803,23 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
         int rank = 0;
         for (int q = 0; q < nent; ++q) rank += (sKey[q] < ki);
         out[1 + npos + nw + rank] = (uint16_t)(ki & 0xFFFFu);
+        const int gq = (int)(ki >> 16);                      // group (tile, warp) = 8 t + w: its first entry has the smallest rank
+        atomicMin(&sWoff[8 * (gq / BD_NT) + (gq % BD_NT) / BD_RPW], rank);
     }
-    for (int x = threadIdx.x; x < nw; x += 128) {            // woff[8 t + w] = entries before the group of (tile t, warp w)
-        const uint32_t bound = (uint32_t)((x >> 3) * BD_NT + (x & 7) * BD_RPW) << 16;
-        int cnt = 0;
-        for (int q = 0; q < nent; ++q) cnt += (sKey[q] < bound);
-        out[1 + npos + x] = (uint16_t)cnt;
+    __syncthreads();
+    // woff[x] = entries before group x = first rank of the next non-empty group (suffix minimum; nent behind the last one)
+    if (threadIdx.x < 32) {
+        int a0 = (2 * lane < nw) ? sWoff[2 * lane] : nent, a1 = (2 * lane + 1 < nw) ? sWoff[2 * lane + 1] : nent;   // nw <= 8 * 7 + 1 <= 64
+        a0 = min(a0, a1);
+        int run = a0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, run, o);
+            if (lane + o < 32) run = min(run, v);
+        }
+        const int nxt = __shfl_down_sync(0xffffffffu, run, 1);                // suffix minimum of the lanes behind me
+        if (2 * lane + 1 < nw) out[1 + npos + 2 * lane + 1] = (uint16_t)min(a1, lane < 31 ? nxt : nent);
+        if (2 * lane < nw) out[1 + npos + 2 * lane] = (uint16_t)run;
     }
     for (int pp = threadIdx.x; pp < P; pp += 128) {
         if ((sTouched[pp >> 5] >> (pp & 31)) & 1u) { const int c = col_of(pp); sPosC[c] = pp; out[1 + c] = (uint16_t)pp; }
