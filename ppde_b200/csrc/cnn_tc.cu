@@ -1508,7 +1508,11 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 }
 
 constexpr int BD_NT = 48;                // columns (touched positions) per tile of the compact delta backward
-constexpr int BD_RPW = BD_NT / 8;        // columns per producer warp (8 warps per producer set)
+constexpr int BD_NSET = 3;               // producer sets of cnn_backward_delta_kernel: set s builds the tiles with it % BD_NSET == s
+constexpr int BD_NW = 6;                 // warps per producer set (3 x 6: 18 producer warps, 23 warps in all = 80 registers)
+constexpr int BD_RPW = BD_NT / BD_NW;    // columns per producer warp (8: one byte per column in the 64-bit mask words)
+constexpr int BD_NTHREADS = (4 + BD_NSET * BD_NW + 1) * 32;   // warps 0-3 epilogue, 4..21 producers, 22 MMA issuer
+constexpr int BD_WARP_MMA = 4 + BD_NSET * BD_NW;              // highest warp id of its scheduler (22 = 2 mod 4)
 constexpr int BD_MC = 64;                // touched positions whose relu-mask bytes travel inside the record (64 bytes each)
 constexpr int BD_TRAIL = 16;             // uint16 words at a FIXED place (just before the mask bytes) of a compact record:
                                          // ntile | (index of the pair list) | tstart[1 .. 14]; the (orow, cfirst) pair list
@@ -1782,17 +1786,17 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
     __syncthreads();
     const int npos = sPre[8];
     const int ntile = (npos + BD_NT - 1) / BD_NT;
-    const int nw = 8 * ntile + 1;
+    const int nw = BD_NW * ntile + 1;
     auto col_of = [&](int pp) -> int { return sPre[pp >> 5] + __popc(sTouched[pp >> 5] & ((1u << (pp & 31)) - 1u)); };
-    // re-key every entry with its place in the producers' work order: tile t = c / BD_NT, producer warp w = (c % BD_NT) % 8,
-    // slot sl = (c % BD_NT) / 8 of that warp, then (side, channel) as before:   key = (48 t + 6 w + sl) << 16 | side << 15 | sl << 12 | channel
+    // re-key every entry with its place in the producers' work order: tile t = c / BD_NT, producer warp w = (c % BD_NT) % BD_NW,
+    // slot sl = (c % BD_NT) / BD_NW of that warp, then (side, channel) as before:   key = (48 t + 8 w + sl) << 16 | side << 15 | sl << 12 | channel
     // The rank sort then yields the list each producer warp of cnn_backward_delta_kernel walks front to back (it used to
     // flatten the entries of its 6 strided columns itself: shuffles, prefix sums and a staging list per tile and warp - 12 % of
     // that kernel's instructions, on the producers' critical path).  Within a column the order (side, channel) is unchanged.
     for (int i = threadIdx.x; i < nent; i += 128) {
         const uint32_t ki = sKey[i];
         const int c = col_of((int)(ki >> 16));
-        const int t = c / BD_NT, r = c - t * BD_NT, w = r & 7, sl = r >> 3;
+        const int t = c / BD_NT, r = c - t * BD_NT, w = r % BD_NW, sl = r / BD_NW;
         sKey[i] = ((uint32_t)(t * BD_NT + w * BD_RPW + sl) << 16) | (ki & 0x81FFu) | ((uint32_t)sl << 12);
     }
     __syncthreads();
@@ -1804,7 +1808,7 @@ __global__ void __launch_bounds__(128, 16) cnn_delta_record_kernel(const __grid_
         for (int q = 0; q < nent; ++q) rank += (sKey[q] < ki);
         out[1 + npos + nw + rank] = (uint16_t)(ki & 0xFFFFu);
         const int gq = (int)(ki >> 16);                      // group (tile, warp) = 8 t + w: its first entry has the smallest rank
-        atomicMin(&sWoff[8 * (gq / BD_NT) + (gq % BD_NT) / BD_RPW], rank);
+        atomicMin(&sWoff[BD_NW * (gq / BD_NT) + (gq % BD_NT) / BD_RPW], rank);
     }
     __syncthreads();
     // woff[x] = entries before group x = first rank of the next non-empty group (suffix minimum; nent behind the last one)
@@ -2416,7 +2420,7 @@ constexpr int BD_NBUF = 3;             // operand tile buffers (3 x 48 KB).  4 b
 constexpr int BD_TS = 100;              // floats per column of the transposed accumulator tile: index t * 20 + a
 constexpr int BD_FLAT = 64;             // entries of a producer warp's flattened list (more are processed in chunks)
 template <bool PROF>
-__global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(const __grid_constant__ BwdParams prm) {
+__global__ void __launch_bounds__(BD_NTHREADS, 1) cnn_backward_delta_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int C = prm.m.C, P = prm.m.P, J2 = 2 * C;
     const int nch = prm.nch;
@@ -2447,17 +2451,17 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
     const uint32_t rec_a = smem_u32(sRec);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < BD_NBUF; ++s) { mbar_init(&full[s], BW_NT_PROD / 64); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < BD_NREC; ++s) { mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BW_NT_PROD / 32 + NT_EPI / 32); }
+        for (int s = 0; s < BD_NBUF; ++s) { mbar_init(&full[s], BD_NW); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < BD_NREC; ++s) { mbar_init(&recfull[s], 1); mbar_init(&recempty[s], BD_NSET * BD_NW + NT_EPI / 32); }
         for (int d = 0; d < BW_NDBUF; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], NT_EPI / 32); }
         fence_barrier_init();
     }
-    if (warp == BW_WARP_MMA) {
+    if (warp == BD_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int j = threadIdx.x; j < J2; j += BW_NTHREADS) sDj[j] = net.d[j] * net.adj_scale;   // (power of two: the operand rows come out scaled, exactly)
+    for (int j = threadIdx.x; j < J2; j += BD_NTHREADS) sDj[j] = net.d[j] * net.adj_scale;   // (power of two: the operand rows come out scaled, exactly)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -2531,7 +2535,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
                 if (rowok) {       // accumulator column j = operand row j holds column c = (j % BD_RPW) * 8 + j / BD_RPW (producers' permutation)
 #pragma unroll
                     for (int j = 0; j < BD_NT; ++j) {
-                        const int c = (j % BD_RPW) * 8 + j / BD_RPW;
+                        const int c = (j % BD_RPW) * BD_NW + j / BD_RPW;
                         if (c < ncol) sts_f32(st_a + (uint32_t)(c * BD_TS * 4), __uint_as_float(y[j]) * unscale);
                     }
                 }
@@ -2570,7 +2574,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             if (lane == 0) mbar_arrive(&recempty[rb]);
         }
         if (PROF && prm.prof && threadIdx.x == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3]; }
-    } else if (warp == BW_WARP_MMA) {
+    } else if (warp == BD_WARP_MMA) {
         // ===== MMA ISSUER: warp-uniform loop, one elected lane issues; also stages the records (bulk copies) =====
         const uint32_t idesc = make_idesc(128, BD_NT);
         const uint32_t ring_addr = smem_u32(ring);
@@ -2661,7 +2665,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
         // A warp first FLATTENS the entries of its <= BD_RPW columns into a private list (slot << 16 | entry) so that the gather
         // keeps 4 W1 rows in flight across column boundaries. =====
         const int pw = warp - 4;
-        const int pset = pw >> 3, w8 = pw & 7;
+        const int pset = pw / BD_NW, w8 = pw - pset * BD_NW;      // set, warp of the set
         const bool lact = 8 * lane < prm.kpad;
         const float* wbase = net.W1p + 8 * lane;
         const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BD_SLOT);
@@ -2686,21 +2690,21 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
             const int tiles = (npos + BD_NT - 1) / BD_NT;
             const uint32_t ps = rs + 2u;                                   // pos[c]
             const uint32_t ws = rs + 2u * (uint32_t)(1 + npos);            // woff[8 t + w]: my entries of tile t are list[woff .. woff')
-            const uint32_t ls = ws + 2u * (uint32_t)(8 * tiles + 1);       // list, in the producers' work order (cnn_delta_record_kernel)
+            const uint32_t ls = ws + 2u * (uint32_t)(BD_NW * tiles + 1);   // list, in the producers' work order (cnn_delta_record_kernel)
             for (int t = 0; t < tiles; ++t, ++it) {
-                if ((it & 1) != pset) continue;
+                if (it % BD_NSET != pset) continue;
                 const int tb = it % BD_NBUF;
                 const uint32_t tparity = (uint32_t)(((it / BD_NBUF) + 1) & 1);
                 const int ncol = min(BD_NT, npos - t * BD_NT);
                 const int cbase = t * BD_NT + w8;                          // my columns: cbase + 8 i, i < BD_RPW, while < t * BD_NT + ncol
-                const int f_lo = lds_u16(ws + 2u * (uint32_t)(8 * t + w8));
-                const int ntot = lds_u16(ws + 2u * (uint32_t)(8 * t + w8 + 1)) - f_lo;
+                const int f_lo = lds_u16(ws + 2u * (uint32_t)(BD_NW * t + w8));
+                const int ntot = lds_u16(ws + 2u * (uint32_t)(BD_NW * t + w8 + 1)) - f_lo;
                 // relu-mask bytes of my columns, both sides (byte i of the 64-bit words = column slot i)
                 unsigned long long m8 = 0ull, m8x = 0ull;
 #pragma unroll
                 for (int i = 0; i < BD_RPW; ++i) {
-                    const int c = cbase + 8 * i;
-                    if (w8 + 8 * i < ncol && lact) {
+                    const int c = cbase + BD_NW * i;
+                    if (w8 + BD_NW * i < ncol && lact) {
                         if (c < BD_MC) {                    // from the record (shared memory)
                             const uint32_t ma = rs + rec_bytes - (uint32_t)(BD_MC * 64) + (uint32_t)(c * 64) + (uint32_t)lane;
                             uint32_t by, bx;
@@ -2814,7 +2818,7 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_delta_kernel(cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == BW_WARP_MMA) {
+    if (warp == BD_WARP_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
@@ -3081,7 +3085,7 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
         if (r0) return r0;
     }
     if (bwd_parts & 2) {
-        bkern<<<m->n_nets * prm.ctas_per_net, tc::BW_NTHREADS, smem, st>>>(prm);
+        bkern<<<m->n_nets * prm.ctas_per_net, compact ? tc::BD_NTHREADS : tc::BW_NTHREADS, smem, st>>>(prm);
         int r = launch_done();
         if (r) return r;
     }
