@@ -22,15 +22,19 @@ _lib.check(m.lib.ppde_cnn_backward_delta_layout(C.byref(m.cnn), n, C.byref(vcap)
 sc = eng.ws.grad_scratch(n)
 wl = sc[off.value:].view(torch.int16)[: n * m.n_nets * rec.value].cpu().numpy().view(np.uint16).reshape(n * m.n_nets, rec.value)
 npos, nent, dup, d0ent, tiles = [], [], [], [], []
+NW, NT = 6, 48                      # tc::BD_NW, tc::BD_NT: record = npos | pos[npos] | woff[NW ntile + 1] | list[nent] | ...
 for r in wl[:3000]:
-    p = int(r[0]); e = int(r[1 + 2 * p])
-    start = r[1 + p: 2 + 2 * p].astype(int); lst = r[2 + 2 * p: 2 + 2 * p + e].astype(int)
+    p = int(r[0]); nt = (p + NT - 1) // NT; nwo = NW * nt + 1
+    woff = r[1 + p: 1 + p + nwo].astype(int); e = int(woff[-1])
+    lst = r[1 + p + nwo: 1 + p + nwo + e].astype(int)
     nd = 0
-    for c in range(p):
-        seg = lst[start[c]: start[c + 1]]
-        ch_y = set(seg[(seg & 0x8000) == 0] & 0x7FFF); ch_x = set(seg[(seg & 0x8000) != 0] & 0x7FFF)
-        nd += len(ch_y & ch_x)
-    npos.append(p); nent.append(e); dup.append(nd); tiles.append((p + 47) // 48)
+    for g in range(nwo - 1):           # entries of (tile, producer warp) group g, slot in bits 12-14, side in bit 15, channel in bits 0-8
+        seg = lst[woff[g]: woff[g + 1]]
+        for sl in range(8):
+            ss = seg[((seg >> 12) & 7) == sl]
+            ch_y = set(ss[(ss & 0x8000) == 0] & 0x1FF); ch_x = set(ss[(ss & 0x8000) != 0] & 0x1FF)
+            nd += len(ch_y & ch_x)
+    npos.append(p); nent.append(e); dup.append(nd); tiles.append(nt)
 npos, nent, dup, tiles = map(np.array, (npos, nent, dup, tiles))
 print(f"records {len(npos)}: touched positions mean {npos.mean():.1f} (p90 {np.percentile(npos, 90):.0f}, max {npos.max()}), entries mean {nent.mean():.1f} "
       f"(p90 {np.percentile(nent, 90):.0f}), same (position, channel) on both sides: {dup.mean():.1f} pairs = {2 * dup.sum() / max(nent.sum(), 1) * 100:.1f} % of the entries; "
