@@ -326,32 +326,32 @@ def main():
             tflop = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12
             gbs = lambda by, ms_: by / (ms_ * 1e-3) / 1e9
             # `traffic` = dram__bytes_read + dram__bytes_write of one launch from the committed `ncu --set full` captures of
-            # round 2 (profiles/r02_ncu_full_summary_v33.txt, 16,384 chains in steady state, scaled to this launch)
+            # round 2 (profiles/r02_ncu_full_summary_v44.txt, 16,384 chains in steady state, scaled to this launch)
             nd_ = (dirty_blocks / n) if dirty_blocks is not None else 2.25
             cand = {
                 "cnn_backward_tc": dict(kernel=("cnn_backward_delta_kernel" if eng.delta else "cnn_backward_tc_kernel"), bound="tensor", unit="TFLOP/s",
                                         work=3 * (4 * Cc * Cc + 200 * P * Cc) * n, peak=pk["bf16_sustained"],
-                                        traffic=((0.765e9 / 16384) if eng.delta else (660.6e6 / 8192)) * n if L == 238 else None,
+                                        traffic=((0.738e9 / 16384) if eng.delta else (660.6e6 / 8192)) * n if L == 238 else None,
                                         note="gradient of the CNN ensemble for every proposal: 3*(4C^2+200PC) algorithmic flops per chain; "
                                              "fp16 hi/lo split = 3 tensor-core passes per flop; " +
                                              ("delta mode: one tile of the touched positions per chain and net, only the adjoint rows that differ are gathered "
-                                              "(~70 W1 rows of 960 B per chain and net from L2); bound by the producers' instruction issue, not by the tensor pipe" if eng.delta else
+                                              "(~60 W1 rows of 960 B per chain and net from L2); bound by the producers' instruction streams, not by the tensor pipe" if eng.delta else
                                               "limited by the L2->SM gather of the winners' W1 rows (422 KB per chain and net)")),
                 "cnn_forward_inc_tc": dict(kernel="cnn_forward_inc_kernel", bound="tensor", unit="TFLOP/s",
                                            # EXECUTED algorithmic flops: only the dirty 16-position blocks are evaluated (the full-evaluation
                                            # equivalent, 3*2*P*C*2C per chain, is reported under roofline.forward_incremental)
                                            work=nd_ * n * 3 * 2 * m.PB * Cc * 2 * Cc, peak=pk["bf16_sustained"],
-                                           traffic=(0.502e9 / 16384) * n if L == 238 else None,
+                                           traffic=(0.505e9 / 16384) * n if L == 238 else None,
                                            note="max-pool winners of every proposal: 3 nets * 2*PB*C*2C flops per dirty PB-position block (PB = 8) "
                                                 "(3 fp16 passes per flop); bound by the shared-memory pipe of the r1 producers (5 table reads per element)"),
                 "cnn_inc_merge": dict(kernel="cnn_inc_merge_kernel", bound="hbm", unit="GB/s",
                                       # per channel: 16 B top-2 list read + 8 B per dirty block key + 16 B list + 8 B winner written
                                       work=int(n * 3 * 2 * Cc * (16 + 8 * nd_ + 24)), peak=pk["hbm_gbs"],
-                                      traffic=(2.643e9 / 16384) * n if L == 238 else None,
+                                      traffic=(2.627e9 / 16384) * n if L == 238 else None,
                                       note="chain-level winner from the row's top-2 list and the dirty blocks' keys (exact, csrc/cnn_tc.cu)"),
                 "pas_propose": dict(kernel="pas_propose_pos_kernel", bound="hbm", unit="GB/s",
                                     work=((4 * NE + L) + ((8 * m.D) if p_holder["p"].fuse_potts else 0)) * n, peak=pk["hbm_gbs"],
-                                    traffic=(1.285e9 / 16384) * n if L == 238 else None,
+                                    traffic=(1.286e9 / 16384) * n if L == 238 else None,
                                     note="reads one gradient row per chain (and, fused, reads / writes the chain's Potts field rows); bound by instruction "
                                          "issue (Philox4x32-10 + race test for each of the 20L entries of every live sub-step: torch.multinomial needs one "
                                          "uniform per entry), not by bytes"),

@@ -23,7 +23,7 @@ $K 200 $SMALL > gpurun_out/${TAG}_plain2.log 2>&1 && \
 $K 600 ncu --set full --clock-control none --import-source on -k regex:"cnn_forward_inc_kernel|cnn_inc_merge_kernel|cnn_backward_delta_kernel|cnn_delta_record_kernel|pas_propose|pas_reverse_accept|cnn_fit_kernel" -s 290 -c 14 -o gpurun_out/${TAG}_full -f $SMALL > gpurun_out/${TAG}_ncu_f.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_f.log
 if [ "$MODE" = "full" ]; then
-$K 200 python tools/bench_potts_full.py 64 128 238 512 1024 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
+$K 500 python tools/bench_potts_full.py 64 128 238 512 1024 > gpurun_out/${TAG}_potts_full_sweep.jsonl 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_potts_full_sweep.jsonl
 PD="python tools/bench_potts_full.py 238"
 $K 200 $PD > gpurun_out/${TAG}_plain3.log 2>&1 && \
 $K 300 ncu --set full --clock-control none --import-source on -k regex:potts_dense_tc_kernel -s 6 -c 1 -o gpurun_out/${TAG}_potts_dense -f $PD > gpurun_out/${TAG}_ncu_p.log 2>&1
