@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Potts expert alone (BASELINE.json configs[4]-style sweep): full re-evaluation as a dense tcgen05 GEMM vs the row-gather
 kernel, and the sampler's incremental field update (k <= S gathered J row differences per chain) for the same chains.
-usage (GPU box): python tools/bench_potts_full.py [L ...]   (Potts-only: lamda = 0, synthetic couplings)"""
+usage (GPU box): python tools/bench_potts_full.py [L ...]   (Potts-only: lamda = 0, synthetic couplings)
+Under torchrun (N ranks, one per GPU) every rank runs the same sweep on its own chains (weak scaling: chains independent, couplings
+replicated, no collective in the path); times are the maximum over the ranks, `chains` is per GPU."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -10,10 +12,16 @@ from ppde_b200.engine import ChainEngine, PoEModel, _ptr, _stream
 from ppde_b200.synthetic import synthetic_problem
 
 Ls = [int(a) for a in sys.argv[1:]] or [64, 128, 238, 512]
+WS, RANK, LOCAL = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+DEV = f"cuda:{LOCAL}"
+torch.cuda.set_device(LOCAL)
+if WS > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device(DEV))
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 for L in Ls:
     pr = synthetic_problem(L, seed=0)
-    m = PoEModel(pr["wt"], pr["J"], pr["h"], pr["win_lo"], pr["cnn"], 0.0, device="cuda:0")
+    m = PoEModel(pr["wt"], pr["J"], pr["h"], pr["win_lo"], pr["cnn"], 0.0, device=DEV)
     for n in ([1024, 16384, 65536, 262144] if L <= 238 else ([1024, 16384, 65536] if L <= 512 else [1024, 16384])):
         rng = np.random.default_rng(0)
         aa = np.tile(pr["wt"], (n, 1)).astype(np.uint8)
@@ -52,12 +60,22 @@ for L in Ls:
                 inc.append(e0.elapsed_time(e1))
             res["incremental"] = min(inc[1:])
             del eng
-        flops = 2.0 * n * m.D * m.D
+        if WS > 1:                 # device times, maximum over the ranks
+            tt = torch.tensor([res["gather"], res["dense"], res["incremental"] if res["incremental"] == res["incremental"] else -1.0], device=DEV)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            res["gather"], res["dense"] = float(tt[0]), float(tt[1])
+            if float(tt[2]) >= 0: res["incremental"] = float(tt[2])
+            if RANK: continue
+        flops = 2.0 * n * m.D * m.D * 1.0
         tf = flops / (res["dense"] * 1e-3) / 1e12
-        print(json.dumps({"L": L, "D": m.D, "chains": n, "gather_ms": round(res["gather"], 3), "dense_ms": round(res["dense"], 3),
+        print(json.dumps({"L": L, "D": m.D, "n_gpus": WS, "chains": n, "chains_total": n * WS,
+                          "dense_alg_TFLOPs_total": round(tf * WS, 1), "gather_ms": round(res["gather"], 3), "dense_ms": round(res["dense"], 3),
                           "incremental_ms": None if res["incremental"] != res["incremental"] else round(res["incremental"], 3),
                           "incremental_GBs": None if res["incremental"] != res["incremental"] else round((8 * m.D + L) * n / (res["incremental"] * 1e-3) / 1e9, 1),
                           "dense_alg_TFLOPs": round(tf, 1), "frac_of_measured_bf16_peak": round(tf / peaks["bf16_tflops"], 3),
                           "note": "2 fp16 passes per algorithmic flop (hi/lo split): executed = 2x"}))
     del m
     torch.cuda.empty_cache()
+if WS > 1:
+    dist.barrier()
+    dist.destroy_process_group()

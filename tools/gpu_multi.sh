@@ -14,6 +14,8 @@ done
 $K python bench.py --gpus 1 --strong --steps 20 --warmup 5 --no-cpu-baseline --no-breakdown > gpurun_out/${TAG}_strong_1gpu.json 2>> gpurun_out/${TAG}_multi.err; echo "strong 1 rc=$?"
 $K $TR --nproc-per-node 8 --master-port 29541 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu-baseline --no-breakdown \
     > gpurun_out/${TAG}_weak_8gpu.json 2>> gpurun_out/${TAG}_multi.err; echo "weak 8 rc=$?"
+# BASELINE.json configs[4] (Potts-only sweep) on all GPUs: every rank the same sweep on its own chains, times = max over ranks
+$K $TR --nproc-per-node 8 --master-port 29551 tools/bench_potts_full.py 238 > gpurun_out/${TAG}_potts_sweep_8gpu.jsonl 2>> gpurun_out/${TAG}_multi.err; echo "potts sweep 8 rc=$?"
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/${TAG}_*gpu*.json")):
