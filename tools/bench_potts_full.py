@@ -22,7 +22,8 @@ peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.absp
 for L in Ls:
     pr = synthetic_problem(L, seed=0)
     m = PoEModel(pr["wt"], pr["J"], pr["h"], pr["win_lo"], pr["cnn"], 0.0, device=DEV)
-    for n in ([1024, 16384, 65536, 262144] if L <= 238 else ([1024, 16384, 65536] if L <= 512 else [1024, 16384])):
+    # (the engine allocates the CNN pools too: 262,144 chains fit up to L = 128, the max-pool cache in blocks of 8 needs 45 GB per 64k chains at L = 238)
+    for n in ([1024, 16384, 65536, 262144] if L <= 128 else [1024, 16384, 65536, 131072] if L <= 238 else ([1024, 16384, 65536] if L <= 512 else [1024, 16384])):
         rng = np.random.default_rng(0)
         aa = np.tile(pr["wt"], (n, 1)).astype(np.uint8)
         idx = rng.integers(0, L, size=(n, 8)); val = rng.integers(0, 20, size=(n, 8))
