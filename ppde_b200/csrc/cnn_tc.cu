@@ -2418,7 +2418,6 @@ constexpr int BD_SLOT = 2 * BD_MAT;     // hi + lo
 constexpr int BD_NBUF = 3;             // operand tile buffers (3 x 48 KB).  4 buffers leave room for only 3 record buffers and
                                        // measured slower (7.1 vs 5.9 ms / 64k chains): the records are what lets the roles run ahead
 constexpr int BD_TS = 100;              // floats per column of the transposed accumulator tile: index t * 20 + a
-constexpr int BD_FLAT = 64;             // entries of a producer warp's flattened list (more are processed in chunks)
 template <bool PROF>
 __global__ void __launch_bounds__(BD_NTHREADS, 1) cnn_backward_delta_kernel(const __grid_constant__ BwdParams prm) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -2428,8 +2427,7 @@ __global__ void __launch_bounds__(BD_NTHREADS, 1) cnn_backward_delta_kernel(cons
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* sT = reinterpret_cast<float*>(ring + BD_NBUF * BW_MAXCH * BD_SLOT);    // [BD_NT][BD_TS] transposed accumulator tile
     float* sDj = sT + BD_NT * BD_TS;                                          // [J2] decoder weights
-    uint32_t* sFlat = reinterpret_cast<uint32_t*>(sDj + J2);                  // [16 producer warps][BD_FLAT] flattened entries
-    uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sFlat + 16 * BD_FLAT) + 15) & ~(uintptr_t)15);   // [BD_NREC][rec]
+    uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sDj + J2) + 15) & ~(uintptr_t)15);   // [BD_NREC][rec]
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRec + BD_NREC * prm.rec) + 7) & ~(uintptr_t)7);
     uint64_t* full = bars;                      // [BD_NBUF] tile buffers: producers -> MMA (8 warp arrivals: one producer set)
     uint64_t* empty = full + BD_NBUF;           // [BD_NBUF] MMA -> producers
@@ -2671,7 +2669,6 @@ __global__ void __launch_bounds__(BD_NTHREADS, 1) cnn_backward_delta_kernel(cons
         const uint32_t ring_lane = smem_u32(ring) + (uint32_t)((lane >> 3) * BD_SLOT);
         const uint32_t unit = (uint32_t)(lane & 7);
         const uint32_t dj_a = smem_u32(sDj);
-        const uint32_t flat_a = smem_u32(sFlat) + (uint32_t)(pw * BD_FLAT * 4);
         const int NB = prm.NB;
         long long pc[4] = {0, 0, 0, 0};
         long long tp = PROF ? clock64() : 0;
@@ -3046,7 +3043,7 @@ static int backward_launch(const ppde_cnn_t* m, const ppde_potts_t* pm, const ui
     const int vcap = compact ? rmax * PPDE_Q : L * PPDE_Q;                       // floats of scratch per (net, chain)
     prm.vcap = vcap;
     const size_t smem_fixed = compact
-        ? 1024 + (size_t)tc::BD_NBUF * tc::BW_MAXCH * tc::BD_SLOT + ((size_t)tc::BD_NT * tc::BD_TS + J2 + 16 * tc::BD_FLAT) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t)
+        ? 1024 + (size_t)tc::BD_NBUF * tc::BW_MAXCH * tc::BD_SLOT + ((size_t)tc::BD_NT * tc::BD_TS + J2) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t)
         : 1024 + (size_t)tc::BW_NBUF * tc::BW_MAXCH * tc::BW_SLOT + ((size_t)L * PPDE_Q + 4 + J2) * sizeof(float) + 16 + 8 + 32 * sizeof(uint64_t);
     int nrec = 2;
     if (compact) {                                   // as many record buffers as fit under the 227 KB limit (3 .. BD_NREC_MAX)
