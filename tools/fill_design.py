@@ -20,7 +20,7 @@ def other(name):
         return f"(no record: {ex})"
 cpu = d.get("cpu_baseline") or {}
 f = {
-    "TAG": f"bench_{tag}", "MS": f"{d['ms_per_step']:.1f}", "VAL": f"{d['value'] / 1e6:.2f}",
+    "TAG": tag, "MS": f"{d['ms_per_step']:.1f}", "VAL": f"{d['value'] / 1e6:.2f}",
     "K_PROP": f"{km['pas_propose'] + km['potts_incremental']:.2f}", "K_FWD": f"{km['cnn_forward_inc_tc']:.2f}",
     "K_MERGE": f"{km['cnn_inc_merge']:.2f}", "K_REC": f"{km['cnn_winner_sort']:.2f}", "K_BWD": f"{km['cnn_backward_tc']:.2f}",
     "K_REV": f"{km['pas_reverse_accept'] + km['cnn_grad_combine']:.2f}", "ROOF_ACH": f"{rf['achieved']:.0f}", "ROOF_FRAC": f"{rf['frac']:.2f}",
