@@ -732,7 +732,8 @@ __device__ __forceinline__ float softmax_clamp_pos_fast(float (&e)[PPDE_Q], cons
     return red_sum1<NW>(sum3, red + 2 * NW);
 }
 
-template <int MINB>
+// UM: the proposal uniforms come from a caller-provided array (teacher-forced parity tests) instead of the Philox streams
+template <int MINB, bool UM>
 __global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p,
                                                                     const __grid_constant__ PhiloxKeys keys) {
     constexpr int NW = PAS_NT / 32;
@@ -797,7 +798,7 @@ __global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_pott
         float best = -1.f; int bidx = 0x7fffffff;
         const uint32_t amask = __ballot_sync(0xffffffffu, active);
         if (active) {
-            const float* um = p.uniforms ? p.uniforms + ((int64_t)s * c.n + b) * NE + i * PPDE_Q : nullptr;
+            const float* um = UM ? p.uniforms + ((int64_t)s * c.n + b) * NE + i * PPDE_Q : nullptr;
             const uint32_t ctr3 = (uint32_t)(s | (KIND_PROPOSAL << 16));
             const float rs3 = 1.0f / s3;
             // Seed of the threshold: -log u <= (1 - u) / u, so r_j >= (p_j / s3) u_j / (1 - u_j); the largest such LOWER bound over
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_pott
             // before anything is evaluated exactly - otherwise every thread evaluates its first four entries (a fifth of the
             // vector) with two divisions and a logarithm each.  u >= k 2^-23 = f - 1 and 1 - u <= 2 - f, f = [1.k], k = x >> 9.
             uint4 wd0 = make_uint4(0u, 0u, 0u, 0u);
-            if (!um) {
+            if (!UM) {
                 wd0 = philox_keyed(keys, (uint32_t)(5 * i), gid, (uint32_t)t, ctr3);
                 const uint32_t ww[4] = {wd0.x, wd0.y, wd0.z, wd0.w};
                 float lb = 0.f;
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_pott
                 const float thr = fmaxf(best, __int_as_float(*(volatile int*)&s_best)) * s3 * (1.0f / 1.00001f);
                 uint4 wd = wd0;
                 float4 u1;                                                       // a lower bound of 1 - u (the test must never skip a winner)
-                if (um) {
+                if (UM) {
                     const float4 u = reinterpret_cast<const float4*>(um)[k];
                     u1 = make_float4(1.0f - u.x, 1.0f - u.y, 1.0f - u.z, 1.0f - u.w);
                 } else {
@@ -835,18 +836,17 @@ __global__ void __launch_bounds__(PAS_NT, MINB) pas_propose_pos_kernel(ppde_pott
                     u1 = make_float4(C2 - __uint_as_float((wd.x >> 9) | 0x3F800000u), C2 - __uint_as_float((wd.y >> 9) | 0x3F800000u),
                                      C2 - __uint_as_float((wd.z >> 9) | 0x3F800000u), C2 - __uint_as_float((wd.w >> 9) | 0x3F800000u));
                 }
-                const bool c0 = e[4 * k] > thr * u1.x, c1 = e[4 * k + 1] > thr * u1.y, c2 = e[4 * k + 2] > thr * u1.z, c3 = e[4 * k + 3] > thr * u1.w;
-                if (c0 | c1 | c2 | c3) {                                         // may still win: exact evaluation, in entry order
+                const float t1[4] = {thr * u1.x, thr * u1.y, thr * u1.z, thr * u1.w};
+                if ((e[4 * k] > t1[0]) | (e[4 * k + 1] > t1[1]) | (e[4 * k + 2] > t1[2]) | (e[4 * k + 3] > t1[3])) {   // may still win: exact evaluation, in entry order
                     asm volatile("" : "+r"(wd.x), "+r"(wd.y), "+r"(wd.z), "+r"(wd.w));   // (keeps the conversions below inside the branch)
                     float4 u;
-                    if (um) u = reinterpret_cast<const float4*>(um)[k];
+                    if (UM) u = reinterpret_cast<const float4*>(um)[k];
                     else u = make_float4(u32_to_unit(wd.x), u32_to_unit(wd.y), u32_to_unit(wd.z), u32_to_unit(wd.w));
                     const float pq[4] = {e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]};
                     const float uq[4] = {u.x, u.y, u.z, u.w};
-                    const bool cq[4] = {c0, c1, c2, c3};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (cq[j]) {
+                        if (pq[j] > t1[j]) {                                     // (the per-entry tests again: only here, in the rare branch)
                             const float r = (pq[j] / s3) / (-logf(uq[j]));
                             if (r > best) { best = r; bidx = i * PPDE_Q + 4 * k + j; atomicMax(&s_best, __float_as_int(r)); }
                         }
@@ -1196,9 +1196,8 @@ extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, c
     }
     if (p->fuse_potts && (!pas_use_pos(c->L) || !c->Gp || !c->Epotts_y || !m->Jsym || !m->h)) return (int)cudaErrorInvalidValue;
     if (pas_use_pos(c->L)) {
-        static const bool minb3 = [] { const char* e = getenv("PPDE_PAS_MINB"); return e && e[0] == '3'; }();
-        if (minb3) pas_propose_pos_kernel<3><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
-        else pas_propose_pos_kernel<4><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
+        if (p->uniforms) pas_propose_pos_kernel<4, true><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
+        else pas_propose_pos_kernel<4, false><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
         return launch_done();
     }
     size_t smem = pas_smem(c->L);
