@@ -326,7 +326,7 @@ def main():
             tflop = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12
             gbs = lambda by, ms_: by / (ms_ * 1e-3) / 1e9
             # `traffic` = dram__bytes_read + dram__bytes_write of one launch from the committed `ncu --set full` captures of
-            # round 2 (profiles/r02_ncu_full_summary_v44.txt, 16,384 chains in steady state, scaled to this launch)
+            # round 2 (profiles/r02_ncu_full_summary_v49.txt, 16,384 chains in steady state, scaled to this launch)
             nd_ = (dirty_blocks / n) if dirty_blocks is not None else 2.25
             cand = {
                 "cnn_backward_tc": dict(kernel=("cnn_backward_delta_kernel" if eng.delta else "cnn_backward_tc_kernel"), bound="tensor", unit="TFLOP/s",
