@@ -2406,12 +2406,13 @@ __global__ void __launch_bounds__(BW_NTHREADS, 1) cnn_backward_tc_kernel(const _
 //     dGc[row, a] = sum over the columns c with pos[c] = row - t, t = 0..4, of Y[(t,a), c]      (ascending c: deterministic)
 // for the output rows the record lists for the tile: the accumulator goes TMEM -> registers -> shared memory [c][(a,t)]
 // (conflict-free, one store per column) and one thread per (row, a) gathers its <= 5 terms and writes the value straight
-// to the scratch (coalesced); cnn_grad_combine_sparse_kernel adds the three nets' lists to the row.  (The first version
+// to the scratch (coalesced); pas_reverse_accept_pos_kernel (or cnn_grad_combine_sparse_kernel) adds the three nets' lists to the
+// row.  (The first version
 // scatter-added column by column into a dense shared-memory row, one warp barrier per column, and flushed / re-zeroed 19 KB per
 // chain and net: 6,100 of the ~9,500 cycles per tile, with the record buffers released only afterwards.)
 // Roles and barriers as in cnn_backward_tc_kernel; differences: every role reads npos from the chain's record (the epilogue
 // releases the record buffers too, it needs the lists), the global tile counter advances by the chain's own tile count,
-// tiles have BD_NT = 48 columns (6 per producer warp).
+// tiles have BD_NT = 48 columns, BD_NSET producer sets of BD_NW warps with BD_RPW columns each (3 x 6 x 8), 23 warps in all.
 constexpr int BD_NREC_MAX = 6;          // record buffers: as many as fit in shared memory (BwdParams.nrec, >= 3)
 constexpr int BD_MAT = BD_NT * KCH * 2; // one [48 x 64] fp16 operand matrix (6 KB)
 constexpr int BD_SLOT = 2 * BD_MAT;     // hi + lo
@@ -2429,12 +2430,12 @@ __global__ void __launch_bounds__(BD_NTHREADS, 1) cnn_backward_delta_kernel(cons
     float* sDj = sT + BD_NT * BD_TS;                                          // [J2] decoder weights
     uint16_t* sRec = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(sDj + J2) + 15) & ~(uintptr_t)15);   // [BD_NREC][rec]
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sRec + BD_NREC * prm.rec) + 7) & ~(uintptr_t)7);
-    uint64_t* full = bars;                      // [BD_NBUF] tile buffers: producers -> MMA (8 warp arrivals: one producer set)
+    uint64_t* full = bars;                      // [BD_NBUF] tile buffers: producers -> MMA (BD_NW warp arrivals: one producer set)
     uint64_t* empty = full + BD_NBUF;           // [BD_NBUF] MMA -> producers
     uint64_t* dfull = empty + BD_NBUF;          // [BW_NDBUF] MMA -> epilogue
     uint64_t* dempty = dfull + BW_NDBUF;        // [BW_NDBUF] epilogue -> MMA (4 warp arrivals)
     uint64_t* recfull = dempty + BW_NDBUF;      // [BD_NREC] record landed (bulk copy, tx bytes)
-    uint64_t* recempty = recfull + BD_NREC_MAX; // [BD_NREC] producers and epilogue done with the record (20 warp arrivals)
+    uint64_t* recempty = recfull + BD_NREC_MAX; // [BD_NREC] producers and epilogue done with the record (18 + 4 warp arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recempty + BD_NREC_MAX);
 
     const int k = blockIdx.x / prm.ctas_per_net;                       // this CTA's net
@@ -2655,13 +2656,13 @@ __global__ void __launch_bounds__(BD_NTHREADS, 1) cnn_backward_delta_kernel(cons
         }
         if (PROF && prm.prof && lane == 0) { long long* o = prm.prof + (size_t)blockIdx.x * 16; o[4] = pc[0]; o[5] = pc[1]; o[6] = pc[2]; o[7] = it; }
     } else {
-        // ===== PRODUCERS: two sets of 8 warps alternate over the tiles.  Warp w of a set owns the columns c = w, w + 8, w + 16, ..
-        // (STRIDED: the touched positions come in runs - the 5 conv rows of a mutated residue carry every winner sitting on them,
-        // both sides, ~4 entries per column, while a moved winner's column carries one - and with contiguous ownership one warp
-        // of the 8 got a whole run, ~2.5x the mean, and the tile waited for it).  The operand row of column c is
-        // r = (c % 8) * BD_RPW + c / 8, so a warp's rows are contiguous; the epilogue undoes the permutation when it writes sT.
-        // A warp first FLATTENS the entries of its <= BD_RPW columns into a private list (slot << 16 | entry) so that the gather
-        // keeps 4 W1 rows in flight across column boundaries. =====
+        // ===== PRODUCERS: BD_NSET sets of BD_NW warps take the tiles in turn (set = it % BD_NSET).  Warp w of a set owns the columns
+        // c = w, w + BD_NW, w + 2 BD_NW, .. of the tile (STRIDED: the touched positions come in runs - the 5 conv rows of a mutated
+        // residue carry every winner sitting on them, both sides, ~4 entries per column, while a moved winner's column carries one -
+        // and with contiguous ownership one warp got a whole run, ~2.5x the mean, and the tile waited for it).  The operand row of
+        // column c is r = (c % BD_NW) * BD_RPW + c / BD_NW, so a warp's rows are contiguous; the epilogue undoes the permutation when
+        // it writes sT.  The record lists the entries in exactly this order (cnn_delta_record_kernel): a warp reads the two offsets of
+        // its (tile, warp) group and walks the list front to back, four W1 rows in flight across column boundaries. =====
         const int pw = warp - 4;
         const int pset = pw / BD_NW, w8 = pw - pset * BD_NW;      // set, warp of the set
         const bool lact = 8 * lane < prm.kpad;
