@@ -284,17 +284,10 @@ __global__ void __launch_bounds__(NT) pas_reverse_accept_kernel(ppde_potts_t m, 
 }
 
 // ======================================================================================================================
-// Register-resident variants (L <= 256: the 20L-entry logit / probability vector is 5 float4 per thread of a 256-thread CTA).
-// Same arithmetic as the kernels above, entry for entry; what changes is where the vector lives and how often the CTA
-// synchronises:
-//   * the probabilities stay in REGISTERS through the max / sum-exp / clamp-renormalise / race passes (the shared-memory
-//     version re-reads and re-writes 19 KB per pass: 35 - 50 % of the shared-memory pipe, ncu r01_v16), so a CTA needs 20 KB of
-//     shared memory instead of 39 KB and 4 x 256 threads are resident per SM instead of 5 x 128;
-//   * edit distance and G[i, cur_i] are updated incrementally along the path (one position changes per sub-step);
-//   * every block reduction has its own scratch and costs ONE barrier (5 per sub-step instead of 11).
-// Reductions are fixed-order (deterministic); the winner of the exponential race is the same entry (lowest index on ties).
+// Block reductions with ONE barrier each (every reduction has its own scratch), used by the position-per-thread kernels below.
+// Round 1 had strided register-resident variants of the two kernels here (float4 index q = tid + k * 256 per thread); the
+// position-per-thread kernels replaced them.
 constexpr int PAS_NT = 256;
-constexpr int PAS_MAXQ = 5;
 
 template <int NW> __device__ __forceinline__ float red_max1(float v, float* red) {
 #pragma unroll
@@ -343,304 +336,6 @@ template <int NW> __device__ __forceinline__ void red_argmax1(float& v, int& idx
     }
 }
 
-// softmax -> clamp -> renormalise of a register-resident logit vector (same formulas as softmax_clamp_inplace): on return
-// pv[k] = clamp(exp(l - m1) / s2), the function returns s3 = sum of them.  red: 3 scratch arrays of NW floats.
-template <int NW>
-__device__ __forceinline__ float softmax_clamp_regs(float4 (&pv)[PAS_MAXQ], int n4, float lmax, float* red) {
-    const float m1 = red_max1<NW>(lmax, red);
-    const float off = (m1 == -INFINITY) ? 0.f : m1;
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < PAS_MAXQ; ++k) {
-        if ((int)threadIdx.x + k * PAS_NT < n4) {
-            float4 v = pv[k];
-            v.x = __expf(v.x - off); v.y = __expf(v.y - off); v.z = __expf(v.z - off); v.w = __expf(v.w - off);
-            pv[k] = v;
-            sum += (v.x + v.y) + (v.z + v.w);
-        }
-    }
-    const float s2 = red_sum1<NW>(sum, red + NW);
-    const float r2 = 1.0f / s2;
-    float sum3 = 0.f;
-#pragma unroll
-    for (int k = 0; k < PAS_MAXQ; ++k) {
-        if ((int)threadIdx.x + k * PAS_NT < n4) {
-            float4 v = pv[k];
-            v.x = clamp_prob(v.x * r2); v.y = clamp_prob(v.y * r2);
-            v.z = clamp_prob(v.z * r2); v.w = clamp_prob(v.w * r2);
-            pv[k] = v;
-            sum3 += (v.x + v.y) + (v.z + v.w);
-        }
-    }
-    return red_sum1<NW>(sum3, red + 2 * NW);
-}
-__device__ __forceinline__ float f4_get(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
-
-__global__ void __launch_bounds__(PAS_NT, 4) pas_propose_reg_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NT = PAS_NT, NW = PAS_NT / 32;
-    const int L = c.L, NE = L * PPDE_Q, n4 = NE / 4;
-    float* sG = reinterpret_cast<float*>(smem_raw);          // [20L] gradient row (frozen along the path, ppde.py:98)
-    float* sCur = sG + NE;                                   // [L]  G[i, cur_i]
-    uint8_t* sAA = reinterpret_cast<uint8_t*>(sCur + L);     // [L]  evolving state
-    uint8_t* sWT = sAA + ((L + 15) & ~15);                   // [L]
-    __shared__ float red[4 * NW];
-    __shared__ int redi[2 * NW];
-    __shared__ int s_best;                                   // bits of the best race quotient so far (positive floats order as ints)
-    __shared__ int s_dist;
-
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const uint32_t gid = (uint32_t)(c.chain_offset + b);
-    const int t = p.t_dev ? *p.t_dev : p.t;
-    const Philox rng(p.seed);
-    const int lo = p.min_pos, hi = p.max_pos;
-    {   // stage the row and the state
-        const float4* g4 = reinterpret_cast<const float4*>(c.G + (int64_t)c.row_cur[b] * NE);
-        float4* s4 = reinterpret_cast<float4*>(sG);
-#pragma unroll
-        for (int k = 0; k < PAS_MAXQ; ++k) { const int q = tid + k * NT; if (q < n4) s4[q] = g4[q]; }
-        const uint8_t* ax = c.aa + (int64_t)b * c.aa_stride;
-        for (int i = tid; i < L; i += NT) { sAA[i] = ax[i]; sWT[i] = m.wt[i]; }
-    }
-    const int span = p.S;                                      // 2*pas-1 values: U in {1..S}  (ppde.py:67)
-    const int U = 1 + (int)(rng(0u, gid, (uint32_t)t, (uint32_t)(KIND_PATHLEN << 16)).x % (uint32_t)span);
-    if (tid == 0) c.U[b] = U;
-    __syncthreads();
-    const int S_eff = p.full_trace ? p.S : U;                  // dead sub-steps (s >= U) only on request
-    for (int s = S_eff + tid; s < p.S; s += NT) {
-        const int64_t o = (int64_t)s * c.n + b;
-        c.idx[o] = -1; c.old_aa[o] = 0; c.lqf[o] = 0.f;
-    }
-    {   // edit distance to WT (utils.py:5-14) and G[i, cur_i], once; both are updated per move below
-        int dpart = 0;
-        for (int i = tid; i < L; i += NT) {
-            dpart += (sAA[i] != sWT[i]);
-            sCur[i] = sG[i * PPDE_Q + sAA[i]];
-        }
-        const int d0 = red_sum1i<NW>(dpart, redi);             // (its barrier also publishes sCur)
-        if (tid == 0) s_dist = d0;
-    }
-    __syncthreads();
-
-    for (int s = 0; s < S_eff; ++s) {
-        const bool at_thr = s_dist >= p.nmut_threshold;       // ppde.py:86-91
-        if (tid == 0) s_best = 0;
-        // Taylor logits with the revert-only mask and the window mask (ppde.py:95-104, utils.py:17-28), in registers
-        float4 pv[PAS_MAXQ];
-        float lmax = -INFINITY;
-        const float4* g4 = reinterpret_cast<const float4*>(sG);
-#pragma unroll
-        for (int k = 0; k < PAS_MAXQ; ++k) {
-            const int q = tid + k * NT;
-            if (q < n4) {
-                const int i = q / 5, a0 = (q - i * 5) * 4;
-                const float4 g = g4[q];
-                const float gc = sCur[i];
-                float4 l;
-                l.x = (g.x - gc) * 0.5f; l.y = (g.y - gc) * 0.5f; l.z = (g.z - gc) * 0.5f; l.w = (g.w - gc) * 0.5f;
-                if (i < lo || i > hi) {
-                    l.x = l.y = l.z = l.w = -INFINITY;
-                } else if (at_thr) {
-                    const int w = revert_only_target(sAA[i], sWT[i]);      // the only legal target: revert to WT
-                    if (a0 + 0 != w) l.x = -INFINITY;
-                    if (a0 + 1 != w) l.y = -INFINITY;
-                    if (a0 + 2 != w) l.z = -INFINITY;
-                    if (a0 + 3 != w) l.w = -INFINITY;
-                }
-                pv[k] = l;
-                lmax = fmaxf(fmaxf(lmax, fmaxf(l.x, l.y)), fmaxf(l.z, l.w));
-            } else {
-                pv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        const float s3 = softmax_clamp_regs<NW>(pv, n4, lmax, red);        // (its barriers also publish s_best = 0)
-        // exponential race: argmax_j p_j / E_j, E_j = -log(u_j)  (= torch.multinomial(p, 1, True)); an entry whose upper bound
-        // p_j / (s3 (1 - u_j)) is below the best quotient seen so far by any thread (s_best, monotone), with a 1e-5 margin, cannot
-        // win and is not evaluated; the quotient itself is evaluated exactly as in pas_propose_kernel.
-        float best = -1.f; int bidx = 0x7fffffff;
-        const float* um = p.uniforms ? p.uniforms + ((int64_t)s * c.n + b) * NE : nullptr;
-#pragma unroll
-        for (int k = 0; k < PAS_MAXQ; ++k) {
-            const int q = tid + k * NT;
-            if (q < n4) {
-                float4 u;
-                if (um) {
-                    u = reinterpret_cast<const float4*>(um)[q];
-                } else {
-                    const uint4 w = rng((uint32_t)q, gid, (uint32_t)t, (uint32_t)(s | (KIND_PROPOSAL << 16)));
-                    u = make_float4(u32_to_unit(w.x), u32_to_unit(w.y), u32_to_unit(w.z), u32_to_unit(w.w));
-                }
-                const float4 pr = pv[k];
-                const float thr = fmaxf(best, __int_as_float(*(volatile int*)&s_best)) * s3;
-                const bool c0 = pr.x * 1.00001f > thr * (1.0f - u.x), c1 = pr.y * 1.00001f > thr * (1.0f - u.y);
-                const bool c2 = pr.z * 1.00001f > thr * (1.0f - u.z), c3 = pr.w * 1.00001f > thr * (1.0f - u.w);
-                if (c0 | c1 | c2 | c3) {                                   // rare after the first few entries: exact evaluation
-                    const float pq[4] = {pr.x, pr.y, pr.z, pr.w};
-                    const float uq[4] = {u.x, u.y, u.z, u.w};
-                    const bool cq[4] = {c0, c1, c2, c3};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (cq[e]) {
-                            const float r = (pq[e] / s3) / (-logf(uq[e]));
-                            if (r > best) { best = r; bidx = q * 4 + e; atomicMax(&s_best, __float_as_int(r)); }
-                        }
-                    }
-                }
-            }
-        }
-        red_argmax1<NW>(best, bidx, red + 3 * NW, redi + NW);
-        {   // the thread that holds the winner's probability records the move
-            const int q = bidx >> 2;
-            if (tid == (q % NT)) {
-                const int kk = q / NT;
-                float4 pw = pv[0];
-#pragma unroll
-                for (int k = 1; k < PAS_MAXQ; ++k) if (kk == k) pw = pv[k];
-                const int pos = bidx / PPDE_Q, a = bidx - pos * PPDE_Q;
-                const int64_t o = (int64_t)s * c.n + b;
-                c.idx[o] = bidx;
-                const uint8_t old = sAA[pos];
-                c.old_aa[o] = old;
-                c.lqf[o] = logf(clamp_prob(f4_get(pw, bidx & 3) / s3));          // Categorical.log_prob
-                if (s < U) {                                                     // ppde.py:111-115 (masked by u_mask)
-                    const uint8_t w = sWT[pos];
-                    s_dist += (int)((uint8_t)a != w) - (int)(old != w);
-                    sAA[pos] = (uint8_t)a;
-                    sCur[pos] = sG[pos * PPDE_Q + a];
-                }
-            }
-        }
-        __syncthreads();
-    }
-    uint8_t* ay = c.aa_y + (int64_t)b * c.aa_stride;
-    for (int i = tid; i < L; i += NT) ay[i] = sAA[i];
-}
-
-__global__ void __launch_bounds__(PAS_NT, 4) pas_reverse_accept_reg_kernel(ppde_potts_t m, ppde_chains_t c, ppde_pas_params_t p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NT = PAS_NT, NW = PAS_NT / 32;
-    const int L = c.L, NE = L * PPDE_Q, n4 = NE / 4;
-    float* sG = reinterpret_cast<float*>(smem_raw);          // [20L] gradient row at y
-    float* sCur = sG + NE;                                   // [L]  G_y[i, z_i]
-    uint8_t* sZ = reinterpret_cast<uint8_t*>(sCur + L);      // [L] trajectory state
-    __shared__ float red[3 * NW];
-    __shared__ int redi[NW];
-    __shared__ int s_flag;
-    __shared__ float s_ratio;
-
-    const int b = blockIdx.x, n = c.n, tid = threadIdx.x;
-    const uint32_t gid = (uint32_t)(c.chain_offset + b);
-    const int t = p.t_dev ? *p.t_dev : p.t;
-    const int rx = c.row_cur[b];
-    const int ry = y_row(rx, b, n);
-    uint8_t* ax = c.aa + (int64_t)b * c.aa_stride;
-    const uint8_t* ay = c.aa_y + (int64_t)b * c.aa_stride;
-    {
-        const float4* g4 = reinterpret_cast<const float4*>(c.G + (int64_t)ry * NE);
-        float4* s4 = reinterpret_cast<float4*>(sG);
-#pragma unroll
-        for (int k = 0; k < PAS_MAXQ; ++k) { const int q = tid + k * NT; if (q < n4) s4[q] = g4[q]; }
-        for (int i = tid; i < L; i += NT) sZ[i] = ax[i];
-    }
-    const int U = c.U[b];
-    if (tid == 0) s_ratio = 0.f;
-    __syncthreads();
-    for (int i = tid; i < L; i += NT) sCur[i] = sG[i * PPDE_Q + sZ[i]];     // G_y[i, x_i]; one entry changes per sub-step
-
-    const int S_eff = p.full_trace ? p.S : U;                      // dead sub-steps (s >= U) only on request
-    for (int s = S_eff + tid; s < p.S; s += NT) c.lqr[(int64_t)s * n + b] = 0.f;
-    for (int s = 0; s < S_eff; ++s) {
-        const int64_t o = (int64_t)s * n + b;
-        const int cidx = c.idx[o];
-        __syncthreads();                                           // previous sub-step's readers of sCur / sZ are done
-        if (tid == 0 && s < U) {                                   // state AFTER move s (ppde.py:124-125)
-            const int pos = cidx / PPDE_Q, a = cidx - pos * PPDE_Q;
-            sZ[pos] = (uint8_t)a;
-            sCur[pos] = sG[cidx];
-        }
-        __syncthreads();
-        float4 pv[PAS_MAXQ];
-        const float4* g4 = reinterpret_cast<const float4*>(sG);
-        float lmax = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < PAS_MAXQ; ++k) {                       // NO masks on the reverse path (ppde.py:126-127)
-            const int q = tid + k * NT;
-            if (q < n4) {
-                const float gc = sCur[q / 5];
-                const float4 g = g4[q];
-                const float4 l = make_float4((g.x - gc) * 0.5f, (g.y - gc) * 0.5f, (g.z - gc) * 0.5f, (g.w - gc) * 0.5f);
-                pv[k] = l;
-                lmax = fmaxf(fmaxf(lmax, fmaxf(l.x, l.y)), fmaxf(l.z, l.w));
-            } else {
-                pv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        const float s3 = softmax_clamp_regs<NW>(pv, n4, lmax, red);
-        {
-            const int q = cidx >> 2;
-            if (tid == (q % NT)) {
-                const int kk = q / NT;
-                float4 pw = pv[0];
-#pragma unroll
-                for (int k = 1; k < PAS_MAXQ; ++k) if (kk == k) pw = pv[k];
-                const float lqr = logf(clamp_prob(f4_get(pw, cidx & 3) / s3));
-                c.lqr[o] = lqr;
-                if (s < U) s_ratio += lqr - c.lqf[o];              // u_mask * (rev - fwd), ppde.py:132 (one thread per sub-step, in order)
-            }
-        }
-    }
-    __syncthreads();
-
-    if (tid == 0) {
-        const float log_ratio = s_ratio;
-        const float e_x = c.E[b], f_x = c.fit[b];
-        const float e_y = c.E_y[b], f_y = c.fit_y[b];
-        const float log_acc = (e_y - e_x) + log_ratio;             // ppde.py:135-136
-        const float u = u32_to_unit(Philox(p.seed)(0u, gid, (uint32_t)t, (uint32_t)(KIND_ACCEPT << 16)).x);
-        const bool acc = expf(log_acc) >= u;                       // '>=' (ppde.py:138); NaN rejects
-        c.log_acc[b] = log_acc;
-        c.accept[b] = acc ? 1 : 0;
-        const float e_rec = acc ? e_y : e_x, f_rec = acc ? f_y : f_x;   // ppde.py:141-143
-        if (c.E_hist) c.E_hist[(int64_t)(t + 1) * n + b] = e_rec;
-        if (c.fit_hist) c.fit_hist[(int64_t)(t + 1) * n + b] = f_rec;
-        // 0: keep current state; 1: take y; 2: fall back to the paper-mode anchor
-        s_flag = acc ? 1 : (p.paper_results ? 2 : 0);
-        if (acc) { c.E[b] = e_y; c.fit[b] = f_y; c.row_cur[b] = ry; }
-        else if (p.paper_results) {                                // x is never refreshed: reject = back to x0 (ppde.py:76-77,139)
-            const int f = c.anchor_fixed ? c.anchor_fixed[b] : (c.row_wt - 2 * n);
-            c.E[b] = c.E_fixed[f]; c.fit[b] = c.fit_fixed[f]; c.row_cur[b] = 2 * n + f;
-        }
-        const bool better = e_rec > c.best_E[b];                   // strict: first occurrence of the max (ppde.py:173)
-        if (better) { c.best_E[b] = e_rec; c.best_fit[b] = f_rec; }
-        s_flag |= better ? 4 : 0;
-    }
-    __syncthreads();
-    const int flag = s_flag & 3;
-    const bool better = (s_flag & 4) != 0;
-    const uint8_t* src = ax;
-    if (flag == 1) src = ay;
-    else if (flag == 2) {
-        const int f = c.anchor_fixed ? c.anchor_fixed[b] : (c.row_wt - 2 * n);
-        src = c.aa_fixed + (int64_t)f * c.aa_stride;
-    }
-    // recorded state (post-accept, pre-reset): best-of-history and the random trajectory (ppde.py:142,146,172-183)
-    int dpart = 0;
-    for (int i = tid; i < L; i += NT) {
-        const uint8_t v = src[i];
-        sZ[i] = v;
-        dpart += (v != m.wt[i]);
-        if (better) c.best_aa[(int64_t)b * c.aa_stride + i] = v;
-        if (c.traj_aa && b == c.traj_chain) c.traj_aa[(int64_t)(t + 1) * c.aa_stride + i] = v;
-    }
-    const int dist = red_sum1i<NW>(dpart, redi);
-    const bool reset = !p.paper_results && dist >= p.nmut_threshold;   // hard reset to WT (ppde.py:148-153)
-    for (int i = tid; i < L; i += NT) ax[i] = reset ? m.wt[i] : sZ[i];
-    if (reset && tid == 0) {
-        const int f = c.row_wt - 2 * n;
-        c.E[b] = c.E_fixed[f]; c.fit[b] = c.fit_fixed[f]; c.row_cur[b] = c.row_wt;
-    }
-}
-
 // ======================================================================================================================
 // Position-per-thread variants (L <= 256; default).  Thread i of a 256-thread CTA owns position i: its 20 gradient entries,
 // logits and probabilities live in REGISTERS for the whole kernel and are indexed by compile-time constants only.
@@ -669,7 +364,7 @@ __device__ __forceinline__ void load_row20(float (&g)[PPDE_Q], const float* src)
     }
 }
 // softmax -> clamp -> renormalise of the logits l (thread-local, -inf for masked / inactive entries): on return
-// e[k] = clamp(exp(l - m1) / s2) for an active thread; returns s3 = sum over the block.  Same formulas as softmax_clamp_regs.
+// e[k] = clamp(exp(l - m1) / s2) for an active thread; returns s3 = sum over the block.  Same formulas as softmax_clamp_inplace.
 template <int NW>
 __device__ __forceinline__ float softmax_clamp_pos(float (&e)[PPDE_Q], bool active, float* red) {
     float lmax = -INFINITY;
@@ -1163,9 +858,6 @@ __global__ void __launch_bounds__(NT) pas_kat_kernel(const uint8_t* __restrict__
 using namespace ppde;
 
 static size_t pas_smem(int L) { return (size_t)(2 * L * PPDE_Q + L) * sizeof(float) + 2 * ((L + 15) & ~15); }
-static size_t pas_reg_smem(int L) { return (size_t)(L * PPDE_Q + L) * sizeof(float) + 2 * ((L + 15) & ~15); }
-// register-resident kernels: the 5 L float4 of a row fit PAS_MAXQ per thread of a PAS_NT-thread CTA (L <= 256)
-static bool pas_use_reg(int L) { return 5 * L <= PAS_NT * PAS_MAXQ; }
 // position-per-thread kernels (default for L <= PAS_NT); PPDE_PAS_POS=0 falls back to the strided kernels (A/B)
 static bool pas_use_pos(int L) {
     static const bool on = [] { const char* e = getenv("PPDE_PAS_POS"); return !(e && e[0] == '0'); }();
@@ -1183,17 +875,6 @@ extern "C" int ppde_pas_propose(const ppde_potts_t* m, const ppde_chains_t* c, c
                                 void* stream) {
     if (int r = pas_check(m, c, p)) return r;
     if (c->n <= 0) return 0;
-    // measured (64k chains, L = 238): shared-memory version 1.86 ms, register-resident version 1.97 ms (the kernel is bound by
-    // instruction issue - Philox + the race test per entry - and the predicated 5-float4 loops execute more of them); the
-    // register-resident REVERSE kernel is the faster one (0.94 vs 1.03 ms).  PPDE_PAS_PROPOSE_REG=1 selects it here (A/B).
-    static const bool propose_reg = [] { const char* e = getenv("PPDE_PAS_PROPOSE_REG"); return e && e[0] == '1'; }();
-    if (propose_reg && pas_use_reg(c->L)) {
-        const size_t smem = pas_reg_smem(c->L);
-        static SmemCache configured_reg;
-        if (cudaError_t e = ensure_dynamic_smem(pas_propose_reg_kernel, smem, configured_reg)) return (int)e;
-        pas_propose_reg_kernel<<<c->n, PAS_NT, smem, (cudaStream_t)stream>>>(*m, *c, *p);
-        return launch_done();
-    }
     if (p->fuse_potts && (!pas_use_pos(c->L) || !c->Gp || !c->Epotts_y || !m->Jsym || !m->h)) return (int)cudaErrorInvalidValue;
     if (pas_use_pos(c->L)) {
         if (p->uniforms) pas_propose_pos_kernel<4, true><<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p, PhiloxKeys(p->seed));
@@ -1219,13 +900,6 @@ extern "C" int ppde_pas_reverse_accept(const ppde_potts_t* m, const ppde_chains_
     }
     if (pas_use_pos(c->L)) {
         pas_reverse_accept_pos_kernel<<<c->n, PAS_NT, 0, (cudaStream_t)stream>>>(*m, *c, *p);
-        return launch_done();
-    }
-    if (pas_use_reg(c->L)) {
-        const size_t smem = pas_reg_smem(c->L);
-        static SmemCache configured_reg;
-        if (cudaError_t e = ensure_dynamic_smem(pas_reverse_accept_reg_kernel, smem, configured_reg)) return (int)e;
-        pas_reverse_accept_reg_kernel<<<c->n, PAS_NT, smem, (cudaStream_t)stream>>>(*m, *c, *p);
         return launch_done();
     }
     size_t smem = pas_smem(c->L);
