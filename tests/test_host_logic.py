@@ -172,3 +172,41 @@ def test_exact_backward_schedule():
     assert full == [31, 63, 95]
     e.delta = False
     assert all(e.full_backward_at(t) for t in range(5))
+
+
+def test_delta_record_work_order_is_consistent():
+    """The three places that permute the columns of a delta-backward tile must agree (csrc/cnn_tc.cu): the record builder ranks
+    the entries by (tile, producer warp w = r % NW, slot sl = r // NW) with r the column inside the tile, a producer warp stores
+    the column of its slot sl into operand row w * RPW + sl, and the epilogue maps accumulator column j back to tile column
+    (j % RPW) * NW + j // RPW.  Host-side restatement with the kernel's constants (BD_NT = 48, BD_NW = 6, BD_RPW = 8); also the
+    per-warp offsets as 'first rank of the next non-empty group' (suffix minimum)."""
+    NT, NW = 48, 6
+    RPW = NT // NW
+    rng = np.random.default_rng(0)
+    for npos in (0, 1, 5, 47, 48, 49, 130, 252):
+        ntile = (npos + NT - 1) // NT
+        cols = np.arange(npos)
+        t, r = cols // NT, cols % NT
+        w, sl = r % NW, r // NW
+        g = t * NT + w * RPW + sl                               # work-order key of a column
+        assert len(set(g.tolist())) == npos                      # a permutation: no two columns share a place
+        row = w * RPW + sl                                      # operand row inside the tile
+        back = (row % RPW) * NW + row // RPW                    # the epilogue's inverse
+        assert np.array_equal(back, r)
+        # entries: a few per column; sorted by (g, side, channel) they must be contiguous per (tile, warp) group, slots ascending
+        ne = rng.integers(0, 4, size=npos)
+        ent = [(int(g[c]), int(s), int(ch)) for c in range(npos) for s, ch in zip(rng.integers(0, 2, ne[c]), rng.choice(476, ne[c], replace=False))]
+        ent.sort()
+        grp = np.array([(NW * (e[0] // NT) + (e[0] % NT) // RPW) for e in ent], dtype=int)
+        nw = NW * ntile + 1
+        first = np.full(nw, 2 ** 31 - 1)
+        for rank, q in enumerate(grp):
+            first[q] = min(first[q], rank)
+        first[-1] = min(first[-1], len(ent))
+        woff = np.minimum.accumulate(np.where(first == 2 ** 31 - 1, len(ent), first)[::-1])[::-1]
+        assert woff[0] == 0 or len(ent) == 0 or grp.min() > 0
+        for q in range(nw - 1):
+            seg = [e for e, gq in zip(ent, grp) if gq == q]
+            assert woff[q + 1] - woff[q] == len(seg)
+            slots = [(e[0] % NT) % RPW for e in seg]
+            assert slots == sorted(slots)
